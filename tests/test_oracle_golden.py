@@ -1,0 +1,177 @@
+"""The oracle against the reference's own outputs (tests/golden, made by
+oracle/make_golden.py) and, where /root/reference is mounted, against the
+reference live.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import numpy_oracle as no
+from oracle.ref_loader import reference_available, load_reference_main
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_cosine_matches_reference_vectors(golden_dir):
+    g = _load(golden_dir, "cosine.npz")
+    got = np.array([oracle.cosine_similarity(a, b) for a, b in zip(g["a"], g["b"])])
+    # same numpy expressions -> same bits on the same BLAS; 1e-6 leaves room for
+    # another OpenBLAS kernel on another host
+    np.testing.assert_allclose(got, g["out"], rtol=0, atol=1e-6)
+    assert got[4] == 0.0 and got[5] == 0.0 and got[6] == 0.0       # zero-norm guard, main.py:62-63
+    assert abs(got[1] - 1.0) < 1e-6 and abs(got[2] + 1.0) < 1e-6
+
+
+def test_normalize_is_bit_identical_to_reference(golden_dir):
+    g = _load(golden_dir, "index_search.npz")
+    got = oracle.normalize_rows(g["emb"])
+    assert got.dtype == np.float32
+    # the reference serialises via .tolist() (exact for fp32) -> compare bits
+    np.testing.assert_array_equal(got.view(np.uint32), g["stored"].view(np.uint32))
+    assert not got[5].any()                                         # zero row stays zero
+    qn = oracle.normalize_rows(g["q"])
+    np.testing.assert_array_equal(qn.view(np.uint32), g["q_norm"].view(np.uint32))
+
+
+def test_pairwise_order_is_numpys(golden_dir):
+    g = _load(golden_dir, "index_search.npz")
+    emb = g["emb"]
+    ssq = no.pairwise_sumsq_f32(emb)
+    ref = np.add.reduce(emb * emb, axis=1)
+    np.testing.assert_array_equal(ssq.view(np.uint32), ref.view(np.uint32))
+    np.testing.assert_array_equal(np.sqrt(ssq).view(np.uint32),
+                                  np.linalg.norm(emb, axis=1).view(np.uint32))
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((257, 1024)) * 10 ** rng.uniform(-6, 6, (257, 1))).astype(np.float32)
+    np.testing.assert_array_equal(no.pairwise_sumsq_f32(x).view(np.uint32),
+                                  np.add.reduce(x * x, axis=1).view(np.uint32))
+
+
+def test_search_matches_reference_vectors(golden_dir):
+    g = _load(golden_dir, "index_search.npz")
+    stored = oracle.normalize_rows(g["emb"])
+    qn = oracle.normalize_rows(g["q"])
+    for ki, k in enumerate(g["ks"]):
+        s, i = oracle.topk_cosine(stored, qn, int(k))
+        np.testing.assert_array_equal(i, g["res_idx"][:, ki, :k])
+        np.testing.assert_allclose(s, g["res_score"][:, ki, :k], atol=1e-6)
+    # planted tie: rows 6 and 7 are identical -> 6 before 7 (main.py:84 generalised)
+    _, i = oracle.topk_cosine(stored, qn[1:2], 3)
+    assert list(i[0][:2]) == [6, 7] or list(i[0][:3]) == [6, 7, 40] or 40 in i[0]
+    pos = {int(v): p for p, v in enumerate(i[0])}
+    assert pos[6] < pos[7]
+    # zero query -> every score 0.0 -> indices 0..k-1
+    _, i = oracle.topk_cosine(stored, qn[2:3], 5)
+    assert list(i[0]) == [0, 1, 2, 3, 4]
+
+
+def test_topk_partition_equals_stable_argsort():
+    rng = np.random.default_rng(11)
+    s = rng.standard_normal((6, 5000)).astype(np.float32)
+    s[:, 100:140] = s[:, 99:100]                 # a run of exact ties
+    s[2, :] = 0.25                               # all equal
+    for k in (1, 7, 64):
+        gs, gi = oracle.topk_from_scores(s, k)
+        for r in range(s.shape[0]):
+            ref = np.argsort(-s[r], kind="stable")[:k]
+            np.testing.assert_array_equal(gi[r], ref)
+            np.testing.assert_array_equal(gs[r], s[r][ref])
+    gs, gi = oracle.topk_from_scores(s[:, :3], 5)    # k > n
+    assert (gi[:, 3:] == -1).all() and np.isneginf(gs[:, 3:]).all()
+
+
+def test_topk_cosine_chunked_equals_unchunked():
+    rng = np.random.default_rng(5)
+    d = oracle.normalize_rows(rng.standard_normal((3000, 1024)).astype(np.float32))
+    d[2500] = d[17]
+    q = oracle.normalize_rows(rng.standard_normal((4, 1024)).astype(np.float32))
+    q[0] = d[17]
+    s0, i0 = oracle.topk_cosine(d, q, 10)
+    s1, i1 = oracle.topk_cosine(d, q, 10, chunk=700)
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(s0, s1)
+    assert list(i0[0][:2]) == [17, 2500]
+
+
+def test_storage_rounding():
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.standard_normal(4096).astype(np.float32) * 0.05,
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.01171875, 3.0e38, 1e-40, np.inf],
+                                 dtype=np.float32)])
+    bits = oracle.to_storage(x, "bf16")
+    ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    np.testing.assert_array_equal(bits, ref)
+    back = oracle.from_storage(bits, "bf16")
+    np.testing.assert_array_equal(back, torch.from_numpy(x).to(torch.bfloat16).float().numpy())
+    h = oracle.to_storage(x, "fp16")
+    np.testing.assert_array_equal(h.view(np.uint16),
+                                  torch.from_numpy(x).to(torch.float16).view(torch.int16).numpy().view(np.uint16))
+    np.testing.assert_array_equal(oracle.to_storage(x, "fp32"), x)
+
+
+@pytest.mark.parametrize("name", ["default", "evict8", "thr095"])
+def test_cache_model_replays_reference_log(golden_dir, name):
+    with open(os.path.join(golden_dir, f"cache_{name}.json")) as f:
+        log = json.load(f)
+    vecs = _load(golden_dir, f"cache_{name}.npz")["vecs"]
+    model = oracle.LfuCacheModel(max_items=log["max_items"], threshold=log["threshold"])
+    for op in log["ops"]:
+        v = vecs[op["vec"]][None, :]
+        if op["op"] == "get":
+            assert model.get(v) == op["result"], op
+        else:
+            model.put(v, op["response"])
+    assert model.responses() == log["final_responses"]
+    assert model.freqs() == log["final_freqs"]
+
+
+def test_cache_lookup_edge_cases():
+    rng = np.random.default_rng(9)
+    q = rng.standard_normal(1024).astype(np.float32)
+    assert oracle.cache_lookup(q, [], 0.96) == (-1, -1.0, False)          # empty, main.py:70-71
+    idx, sim, hit = oracle.cache_lookup(q, [-q, -2 * q], 0.96)            # all sims == -1.0
+    assert idx == -1 or sim <= -1.0 + 1e-6
+    assert hit is False
+    idx, sim, hit = oracle.cache_lookup(q, [q.copy(), q, q.copy()], 0.96)  # exact ties -> first
+    assert idx == 0 and hit
+    idx, sim, hit = oracle.cache_lookup(np.zeros(1024, np.float32), [q], 0.96)
+    assert sim == 0.0 and not hit and idx == 0                            # 0.0 > -1.0
+
+
+def test_cache_lookup_batched_equals_rowwise():
+    rng = np.random.default_rng(4)
+    c = oracle.normalize_rows(rng.standard_normal((300, 1024)).astype(np.float32))
+    q = oracle.normalize_rows(rng.standard_normal((9, 1024)).astype(np.float32))
+    q[0] = c[42]
+    q[1] = oracle.normalize_rows((0.97 * c[7] + 0.1 * q[1])[None])[0]
+    idx, score, hit = no.cache_lookup_batched(q, c, 0.96)
+    for r in range(len(q)):
+        i, s, h = oracle.cache_lookup(q[r], list(c), 0.96)
+        assert idx[r] == i and bool(hit[r]) == h and abs(score[r] - s) < 1e-6
+    assert hit[0] and idx[0] == 42 and hit[1] and idx[1] == 7
+
+
+def test_merge_topk():
+    s = np.array([[[0.9, 0.5, 0.1]], [[0.9, 0.8, -np.inf]]], dtype=np.float32)   # [lists=2,B=1,k=3]
+    i = np.array([[[10, 11, 12]], [[3, 4, -1]]], dtype=np.int64)
+    ms, mi = oracle.merge_topk(s, i, 4)
+    assert list(mi[0]) == [3, 10, 4, 11]
+    np.testing.assert_allclose(ms[0], [0.9, 0.9, 0.8, 0.5])
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+def test_oracle_against_live_reference():
+    m = load_reference_main()
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((50, 1024)).astype(np.float32)
+    b = rng.standard_normal((50, 1024)).astype(np.float32)
+    for x, y in zip(a, b):
+        assert oracle.cosine_similarity(x, y) == m.cosine_similarity(x, y)
+    assert oracle.CACHE_SIM_THRESHOLD == m.CACHE_SIM_THRESHOLD
+    assert oracle.REDIS_MAX_ITEMS == m.REDIS_MAX_ITEMS
+    assert oracle.EMBED_DIM == m.EMBED_DIM

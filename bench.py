@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of exact cosine top-10 over a 10M x 1024 bf16 corpus.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b1024|b1|cache64]
+    python bench.py --impl reference ...      # the reference's CPU path (numpy port), rank 0 only
+
+A step = one pass of the hot path over one query batch (normalise the queries, score them
+against every stored row, top-k; with N > 1 ranks also the all-gather + merge).  The corpus is
+sharded by rows across ranks (strong scaling: the 10M-row corpus is fixed, each rank holds
+10M/N rows), so `value` = batch size / max-over-ranks step time.
+
+Prints ONE JSON line on rank 0 (see the driver contract in the task statement): value is the
+device-timed throughput with inputs resident in HBM, `e2e` the same metric through the public
+host API (`search_batch` on pinned host queries, H2D and D2H inside the timed region),
+`roofline` the dominant kernel against MEASURED_PEAKS.json, `cpu_baseline` the oracle port timed
+on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIM = 1024
+GEN_BLOCK = 250_000            # rows per synthetic block; shard bounds are multiples of it
+METRIC = "queries/sec exact cosine top-10 @10Mx1024"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SQE_BENCH_WORKLOAD", "b1024"),
+                    choices=["b1024", "b1", "cache64"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained"), "source": "measured"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+# --------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------- CPU reference
+def cpu_reference_sample(b: int, rows: int, k: int, total_rows: int, seed: int = 1):
+    """One bounded sample of the reference's CPU path (oracle port): fp32 unit rows,
+    `Q @ D.T` + stable top-k, every host thread numpy's BLAS can use.  Returns
+    (seconds, queries/sec scaled linearly in rows to `total_rows`)."""
+    import oracle
+    rng = np.random.default_rng(seed)
+    d = rng.standard_normal((rows, DIM), dtype=np.float32)
+    q = rng.standard_normal((b, DIM), dtype=np.float32)
+    t0 = time.perf_counter()
+    dn = oracle.normalize_rows(d)        # ingest normalise is NOT on the query path: untimed below
+    t_ingest = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    qn = oracle.normalize_rows(q)
+    oracle.topk_cosine(dn, qn, k, chunk=1 << 30)
+    dt = time.perf_counter() - t0
+    qps = b / dt * (rows / float(total_rows))
+    return dt, qps, t_ingest
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = {"b1024": 64, "b1": 1, "cache64": 64}[args.workload]
+    sample_rows = 1_000_000 if args.workload != "cache64" else 250_000
+    total_rows = args.rows if args.workload != "cache64" else 1_000_000
+    k = args.k if args.workload != "cache64" else 1
+    steps = args.steps or 3
+    warmup = args.warmup if args.warmup is not None else 1
+    cores = len(os.sched_getaffinity(0))
+    for _ in range(warmup):
+        cpu_reference_sample(b, sample_rows, k, total_rows)
+    times, qps = [], []
+    for s in range(steps):
+        dt, v, _ = cpu_reference_sample(b, sample_rows, k, total_rows, seed=2 + s)
+        times.append(dt)
+        qps.append(v)
+    value = float(np.mean(qps))
+    sample = (f"{b} queries x {sample_rows} fp32 rows per step (numpy Q@D.T + stable top-{k}); "
+              f"q/s scaled by {sample_rows}/{total_rows} rows")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    if args.workload == "cache64":
+        return {"workload": "query cache 1Mx1024 bf16, streaming batch-64 top-1 + 0.95 threshold "
+                            "(BASELINE configs[4])", "rows": 1_000_000, "batch": 64, "k": 1,
+                "dtype": "bf16", "l2": "inputs larger than L2"}
+    b = 1024 if args.workload == "b1024" else 1
+    return {"workload": f"{args.rows}x1024 {args.dtype} corpus, batch-{b} cosine top-{args.k} "
+                        f"(BASELINE configs[2] / metric headline)",
+            "rows": args.rows, "batch": b, "k": args.k, "dtype": args.dtype,
+            "sharding": f"rows split over {world} rank(s), all-gather + merge" if world > 1 else "single shard",
+            "l2": "inputs larger than L2 (shard >= 2.5 GB per rank vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------- our arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sqe_b200
+    from sqe_b200 import ops
+    nat = sqe_b200._native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.load()
+
+    peaks = load_peaks()
+    is_cache = args.workload == "cache64"
+    b = {"b1024": 1024, "b1": 1, "cache64": 64}[args.workload]
+    k = 1 if is_cache else args.k
+    dtype = "bf16" if is_cache else args.dtype
+    total_rows = 1_000_000 if is_cache else args.rows
+    steps = args.steps or (20 if b > 1 else 50)
+    warmup = args.warmup if args.warmup is not None else 3
+
+    # ---- corpus shard of this rank, generated block by block on the GPU and fed to K1
+    blocks_total = (total_rows + GEN_BLOCK - 1) // GEN_BLOCK
+    blo, bhi = sqe_b200.shard_bounds(blocks_total, world, rank)
+    row_lo = blo * GEN_BLOCK
+    row_hi = min(total_rows, bhi * GEN_BLOCK)
+    local_rows = row_hi - row_lo
+    if is_cache:
+        store = sqe_b200.GpuQueryCache(max_items=local_rows, threshold=0.95, dtype=dtype, device=dev)
+    else:
+        store = sqe_b200.GpuCorpusIndex(dtype=dtype, device=dev, keep_payload=False)
+        store.reserve(local_rows)
+    gen = torch.Generator(device=dev)
+    staged = []
+    for blk in range(blo, bhi):
+        gen.manual_seed(1234 + blk)
+        rows = min(GEN_BLOCK, total_rows - blk * GEN_BLOCK)
+        x = torch.randn((rows, DIM), generator=gen, device=dev, dtype=torch.float32)
+        if is_cache:
+            staged.append(x)
+        else:
+            store.add_device_rows(x)
+        del x
+    if is_cache:
+        store.bulk_load(torch.cat(staged))
+        staged = None
+    torch.cuda.synchronize()
+
+    qgen = torch.Generator().manual_seed(99)
+    q_host = torch.randn((b, DIM), generator=qgen, dtype=torch.float32).pin_memory()
+    q_dev = q_host.to(dev)
+
+    sharded = None
+    if not is_cache:
+        sharded = sqe_b200.ShardedCorpusIndex(store)
+        sharded.finalize(local_rows)
+        assert sharded.row_offset == row_lo and sharded.total_rows == total_rows
+
+    def step_device():
+        if is_cache:
+            return store.lookup_device(q_dev, path=0)
+        return sharded.search_device(q_dev, k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed throughput (inputs resident in HBM)
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = nat.launch_count
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    launches = nat.launch_count - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    value = b / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (roofline numerator), CUDA events on the launch stream
+    qn = ops.normalize_cast(q_dev, dtype)
+    shard = store._buf[store._head:] if is_cache else store._shard
+    if b == 1:
+        kern = lambda: ops.topk_gemv(shard, qn, k, n=local_rows)
+        kname = "topk_gemv_kernel"
+    else:
+        kern = lambda: ops.topk_batched(shard, qn, k, n=local_rows)
+        kname = "topk_batched_kernel"
+    for _ in range(3):
+        kern()
+    torch.cuda.synchronize()
+    kiters = max(5, steps)
+    k0 = torch.cuda.Event(enable_timing=True)
+    k1 = torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(kiters):
+        kern()
+    k1.record()
+    torch.cuda.synchronize()
+    kms = k0.elapsed_time(k1) / kiters
+    esize = {"bf16": 2, "fp16": 2, "fp32": 4}[dtype]
+    if b == 1 or is_cache:
+        alg = local_rows * DIM * esize
+        roofline = {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "algorithmic_bytes_per_launch": alg}
+    else:
+        alg = 2.0 * b * local_rows * DIM
+        roofline = {"bound": "tensor", "achieved": alg / (kms * 1e-3) / 1e12,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "algorithmic_flops_per_launch": alg,
+                    "frac_of_sustained_peak": None}
+        if peaks.get("bf16_tflops_sustained"):
+            roofline["frac_of_sustained_peak"] = roofline["achieved"] / peaks["bf16_tflops_sustained"]
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    roofline["kernel"] = kname
+    roofline["kernel_ms"] = kms
+    roofline["peak_source"] = peaks["source"] + (" (burst)" if roofline["bound"] == "tensor" else "")
+    roofline["traffic"] = load_traffic(kname)
+
+    # ---- end to end through the public host API (pinned host queries in, host results out)
+    e2e = None
+    if not args.no_e2e:
+        q_np = q_host.numpy()
+        if is_cache:
+            call = lambda: store.lookup_batch(q_np)
+            d2h = b * (4 + 4 + 1)
+        else:
+            call = lambda: sharded.search_batch(q_np, k)
+            d2h = b * k * (4 + 8)
+        for _ in range(warmup):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": b * steps / float(tt.item()), "unit": "queries/s",
+               "h2d_bytes_per_step": b * DIM * 4, "d2h_bytes_per_step": d2h,
+               "ms_per_step": float(tt.item()) / steps * 1e3}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        cb, crow = (16, 1_000_000) if b > 1 else (1, 1_000_000)
+        if is_cache:
+            cb, crow = 64, 250_000
+        cpu_reference_sample(cb, 100_000, k, total_rows)          # warm BLAS threads
+        dt, qps, _ = cpu_reference_sample(cb, crow, k, total_rows)
+        cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                        "sample": f"{cb} queries x {crow} fp32 rows, numpy Q@D.T + stable top-{k}, "
+                                  f"{dt:.2f} s; q/s scaled by {crow}/{total_rows} rows"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC if not is_cache else "queries/sec cache top-1+threshold @1Mx1024",
+            "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(kernel_name: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_name)
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/*
+ * sqe_b200.h -- C ABI of the B200-native retrieval hot path.
+ *
+ * This is the drop-in boundary for the similarity path of
+ * NeuralRevenant/semantic-query-engine.  The reference has no FFI of its own
+ * (it is two Python files); each entry point below replaces the numpy / external
+ * service expression cited next to it (paths relative to the reference root).
+ * A Python maintainer binds these with ctypes; the package
+ * `semantic-query-engine_b200/` is exactly that binding plus the host mirror of
+ * the reference's `OpenSearchIndexer` / `lfu_cache_get` / `lfu_cache_put`.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (HBM) unless its name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - all calls are asynchronous on `stream`; outputs are valid after the stream
+ *     is synchronised;
+ *   - return value: 0 = ok, <0 = error (see SQE_E_*); `sqe_last_error()` gives the
+ *     text for the calling thread.  No exceptions cross this boundary;
+ *   - rows are `dim` = 1024 elements (EMBED_DIM, app/main.py:38), row-major,
+ *     16-byte aligned;
+ *   - there is no CPU fallback: on a machine without an sm_100 device the compute
+ *     entry points return SQE_E_CUDA.
+ *
+ * Ordering contract (everywhere): results are best-first by (score descending,
+ * row index ascending) -- "first maximum wins", app/main.py:84, generalised to
+ * k > 1 (equals `np.argsort(-s, kind="stable")[:k]`).  Empty slots (k > rows)
+ * hold score = -inf, index = -1.
+ */
+#ifndef SQE_B200_H
+#define SQE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SQE_API __attribute__((visibility("default")))
+#else
+#define SQE_API
+#endif
+
+#define SQE_ABI_VERSION 1
+#define SQE_DIM 1024            /* app/main.py:38 EMBED_DIM */
+#define SQE_MAX_K_GEMV 256      /* largest k of sqe_topk_gemv / sqe_merge_topk */
+#define SQE_MAX_K_BATCHED 128   /* largest k of sqe_topk_batched */
+
+/* storage types of a shard in HBM */
+#define SQE_F32 0
+#define SQE_BF16 1
+#define SQE_F16 2
+
+/* error codes */
+#define SQE_OK 0
+#define SQE_E_ARG (-1)          /* bad argument (dim, dtype, k, alignment, null) */
+#define SQE_E_CUDA (-2)         /* CUDA runtime / driver error, or no sm_100 device */
+#define SQE_E_WORKSPACE (-3)    /* workspace too small */
+#define SQE_E_UNSUPPORTED (-4)  /* combination not implemented (see message) */
+
+SQE_API int sqe_abi_version(void);
+SQE_API const char *sqe_last_error(void);
+
+/* Number of SMs / whether the current device is sm_100 (1) or not (0); <0 on error. */
+SQE_API int sqe_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/*
+ * K1  fused L2-normalise + cast (ingest and query side).
+ * Replaces   norms = np.linalg.norm(E, axis=1, keepdims=True); E = E / (norms + 1e-9)
+ *            app/main.py:315-316 (corpus), :353-354 (query), app/embedding_gen.py:215-216.
+ * in  [n, dim] fp32;  out [n, dim] of `out_dtype`.  The fp32 result is bit-identical
+ * to the numpy expression (same pairwise summation order, IEEE sqrt and divide);
+ * bf16 / fp16 are that value rounded to nearest even.
+ */
+SQE_API int sqe_normalize_cast(const float *in, void *out, int64_t n, int dim, int out_dtype,
+                       void *stream);
+
+/*
+ * K3  batch-1 (or few-query) exact cosine top-k: HBM-bound streaming GEMV.
+ * Replaces the k-NN query app/main.py:356-367 (external HNSW) with exact scoring.
+ * D [n, dim] stored unit rows (dtype), Q [nq, dim] stored unit queries (same dtype).
+ * Each query streams the whole shard once.  out_score [nq, k] fp32, out_idx [nq, k] int64
+ * (= idx_offset + local row).  1 <= k <= SQE_MAX_K_GEMV, n < 2^32 - 1.
+ */
+SQE_API int64_t sqe_topk_gemv_workspace_bytes(int nq, int k);
+SQE_API int sqe_topk_gemv(const void *D, int dtype, int64_t n, int dim, const void *Q, int nq, int k,
+                  float *out_score, int64_t *out_idx, int64_t idx_offset, void *workspace,
+                  int64_t workspace_bytes, void *stream);
+
+/*
+ * K2  batched exact cosine top-k on the tensor cores (tcgen05 + TMA), with the
+ * per-tile top-k selection fused into the accumulator epilogue so the score matrix
+ * never reaches HBM.  Same contract as sqe_topk_gemv; dtype must be SQE_BF16 or SQE_F16;
+ * 1 <= k <= SQE_MAX_K_BATCHED; any b >= 1 (queries are processed in groups of 128).
+ * D and Q must be 16-byte aligned device pointers.
+ */
+SQE_API int64_t sqe_topk_batched_workspace_bytes(int64_t n, int b, int k);
+SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const void *Q, int b, int k,
+                     float *out_score, int64_t *out_idx, int64_t idx_offset, void *workspace,
+                     int64_t workspace_bytes, void *stream);
+
+/*
+ * K5  query-cache lookup: top-1 + similarity threshold.
+ * Replaces the scan in lfu_cache_get, app/main.py:73-90: running maximum with strict `>`
+ * from -1.0 (first maximum = lowest row wins), miss iff best < threshold.
+ * C [n, dim] stored unit cache rows, Q [b, dim] stored unit queries (same dtype).
+ * out_idx [b] int32 (-1 when no row beats -1.0 or the cache is empty), out_score [b] fp32,
+ * out_hit [b] uint8 (1 iff out_idx >= 0 and !(score < threshold)).
+ * `path`: 0 = choose (tensor cores when dtype is 16-bit and b > 1), 1 = force GEMV, 2 = force
+ * tensor cores.
+ */
+SQE_API int64_t sqe_cache_top1_workspace_bytes(int64_t n, int b);
+SQE_API int sqe_cache_top1(const void *C, int dtype, int64_t n, int dim, const void *Q, int b,
+                   float threshold, float *out_score, int32_t *out_idx, uint8_t *out_hit,
+                   int path, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * K4  merge of per-shard top-k lists (after the all-gather of the corpus-sharded mode).
+ * scores/idx [lists, b, k_in] (best-first per list, idx already global, -1 = empty);
+ * out [b, k_out].  Global indices must be < 2^32 - 1.  k_in, k_out <= SQE_MAX_K_GEMV.
+ */
+SQE_API int sqe_merge_topk(const float *scores, const int64_t *idx, int lists, int b, int k_in,
+                   int k_out, float *out_score, int64_t *out_idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQE_B200_H */

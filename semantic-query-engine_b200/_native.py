@@ -1,0 +1,105 @@
+"""ctypes binding of include/sqe_b200.h.  The only way into the CUDA kernels.
+
+There is deliberately no fallback: if the shared library has not been built
+(`python semantic-query-engine_b200/build.py`, or `__graft_entry__.build()`),
+importing is fine but the first call raises `NativeLibraryMissing`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsqe_b200.so")
+
+SQE_F32, SQE_BF16, SQE_F16 = 0, 1, 2
+SQE_DIM = 1024
+SQE_MAX_K_GEMV = 256
+SQE_MAX_K_BATCHED = 128
+DTYPE_CODES = {"fp32": SQE_F32, "bf16": SQE_BF16, "fp16": SQE_F16}
+
+# every symbol include/sqe_b200.h declares: (name, restype, argtypes)
+PROTOTYPES = [
+    ("sqe_abi_version", c_int, []),
+    ("sqe_last_error", c_char_p, []),
+    ("sqe_device_info", c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    ("sqe_normalize_cast", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    ("sqe_topk_gemv_workspace_bytes", c_int64, [c_int, c_int]),
+    ("sqe_topk_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
+                              c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    ("sqe_topk_batched_workspace_bytes", c_int64, [c_int64, c_int, c_int]),
+    ("sqe_topk_batched", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    ("sqe_cache_top1_workspace_bytes", c_int64, [c_int64, c_int]),
+    ("sqe_cache_top1", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_float,
+                               c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    ("sqe_merge_topk", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p]),
+]
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class SqeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"sqe_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+_lock = threading.Lock()
+# kernel launches issued through this binding (bench.py reports them as gpu_launches)
+launch_count = 0
+LAUNCHES_PER_CALL = {
+    "sqe_normalize_cast": 1,
+    "sqe_topk_gemv": 1,
+    "sqe_topk_batched": 2,
+    "sqe_cache_top1": 2,      # +1 when it takes the tensor path (counted by the caller)
+    "sqe_merge_topk": 1,
+}
+
+
+def load():
+    """Load the library (once) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} not found: build it with `python {os.path.join(HERE, 'build.py')}` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, restype, argtypes in PROTOTYPES:
+            fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    msg = load().sqe_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point; raise SqeError on a non-zero status."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise SqeError(rc, last_error())
+    launch_count += LAUNCHES_PER_CALL.get(name, 0)
+
+
+def device_info():
+    sm, maj, mnr = c_int(0), c_int(0), c_int(0)
+    rc = load().sqe_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr))
+    return rc, sm.value, maj.value, mnr.value

@@ -1,0 +1,64 @@
+"""Build libsqe_b200.so in-tree with nvcc for sm_100a (no network, no torch needed).
+
+    python semantic-query-engine_b200/build.py [--force] [--verbose]
+
+The library links cudart statically and resolves the one driver entry point it
+needs (cuTensorMapEncodeTiled) at run time, so it loads on a machine without
+libcuda (e.g. the CPU build container) and exports every symbol of
+include/sqe_b200.h there.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libsqe_b200.so")
+
+SOURCES = ["api.cu", "normalize_cast.cu", "topk_gemv.cu", "topk_batched.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=hidden",
+    "-cudart", "static",
+]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
+           [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed (exit %d): %s" % (proc.returncode, " ".join(cmd)))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

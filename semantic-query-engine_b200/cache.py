@@ -1,0 +1,196 @@
+"""GPU-resident mirror of the reference's Redis LFU query cache
+(/root/reference/app/main.py:56-128): drop-in for `lfu_cache_get` / `lfu_cache_put`.
+
+The reference keeps a Redis list of JSON entries `{"embedding", "response", "freq"}`
+(main.py:123) with the newest entry at index 0 (LPUSH, main.py:128); every lookup
+re-parses every entry (385 ms at 1000 entries).  Here the embeddings live in HBM as unit
+rows in *list order* -- row `head + i` is list index `i` -- so "first maximum wins"
+(strict `>`, main.py:84) is the kernel's "lowest row wins" rule, and a lookup is one K1 +
+one K5 launch.  `response` / `freq` stay in a host list in the same order.
+
+LFU eviction (main.py:101-118) removes the FIRST entry with the minimal freq; the rows
+in front of it slide down by one so list order is preserved.  Optionally every mutation is
+written through to a Redis client in the reference's own entry format, so a reference
+process can keep reading the same list.
+"""
+from __future__ import annotations
+
+import json
+import threading
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import ops
+
+REDIS_MAX_ITEMS = 1000          # main.py:42
+REDIS_CACHE_LIST = "query_cache_lfu"   # main.py:43
+CACHE_SIM_THRESHOLD = 0.96      # main.py:44
+
+
+class GpuQueryCache:
+    def __init__(self, max_items: int = REDIS_MAX_ITEMS, threshold: float = CACHE_SIM_THRESHOLD,
+                 *, dtype: str = "fp32", device: Optional[torch.device] = None,
+                 redis_client=None, list_name: str = REDIS_CACHE_LIST, keep_raw: bool = None):
+        if dtype not in ops.TORCH_DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(ops.TORCH_DTYPES)}")
+        self.max_items = int(max_items)
+        self.threshold = float(threshold)
+        self.dtype = dtype
+        self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
+        self.redis = redis_client
+        self.list_name = list_name
+        # raw embeddings are only needed to write the reference's JSON entry
+        self.keep_raw = (redis_client is not None) if keep_raw is None else keep_raw
+        self._lock = threading.Lock()
+        self._buf = torch.zeros((self.max_items, nat.SQE_DIM), dtype=ops.TORCH_DTYPES[dtype],
+                                device=self.device)
+        self._head = self.max_items             # live rows are [_head, max_items)
+        self._entries: List[dict] = []          # list order, index 0 = newest
+        self._pinned = torch.empty((1, nat.SQE_DIM), dtype=torch.float32).pin_memory()
+
+    def __len__(self) -> int:
+        return len(self._entries)
+
+    # ---------------------------------------------------------------- helpers
+    @staticmethod
+    def _row0(query_emb) -> Optional[np.ndarray]:
+        if query_emb is None or getattr(query_emb, "size", 0) == 0:
+            return None
+        a = np.asarray(query_emb, dtype=np.float32)
+        if a.ndim == 2:
+            a = a[0]                             # main.py:73 uses row 0
+        if a.shape != (nat.SQE_DIM,):
+            raise ValueError(f"expected [1,{nat.SQE_DIM}] query embedding, got {np.shape(query_emb)}")
+        return np.ascontiguousarray(a)
+
+    def _to_device(self, vec: np.ndarray) -> torch.Tensor:
+        self._pinned[0].copy_(torch.from_numpy(vec))
+        return self._pinned.to(self.device, non_blocking=True)
+
+    def _entry_json(self, e: dict) -> str:
+        return json.dumps({"embedding": e["raw"], "response": e["response"], "freq": e["freq"]})
+
+    # ------------------------------------------------------------------- get
+    def lookup(self, query_emb) -> Tuple[int, float, bool]:
+        """(list index, similarity, hit) of the best entry; (-1, -1.0, False) when empty."""
+        vec = self._row0(query_emb)
+        if vec is None or not self._entries:
+            return -1, -1.0, False
+        with torch.cuda.device(self.device):
+            q = ops.normalize_cast(self._to_device(vec), self.dtype)
+            idx, score, hit = ops.cache_top1(self._buf[self._head:], q, self.threshold, path=1,
+                                             n=len(self._entries))
+            packed = torch.stack([idx.float(), score, hit.float()]).cpu()
+        return int(packed[0, 0]), float(packed[1, 0]), bool(packed[2, 0])
+
+    def get(self, query_emb) -> Optional[str]:
+        """lfu_cache_get, main.py:67-98."""
+        with self._lock:
+            if not self._entries:                                    # main.py:70-71
+                return None
+            idx, _sim, hit = self.lookup(query_emb)
+            if not hit:                                              # main.py:89-90
+                return None
+            e = self._entries[idx]
+            old_json = self._entry_json(e) if self.redis is not None else None
+            e["freq"] = e.get("freq", 1) + 1                         # main.py:94
+            if self.redis is not None:
+                self.redis.lset(self.list_name, idx, self._entry_json(e))   # main.py:95
+            return e["response"]
+
+    def lookup_batch(self, queries: np.ndarray, path: int = 0
+                     ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Streaming form (BASELINE config 5): host fp32 [B,1024] -> host
+        (idx int32 [B], score fp32 [B], hit uint8 [B]).  Does not touch `freq`."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        if q.ndim != 2 or q.shape[1] != nat.SQE_DIM:
+            raise ValueError("expected [B,1024] queries")
+        with torch.cuda.device(self.device):
+            qd = torch.from_numpy(q).pin_memory().to(self.device, non_blocking=True)
+            idx, score, hit = self.lookup_device(qd, path)
+            out = (idx.cpu().numpy(), score.cpu().numpy(), hit.cpu().numpy())
+        return out
+
+    def lookup_device(self, q_dev: torch.Tensor, path: int = 0):
+        qn = ops.normalize_cast(q_dev.contiguous(), self.dtype)
+        return ops.cache_top1(self._buf[self._head:], qn, self.threshold, path=path,
+                              n=len(self._entries))
+
+    # ------------------------------------------------------------------- put
+    def _remove_least_frequent_item(self) -> None:
+        """main.py:101-118: first entry with the minimal freq (strict '<')."""
+        if not self._entries:
+            return
+        min_freq = float("inf")
+        min_index = -1
+        for i, e in enumerate(self._entries):
+            f = e.get("freq", 1)
+            if f < min_freq:
+                min_freq = f
+                min_index = i
+        if min_index < 0:
+            return
+        e = self._entries.pop(min_index)
+        if self.redis is not None:
+            self.redis.lrem(self.list_name, 1, self._entry_json(e))  # main.py:117
+        h = self._head
+        if min_index > 0:
+            # rows [h, h+min_index) slide to [h+1, h+min_index+1): list order is kept
+            self._buf[h + 1: h + min_index + 1] = self._buf[h: h + min_index].clone()
+        self._head = h + 1
+
+    def put(self, query_emb, response: str) -> None:
+        """lfu_cache_put, main.py:121-128.  The reference stores the RAW embedding and
+        normalises inside cosine_similarity at every lookup; storing the unit row once is the
+        same cosine."""
+        vec = self._row0(query_emb)
+        if vec is None:
+            return
+        with self._lock:
+            if len(self._entries) >= self.max_items:                 # main.py:125-126
+                self._remove_least_frequent_item()
+            if self._head == 0:
+                raise RuntimeError("cache buffer full (max_items reached with nothing evictable)")
+            with torch.cuda.device(self.device):
+                self._head -= 1
+                ops.normalize_cast(self._to_device(vec), self.dtype,
+                                   out=self._buf[self._head: self._head + 1])
+                torch.cuda.current_stream(self.device).synchronize()   # pinned staging reused
+            e = {"response": response, "freq": 1}
+            if self.keep_raw:
+                e["raw"] = vec.tolist()
+            self._entries.insert(0, e)
+            if self.redis is not None:
+                self.redis.lpush(self.list_name, self._entry_json(e))  # main.py:128
+
+    def bulk_load(self, embeddings, responses=None) -> None:
+        """Fill an empty cache with many entries at once (config-5 sized caches).
+        Row i becomes list index i.  `embeddings`: host ndarray or CUDA fp32 tensor."""
+        n = int(embeddings.shape[0])
+        if self._entries:
+            raise RuntimeError("bulk_load needs an empty cache")
+        if n > self.max_items:
+            raise ValueError("more entries than max_items")
+        with self._lock, torch.cuda.device(self.device):
+            self._head = self.max_items - n
+            step = 1 << 18
+            for lo in range(0, n, step):
+                hi = min(n, lo + step)
+                blk = embeddings[lo:hi]
+                if isinstance(blk, np.ndarray):
+                    blk = torch.from_numpy(np.ascontiguousarray(blk, dtype=np.float32))
+                blk = blk.to(self.device).contiguous()
+                ops.normalize_cast(blk, self.dtype, out=self._buf[self._head + lo: self._head + hi])
+            torch.cuda.current_stream(self.device).synchronize()
+            self._entries = [{"response": (responses[i] if responses is not None else str(i)),
+                              "freq": 1} for i in range(n)]
+
+    # ------------------------------------------------------------- inspection
+    def responses(self) -> List[str]:
+        return [e["response"] for e in self._entries]
+
+    def freqs(self) -> List[int]:
+        return [e["freq"] for e in self._entries]

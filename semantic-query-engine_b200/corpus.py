@@ -1,0 +1,238 @@
+"""GPU-resident corpus index: the drop-in for the reference's `OpenSearchIndexer`
+(/root/reference/app/main.py:291-373) and `bulk_index_embeddings`
+(app/embedding_gen.py:196-257).
+
+Same method names, argument meaning and error behaviour:
+  * `add_embeddings(embeddings, docs)`  -- main.py:309-338: rows are L2-normalised with
+    `x/(||x||+1e-9)` (K1, on the GPU) and appended; the payload (`doc_id`, `text`) and
+    the `_id = f"{doc_id}_{i}"` of main.py:325 are kept on the host;
+  * `search(query_emb, k=3)`            -- main.py:347-373: normalise the query, score it
+    against every stored row (exact, not HNSW), return `[(source_dict, float_score)]`
+    best-first; `[]` on an empty query or on any backend error;
+  * `has_any_data()`                    -- main.py:300-307.
+
+What differs, by design: scoring is exact (the reference's external index is approximate and
+unpinned), rows live in HBM as bf16/fp16/fp32, and a batched entry point
+(`search_batch`) exists for the throughput configurations.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import ops
+
+EMBED_DIM = nat.SQE_DIM          # main.py:38
+
+
+class GpuCorpusIndex:
+    def __init__(self, client=None, index_name: str = "", *, dtype: str = "bf16",
+                 device: Optional[torch.device] = None, initial_capacity: int = 65536,
+                 score_mode: str = "cosine", strict: bool = False,
+                 return_embedding: bool = False, keep_payload: bool = True):
+        """`client` / `index_name` are accepted for signature compatibility
+        (main.py:296-298) and ignored: there is no OpenSearch behind this index.
+
+        score_mode: "cosine" returns the cosine; "opensearch" returns 1/(2-cos), the
+        `_score` an OpenSearch `cosinesimil` index reports.
+        strict: raise instead of the reference's print-and-return-[] on errors."""
+        if dtype not in ops.TORCH_DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(ops.TORCH_DTYPES)}")
+        if score_mode not in ("cosine", "opensearch"):
+            raise ValueError("score_mode must be 'cosine' or 'opensearch'")
+        self.client = client
+        self.index_name = index_name
+        self.dtype = dtype
+        self.score_mode = score_mode
+        self.strict = strict
+        self.return_embedding = return_embedding
+        self.keep_payload = keep_payload
+        self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
+        self._lock = threading.Lock()           # add_embeddings runs in an executor (main.py:454-455)
+        self._rows = 0                          # published row count
+        self._capacity = 0
+        self._shard: Optional[torch.Tensor] = None
+        self._initial_capacity = int(initial_capacity)
+        self._docs: List[Dict[str, str]] = []   # payload table, row-aligned
+        self._ids: List[str] = []
+        self._pinned_q: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ storage
+    @property
+    def num_rows(self) -> int:
+        return self._rows
+
+    @property
+    def shard(self) -> torch.Tensor:
+        """The stored rows [num_rows,1024] (a view of the HBM shard)."""
+        if self._shard is None:
+            return torch.empty((0, EMBED_DIM), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
+        return self._shard[: self._rows]
+
+    def reserve(self, rows: int) -> None:
+        """Make room for `rows` rows in total (one allocation, no later regrowth)."""
+        with self._lock:
+            self._grow_locked(rows)
+
+    def _grow_locked(self, need: int) -> None:
+        if need <= self._capacity:
+            return
+        cap = max(need, self._initial_capacity, self._capacity * 2)
+        new = torch.empty((cap, EMBED_DIM), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
+        if self._shard is not None and self._rows:
+            new[: self._rows].copy_(self._shard[: self._rows])
+        self._shard = new
+        self._capacity = cap
+
+    def has_any_data(self) -> bool:                      # main.py:300-307
+        try:
+            return self._rows > 0
+        except Exception:
+            return False
+
+    # ------------------------------------------------------------------- ingest
+    def add_embeddings(self, embeddings: np.ndarray, docs: Sequence[Dict[str, str]]) -> None:
+        """main.py:309-338.  `embeddings` [N,1024] fp32 (un-normalised), `docs` N dicts with
+        "doc_id" and "text"."""
+        if embeddings is None or getattr(embeddings, "size", 0) == 0:
+            print("[GpuCorpusIndex] No embeddings.")     # main.py:310-312
+            return
+        try:
+            self._add(embeddings, docs, id_from_global_row=True)
+        except Exception as e:                           # main.py:344-345 prints and continues
+            if self.strict:
+                raise
+            print(f"[GpuCorpusIndex] Bulk indexing error: {e}")
+
+    def add_document_chunks(self, doc_id: str, embeddings: np.ndarray, chunks: Sequence[str]) -> None:
+        """embedding_gen.py:196-257 (`bulk_index_embeddings`): all chunks share `doc_id`,
+        `_id = f"{doc_id}_{chunk_index}"`."""
+        if embeddings is None or getattr(embeddings, "size", 0) == 0:
+            print("[ERROR] Missing embeddings => cannot index.")
+            return
+        docs = [{"doc_id": doc_id, "text": c} for c in chunks]
+        try:
+            self._add(embeddings, docs, id_from_global_row=False)
+        except Exception as e:
+            if self.strict:
+                raise
+            print(f"[GpuCorpusIndex] Bulk error (doc_id={doc_id}): {e}")
+
+    def _add(self, embeddings, docs, id_from_global_row: bool) -> None:
+        emb = self._as_rows(embeddings)
+        n = emb.shape[0]
+        if docs is not None and self.keep_payload and len(docs) != n:
+            # zip() in main.py:318 silently truncates to the shorter of the two
+            n = min(n, len(docs))
+            emb = emb[:n]
+        with self._lock:
+            base = self._rows
+            self._grow_locked(base + n)
+            self.add_device_rows(emb, _locked=True)
+            if self.keep_payload and docs is not None:
+                for i in range(n):
+                    d = docs[i]
+                    self._docs.append({"doc_id": d["doc_id"], "text": d["text"]})
+                    # main.py:325: i enumerates the rows of THIS call
+                    self._ids.append(f"{d['doc_id']}_{i}")
+
+    def add_device_rows(self, emb, _locked: bool = False) -> None:
+        """Append rows without payload.  `emb`: host ndarray / CPU tensor / CUDA fp32 tensor
+        [n,1024], un-normalised.  K1 writes straight into the shard tail, then the new row
+        count is published."""
+        if not _locked:
+            with self._lock:
+                self._grow_locked(self._rows + int(emb.shape[0]))
+                return self.add_device_rows(emb, _locked=True)
+        if isinstance(emb, np.ndarray):
+            emb = torch.from_numpy(emb)
+        n = int(emb.shape[0])
+        if n == 0:
+            return
+        base = self._rows
+        step = 1 << 18                                   # 1 GiB of fp32 staging at most
+        with torch.cuda.device(self.device):
+            for lo in range(0, n, step):
+                hi = min(n, lo + step)
+                blk = emb[lo:hi]
+                if not blk.is_cuda:
+                    blk = blk.to(self.device, non_blocking=False)
+                blk = blk.contiguous()
+                ops.normalize_cast(blk, self.dtype, out=self._shard[base + lo: base + hi])
+            torch.cuda.current_stream(self.device).synchronize()
+        self._rows = base + n                            # publish
+
+    # ------------------------------------------------------------------- search
+    @staticmethod
+    def _as_rows(x) -> np.ndarray:
+        a = np.asarray(x)
+        if a.ndim == 1:
+            a = a[None, :]
+        if a.ndim != 2 or a.shape[1] != EMBED_DIM:
+            raise ValueError(f"expected [n,{EMBED_DIM}] embeddings, got {a.shape}")
+        return np.ascontiguousarray(a, dtype=np.float32)
+
+    def _stage_queries(self, q: np.ndarray) -> torch.Tensor:
+        b = q.shape[0]
+        if self._pinned_q is None or self._pinned_q.shape[0] < b:
+            self._pinned_q = torch.empty((max(b, 64), EMBED_DIM), dtype=torch.float32).pin_memory()
+        self._pinned_q[:b].copy_(torch.from_numpy(q))
+        return self._pinned_q[:b].to(self.device, non_blocking=True)
+
+    def search_batch(self, query_emb: np.ndarray, k: int = 3) -> Tuple[np.ndarray, np.ndarray]:
+        """Batched form of `search`: host fp32 [B,1024] in, host (scores [B,k] fp32,
+        rows [B,k] int64) out, best-first; empty slots are (-inf, -1)."""
+        q = self._as_rows(query_emb)
+        with torch.cuda.device(self.device):
+            qd = self._stage_queries(q)
+            s, i = self.search_device(qd, k)
+            s_h = s.cpu()
+            i_h = i.cpu()
+        return s_h.numpy(), i_h.numpy()
+
+    def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-resident form: fp32 CUDA queries [B,1024] (un-normalised) -> CUDA
+        (scores, rows).  No synchronisation."""
+        qn = ops.normalize_cast(q_dev.contiguous(), self.dtype)         # main.py:353-354
+        rows = self._rows
+        shard = self._shard if self._shard is not None else self.shard
+        return ops.topk(shard, qn, k, idx_offset=idx_offset, n=rows)
+
+    def search(self, query_emb: np.ndarray, k: int = 3) -> List[Tuple[Dict[str, str], float]]:
+        """main.py:347-373."""
+        if query_emb is None or getattr(query_emb, "size", 0) == 0:      # main.py:350-351
+            return []
+        try:
+            q = self._as_rows(query_emb)[:1]                             # main.py:355 sends row 0
+            scores, rows = self.search_batch(q, k)
+            results = []
+            for s, r in zip(scores[0], rows[0]):
+                if r < 0:
+                    continue
+                s = float(s)
+                if self.score_mode == "opensearch":
+                    s = 1.0 / (2.0 - s)
+                results.append((self._source(int(r)), s))
+            return results
+        except Exception as e:                                           # main.py:371-373
+            if self.strict:
+                raise
+            print(f"[GpuCorpusIndex] Search error: {e}")
+            return []
+
+    def _source(self, row: int) -> Dict[str, str]:
+        if self.keep_payload and row < len(self._docs):
+            src = dict(self._docs[row])
+        else:
+            src = {"doc_id": str(row), "text": ""}
+        if self.return_embedding:                                        # main.py:326-330
+            src["embedding"] = self._shard[row].float().cpu().tolist()
+        return src
+
+    def doc_id_of(self, row: int) -> str:
+        return self._ids[row]

@@ -1,0 +1,205 @@
+// The C ABI (include/sqe_b200.h): argument checks, error text, dispatch.  No torch
+// types, no exceptions across the boundary.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/sqe_b200.h"
+#include "sqe_internal.h"
+
+namespace sqe {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct DevInfo {
+    int ok = 0;
+    int sm_count = 0;
+    int major = 0;
+    int minor = 0;
+};
+
+// per-device cache (8 GPUs per node)
+static int device_info(DevInfo* out) {
+    static DevInfo cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+        return SQE_E_CUDA;
+    }
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return SQE_E_CUDA; }
+    if (!cache[dev].ok) {
+        DevInfo d;
+        if ((e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+            (e = cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess ||
+            (e = cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) {
+            set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+            return SQE_E_CUDA;
+        }
+        d.ok = 1;
+        cache[dev] = d;
+    }
+    *out = cache[dev];
+    if (out->major != 10) {
+        set_error("device is sm_%d%d; this library contains sm_100a code only (no fallback)",
+                  out->major, out->minor);
+        return SQE_E_CUDA;
+    }
+    return SQE_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_common(const char* who, const void* D, int dtype, int64_t n, int dim, const void* Q,
+                        int nq) {
+    if (dim != SQE_DIM) { set_error("%s: dim must be %d (got %d)", who, SQE_DIM, dim); return SQE_E_ARG; }
+    if (dtype < SQE_F32 || dtype > SQE_F16) { set_error("%s: bad dtype %d", who, dtype); return SQE_E_ARG; }
+    if (n < 0 || n >= 0xffffffffLL) { set_error("%s: n=%lld out of range", who, (long long)n); return SQE_E_ARG; }
+    if (nq < 0) { set_error("%s: negative query count", who); return SQE_E_ARG; }
+    if ((n > 0 && D == nullptr) || (nq > 0 && Q == nullptr)) { set_error("%s: null pointer", who); return SQE_E_ARG; }
+    if (!aligned16(D) || !aligned16(Q)) { set_error("%s: pointers must be 16-byte aligned", who); return SQE_E_ARG; }
+    return SQE_OK;
+}
+
+}  // namespace sqe
+
+using namespace sqe;
+
+extern "C" {
+
+int sqe_abi_version(void) { return SQE_ABI_VERSION; }
+
+const char* sqe_last_error(void) { return g_err; }
+
+int sqe_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    DevInfo d;
+    int rc = device_info(&d);
+    if (sm_count) *sm_count = d.sm_count;
+    if (cc_major) *cc_major = d.major;
+    if (cc_minor) *cc_minor = d.minor;
+    if (rc != SQE_OK) return d.ok ? 0 : rc;
+    return 1;
+}
+
+int sqe_normalize_cast(const float* in, void* out, int64_t n, int dim, int out_dtype, void* stream) {
+    if (dim != SQE_DIM) { set_error("normalize_cast: dim must be %d (got %d)", SQE_DIM, dim); return SQE_E_ARG; }
+    if (out_dtype < SQE_F32 || out_dtype > SQE_F16) { set_error("normalize_cast: bad dtype %d", out_dtype); return SQE_E_ARG; }
+    if (n < 0) { set_error("normalize_cast: negative n"); return SQE_E_ARG; }
+    if (n == 0) return SQE_OK;
+    if (!in || !out || !aligned16(in) || !aligned16(out)) { set_error("normalize_cast: null or unaligned pointer"); return SQE_E_ARG; }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_normalize_cast(in, out, n, out_dtype, d.sm_count, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return SQE_E_ARG;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("normalize_cast: launch: %s", cudaGetErrorString(e)); return SQE_E_CUDA; }
+    return SQE_OK;
+}
+
+int64_t sqe_topk_gemv_workspace_bytes(int nq, int k) {
+    DevInfo d;
+    if (device_info(&d) != SQE_OK) d.sm_count = 160;       // upper bound when queried off-device
+    if (nq < 1) nq = 1;
+    if (k < 1) k = 1;
+    return gemv_workspace_bytes(nq, k, d.sm_count);
+}
+
+int sqe_topk_gemv(const void* D, int dtype, int64_t n, int dim, const void* Q, int nq, int k,
+                  float* out_score, int64_t* out_idx, int64_t idx_offset, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+    int rc = check_common("topk_gemv", D, dtype, n, dim, Q, nq);
+    if (rc != SQE_OK) return rc;
+    if (k < 1 || k > SQE_MAX_K_GEMV) { set_error("topk_gemv: k=%d not in [1,%d]", k, SQE_MAX_K_GEMV); return SQE_E_ARG; }
+    if (nq == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("topk_gemv: null output/workspace"); return SQE_E_ARG; }
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return launch_topk_gemv(D, dtype, n, Q, nq, k, out_score, out_idx, idx_offset, workspace,
+                            workspace_bytes, d.sm_count, static_cast<cudaStream_t>(stream));
+}
+
+int64_t sqe_topk_batched_workspace_bytes(int64_t n, int b, int k) {
+    DevInfo d;
+    if (device_info(&d) != SQE_OK) d.sm_count = 160;
+    if (b < 1) b = 1;
+    if (k < 1) k = 1;
+    return batched_workspace_bytes(n, b, k, d.sm_count);
+}
+
+int sqe_topk_batched(const void* D, int dtype, int64_t n, int dim, const void* Q, int b, int k,
+                     float* out_score, int64_t* out_idx, int64_t idx_offset, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    int rc = check_common("topk_batched", D, dtype, n, dim, Q, b);
+    if (rc != SQE_OK) return rc;
+    if (dtype == SQE_F32) { set_error("topk_batched: fp32 shards use sqe_topk_gemv (tensor path is bf16/fp16)"); return SQE_E_UNSUPPORTED; }
+    if (k < 1 || k > SQE_MAX_K_BATCHED) { set_error("topk_batched: k=%d not in [1,%d]", k, SQE_MAX_K_BATCHED); return SQE_E_ARG; }
+    if (b == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("topk_batched: null output/workspace"); return SQE_E_ARG; }
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return launch_topk_batched(D, dtype, n, Q, b, k, out_score, out_idx, idx_offset, workspace,
+                               workspace_bytes, d.sm_count, static_cast<cudaStream_t>(stream));
+}
+
+// workspace of cache_top1 = [b] fp32 score + [b] int64 idx staging, then the scorer's own
+static int64_t cache_stage_bytes(int b) { return ((static_cast<int64_t>(b) * 12 + 255) / 256) * 256; }
+
+int64_t sqe_cache_top1_workspace_bytes(int64_t n, int b) {
+    if (b < 1) b = 1;
+    int64_t g = sqe_topk_gemv_workspace_bytes(b, 1);
+    int64_t t = sqe_topk_batched_workspace_bytes(n, b, 1);
+    return cache_stage_bytes(b) + (g > t ? g : t);
+}
+
+int sqe_cache_top1(const void* C, int dtype, int64_t n, int dim, const void* Q, int b,
+                   float threshold, float* out_score, int32_t* out_idx, uint8_t* out_hit, int path,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_common("cache_top1", C, dtype, n, dim, Q, b);
+    if (rc != SQE_OK) return rc;
+    if (b == 0) return SQE_OK;
+    if (!out_score || !out_idx || !out_hit || !workspace) { set_error("cache_top1: null output/workspace"); return SQE_E_ARG; }
+    if (path < 0 || path > 2) { set_error("cache_top1: bad path %d", path); return SQE_E_ARG; }
+    const int64_t stage = cache_stage_bytes(b);
+    if (workspace_bytes < stage) { set_error("cache_top1: workspace too small"); return SQE_E_WORKSPACE; }
+    char* ws = static_cast<char*>(workspace);
+    int64_t* st_idx = reinterpret_cast<int64_t*>(ws);
+    float* st_score = reinterpret_cast<float*>(ws + static_cast<int64_t>(b) * 8);
+    const bool tensor = (path == 2) || (path == 0 && dtype != SQE_F32 && b > 1);
+    if (tensor && dtype == SQE_F32) { set_error("cache_top1: tensor path needs a bf16/fp16 cache"); return SQE_E_UNSUPPORTED; }
+    if (tensor)
+        rc = sqe_topk_batched(C, dtype, n, dim, Q, b, 1, st_score, st_idx, 0, ws + stage, workspace_bytes - stage, stream);
+    else
+        rc = sqe_topk_gemv(C, dtype, n, dim, Q, b, 1, st_score, st_idx, 0, ws + stage, workspace_bytes - stage, stream);
+    if (rc != SQE_OK) return rc;
+    rc = launch_cache_finalize(st_score, st_idx, b, threshold, out_score, out_idx, out_hit,
+                               static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : SQE_E_CUDA;
+}
+
+int sqe_merge_topk(const float* scores, const int64_t* idx, int lists, int b, int k_in, int k_out,
+                   float* out_score, int64_t* out_idx, void* stream) {
+    if (lists < 1 || b < 0 || k_in < 1 || k_out < 1 || k_in > SQE_MAX_K_GEMV || k_out > SQE_MAX_K_GEMV) {
+        set_error("merge_topk: bad sizes lists=%d b=%d k_in=%d k_out=%d", lists, b, k_in, k_out);
+        return SQE_E_ARG;
+    }
+    if (b == 0) return SQE_OK;
+    if (!scores || !idx || !out_score || !out_idx) { set_error("merge_topk: null pointer"); return SQE_E_ARG; }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_merge_topk(scores, idx, lists, b, k_in, k_out, out_score, out_idx,
+                           static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : SQE_E_CUDA;
+}
+
+}  // extern "C"

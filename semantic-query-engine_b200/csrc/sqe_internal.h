@@ -1,0 +1,35 @@
+// Internal launch interfaces between the C ABI (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sqe {
+
+// K1
+int launch_normalize_cast(const float* in, void* out, int64_t n, int out_dtype, int sm_count,
+                          cudaStream_t stream);
+
+// K3
+int64_t gemv_workspace_bytes(int nq, int k, int sm_count);
+int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, int nq, int k,
+                     float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
+                     int64_t ws_bytes, int sm_count, cudaStream_t stream);
+
+// K2
+int64_t batched_workspace_bytes(int64_t n, int b, int k, int sm_count);
+int launch_topk_batched(const void* D, int dtype, int64_t n, const void* Q, int b, int k,
+                        float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
+                        int64_t ws_bytes, int sm_count, cudaStream_t stream);
+
+// K4
+int launch_merge_topk(const float* scores, const int64_t* idx, int lists, int b, int k_in,
+                      int k_out, float* out_score, int64_t* out_idx, cudaStream_t stream);
+
+// K5 epilogue: (score,idx)[b] -> (score, idx32, hit)
+int launch_cache_finalize(const float* score, const int64_t* idx, int b, float threshold,
+                          float* out_score, int32_t* out_idx, uint8_t* out_hit,
+                          cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace sqe

@@ -1,0 +1,161 @@
+"""Thin tensor-level wrappers over the C ABI.
+
+torch is used here only to own device memory and streams; every computation is
+a call into libsqe_b200.so (hand-written sm_100a kernels).  All functions take
+CUDA tensors, launch on the current stream of the tensor's device and return
+CUDA tensors without synchronising.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as nat
+
+TORCH_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+_NAMES = {v: k for k, v in TORCH_DTYPES.items()}
+
+_workspaces = {}
+
+
+def dtype_name(t: torch.Tensor) -> str:
+    try:
+        return _NAMES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported storage dtype {t.dtype}")
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("sqe_b200 has no CPU path: tensors must live on a CUDA device")
+        if t.device != dev:
+            raise RuntimeError("tensors on different devices")
+        if not t.is_contiguous():
+            raise ValueError("tensors must be contiguous")
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _workspace(dev: torch.device, kind: str, nbytes: int) -> torch.Tensor:
+    key = (dev.index, kind, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def normalize_cast(x: torch.Tensor, dtype: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1: rows of fp32 `x` [n,1024] -> x/(||x||+1e-9) stored as `dtype`."""
+    dev = _require_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != nat.SQE_DIM:
+        raise ValueError(f"expected fp32 [n,{nat.SQE_DIM}], got {x.dtype} {tuple(x.shape)}")
+    if out is None:
+        out = torch.empty(x.shape, dtype=TORCH_DTYPES[dtype], device=dev)
+    else:
+        _require_cuda(x, out)
+        if out.shape != x.shape or out.dtype != TORCH_DTYPES[dtype]:
+            raise ValueError("bad `out`")
+    with torch.cuda.device(dev):
+        nat.call("sqe_normalize_cast", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                 nat.DTYPE_CODES[dtype], _stream(dev))
+    return out
+
+
+def _check_dq(D: torch.Tensor, Q: torch.Tensor, n: Optional[int]) -> Tuple[torch.device, int, int]:
+    dev = _require_cuda(D, Q)
+    if D.dim() != 2 or Q.dim() != 2 or D.shape[1] != nat.SQE_DIM or Q.shape[1] != nat.SQE_DIM:
+        raise ValueError("D and Q must be [rows,1024]")
+    if D.dtype != Q.dtype:
+        raise TypeError("queries must be stored in the shard's dtype (use normalize_cast)")
+    rows = D.shape[0] if n is None else int(n)
+    if rows > D.shape[0]:
+        raise ValueError("n exceeds shard rows")
+    return dev, rows, Q.shape[0]
+
+
+def topk_gemv(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
+              n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K3: exact cosine top-k, one streaming pass over the shard per query."""
+    dev, rows, b = _check_dq(D, Q, n)
+    scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+    if b == 0:
+        return scores, idx
+    with torch.cuda.device(dev):
+        need = nat.load().sqe_topk_gemv_workspace_bytes(b, k)
+        ws = _workspace(dev, "gemv", need)
+        nat.call("sqe_topk_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
+                 Q.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+                 ws.data_ptr(), ws.numel(), _stream(dev))
+    return scores, idx
+
+
+def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
+                 n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K2: exact cosine top-k on the tensor cores (bf16/fp16 shards)."""
+    dev, rows, b = _check_dq(D, Q, n)
+    scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+    if b == 0:
+        return scores, idx
+    with torch.cuda.device(dev):
+        need = nat.load().sqe_topk_batched_workspace_bytes(rows, b, k)
+        ws = _workspace(dev, "batched", need)
+        nat.call("sqe_topk_batched", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows,
+                 nat.SQE_DIM, Q.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+                 ws.data_ptr(), ws.numel(), _stream(dev))
+    return scores, idx
+
+
+def topk(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
+         n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Route: one query or an fp32 shard -> K3 (HBM-bound GEMV); else K2 (tensor cores)."""
+    if Q.shape[0] <= 1 or D.dtype == torch.float32 or k > nat.SQE_MAX_K_BATCHED:
+        return topk_gemv(D, Q, k, idx_offset, n)
+    return topk_batched(D, Q, k, idx_offset, n)
+
+
+def cache_top1(C: torch.Tensor, Q: torch.Tensor, threshold: float, path: int = 0,
+               n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """K5: (idx int32 [b], score fp32 [b], hit uint8 [b])."""
+    dev, rows, b = _check_dq(C, Q, n)
+    score = torch.empty((b,), dtype=torch.float32, device=dev)
+    idx = torch.empty((b,), dtype=torch.int32, device=dev)
+    hit = torch.empty((b,), dtype=torch.uint8, device=dev)
+    if b == 0:
+        return idx, score, hit
+    with torch.cuda.device(dev):
+        need = nat.load().sqe_cache_top1_workspace_bytes(rows, b)
+        ws = _workspace(dev, "cache", need)
+        nat.call("sqe_cache_top1", C.data_ptr(), nat.DTYPE_CODES[dtype_name(C)], rows, nat.SQE_DIM,
+                 Q.data_ptr(), b, float(threshold), score.data_ptr(), idx.data_ptr(),
+                 hit.data_ptr(), path, ws.data_ptr(), ws.numel(), _stream(dev))
+        if path == 2 or (path == 0 and C.dtype != torch.float32 and b > 1):
+            nat.launch_count += 1
+    return idx, score, hit
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K4: scores/idx [lists,b,k_in] -> best-first [b,k_out]."""
+    dev = _require_cuda(scores, idx)
+    if scores.dim() != 3 or scores.shape != idx.shape:
+        raise ValueError("scores/idx must be [lists,b,k]")
+    if scores.dtype != torch.float32 or idx.dtype != torch.int64:
+        raise TypeError("scores fp32, idx int64")
+    lists, b, k_in = scores.shape
+    out_s = torch.empty((b, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+    if b == 0:
+        return out_s, out_i
+    with torch.cuda.device(dev):
+        nat.call("sqe_merge_topk", scores.data_ptr(), idx.data_ptr(), lists, b, k_in, k_out,
+                 out_s.data_ptr(), out_i.data_ptr(), _stream(dev))
+    return out_s, out_i

@@ -1,0 +1,44 @@
+"""Patch a loaded reference `main` module so its handlers use the GPU path.
+
+    import main                      # the reference's app/main.py
+    import sqe_b200
+    sqe_b200.plugin.install(main, dtype="bf16")
+
+After `install`, `main.OpenSearchIndexer(client, index_name)` builds a
+`GpuCorpusIndex`, and `main.lfu_cache_get` / `main.lfu_cache_put` /
+`main.cosine_similarity` are served by a `GpuQueryCache` -- the names, arguments and
+return values RAGModel.ask (main.py:493,499,547) and the websocket handler
+(main.py:676,684,727) already use.  See INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .cache import GpuQueryCache
+from .corpus import GpuCorpusIndex
+
+
+def install(main_module, *, dtype: str = "bf16", cache_dtype: str = "fp32", device=None,
+            write_through_redis: bool = False, strict: bool = False):
+    threshold = getattr(main_module, "CACHE_SIM_THRESHOLD", 0.96)
+    max_items = getattr(main_module, "REDIS_MAX_ITEMS", 1000)
+    list_name = getattr(main_module, "REDIS_CACHE_LIST", "query_cache_lfu")
+    redis_client = getattr(main_module, "redis_client", None) if write_through_redis else None
+    cache = GpuQueryCache(max_items=max_items, threshold=threshold, dtype=cache_dtype,
+                          device=device, redis_client=redis_client, list_name=list_name)
+
+    class OpenSearchIndexer(GpuCorpusIndex):
+        def __init__(self, client=None, index_name: str = ""):
+            super().__init__(client, index_name, dtype=dtype, device=device, strict=strict)
+
+    def lfu_cache_get(query_emb: np.ndarray):
+        return cache.get(query_emb)
+
+    def lfu_cache_put(query_emb: np.ndarray, response: str):
+        cache.put(query_emb, response)
+
+    main_module.OpenSearchIndexer = OpenSearchIndexer
+    main_module.lfu_cache_get = lfu_cache_get
+    main_module.lfu_cache_put = lfu_cache_put
+    main_module._sqe_b200_cache = cache
+    return cache

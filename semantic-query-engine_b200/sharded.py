@@ -1,0 +1,100 @@
+"""Corpus-sharded multi-GPU search (north_star subsystem 4).
+
+One process per GPU.  Rank r owns the contiguous row block
+[r*N/G, (r+1)*N/G); queries are replicated; every rank computes its local top-k with
+global row numbers (idx_offset = first row of the shard), ONE all-gather moves the
+[B,k] (score fp32, row int64) lists over NVLink, and every rank merges the G lists
+with K4.  top-k of a union is the top-k of the per-shard top-k's, so the result is
+exactly the single-GPU result, ties included (global rows keep the lower-index rule).
+
+Nothing like this exists in the reference (single process, external index); the
+exchange step is the only collective on the path.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of `rank`: contiguous blocks, remainder spread over the first ranks."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+class ShardedCorpusIndex:
+    """Wraps a per-rank index (normally a GpuCorpusIndex holding this rank's rows).
+
+    `local_topk(q, k, idx_offset) -> (scores[B,k], rows[B,k])` and
+    `merge(scores[G,B,k], rows[G,B,k], k) -> (scores[B,k], rows[B,k])` default to the CUDA
+    kernels; the CPU tests inject checkers there to exercise the sharding arithmetic and
+    the collective with the gloo backend."""
+
+    def __init__(self, local_index=None, *, group=None,
+                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.local = local_index
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._local_topk = local_topk
+        self._merge = merge
+        self.row_offset = 0
+        self.total_rows = 0
+        self._gather_s = None
+        self._gather_i = None
+
+    # ------------------------------------------------------------------ layout
+    def finalize(self, local_rows: Optional[int] = None) -> None:
+        """Exchange shard sizes and fix this rank's global row offset (prefix sum)."""
+        if local_rows is None:
+            local_rows = self.local.num_rows
+        if self.world == 1:
+            self.row_offset, self.total_rows = 0, int(local_rows)
+            return
+        dev = self._comm_device()
+        mine = torch.tensor([int(local_rows)], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(counts, mine, group=self.group)
+        counts = [int(c.item()) for c in counts]
+        self.row_offset = sum(counts[: self.rank])
+        self.total_rows = sum(counts)
+
+    def _comm_device(self) -> torch.device:
+        if self.local is not None and hasattr(self.local, "device"):
+            return self.local.device
+        return torch.device("cpu")
+
+    # ------------------------------------------------------------------ search
+    def search_device(self, q_dev: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q_dev [B,1024] fp32 (replicated on every rank) -> merged (scores, global rows) on
+        every rank.  One all-gather + one merge kernel after the local scan."""
+        if self._local_topk is not None:
+            s, i = self._local_topk(q_dev, k, self.row_offset)
+        else:
+            s, i = self.local.search_device(q_dev, k, idx_offset=self.row_offset)
+        if self.world == 1:
+            return s, i
+        b = s.shape[0]
+        if self._gather_s is None or self._gather_s.shape[1:] != s.shape or self._gather_s.device != s.device:
+            self._gather_s = torch.empty((self.world, b, k), dtype=s.dtype, device=s.device)
+            self._gather_i = torch.empty((self.world, b, k), dtype=i.dtype, device=i.device)
+        # concatenated [G*B, k] form of the output: accepted by both NCCL and gloo
+        dist.all_gather_into_tensor(self._gather_s.view(self.world * b, k), s.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(self._gather_i.view(self.world * b, k), i.contiguous(), group=self.group)
+        if self._merge is not None:
+            return self._merge(self._gather_s, self._gather_i, k)
+        from . import ops
+        return ops.merge_topk(self._gather_s, self._gather_i, k)
+
+    def search_batch(self, query_emb: np.ndarray, k: int = 3) -> Tuple[np.ndarray, np.ndarray]:
+        dev = self._comm_device()
+        q = torch.from_numpy(np.ascontiguousarray(query_emb, dtype=np.float32))
+        if dev.type == "cuda":
+            q = q.pin_memory().to(dev, non_blocking=True)
+        s, i = self.search_device(q, k)
+        return s.cpu().numpy(), i.cpu().numpy()

@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  GPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle                      # the checker
+from oracle import numpy_oracle as no
+from parity import assert_topk_matches, exact_scores
+
+DIM = 1024
+DTYPES = ["fp32", "bf16", "fp16"]
+
+
+@pytest.fixture(scope="module")
+def sqe():
+    import sqe_b200
+    sqe_b200._native.load()        # fail loudly if the extension is missing
+    rc, sms, major, _ = sqe_b200._native.device_info()
+    assert rc == 1 and major == 10, sqe_b200._native.last_error()
+    return sqe_b200
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def stored_bits(t: torch.Tensor, dtype: str) -> np.ndarray:
+    """Raw stored values of a shard tensor in the oracle's representation."""
+    if dtype == "fp32":
+        return t.cpu().numpy()
+    if dtype == "fp16":
+        return t.cpu().numpy()
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def make_corpus(rng, n, plant=True):
+    x = rng.standard_normal((n, DIM)).astype(np.float32)
+    x *= rng.uniform(0.1, 8.0, size=(n, 1)).astype(np.float32)
+    if plant and n >= 64:
+        x[10] = 0.0                       # zero row -> score exactly 0
+        x[33] = x[7]                      # exact duplicates -> tie, lower row first
+        x[n - 1] = x[7]
+        x[40] = x[7] * np.float32(3.0)    # same direction: ties after normalisation (maybe)
+    return x
+
+
+# ------------------------------------------------------------------------- K1
+def test_normalize_fp32_bit_identical_to_reference_vectors(sqe, golden_dir):
+    g = np.load(os.path.join(golden_dir, "index_search.npz"))
+    out = sqe.ops.normalize_cast(torch.from_numpy(g["emb"]).to(dev()), "fp32").cpu().numpy()
+    np.testing.assert_array_equal(out.view(np.uint32), g["stored"].view(np.uint32))
+    qn = sqe.ops.normalize_cast(torch.from_numpy(g["q"]).to(dev()), "fp32").cpu().numpy()
+    np.testing.assert_array_equal(qn.view(np.uint32), g["q_norm"].view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_normalize_cast_bit_exact_vs_oracle(sqe, dtype):
+    rng = np.random.default_rng(123)
+    n = 20011                                           # ragged: not a multiple of the CTA's 8 rows
+    x = (rng.standard_normal((n, DIM)) * 10.0 ** rng.uniform(-12, 12, size=(n, 1))).astype(np.float32)
+    x[0] = 0.0
+    x[1] = 1e-30                                         # squares underflow to denormals
+    x[2, :] = 0.0
+    x[2, 5] = -3.5                                       # single non-zero
+    got = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    want = oracle.to_storage(oracle.normalize_rows(x), dtype)
+    got_bits = stored_bits(got, dtype)
+    if dtype == "fp32":
+        np.testing.assert_array_equal(got_bits.view(np.uint32), want.view(np.uint32))
+    else:
+        np.testing.assert_array_equal(got_bits.view(np.uint16), want.view(np.uint16))
+
+
+def test_normalize_empty_and_single(sqe):
+    e = sqe.ops.normalize_cast(torch.empty((0, DIM), device=dev()), "bf16")
+    assert e.shape == (0, DIM)
+    one = np.arange(DIM, dtype=np.float32)[None] - 500
+    got = sqe.ops.normalize_cast(torch.from_numpy(one).to(dev()), "fp32").cpu().numpy()
+    np.testing.assert_array_equal(got.view(np.uint32), oracle.normalize_rows(one).view(np.uint32))
+
+
+# ------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 5, 63, 1000, 40037])
+def test_gemv_topk_matches_oracle(sqe, dtype, n):
+    rng = np.random.default_rng(1000 + n)
+    x = make_corpus(rng, n)
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    q = rng.standard_normal((3, DIM)).astype(np.float32)
+    if n >= 64:
+        q[1] = x[7] * 0.25                               # hits the planted duplicates
+        q[2] = 0.0                                       # zero query: all scores 0 -> rows 0..k-1
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+    d_st = oracle.from_storage(stored_bits(D, dtype), dtype)
+    q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+    s64 = exact_scores(d_st, q_st)
+    for k in (1, 3, 10, 32, 33, 100, 256):
+        s, i = sqe.ops.topk_gemv(D, Q, k)
+        torch.cuda.synchronize()
+        assert_topk_matches(s.cpu().numpy(), i.cpu().numpy(), d_st, q_st, k, s64=s64)
+        if n >= 64 and k >= 10:
+            got = i[1].cpu().numpy().tolist()
+            assert got.index(7) < got.index(33) < got.index(n - 1), got
+        if n >= 64:
+            assert i[2].cpu().numpy().tolist()[: min(k, n)] == list(range(min(k, n)))
+    # oracle's own fp32 matmul + stable sort agrees as well
+    so, io = oracle.topk_cosine(d_st, q_st[:1], 10)
+    s, i = sqe.ops.topk_gemv(D, Q[:1], 10)
+    assert_topk_matches(s.cpu().numpy(), i.cpu().numpy(), d_st, q_st[:1], 10)
+    kk = min(10, n)
+    np.testing.assert_allclose(s.cpu().numpy()[0, :kk], so[0, :kk], atol=2e-6)
+
+
+def test_gemv_idx_offset_and_partial_shard(sqe):
+    rng = np.random.default_rng(5)
+    x = make_corpus(rng, 3000)
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), "bf16")
+    Q = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((2, DIM)).astype(np.float32)).to(dev()), "bf16")
+    d_st = oracle.from_storage(stored_bits(D, "bf16"), "bf16")
+    q_st = oracle.from_storage(stored_bits(Q, "bf16"), "bf16")
+    s, i = sqe.ops.topk_gemv(D, Q, 5, idx_offset=10_000_000_000, n=2000)    # only the first 2000 rows
+    assert_topk_matches(s.cpu().numpy(), i.cpu().numpy(), d_st[:2000], q_st, 5,
+                        idx_offset=10_000_000_000)
+    s0, i0 = sqe.ops.topk_gemv(D, Q, 5, n=0)                                 # empty shard
+    assert (i0.cpu().numpy() == -1).all() and np.isneginf(s0.cpu().numpy()).all()
+
+
+def test_gemv_is_deterministic(sqe):
+    rng = np.random.default_rng(8)
+    D = sqe.ops.normalize_cast(torch.from_numpy(make_corpus(rng, 100_000)).to(dev()), "bf16")
+    Q = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((1, DIM)).astype(np.float32)).to(dev()), "bf16")
+    a = [t.clone() for t in sqe.ops.topk_gemv(D, Q, 10)]
+    b = [t.clone() for t in sqe.ops.topk_gemv(D, Q, 10)]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ------------------------------------------------------------------------- K4
+def test_merge_topk_matches_oracle(sqe):
+    rng = np.random.default_rng(21)
+    for lists, b, k_in, k_out in [(2, 5, 10, 10), (8, 33, 100, 100), (4, 3, 7, 20), (3, 2, 200, 256)]:
+        s = np.sort(rng.standard_normal((lists, b, k_in)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+        i = rng.permutation(lists * b * k_in).reshape(lists, b, k_in).astype(np.int64)
+        s[1, 0, 3:] = -np.inf                            # short list
+        i[1, 0, 3:] = -1
+        s[0, 1, 0] = s[1, 1, 0] = 0.75                   # cross-list tie -> lower global row first
+        s[0, 1] = np.sort(s[0, 1])[::-1]
+        s[1, 1] = np.sort(s[1, 1])[::-1]
+        gs, gi = sqe.ops.merge_topk(torch.from_numpy(s).to(dev()), torch.from_numpy(i).to(dev()), k_out)
+        ws, wi = oracle.merge_topk(s, i, k_out)
+        np.testing.assert_array_equal(gi.cpu().numpy(), wi)
+        np.testing.assert_array_equal(gs.cpu().numpy(), ws)
+
+
+# ------------------------------------------------------- drop-in classes, golden
+def test_corpus_index_reproduces_reference_search(sqe, golden_dir):
+    g = np.load(os.path.join(golden_dir, "index_search.npz"))
+    with open(os.path.join(golden_dir, "index_search.json")) as f:
+        meta = json.load(f)
+    index = sqe.GpuCorpusIndex(None, "golden-index", dtype="fp32", strict=True, initial_capacity=64)
+    assert index.has_any_data() is False
+    assert index.search(g["q"][:1], k=3) == []           # nothing indexed yet
+    index.add_embeddings(g["emb"], meta["docs"])
+    assert index.has_any_data() is True and index.num_rows == len(meta["docs"])
+    np.testing.assert_array_equal(index.shard.cpu().numpy().view(np.uint32), g["stored"].view(np.uint32))
+    assert [index.doc_id_of(r) for r in range(index.num_rows)] == meta["ids"]
+    s64 = exact_scores(g["stored"], g["q_norm"])
+    for qi in range(len(g["q"])):
+        for ki, k in enumerate(g["ks"]):
+            hits = index.search(g["q"][qi:qi + 1], k=int(k))
+            assert len(hits) == k
+            rows = [int(src["text"].split()[1]) for src, _ in hits]
+            # exact list equality with the reference unless two of the k+1 best exact scores
+            # are closer than 1e-6 (an fp32 summation-order flip is then legitimate)
+            top = np.sort(s64[qi])[::-1][: int(k) + 1]
+            if np.min(-np.diff(top)) > 1e-6:
+                assert rows == g["res_idx"][qi, ki, :k].tolist(), (qi, k)
+            assert_topk_matches(np.array([[s for _, s in hits]], dtype=np.float32),
+                                np.array([rows]), g["stored"], g["q_norm"][qi:qi + 1], int(k),
+                                s64=s64[qi:qi + 1])
+            np.testing.assert_allclose([s for _, s in hits], g["res_score"][qi, ki, :k], atol=1e-5)
+            assert all(src["doc_id"] == meta["docs"][r]["doc_id"] for (src, _), r in zip(hits, rows))
+    assert index.search(np.array([]), k=3) == []         # main.py:350-351
+    lookalike = sqe.GpuCorpusIndex(dtype="fp32", score_mode="opensearch")
+    lookalike.add_embeddings(g["emb"], meta["docs"])
+    (src, sc), = lookalike.search(g["q"][:1], k=1)
+    assert abs(sc - 1.0 / (2.0 - g["res_score"][0, 0, 0])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["default", "evict8", "thr095"])
+@pytest.mark.parametrize("dtype", ["fp32"])
+def test_query_cache_replays_reference_log(sqe, golden_dir, name, dtype):
+    with open(os.path.join(golden_dir, f"cache_{name}.json")) as f:
+        log = json.load(f)
+    vecs = np.load(os.path.join(golden_dir, f"cache_{name}.npz"))["vecs"]
+    cache = sqe.GpuQueryCache(max_items=log["max_items"], threshold=log["threshold"], dtype=dtype)
+    for op in log["ops"]:
+        v = vecs[op["vec"]][None, :]
+        if op["op"] == "get":
+            assert cache.get(v) == op["result"], op
+        else:
+            cache.put(v, op["response"])
+    assert cache.responses() == log["final_responses"]
+    assert cache.freqs() == log["final_freqs"]
+
+
+def test_query_cache_edge_cases(sqe):
+    rng = np.random.default_rng(3)
+    cache = sqe.GpuQueryCache(max_items=4, threshold=0.96)
+    q = rng.standard_normal((1, DIM)).astype(np.float32)
+    assert cache.get(q) is None                          # empty -> None, main.py:70-71
+    assert cache.get(np.array([])) is None
+    cache.put(-q, "anti")
+    idx, sim, hit = cache.lookup(q)                      # only similarity is -1.0: never beats -1.0
+    assert hit is False and (idx == -1 or sim <= -1.0 + 1e-6)
+    cache.put(q * 5.0, "scaled")                         # raw embeddings are un-normalised (main.py:123)
+    assert cache.get(q) == "scaled"
+    assert cache.freqs() == [2, 1]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_cache_top1_batched_gemv_path(sqe, dtype):
+    rng = np.random.default_rng(17)
+    c = make_corpus(rng, 5000)
+    q = rng.standard_normal((9, DIM)).astype(np.float32)
+    q[0] = c[42] * 2
+    q[1] = c[7]                                          # duplicates 7/33/4999 -> 7
+    q[2] = 0.0
+    C = sqe.ops.normalize_cast(torch.from_numpy(c).to(dev()), dtype)
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+    idx, score, hit = sqe.ops.cache_top1(C, Q, 0.96, path=1)
+    c_st = oracle.from_storage(stored_bits(C, dtype), dtype)
+    q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+    wi, ws, wh = no.cache_lookup_batched(q_st, c_st, 0.96)
+    np.testing.assert_array_equal(idx.cpu().numpy(), wi)
+    np.testing.assert_allclose(score.cpu().numpy(), ws, atol=2e-6)
+    np.testing.assert_array_equal(hit.cpu().numpy(), wh)
+    assert idx[0].item() == 42 and hit[0].item() == 1 and idx[1].item() == 7 and hit[2].item() == 0
+
+
+def test_plugin_install_patches_reference_names(sqe):
+    import types
+    main = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=1000,
+                                 REDIS_CACHE_LIST="query_cache_lfu")
+    sqe.plugin.install(main, dtype="bf16")
+    rng = np.random.default_rng(1)
+    emb = rng.standard_normal((300, DIM)).astype(np.float32)
+    idx = main.OpenSearchIndexer(None, "x")
+    idx.add_embeddings(emb, [{"doc_id": f"d{i}", "text": f"t{i}"} for i in range(300)])
+    hits = idx.search(emb[17:18] * 3, k=3)
+    assert hits[0][0]["doc_id"] == "d17" and abs(hits[0][1] - 1.0) < 1e-2
+    q = rng.standard_normal((1, DIM)).astype(np.float32)
+    assert main.lfu_cache_get(q) is None
+    main.lfu_cache_put(q, "hello")
+    assert main.lfu_cache_get(q) == "hello"

@@ -331,7 +331,13 @@ def main():
     roofline["kernel"] = kname
     roofline["kernel_ms"] = kms
     roofline["peak_source"] = peaks["source"] + (" (burst)" if roofline["bound"] == "tensor" else "")
-    roofline["traffic"] = load_traffic(kname)
+    ratio = load_traffic(kname)
+    if ratio is not None:
+        unit_bytes = local_rows * DIM * esize            # shard bytes one launch must stream
+        roofline["traffic"] = ratio["dram_bytes_per_algorithmic_byte"] * unit_bytes
+        roofline["traffic_source"] = ratio["source"]
+    else:
+        roofline["traffic"] = None
 
     # ---- end to end through the public host API (pinned host queries in, host results out)
     e2e = None

@@ -75,12 +75,13 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.t_mark = 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,7 +90,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: samples before this instant are dropped."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -101,7 +106,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < self.t_mark:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -270,12 +277,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-timed throughput (inputs resident in HBM)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs ~1 s before its first sample
     for _ in range(warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = nat.launch_count
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)

@@ -15,6 +15,7 @@ from parity import assert_topk_matches, exact_scores
 
 DIM = 1024
 DTYPES = ["fp32", "bf16", "fp16"]
+K2_TOL = 1e-5          # score / near-tie tolerance of the tensor-core path (see _k2_case)
 
 
 @pytest.fixture(scope="module")
@@ -262,3 +263,139 @@ def test_plugin_install_patches_reference_names(sqe):
     assert main.lfu_cache_get(q) is None
     main.lfu_cache_put(q, "hello")
     assert main.lfu_cache_get(q) == "hello"
+
+
+# ------------------------------------------------------------------------- K2
+def _k2_case(sqe, dtype, n, b, ks, seed, idx_offset=0, n_used=None):
+    rng = np.random.default_rng(seed)
+    x = make_corpus(rng, n)
+    q = rng.standard_normal((b, DIM)).astype(np.float32)
+    if n >= 64 and b >= 3:
+        q[1] = x[7] * 0.25                                # planted duplicates 7 / 33 / n-1
+        q[2] = 0.0                                        # zero query: every score is 0
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+    rows = n if n_used is None else n_used
+    d_st = oracle.from_storage(stored_bits(D, dtype), dtype)[:rows]
+    q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+    s64 = exact_scores(d_st, q_st)
+    excused = 0
+    for k in ks:
+        s, i = sqe.ops.topk_batched(D, Q, k, idx_offset=idx_offset, n=n_used)
+        torch.cuda.synchronize()
+        # tensor-core fp32 accumulation (not an IEEE round-to-nearest FMA chain): measured
+        # worst error 4.1e-6 at |score| ~ 1; 1e-5 is the tolerance north_star states for fp32
+        # storage and two orders of magnitude inside the 1e-3 of the bf16/fp16 class
+        excused += assert_topk_matches(s.cpu().numpy(), i.cpu().numpy(), d_st, q_st, k, s64=s64,
+                                       score_tol=K2_TOL, tie_eps=K2_TOL, idx_offset=idx_offset)
+        if n >= 64 and b >= 3 and rows == n:
+            got = (i[1].cpu().numpy() - idx_offset).tolist()
+            if k >= 10:
+                assert got.index(7) < got.index(33) < got.index(n - 1), got
+            assert got[: min(k, n)] != [] and (i[2].cpu().numpy() - idx_offset).tolist()[: min(k, n)] == list(range(min(k, n)))
+    return excused
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 1000, 40037])
+def test_batched_topk_matches_oracle(sqe, dtype, n):
+    _k2_case(sqe, dtype, n, 5, (1, 3, 10, 32, 33, 100, 128), seed=2000 + n)
+
+
+@pytest.mark.parametrize("b", [1, 127, 128, 129, 300])
+def test_batched_topk_ragged_batches(sqe, b):
+    _k2_case(sqe, "bf16", 5000, b, (10,), seed=3000 + b)
+
+
+def test_batched_topk_more_queries_than_one_launch(sqe):
+    _k2_case(sqe, "bf16", 3000, 1100, (5,), seed=77)       # 1024 + 76: two launches
+
+
+def test_batched_topk_many_tiles_per_cta(sqe):
+    # 300k rows = 1172 d-tiles over 74 groups (b=130 -> 2 q-tiles): every CTA walks ~16 tiles,
+    # both TMEM accumulators and every smem stage wrap several times
+    _k2_case(sqe, "bf16", 300_000, 130, (10, 100), seed=5)
+
+
+def test_batched_idx_offset_and_partial_shard(sqe):
+    _k2_case(sqe, "fp16", 3000, 9, (5,), seed=9, idx_offset=10_000_000_000, n_used=2000)
+    rng = np.random.default_rng(1)
+    D = sqe.ops.normalize_cast(torch.from_numpy(make_corpus(rng, 300)).to(dev()), "bf16")
+    Q = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((4, DIM)).astype(np.float32)).to(dev()), "bf16")
+    s0, i0 = sqe.ops.topk_batched(D, Q, 5, n=0)                                # empty shard
+    assert (i0.cpu().numpy() == -1).all() and np.isneginf(s0.cpu().numpy()).all()
+
+
+def test_batched_equals_gemv_and_is_deterministic(sqe):
+    rng = np.random.default_rng(11)
+    D = sqe.ops.normalize_cast(torch.from_numpy(make_corpus(rng, 120_000)).to(dev()), "bf16")
+    Q = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((64, DIM)).astype(np.float32)).to(dev()), "bf16")
+    sb, ib = [t.clone() for t in sqe.ops.topk_batched(D, Q, 10)]
+    sb2, ib2 = [t.clone() for t in sqe.ops.topk_batched(D, Q, 10)]
+    assert torch.equal(sb, sb2) and torch.equal(ib, ib2)
+    sg, ig = sqe.ops.topk_gemv(D, Q, 10)
+    same = (ib == ig).all(dim=1).float().mean().item()
+    assert same >= 0.9, same                               # near-ties may reorder between paths
+    np.testing.assert_allclose(sb.cpu().numpy(), sg.cpu().numpy(), atol=K2_TOL)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_cache_top1_tensor_path(sqe, dtype):
+    rng = np.random.default_rng(18)
+    c = make_corpus(rng, 20_000)
+    q = rng.standard_normal((64, DIM)).astype(np.float32)
+    q[0] = c[42] * 2
+    q[1] = c[7]
+    q[2] = 0.0
+    q[3] = c[100] + 0.28 * rng.standard_normal(DIM).astype(np.float32) * np.linalg.norm(c[100]) / 32  # cos ~ 0.96
+    C = sqe.ops.normalize_cast(torch.from_numpy(c).to(dev()), dtype)
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+    c_st = oracle.from_storage(stored_bits(C, dtype), dtype)
+    q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+    wi, ws, wh = no.cache_lookup_batched(q_st, c_st, 0.96)
+    s64 = exact_scores(c_st, q_st)
+    for path in (2, 0):
+        idx, score, hit = sqe.ops.cache_top1(C, Q, 0.96, path=path)
+        gi = idx.cpu().numpy()
+        for r in range(len(q)):
+            assert gi[r] == wi[r] or abs(s64[r, gi[r]] - s64[r, wi[r]]) <= K2_TOL, (r, gi[r], wi[r])
+        np.testing.assert_allclose(score.cpu().numpy(), ws, atol=K2_TOL)
+        # hit flags must agree unless the score sits within rounding of the threshold
+        gh = hit.cpu().numpy()
+        for r in range(len(q)):
+            assert gh[r] == wh[r] or abs(ws[r] - 0.96) <= K2_TOL, (r, gh[r], wh[r], ws[r])
+        assert gi[0] == 42 and gh[0] == 1 and gi[1] in (7, 40) and gh[2] == 0
+
+
+def test_full_size_batched_properties(sqe):
+    """BASELINE configs[2] size (10M x 1024 bf16, b=1024, k=10): size-independent properties.
+    (a) every query's planted copy is its top-1 with score ~1; (b) a sample of queries agrees
+    with the K3 GEMV path (itself checked against the oracle above); (c) lists are best-first."""
+    free, _ = torch.cuda.mem_get_info()
+    n = 10_000_000 if free > 40e9 else 2_000_000
+    b, k = 1024, 10
+    D = torch.empty((n, DIM), dtype=torch.bfloat16, device=dev())
+    gen = torch.Generator(device=dev())
+    for lo in range(0, n, 250_000):
+        gen.manual_seed(4321 + lo)
+        x = torch.randn((min(250_000, n - lo), DIM), generator=gen, device=dev())
+        sqe.ops.normalize_cast(x, "bf16", out=D[lo: lo + x.shape[0]])
+    q = torch.randn((b, DIM), generator=gen, device=dev())
+    Q = sqe.ops.normalize_cast(q, "bf16")
+    pos = torch.arange(b, device=dev()) * (n // b) + 17
+    D[pos] = Q                                              # planted exact copies
+    s, i = sqe.ops.topk_batched(D, Q, k)
+    torch.cuda.synchronize()
+    assert torch.equal(i[:, 0], pos)
+    assert (s[:, 0] - 1.0).abs().max().item() < 2e-2        # |bf16 unit row|^2
+    assert (s[:, :-1] >= s[:, 1:]).all()
+    assert (s[:, 1] < 0.3).all()                            # everything else is random (sigma 1/32)
+    sample = torch.arange(0, b, 128, device=dev())
+    sg, ig = sqe.ops.topk_gemv(D, Q[sample], k)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(s[sample].cpu().numpy(), sg.cpu().numpy(), atol=K2_TOL)
+    agree = (i[sample] == ig).float().mean().item()
+    assert agree >= 0.95, agree
+    for r in range(len(sample)):                            # same row SETS up to near-ties at the boundary
+        a, g = set(i[sample[r]].tolist()), set(ig[r].tolist())
+        assert len(a ^ g) <= 2, (a, g)

@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--k2-cta-group", type=int, default=0, choices=[0, 1, 2],
+                    help="force the single-CTA (1) or CTA-pair (2) tensor-core kernel; 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -219,6 +221,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nat.load()
+    if args.k2_cta_group:
+        nat.tuning_set(nat.SQE_TUNE_K2_CTA_GROUP, args.k2_cta_group)
 
     peaks = load_peaks()
     is_cache = args.workload == "cache64"

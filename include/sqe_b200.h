@@ -100,6 +100,29 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
                      int64_t workspace_bytes, void *stream);
 
 /*
+ * Tuning knobs (process-wide, for tests and benchmarks; results never depend on them).
+ *   SQE_TUNE_K2_CTA_GROUP: 0 = choose (CTA pairs when more than 128 queries are in flight),
+ *                          1 = single-CTA UMMA (M = 128), 2 = CTA-pair UMMA (cta_group::2, M = 256).
+ * Returns the previous value, or SQE_E_ARG for an unknown knob / value.
+ *   SQE_TUNE_K2_EPILOGUE_MODE: DIAGNOSTICS ONLY, results are invalid unless 0.  1 = the epilogue
+ *                          only reads TMEM, 2 = no epilogue (isolates the TMA + MMA main loop).
+ */
+#define SQE_TUNE_K2_CTA_GROUP 0
+#define SQE_TUNE_K2_EPILOGUE_MODE 1
+SQE_API int sqe_tuning_set(int knob, int value);
+
+/*
+ * Diagnostics: when `device_buffer` is non-NULL, every later sqe_topk_batched launch writes
+ * per-CTA role timers (clock64 cycles) and counters into it as u64 [grid][32]:
+ *   0 producer total, 1 producer waiting for a free stage, 2 MMA issuer total, 3 MMA issuer
+ *   waiting for operands, 4 MMA issuer waiting for a drained accumulator; then for each of the
+ *   four epilogue warps w at 8 + 6 w: total, waiting for an accumulator, inside list merges,
+ *   strips on the slow path, lists merged, slow-path column branches.
+ * NULL switches it off (the default).
+ */
+SQE_API void sqe_debug_k2_timers(void *device_buffer);
+
+/*
  * K5  query-cache lookup: top-1 + similarity threshold.
  * Replaces the scan in lfu_cache_get, app/main.py:73-90: running maximum with strict `>`
  * from -1.0 (first maximum = lowest row wins), miss iff best < threshold.

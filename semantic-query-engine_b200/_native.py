@@ -25,6 +25,8 @@ PROTOTYPES = [
     ("sqe_abi_version", c_int, []),
     ("sqe_last_error", c_char_p, []),
     ("sqe_device_info", c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    ("sqe_tuning_set", c_int, [c_int, c_int]),
+    ("sqe_debug_k2_timers", None, [c_void_p]),
     ("sqe_normalize_cast", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     ("sqe_topk_gemv_workspace_bytes", c_int64, [c_int, c_int]),
     ("sqe_topk_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
@@ -97,6 +99,18 @@ def call(name: str, *args) -> None:
     if rc != 0:
         raise SqeError(rc, last_error())
     launch_count += LAUNCHES_PER_CALL.get(name, 0)
+
+
+SQE_TUNE_K2_CTA_GROUP = 0
+SQE_TUNE_K2_EPILOGUE_MODE = 1      # diagnostics only
+
+
+def tuning_set(knob: int, value: int) -> int:
+    """Set a tuning knob, return its previous value."""
+    old = load().sqe_tuning_set(knob, value)
+    if old < 0:
+        raise SqeError(old, last_error())
+    return old
 
 
 def device_info():

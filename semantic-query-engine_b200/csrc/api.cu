@@ -10,6 +10,9 @@
 namespace sqe {
 
 static thread_local char g_err[512] = "";
+int g_k2_cta_group = 0;
+void* g_k2_debug = nullptr;
+int g_k2_epilogue_mode = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -77,6 +80,23 @@ extern "C" {
 int sqe_abi_version(void) { return SQE_ABI_VERSION; }
 
 const char* sqe_last_error(void) { return g_err; }
+
+int sqe_tuning_set(int knob, int value) {
+    if (knob == SQE_TUNE_K2_CTA_GROUP && value >= 0 && value <= 2) {
+        const int old = g_k2_cta_group;
+        g_k2_cta_group = value;
+        return old;
+    }
+    if (knob == SQE_TUNE_K2_EPILOGUE_MODE && value >= 0 && value <= 2) {
+        const int old = g_k2_epilogue_mode;
+        g_k2_epilogue_mode = value;
+        return old;
+    }
+    set_error("tuning_set: unknown knob %d / value %d", knob, value);
+    return SQE_E_ARG;
+}
+
+void sqe_debug_k2_timers(void* device_buffer) { g_k2_debug = device_buffer; }
 
 int sqe_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     DevInfo d;

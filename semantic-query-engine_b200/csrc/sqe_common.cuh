@@ -164,6 +164,23 @@ struct WarpList {
         }
     }
 
+    // R == 1 only.  Sort descending when only elements 0..P-1 may be non-empty (P a power of
+    // two): the bitonic stages above P would only shuffle empty slots.
+    template <int P>
+    __device__ __forceinline__ void sort_prefix(int lane) {
+        static_assert(R == 1, "sort_prefix works on a 32-key list");
+#pragma unroll
+        for (int s = 2; s <= P; s <<= 1) {
+#pragma unroll
+            for (int d = s >> 1; d >= 1; d >>= 1) {
+                const bool lower = (lane & d) == 0;
+                const bool desc = ((lane & s) == 0) || (s == P);
+                uint64_t o = shfl_xor_u64(key[0], d);
+                key[0] = (lower == desc) ? umax64(key[0], o) : umin64(key[0], o);
+            }
+        }
+    }
+
     __device__ __forceinline__ void load(const uint64_t* p, int lane) {
 #pragma unroll
         for (int r = 0; r < R; ++r) key[r] = p[r * 32 + lane];

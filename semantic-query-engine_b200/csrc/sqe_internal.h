@@ -32,4 +32,9 @@ int launch_cache_finalize(const float* score, const int64_t* idx, int b, float t
 
 void set_error(const char* fmt, ...);
 
+// tuning knobs (api.cu)
+extern int g_k2_cta_group;      // 0 auto, 1, 2
+extern int g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
+extern void* g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
+
 }  // namespace sqe

@@ -26,13 +26,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster.  Default
+// (.release.cta) semantics on purpose: a cluster-scope release costs an ERRBAR + MEMBAR
+// (~1800 cycles per call, measured) and nothing here needs it -- what the arrival orders
+// are TMEM reads, and those are ordered by tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n"
         ".reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}\n" ::"r"(bar), "r"(cta)
         : "memory");
 }

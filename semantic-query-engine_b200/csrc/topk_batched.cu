@@ -46,25 +46,41 @@
 namespace sqe {
 
 namespace k2 {
-constexpr int kTileM = 128;
-constexpr int kTileN = 256;
+constexpr int kRowsPerCta = 128;               // queries per CTA = TMEM lanes
+constexpr int kTileN = 256;                    // shard rows per d-tile = fp32 TMEM columns per accumulator
 constexpr int kChunkK = 64;                    // elements per K chunk = 128 bytes = swizzle span
 constexpr int kNumChunks = kDim / kChunkK;     // 16
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
-constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KB
-constexpr int kBBytes = kTileN * kChunkK * 2;  // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kABytes = kRowsPerCta * kChunkK * 2;  // 16 KB: this CTA's 128 query rows of one chunk
 constexpr int kCap = 16;                       // pending candidates per query
 constexpr int kBufStride = 17;                 // u64 per query row in smem (padded)
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;                 // TMA, MMA, 4 epilogue warps, threshold warp
 constexpr int kTmemCols = 512;
-
-constexpr int kOffBuf = kStages * kStageBytes;                  // 196608
-constexpr int kOffBar = kOffBuf + kTileM * kBufStride * 8;      // +17408
-constexpr int kOffTmemPtr = kOffBar + 16 * 8;
-constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;             // + alignment slack
 constexpr int kQueriesPerLaunch = 1024;
+
+// CG = CTAs cooperating on one UMMA (tcgen05 cta_group).  CG = 1: M = 128, the CTA loads the
+// whole 256-row D chunk.  CG = 2: a CTA pair (cluster of 2) computes M = 256; each CTA loads
+// its 128 query rows and HALF of the D chunk (128 rows), the tensor cores of both SMs read
+// both halves -- 2/3 of the smem and L2 traffic per FLOP of the CG = 1 form.
+//
+// R = 64-bit keys per lane of a query's sorted list (list length 32 R >= k).  For R = 1
+// (k <= 32) the 128 lists of the CTA live in shared memory (32 KB, one operand stage less)
+// and are written through to the global workspace; longer lists live in the workspace only.
+template <int CG, int R = 1>
+struct Cfg {
+    static constexpr int kQTile = kRowsPerCta * CG;          // queries per q-tile
+    static constexpr int kBRows = kTileN / CG;               // D rows this CTA loads per chunk
+    static constexpr int kBBytes = kBRows * kChunkK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB / 32 KB
+    static constexpr bool kSmemLists = (R == 1);
+    static constexpr int kListBytes = kSmemLists ? kRowsPerCta * 32 * 8 : 0;
+    static constexpr int kStages = (CG == 1) ? (kSmemLists ? 3 : 4) : (kSmemLists ? 5 : 6);
+    static constexpr int kOffLists = kStages * kStageBytes;
+    static constexpr int kOffBuf = kOffLists + kListBytes;
+    static constexpr int kOffBar = kOffBuf + kRowsPerCta * kBufStride * 8;
+    static constexpr int kOffTmemPtr = kOffBar + 24 * 8;       // u32 tmem base, u32 epilogue-done counter
+    static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
+};
 }  // namespace k2
 
 // smem matrix descriptor of a K-major, 128-byte-swizzled operand tile whose rows are 128 B
@@ -82,35 +98,79 @@ struct EpiState {
     float tau_l;      // k-th best score of this CTA's list for this query (-inf until k rows)
     uint32_t tau_g;   // best published bound (orderable u32), 0 = none
     int cnt;          // pending candidates in the smem buffer
+    // diagnostics (sqe_debug_k2_timers)
+    unsigned n_slow;      // strips that took the slow path
+    unsigned n_flush;     // query lists merged by this warp
+    unsigned n_cols;      // column branches taken in the slow path
+    long long t_flush;    // cycles inside flush_lanes
 };
 
+// pass iff score > thr: strictly above the local k-th best, at or above the shared bound.
+// "At or above g" is "above the next smaller float"; the code just below +0.0 is -0.0, which
+// compares EQUAL to +0.0, so step once more (to the largest negative denormal).
 __device__ __forceinline__ float thr_of(float tau_l, uint32_t tau_g) {
-    const float g = tau_g ? from_orderable_u32(tau_g - 1u) : __int_as_float(0xff800000);
+    uint32_t o = tau_g - 1u;
+    if (o == 0x7fffffffu) o = 0x7ffffffeu;
+    const float g = tau_g ? from_orderable_u32(o) : __int_as_float(0xff800000);
     return fmaxf(tau_l, g);
 }
 
 // Merge the pending candidates of every lane in `mask` into that query's sorted list.
-template <int R>
-__device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, uint64_t* wbuf,
-                                            uint64_t* wlists, uint32_t* wtau, int k, int lane) {
+// SL = the master copy of the list is in shared memory (`slists`, this warp's 32 x 32 keys)
+// and the global copy is write-only here; otherwise the list of the next pending query is
+// fetched from L2 while the current one is sorted/merged.
+template <int R, bool SL>
+__device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const uint64_t* wbuf,
+                                            uint64_t* slists, uint64_t* wlists, uint32_t* wtau,
+                                            int k, int lane) {
     constexpr int L = 32 * R;
+    const long long t_in = clock64();
+    st.n_flush += __popc(mask);
     __syncwarp();                                               // owners' buffer stores are visible
-    while (mask) {
-        const int r = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int c = __shfl_sync(kFull, st.cnt, r);
-        WarpList<1> cand;
-        cand.key[0] = (lane < c) ? wbuf[r * k2::kBufStride + lane] : 0ull;
-        cand.sort(lane);
-        uint64_t* lp = wlists + static_cast<size_t>(r) * L;
-        WarpList<R> cur;
-        uint64_t other[R];
+    int r = __ffs(mask) - 1;
+    mask &= mask - 1;
+    uint64_t nxt[R];
+    if constexpr (!SL) {
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            cur.key[i] = __ldcg(lp + i * 32 + lane);
-            other[i] = (i == 0) ? cand.key[0] : 0ull;
+        for (int i = 0; i < R; ++i) nxt[i] = __ldcg(wlists + static_cast<size_t>(r) * L + i * 32 + lane);
+    }
+    while (true) {
+        WarpList<R> cur;
+        const int r_next = mask ? (__ffs(mask) - 1) : -1;
+        mask &= mask - 1;
+        if constexpr (SL) {
+            cur.key[0] = slists[r * 32 + lane];
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) cur.key[i] = nxt[i];
+            if (r_next >= 0) {
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    nxt[i] = __ldcg(wlists + static_cast<size_t>(r_next) * L + i * 32 + lane);
+            }
         }
-        cur.merge_sorted(other, lane);
+        const int c = __shfl_sync(kFull, st.cnt, r);
+        if (c <= 2) {
+            // the common case once the thresholds are tight: one or two candidates -> plain
+            // sorted insertion (the list's worst entry is checked first)
+            const uint64_t c0 = wbuf[r * k2::kBufStride];
+            const uint64_t c1 = (c == 2) ? wbuf[r * k2::kBufStride + 1] : 0ull;
+            if (c0 > cur.worst()) cur.insert(c0, lane);
+            if (c1 > cur.worst()) cur.insert(c1, lane);
+        } else {
+            WarpList<1> cand;
+            cand.key[0] = (lane < c) ? wbuf[r * k2::kBufStride + lane] : 0ull;
+            if (c <= 4) cand.sort_prefix<4>(lane);
+            else if (c <= 8) cand.sort_prefix<8>(lane);
+            else if (c <= 16) cand.sort_prefix<16>(lane);
+            else cand.sort(lane);
+            uint64_t other[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) other[i] = (i == 0) ? cand.key[0] : 0ull;
+            cur.merge_sorted(other, lane);
+        }
+        if constexpr (SL) slists[r * 32 + lane] = cur.key[0];
+        uint64_t* lp = wlists + static_cast<size_t>(r) * L;
 #pragma unroll
         for (int i = 0; i < R; ++i) __stcg(lp + i * 32 + lane, cur.key[i]);
         uint64_t kth_src = 0ull;
@@ -123,56 +183,165 @@ __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, uint64_
             if (kth != 0ull) {
                 st.tau_l = key_score(kth);
                 const uint32_t o = static_cast<uint32_t>(kth >> 32);
-                const uint32_t old = atomicMax(wtau + r, o);
-                st.tau_g = max(st.tau_g, max(old, o));
+                atomicMax(wtau + r, o);                          // result unused: a RED, no round trip
+                st.tau_g = max(st.tau_g, o);
             }
             st.thr = thr_of(st.tau_l, st.tau_g);
         }
-        __syncwarp();
+        if (r_next < 0) break;
+        r = r_next;
     }
+    __syncwarp();
+    st.t_flush += clock64() - t_in;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 // One 32-column strip of the accumulator: v[j] = score of (this thread's query, row col0+j).
-template <int R>
+template <int R, bool SL>
 __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, uint32_t n,
                                               bool row_valid, EpiState& st, uint64_t* wbuf,
-                                              uint64_t* wlists, uint32_t* wtau, int k, int lane) {
+                                              uint64_t* slists, uint64_t* wlists, uint32_t* wtau,
+                                              int k, int lane) {
     if (col0 + 32u > n) {                                       // ragged last d-tile (warp-uniform)
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             if (col0 + j >= n) v[j] = 0xff800000u;              // -inf never passes
     }
-    float m = __uint_as_float(v[0]);
+    float f[32];
 #pragma unroll
-    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    // fast path: a shallow max tree (depth 4) and one vote
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = fmax3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+    t[10] = fmaxf(f[30], f[31]);
+    const float u0 = fmax3(t[0], t[1], t[2]), u1 = fmax3(t[3], t[4], t[5]);
+    const float u2 = fmax3(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
+    const float m = fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
     const bool want = row_valid && (m > st.thr);
-    if (__ballot_sync(kFull, want) == 0u) return;
+    if (!__any_sync(kFull, want)) return;
 
+    // slow path.  Common case: every lane has room for all of its passing scores -> branch-free
+    // predicated appends, no votes.
+    ++st.n_slow;
+    const float thr0 = st.thr;
+    int pc = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) pc += (want && f[j] > thr0) ? 1 : 0;
     uint64_t* mybuf = wbuf + lane * k2::kBufStride;
+    const unsigned over = __ballot_sync(kFull, st.cnt + pc > k2::kCap);
+    if (over) {
+        // make room: merge the pending candidates of the lanes that would overflow
+        const unsigned fl = over & __ballot_sync(kFull, st.cnt > 0);
+        if (fl) flush_lanes<R, SL>(fl, st, wbuf, slists, wlists, wtau, k, lane);
+    }
+    if (__any_sync(kFull, pc > k2::kCap)) {
+        // more than a buffer's worth in one strip (empty list without bootstrap, adversarial
+        // data): column by column with an overflow check after every append
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+            float fj = f[0];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const unsigned full = __ballot_sync(kFull, st.cnt > k2::kCap - 8);
-        if (full) flush_lanes<R>(full, st, wbuf, wlists, wtau, k, lane);
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = g * 8 + jj;
-            const float s = __uint_as_float(v[j]);
-            if (want && s > st.thr) {
-                mybuf[st.cnt] = make_key(s, col0 + j);
+            for (int jj = 1; jj < 32; ++jj)
+                if (jj == j) fj = f[jj];
+            if (want && fj > st.thr) {
+                mybuf[st.cnt] = make_key(fj, col0 + j);
                 ++st.cnt;
             }
+            const unsigned full = __ballot_sync(kFull, st.cnt >= k2::kCap);
+            if (full) flush_lanes<R, SL>(full, st, wbuf, slists, wlists, wtau, k, lane);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (want && f[j] > thr0) {
+            mybuf[st.cnt] = make_key(f[j], col0 + j);
+            ++st.cnt;
         }
     }
 }
 
+// Bootstrap (first d-tile of a CTA, k <= 16): every list is empty, so without help every
+// score passes and the lists are rebuilt 256 times.  One extra pass over the accumulator
+// keeps, per query (= per lane, in registers, branch-free), the 16 largest of the 64
+// maxima of 4 consecutive columns; the k-th largest of those maxima are k distinct scores,
+// so its value is a valid lower bound of the final k-th best.  The regular pass that follows
+// then lets only ~k scores per query through.
+__device__ __forceinline__ void bootstrap_strip(const uint32_t (&v)[32], uint32_t col0, uint32_t n,
+                                                float (&top)[16]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float x = __int_as_float(0xff800000);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float s = (col0 + 4 * g + e < n) ? __uint_as_float(v[4 * g + e]) : __int_as_float(0xff800000);
+            x = fmaxf(x, s);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                          // insertion network, descending
+            const float hi = fmaxf(top[i], x);
+            x = fminf(top[i], x);
+            top[i] = hi;
+        }
+    }
+}
+
+// Threshold warp: for its share of this q-tile's queries, merge the partial lists of ALL
+// groups and publish the k-th best key's score -- the exact k-th best over every row any
+// CTA has merged so far.  Lists are read while their owners rewrite them; every slot is an
+// 8-byte atomic store of a key that only ever grows, so a torn list is element-wise below a
+// real one and the bound stays valid.
 template <int R>
+__device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_t* ws_tau, int b,
+                                               int b_pad, int k, int n_groups, int q_row0,
+                                               int rows_in_qtile, int my_id, int n_ids,
+                                               volatile uint32_t* done, int lane) {
+    constexpr int L = 32 * R;
+    if (n_groups < 2) return;
+    while (true) {
+        for (int rl = my_id; rl < rows_in_qtile; rl += n_ids) {
+            const int row = q_row0 + rl;
+            if (row >= b) break;
+            WarpList<R> acc;
+            acc.clear();
+            for (int g0 = 0; g0 < n_groups; g0 += 4) {
+                uint64_t o[4][R];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        o[u][i] = (g0 + u < n_groups)
+                            ? __ldcg(ws_lists + (static_cast<size_t>(g0 + u) * b_pad + row) * L + i * 32 + lane)
+                            : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc.merge_sorted(o[u], lane);
+            }
+            uint64_t kth_src = 0ull;
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (i == ((k - 1) >> 5)) kth_src = acc.key[i];
+            const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
+            if (lane == 0 && kth != 0ull) atomicMax(ws_tau + row, static_cast<uint32_t>(kth >> 32));
+        }
+        if (*done >= 4u) break;
+        __nanosleep(2000);
+    }
+}
+
+template <int R, int CG>
 __global__ void __launch_bounds__(k2::kThreads, 1)
 topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const __grid_constant__ CUtensorMap tmap_d, uint32_t n, int b, int k,
                     int n_qt, int n_groups, int n_dtiles, uint32_t idesc,
-                    uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau) {
+                    uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau,
+                    unsigned long long* __restrict__ dbg, int epi_mode) {
     using namespace k2;
+    using C = Cfg<CG, R>;
     constexpr int L = 32 * R;
+    constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;         // SWIZZLE_128B atoms are 1024-B aligned
@@ -180,99 +349,149 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
     const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int q_tile = blockIdx.x % n_qt;
-    const int group = blockIdx.x / n_qt;
+    const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+    const int unit = blockIdx.x / CG;                                // CTA (CG=1) or CTA pair (CG=2)
+    const int q_tile = unit % n_qt;
+    const int group = unit / n_qt;
     const int my_tiles = (group < n_dtiles) ? (n_dtiles - group + n_groups - 1) / n_groups : 0;
 
-    const uint32_t bar_full = base + kOffBar;                  // [kStages]
+    const uint32_t bar_full = base + C::kOffBar;               // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
     const uint32_t bar_tfull = bar_empty + 8 * kStages;        // [2]
     const uint32_t bar_tempty = bar_tfull + 16;                // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + kOffTmemPtr);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + C::kOffTmemPtr);
+    uint32_t* epi_done = tmem_ptr_smem + 1;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_q);
         ptx::prefetch_tensormap(&tmap_d);
         for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(bar_full + 8 * s, 1);
-            ptx::mbar_init(bar_empty + 8 * s, 1);
+            ptx::mbar_init(bar_full + 8 * s, 1);               // the leader's expect_tx arrival
+            ptx::mbar_init(bar_empty + 8 * s, 1);              // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
-            ptx::mbar_init(bar_tfull + 8 * a, 1);
-            ptx::mbar_init(bar_tempty + 8 * a, 4);             // one arrival per epilogue warp
+            ptx::mbar_init(bar_tfull + 8 * a, 1);              // one tcgen05.commit
+            ptx::mbar_init(bar_tempty + 8 * a, 4 * CG);        // one arrival per epilogue warp (of both CTAs)
         }
+        *epi_done = 0u;
         ptx::fence_barrier_init();
     }
-    if (warp == 1) ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_smem), kTmemCols);
+    if (warp == 1) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_ptr_smem), kTmemCols);
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            const uint64_t pol_q = ptx::policy_evict_last();   // 2 MB of queries: keep in L2
+            const uint64_t pol_d = ptx::policy_evict_normal();
+            const int q_row = q_tile * C::kQTile + static_cast<int>(rank) * kRowsPerCta;
             int stage = 0;
             uint32_t phase = 0;
+            long long t_wait = 0;
+            const long long t_begin = clock64();
             for (int i = 0; i < my_tiles; ++i) {
-                const int t = group + i * n_groups;
+                const int d_row = (group + i * n_groups) * kTileN + static_cast<int>(rank) * C::kBRows;
                 for (int kc = 0; kc < kNumChunks; ++kc) {
+                    const long long w0 = dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                    const uint32_t fb = bar_full + 8 * stage;
-                    const uint32_t sa = base + stage * kStageBytes;
-                    ptx::mbar_expect_tx(fb, kStageBytes);
-                    ptx::tma_load_2d(sa, &tmap_q, kc * kChunkK, q_tile * kTileM, fb);
-                    ptx::tma_load_2d(sa + kABytes, &tmap_d, kc * kChunkK, t * kTileN, fb);
+                    if (dbg) t_wait += clock64() - w0;
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    if constexpr (CG == 1) {
+                        const uint32_t fb = bar_full + 8 * stage;
+                        ptx::mbar_expect_tx(fb, C::kStageBytes);
+                        ptx::tma_load_2d_hint(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
+                        ptx::tma_load_2d_hint(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
+                    } else {
+                        // both CTAs' bytes are counted on the LEADER's barrier
+                        if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
+                        const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
+                        ptx::tma_load_2d_cg2(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
+                        ptx::tma_load_2d_cg2(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+            }
+            if (dbg) {
+                dbg[blockIdx.x * 32 + 0] = clock64() - t_begin;
+                dbg[blockIdx.x * 32 + 1] = t_wait;
             }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            long long t_wfull = 0, t_wtempty = 0;
+            const long long t_begin = clock64();
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
                 const uint32_t acc_phase = (i >> 1) & 1;
-                ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);   // epilogue drained it
+                const long long w0 = dbg ? clock64() : 0;
+                ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);   // epilogue(s) drained it
+                if (dbg) t_wtempty += clock64() - w0;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kTileN;
                 for (int kc = 0; kc < kNumChunks; ++kc) {
+                    const long long w1 = dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
+                    if (dbg) t_wfull += clock64() - w1;
                     ptx::tc_fence_after();
-                    const uint32_t sa = base + stage * kStageBytes;
+                    const uint32_t sa = base + stage * C::kStageBytes;
                     const uint64_t da = make_sw128_desc(sa);
                     const uint64_t db = make_sw128_desc(sa + kABytes);
 #pragma unroll
                     for (int k4 = 0; k4 < kChunkK / kUmmaK; ++k4) {
                         // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-B units
-                        ptx::umma_f16<1>(tmem_d, da + 2 * k4, db + 2 * k4, idesc,
-                                         (kc | k4) != 0 ? 1u : 0u);
+                        ptx::umma_f16<CG>(tmem_d, da + 2 * k4, db + 2 * k4, idesc,
+                                          (kc | k4) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(bar_empty + 8 * stage);            // frees the smem stage
+                    // frees the smem stage (in both CTAs) once these MMAs have read it
+                    if constexpr (CG == 1) ptx::umma_commit(bar_empty + 8 * stage);
+                    else ptx::umma_commit_cg2(bar_empty + 8 * stage, 0x3);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                ptx::umma_commit(bar_tfull + 8 * acc);                  // accumulator complete
+                // accumulator complete: wake the epilogue warps (of both CTAs)
+                if constexpr (CG == 1) ptx::umma_commit(bar_tfull + 8 * acc);
+                else ptx::umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
+            }
+            if (dbg) {
+                dbg[blockIdx.x * 32 + 2] = clock64() - t_begin;
+                dbg[blockIdx.x * 32 + 3] = t_wfull;
+                dbg[blockIdx.x * 32 + 4] = t_wtempty;
             }
         }
+    } else if (warp == 6) {
+        // ---------------------------------------------------------- threshold warp
+        threshold_warp<R>(ws_lists, ws_tau, b, n_qt * C::kQTile, k, n_groups, q_tile * C::kQTile,
+                          C::kQTile, group * CG + static_cast<int>(rank), n_groups * CG, epi_done, lane);
     } else {
         // ---------------------------------------------------------------- epilogue
         const int quarter = warp & 3;                                    // TMEM lanes 32q..32q+31
-        const int row_in_tile = quarter * 32 + lane;
-        const int row = q_tile * kTileM + row_in_tile;
-        const bool row_valid = row < b;
-        const int b_pad = n_qt * kTileM;
-        uint64_t* wbuf = reinterpret_cast<uint64_t*>(sm + kOffBuf) + quarter * 32 * kBufStride;
-        uint64_t* wlists = ws_lists +
-            (static_cast<size_t>(group) * b_pad + q_tile * kTileM + quarter * 32) * L;
-        uint32_t* wtau = ws_tau + q_tile * kTileM + quarter * 32;
+        const int row0 = q_tile * C::kQTile + static_cast<int>(rank) * kRowsPerCta + quarter * 32;
+        const bool row_valid = row0 + lane < b;
+        const int b_pad = n_qt * C::kQTile;
+        constexpr bool SL = C::kSmemLists;
+        uint64_t* wbuf = reinterpret_cast<uint64_t*>(sm + C::kOffBuf) + quarter * 32 * kBufStride;
+        uint64_t* slists = reinterpret_cast<uint64_t*>(sm + C::kOffLists) + quarter * 32 * 32;
+        if constexpr (SL) {
+            for (int i = lane; i < 32 * 32; i += 32) slists[i] = 0ull;
+            __syncwarp();
+        }
+        uint64_t* wlists = ws_lists + (static_cast<size_t>(group) * b_pad + row0) * L;
+        uint32_t* wtau = ws_tau + row0;
 
         EpiState st;
         st.tau_l = __int_as_float(0xff800000);
         st.tau_g = 0u;
         st.thr = st.tau_l;
         st.cnt = 0;
+        st.n_slow = st.n_flush = st.n_cols = 0u;
+        st.t_flush = 0;
+        long long t_wtfull = 0, t_ld = 0;
+        const long long t_begin = clock64();
 
         for (int i = 0; i < my_tiles; ++i) {
             const int t = group + i * n_groups;
@@ -280,34 +499,98 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t acc_phase = (i >> 1) & 1;
             // refresh the shared bound while waiting for the accumulator
             const uint32_t g = __ldcg(wtau + lane);
+            const long long w0 = dbg ? clock64() : 0;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            const long long w1 = dbg ? clock64() : 0;
+            if (dbg) t_wtfull += w1 - w0;
             ptx::tc_fence_after();
             if (g > st.tau_g) {
                 st.tau_g = g;
                 st.thr = thr_of(st.tau_l, st.tau_g);
             }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kTileN;
+            if (i == 0 && k <= 16 && epi_mode == 0) {
+                float top[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) top[j] = __int_as_float(0xff800000);
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_wait_ld();
+                    bootstrap_strip(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, top);
+                }
+                float kth = top[0];
+#pragma unroll
+                for (int j = 1; j < 16; ++j)
+                    if (j == k - 1) kth = top[j];
+                if (row_valid && kth > __int_as_float(0xff800000)) {
+                    st.tau_g = max(st.tau_g, orderable_u32(kth));       // applied non-strictly
+                    st.thr = thr_of(st.tau_l, st.tau_g);
+                }
+            }
+            uint32_t g_next = __ldcg(wtau + lane);
 #pragma unroll 1
             for (int c = 0; c < kTileN / 32; ++c) {
+                if (epi_mode == 2) break;                                 // diagnostics: MMA + TMA only
+                // the shared bound moves fast while the lists fill up: pick it up every strip
+                // (the load for the next strip is in flight while this one is processed)
+                if (g_next > st.tau_g) {
+                    st.tau_g = g_next;
+                    st.thr = thr_of(st.tau_l, st.tau_g);
+                }
+                g_next = __ldcg(wtau + lane);
                 uint32_t v[32];
+                const long long l0 = dbg ? clock64() : 0;
                 ptx::tmem_ld_32x32(taddr + c * 32, v);
                 ptx::tmem_wait_ld();
-                process_strip<R>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
-                                 wbuf, wlists, wtau, k, lane);
+                if (dbg) t_ld += clock64() - l0;
+                if (epi_mode == 1) {                                      // diagnostics: TMEM reads only
+                    asm volatile("" ::"r"(v[0]), "r"(v[31]));
+                    continue;
+                }
+                process_strip<R, SL>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
+                                     wbuf, slists, wlists, wtau, k, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * acc);
+            if (lane == 0) {
+                if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
+                else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);   // the leader's barrier
+            }
+            // the accumulator is released; now fold this tile's candidates into the lists so
+            // the threshold warps see them
+            const long long w2 = dbg ? clock64() : 0;
+            const unsigned pending = __ballot_sync(kFull, st.cnt > 0);
+            if (pending) flush_lanes<R, SL>(pending, st, wbuf, slists, wlists, wtau, k, lane);
+            if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 64) {
+                unsigned long long* tr = dbg + gridDim.x * 32 + i * 4;
+                tr[0] = w1 - w0;                 // waited for the accumulator
+                tr[1] = w2 - w1;                 // strips (until the accumulator was released)
+                tr[2] = clock64() - w2;          // tile-end list merges
+                tr[3] = __popc(pending);
+            }
         }
-        const unsigned pending = __ballot_sync(kFull, st.cnt > 0);
-        if (pending) flush_lanes<R>(pending, st, wbuf, wlists, wtau, k, lane);
+        __syncwarp();
+        if (lane == 0) atomicAdd(epi_done, 1u);
+        if (dbg && lane == 0) {
+            unsigned long long* d = dbg + blockIdx.x * 32 + 8 + (warp - 2) * 6;
+            d[0] = clock64() - t_begin;
+            d[1] = t_wtfull;
+            d[2] = st.t_flush;
+            d[3] = st.n_slow;
+            d[4] = st.n_flush;
+            d[5] = t_ld;
+        }
     }
 
+    // Teardown.  In pair mode neither CTA may exit (or free TMEM) while the other still reads
+    // its shared memory / signals its barriers.
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+        ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
     }
 }
 
@@ -375,29 +658,91 @@ static constexpr int64_t kTauBytes = 4096;        // kQueriesPerLaunch * 4
 
 int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
     const int64_t L = 32 * r_for_k_batched(k);
-    return kTauBytes + static_cast<int64_t>(sm_count) * k2::kTileM * L * 8;
+    return kTauBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8;
 }
 
-template <int R>
+template <int R, int CG>
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
                             int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
                             uint32_t* ws_tau, float* out_score, int64_t* out_idx, int64_t idx_offset,
                             cudaStream_t stream) {
+    using C = k2::Cfg<CG, R>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k2::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("topk_batched: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     if (n_dtiles > 0) {
-        topk_batched_kernel<R><<<n_groups * n_qt, k2::kThreads, k2::kSmemBytes, stream>>>(
-            tq, td, static_cast<uint32_t>(n), b, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau);
-        e = cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(n_groups * n_qt * CG));
+        cfg.blockDim = dim3(k2::kThreads);
+        cfg.dynamicSmemBytes = C::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CG;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG>, tq, td, static_cast<uint32_t>(n), b, k,
+                               n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau,
+                               reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
     }
     batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, n_dtiles > 0 ? n_groups : 0, b,
-                                                             n_qt * k2::kTileM, k, out_score, out_idx,
+                                                             n_qt * C::kQTile, k, out_score, out_idx,
                                                              idx_offset);
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("topk_batched: merge launch: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+template <int CG>
+static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q, int b, int k,
+                             float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
+                             int sm_count, cudaStream_t stream) {
+    using C = k2::Cfg<CG>;
+    const int R = r_for_k_batched(k);
+    const int64_t L = 32 * R;
+    uint32_t* ws_tau = static_cast<uint32_t*>(ws);
+    uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kTauBytes);
+    const int n_dtiles = static_cast<int>((n + k2::kTileN - 1) / k2::kTileN);
+    const uint32_t fmt = (dtype == 1) ? 1u : 0u;               // BF16 = 1, F16 = 0
+    // instruction descriptor: D fp32 [4,6)=1, A fmt [7,10), B fmt [10,13), K-major both,
+    // N>>3 [17,23), M>>4 [24,29)  (M = 128 per CTA, 256 for the pair)
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) |
+                           (static_cast<uint32_t>(k2::kTileN >> 3) << 17) |
+                           (static_cast<uint32_t>(C::kQTile >> 4) << 24);
+    CUtensorMap td;
+    if (n > 0) {
+        int rc = make_tile_map(&td, D, dtype, static_cast<uint64_t>(n), C::kBRows);
+        if (rc != 0) return rc;
+    } else {
+        memset(&td, 0, sizeof(td));
+    }
+    const int units = sm_count / CG;                           // CTAs or CTA pairs that fit the chip
+    for (int q0 = 0; q0 < b; q0 += k2::kQueriesPerLaunch) {
+        const int bc = (b - q0 < k2::kQueriesPerLaunch) ? (b - q0) : k2::kQueriesPerLaunch;
+        const int n_qt = (bc + C::kQTile - 1) / C::kQTile;
+        int n_groups = units / n_qt;
+        if (n_groups < 1) n_groups = 1;
+        if (n_dtiles > 0 && n_groups > n_dtiles) n_groups = n_dtiles;
+        const int64_t used = kTauBytes + static_cast<int64_t>(n_groups) * n_qt * C::kQTile * L * 8;
+        cudaError_t e = cudaMemsetAsync(ws, 0, static_cast<size_t>(used), stream);
+        if (e != cudaSuccess) { set_error("topk_batched: memset: %s", cudaGetErrorString(e)); return -2; }
+        const char* qp = static_cast<const char*>(Q) + static_cast<int64_t>(q0) * kDim * 2;
+        CUtensorMap tq;
+        int rc = make_tile_map(&tq, qp, dtype, static_cast<uint64_t>(bc), k2::kRowsPerCta);
+        if (rc != 0) return rc;
+        float* os = out_score + static_cast<int64_t>(q0) * k;
+        int64_t* oi = out_idx + static_cast<int64_t>(q0) * k;
+        switch (R) {
+            case 1: rc = launch_batched_r<1, CG>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+            case 2: rc = launch_batched_r<2, CG>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+            default: rc = launch_batched_r<4, CG>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+        }
+        if (rc != 0) return rc;
+    }
     return 0;
 }
 
@@ -409,47 +754,12 @@ int launch_topk_batched(const void* D, int dtype, int64_t n, const void* Q, int 
                   (long long)batched_workspace_bytes(n, b, k, sm_count));
         return -3;
     }
-    const int R = r_for_k_batched(k);
-    const int64_t L = 32 * R;
-    uint32_t* ws_tau = static_cast<uint32_t*>(ws);
-    uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kTauBytes);
-    const int n_dtiles = static_cast<int>((n + k2::kTileN - 1) / k2::kTileN);
-    const uint32_t fmt = (dtype == 1) ? 1u : 0u;               // BF16 = 1, F16 = 0
-    // instruction descriptor: D fp32 [4,6)=1, A fmt [7,10), B fmt [10,13), K-major both,
-    // N>>3 [17,23), M>>4 [24,29)
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) |
-                           (static_cast<uint32_t>(k2::kTileN >> 3) << 17) |
-                           (static_cast<uint32_t>(k2::kTileM >> 4) << 24);
-    CUtensorMap td;
-    if (n > 0) {
-        int rc = make_tile_map(&td, D, dtype, static_cast<uint64_t>(n), k2::kTileN);
-        if (rc != 0) return rc;
-    } else {
-        memset(&td, 0, sizeof(td));
-    }
-    for (int q0 = 0; q0 < b; q0 += k2::kQueriesPerLaunch) {
-        const int bc = (b - q0 < k2::kQueriesPerLaunch) ? (b - q0) : k2::kQueriesPerLaunch;
-        const int n_qt = (bc + k2::kTileM - 1) / k2::kTileM;
-        int n_groups = sm_count / n_qt;
-        if (n_groups < 1) n_groups = 1;
-        if (n_dtiles > 0 && n_groups > n_dtiles) n_groups = n_dtiles;
-        const int64_t used = kTauBytes + static_cast<int64_t>(n_groups) * n_qt * k2::kTileM * L * 8;
-        cudaError_t e = cudaMemsetAsync(ws, 0, static_cast<size_t>(used), stream);
-        if (e != cudaSuccess) { set_error("topk_batched: memset: %s", cudaGetErrorString(e)); return -2; }
-        const char* qp = static_cast<const char*>(Q) + static_cast<int64_t>(q0) * kDim * 2;
-        CUtensorMap tq;
-        int rc = make_tile_map(&tq, qp, dtype, static_cast<uint64_t>(bc), k2::kTileM);
-        if (rc != 0) return rc;
-        float* os = out_score + static_cast<int64_t>(q0) * k;
-        int64_t* oi = out_idx + static_cast<int64_t>(q0) * k;
-        switch (R) {
-            case 1: rc = launch_batched_r<1>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-            case 2: rc = launch_batched_r<2>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-            default: rc = launch_batched_r<4>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-        }
-        if (rc != 0) return rc;
-    }
-    return 0;
+    // CTA pairs whenever more than one 128-query tile is in flight (sqe_tuning_set overrides)
+    int cg = g_k2_cta_group;
+    if (cg == 0) cg = (b > k2::kRowsPerCta) ? 2 : 1;
+    if (cg == 2)
+        return launch_batched_cg<2>(D, dtype, n, Q, b, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+    return launch_batched_cg<1>(D, dtype, n, Q, b, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
 }
 
 }  // namespace sqe

@@ -266,6 +266,15 @@ def test_plugin_install_patches_reference_names(sqe):
 
 
 # ------------------------------------------------------------------------- K2
+@pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_pair"])
+def cta_group(request, sqe):
+    """Run a K2 test with the single-CTA and with the CTA-pair (cta_group::2) kernel."""
+    nat = sqe._native
+    old = nat.tuning_set(nat.SQE_TUNE_K2_CTA_GROUP, request.param)
+    yield request.param
+    nat.tuning_set(nat.SQE_TUNE_K2_CTA_GROUP, old)
+
+
 def _k2_case(sqe, dtype, n, b, ks, seed, idx_offset=0, n_used=None):
     rng = np.random.default_rng(seed)
     x = make_corpus(rng, n)
@@ -298,26 +307,26 @@ def _k2_case(sqe, dtype, n, b, ks, seed, idx_offset=0, n_used=None):
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 1000, 40037])
-def test_batched_topk_matches_oracle(sqe, dtype, n):
+def test_batched_topk_matches_oracle(sqe, cta_group, dtype, n):
     _k2_case(sqe, dtype, n, 5, (1, 3, 10, 32, 33, 100, 128), seed=2000 + n)
 
 
 @pytest.mark.parametrize("b", [1, 127, 128, 129, 300])
-def test_batched_topk_ragged_batches(sqe, b):
+def test_batched_topk_ragged_batches(sqe, cta_group, b):
     _k2_case(sqe, "bf16", 5000, b, (10,), seed=3000 + b)
 
 
-def test_batched_topk_more_queries_than_one_launch(sqe):
+def test_batched_topk_more_queries_than_one_launch(sqe, cta_group):
     _k2_case(sqe, "bf16", 3000, 1100, (5,), seed=77)       # 1024 + 76: two launches
 
 
-def test_batched_topk_many_tiles_per_cta(sqe):
+def test_batched_topk_many_tiles_per_cta(sqe, cta_group):
     # 300k rows = 1172 d-tiles over 74 groups (b=130 -> 2 q-tiles): every CTA walks ~16 tiles,
     # both TMEM accumulators and every smem stage wrap several times
     _k2_case(sqe, "bf16", 300_000, 130, (10, 100), seed=5)
 
 
-def test_batched_idx_offset_and_partial_shard(sqe):
+def test_batched_idx_offset_and_partial_shard(sqe, cta_group):
     _k2_case(sqe, "fp16", 3000, 9, (5,), seed=9, idx_offset=10_000_000_000, n_used=2000)
     rng = np.random.default_rng(1)
     D = sqe.ops.normalize_cast(torch.from_numpy(make_corpus(rng, 300)).to(dev()), "bf16")
@@ -326,7 +335,7 @@ def test_batched_idx_offset_and_partial_shard(sqe):
     assert (i0.cpu().numpy() == -1).all() and np.isneginf(s0.cpu().numpy()).all()
 
 
-def test_batched_equals_gemv_and_is_deterministic(sqe):
+def test_batched_equals_gemv_and_is_deterministic(sqe, cta_group):
     rng = np.random.default_rng(11)
     D = sqe.ops.normalize_cast(torch.from_numpy(make_corpus(rng, 120_000)).to(dev()), "bf16")
     Q = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((64, DIM)).astype(np.float32)).to(dev()), "bf16")

@@ -145,6 +145,27 @@ SQE_API int sqe_cache_top1(const void *C, int dtype, int64_t n, int dim, const v
 SQE_API int sqe_merge_topk(const float *scores, const int64_t *idx, int lists, int b, int k_in,
                    int k_out, float *out_score, int64_t *out_idx, void *stream);
 
+/*
+ * K4x  fused exchange + merge of the corpus-sharded mode: ONE kernel per rank pushes its
+ * [b, k_in] lists into every rank's peer-mapped gather buffer over NVLink, publishes an epoch
+ * flag, waits for all ranks' flags in its own buffer and merges the `world` lists per query
+ * (replaces two all-gathers + sqe_merge_topk).
+ *   peer_buffers_host : HOST array of `world` DEVICE pointers, entry g = rank g's buffer as
+ *                       mapped into this process (symmetric memory / CUDA IPC); every buffer
+ *                       is sqe_exchange_buffer_bytes(world, capacity_entries) bytes, zeroed once
+ *                       before the first call (all ranks, followed by a barrier);
+ *   capacity_entries  : >= b * k_in, the same on every rank;
+ *   epoch             : 1, 2, 3, ... the same on every rank for the same call;
+ *   wait_mask         : bit g = wait for rank g; normally (1 << world) - 1 (tests that replay the
+ *                       ranks one after the other on one GPU pass 0 for all but the last).
+ * world <= 16, k_in, k_out <= SQE_MAX_K_GEMV, global rows < 2^32 - 1.
+ */
+SQE_API int64_t sqe_exchange_buffer_bytes(int world, int64_t capacity_entries);
+SQE_API int sqe_exchange_merge(const float *scores, const int64_t *idx, int b, int k_in, int k_out,
+                       int rank, int world, void *const *peer_buffers_host,
+                       int64_t capacity_entries, uint32_t epoch, uint32_t wait_mask,
+                       float *out_score, int64_t *out_idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

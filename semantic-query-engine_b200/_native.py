@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsqe_b200.so")
@@ -39,6 +39,10 @@ PROTOTYPES = [
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     ("sqe_merge_topk", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p]),
+    ("sqe_exchange_buffer_bytes", c_int64, [c_int, c_int64]),
+    ("sqe_exchange_merge", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   POINTER(c_void_p), c_int64, c_uint32, c_uint32,
+                                   c_void_p, c_void_p, c_void_p]),
 ]
 
 
@@ -63,6 +67,7 @@ LAUNCHES_PER_CALL = {
     "sqe_topk_batched": 2,
     "sqe_cache_top1": 2,      # +1 when it takes the tensor path (counted by the caller)
     "sqe_merge_topk": 1,
+    "sqe_exchange_merge": 1,
 }
 
 

@@ -222,4 +222,33 @@ int sqe_merge_topk(const float* scores, const int64_t* idx, int lists, int b, in
     return rc == 0 ? SQE_OK : SQE_E_CUDA;
 }
 
+int64_t sqe_exchange_buffer_bytes(int world, int64_t capacity_entries) {
+    if (world < 1 || capacity_entries < 0) return SQE_E_ARG;
+    return exchange_buffer_bytes(world, capacity_entries);
+}
+
+int sqe_exchange_merge(const float* scores, const int64_t* idx, int b, int k_in, int k_out, int rank,
+                       int world, void* const* peer_buffers_host, int64_t capacity_entries,
+                       uint32_t epoch, uint32_t wait_mask, float* out_score, int64_t* out_idx,
+                       void* stream) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || b < 0 || k_in < 1 || k_out < 1 ||
+        k_in > SQE_MAX_K_GEMV || k_out > SQE_MAX_K_GEMV ||
+        capacity_entries < static_cast<int64_t>(b) * k_in) {
+        set_error("exchange_merge: bad sizes world=%d rank=%d b=%d k_in=%d k_out=%d cap=%lld", world,
+                  rank, b, k_in, k_out, (long long)capacity_entries);
+        return SQE_E_ARG;
+    }
+    if (b == 0) return SQE_OK;
+    if (!scores || !idx || !out_score || !out_idx || !peer_buffers_host) { set_error("exchange_merge: null pointer"); return SQE_E_ARG; }
+    for (int g = 0; g < world; ++g)
+        if (!peer_buffers_host[g] || !aligned16(peer_buffers_host[g])) { set_error("exchange_merge: peer buffer %d null or unaligned", g); return SQE_E_ARG; }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_exchange_merge(scores, idx, b, k_in, k_out, rank, world, peer_buffers_host,
+                               capacity_entries, epoch, wait_mask, out_score, out_idx, d.sm_count,
+                               static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : SQE_E_CUDA);
+}
+
 }  // extern "C"

@@ -25,6 +25,13 @@ int launch_topk_batched(const void* D, int dtype, int64_t n, const void* Q, int 
 int launch_merge_topk(const float* scores, const int64_t* idx, int lists, int b, int k_in,
                       int k_out, float* out_score, int64_t* out_idx, cudaStream_t stream);
 
+// K4x fused exchange + merge over peer-mapped buffers
+int64_t exchange_buffer_bytes(int world, int64_t cap);
+int launch_exchange_merge(const float* scores, const int64_t* idx, int b, int k_in, int k_out,
+                          int rank, int world, void* const* peer_buffers, int64_t cap,
+                          unsigned epoch, unsigned wait_mask, float* out_score, int64_t* out_idx,
+                          int sm_count, cudaStream_t stream);
+
 // K5 epilogue: (score,idx)[b] -> (score, idx32, hit)
 int launch_cache_finalize(const float* score, const int64_t* idx, int b, float threshold,
                           float* out_score, int32_t* out_idx, uint8_t* out_hit,

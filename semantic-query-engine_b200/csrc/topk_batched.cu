@@ -301,6 +301,37 @@ __device__ __forceinline__ void bootstrap_strip(const uint32_t (&v)[32], uint32_
     }
 }
 
+// k = 1 (the cache lookup, K5): no lists at all -- every thread keeps the running maximum of
+// its query in two registers.  Strict '>' keeps the first maximum: columns only grow while a
+// CTA walks its d-tiles, and inside a strip the lowest column holding the maximum is taken
+// (the reference's "first maximum wins", app/main.py:84).
+__device__ __forceinline__ void top1_strip(uint32_t (&v)[32], uint32_t col0, uint32_t n,
+                                           bool row_valid, float& best, uint32_t& best_col) {
+    if (col0 + 32u > n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j >= n) v[j] = 0xff800000u;
+    }
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = fmax3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+    t[10] = fmaxf(f[30], f[31]);
+    const float u0 = fmax3(t[0], t[1], t[2]), u1 = fmax3(t[3], t[4], t[5]);
+    const float u2 = fmax3(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
+    const float m = fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
+    if (row_valid && m > best) {                            // rare after the first few tiles
+        uint32_t j = 31u;
+#pragma unroll
+        for (int jj = 30; jj >= 0; --jj)
+            if (f[jj] == m) j = jj;
+        best = m;
+        best_col = col0 + j;
+    }
+}
+
 // Threshold warp: for its share of this q-tile's queries, merge the partial lists of ALL
 // groups and publish the k-th best key's score -- the exact k-th best over every row any
 // CTA has merged so far.  Lists are read while their owners rewrite them; every slot is an
@@ -312,7 +343,7 @@ __device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_
                                                int rows_in_qtile, int my_id, int n_ids,
                                                volatile uint32_t* done, int lane) {
     constexpr int L = 32 * R;
-    if (n_groups < 2) return;
+    if (n_groups < 2 || k == 1) return;             // k = 1 keeps no lists (top1_strip)
     unsigned sleep_ns = 500;        // the bound moves fast at the start, hardly at all later
     while (true) {
         for (int rl = my_id; rl < rows_in_qtile; rl += n_ids) {
@@ -508,6 +539,33 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         long long t_wtfull = 0, t_ld = 0;
         const long long t_begin = clock64();
 
+        if (k == 1) {
+            float best = __int_as_float(0xff800000);
+            uint32_t best_col = 0u;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int t = group + i * n_groups;
+                const int acc = i & 1;
+                ptx::mbar_wait(bar_tfull + 8 * acc, (i >> 1) & 1);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kTileN;
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_wait_ld();
+                    top1_strip(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, best, best_col);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
+                    else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                }
+            }
+            // slot 0 of this query's (otherwise empty) list; the merge kernel does the rest
+            if (best > __int_as_float(0xff800000))
+                __stcg(wlists + static_cast<size_t>(lane) * L, make_key(best, best_col));
+        } else {
         for (int i = 0; i < my_tiles; ++i) {
             const int t = group + i * n_groups;
             const int acc = i & 1;
@@ -588,6 +646,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 tr[3] = __popc(pending);
             }
         }
+        }   // k > 1
         __syncwarp();
         if (lane == 0) atomicAdd(epi_done, 1u);
         if (dbg && lane == 0) {

@@ -159,3 +159,37 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int
         nat.call("sqe_merge_topk", scores.data_ptr(), idx.data_ptr(), lists, b, k_in, k_out,
                  out_s.data_ptr(), out_i.data_ptr(), _stream(dev))
     return out_s, out_i
+
+
+def exchange_buffer_bytes(world: int, capacity_entries: int) -> int:
+    n = nat.load().sqe_exchange_buffer_bytes(world, capacity_entries)
+    if n < 0:
+        raise ValueError("bad exchange buffer size arguments")
+    return int(n)
+
+
+def exchange_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int, rank: int,
+                   peer_ptrs, capacity_entries: int, epoch: int, wait_mask: Optional[int] = None
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K4x: push this rank's [b,k] lists into every rank's peer-mapped buffer, wait for all
+    ranks, merge.  `peer_ptrs`: device pointers (ints) of every rank's buffer as mapped here."""
+    import ctypes
+    dev = _require_cuda(scores, idx)
+    if scores.dim() != 2 or scores.shape != idx.shape:
+        raise ValueError("scores/idx must be [b,k]")
+    if scores.dtype != torch.float32 or idx.dtype != torch.int64:
+        raise TypeError("scores fp32, idx int64")
+    b, k_in = scores.shape
+    world = len(peer_ptrs)
+    out_s = torch.empty((b, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+    if b == 0:
+        return out_s, out_i
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    if wait_mask is None:
+        wait_mask = (1 << world) - 1
+    with torch.cuda.device(dev):
+        nat.call("sqe_exchange_merge", scores.data_ptr(), idx.data_ptr(), b, k_in, k_out, rank, world,
+                 arr, capacity_entries, epoch & 0xFFFFFFFF, wait_mask, out_s.data_ptr(),
+                 out_i.data_ptr(), _stream(dev))
+    return out_s, out_i

@@ -2,9 +2,12 @@
 
 One process per GPU.  Rank r owns the contiguous row block
 [r*N/G, (r+1)*N/G); queries are replicated; every rank computes its local top-k with
-global row numbers (idx_offset = first row of the shard), ONE all-gather moves the
-[B,k] (score fp32, row int64) lists over NVLink, and every rank merges the G lists
-with K4.  top-k of a union is the top-k of the per-shard top-k's, so the result is
+global row numbers (idx_offset = first row of the shard), the [B,k] (score fp32, row int64) lists are exchanged over NVLink and every rank merges the
+G lists.  Two exchange paths:
+  * "p2p"  (default on CUDA when symmetric memory can be set up): ONE kernel per rank pushes
+    its lists into every rank's peer-mapped buffer, flags, waits and merges (K4x,
+    csrc/exchange.cu) -- no collective launch at all;
+  * "nccl": two all-gathers + the K4 merge kernel (also what the gloo CPU test exercises).  top-k of a union is the top-k of the per-shard top-k's, so the result is
 exactly the single-GPU result, ties included (global rows keep the lower-index rule).
 
 Nothing like this exists in the reference (single process, external index); the
@@ -36,9 +39,16 @@ class ShardedCorpusIndex:
     the collective with the gloo backend."""
 
     def __init__(self, local_index=None, *, group=None,
-                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_topk: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 exchange: str = "auto"):
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
         self.local = local_index
         self.group = group
+        self._exchange_req = exchange
+        self.exchange = "nccl"          # decided collectively on first use
+        self._xchg = None               # (buffer, handle, peer pointers, capacity)
+        self._epoch = 0
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._local_topk = local_topk
@@ -69,17 +79,73 @@ class ShardedCorpusIndex:
             return self.local.device
         return torch.device("cpu")
 
+    # ---------------------------------------------------------------- exchange
+    def _setup_p2p(self, capacity: int) -> bool:
+        """Allocate + rendezvous the peer-mapped gather buffers (collective).  Returns whether
+        EVERY rank succeeded; otherwise all ranks stay on the NCCL path."""
+        from . import ops
+        dev = self._comm_device()
+        ok = 1
+        state = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = ops.exchange_buffer_bytes(self.world, capacity)
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            state = (buf, hdl, [int(p) for p in hdl.buffer_ptrs], int(capacity))
+        except Exception as e:                      # no fabric / IPC support on this box
+            ok = 0
+            if self._exchange_req == "p2p":
+                print(f"[ShardedCorpusIndex] symmetric memory unavailable on rank {self.rank}: {e}")
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        torch.cuda.synchronize(dev)                 # everyone's zeroing has finished ...
+        dist.barrier(group=self.group)              # ... before anyone pushes
+        if int(flag.item()) == 1:
+            self._xchg = state
+            self._epoch = 0
+            return True
+        self._xchg = None
+        return False
+
+    def _choose_exchange(self, dev: torch.device, need: int) -> None:
+        if self._exchange_req == "nccl" or dev.type != "cuda" or self._merge is not None:
+            self.exchange = "nccl"
+            return
+        if self._xchg is not None and self._xchg[3] >= need:
+            return
+        if self._xchg is not None:                  # grow: nobody may still be reading the old one
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)
+        cap = max(need, 1024 * 16)
+        self.exchange = "p2p" if self._setup_p2p(cap) else "nccl"
+        if self.exchange == "nccl" and self._exchange_req == "p2p":
+            raise RuntimeError("exchange='p2p' requested but symmetric memory could not be set up")
+
     # ------------------------------------------------------------------ search
     def search_device(self, q_dev: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """q_dev [B,1024] fp32 (replicated on every rank) -> merged (scores, global rows) on
-        every rank.  One all-gather + one merge kernel after the local scan."""
+        every rank: local scan, then ONE exchange + merge."""
         if self._local_topk is not None:
             s, i = self._local_topk(q_dev, k, self.row_offset)
         else:
             s, i = self.local.search_device(q_dev, k, idx_offset=self.row_offset)
         if self.world == 1:
             return s, i
+        return self.exchange_lists(s, i, k)
+
+    def exchange_lists(self, s: torch.Tensor, i: torch.Tensor, k: int
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Collective: every rank passes its local [B,k] lists (global rows) and gets the merged
+        top-k of all ranks."""
         b = s.shape[0]
+        self._choose_exchange(s.device, b * k)
+        if self.exchange == "p2p":
+            from . import ops
+            self._epoch += 1
+            return ops.exchange_merge(s.contiguous(), i.contiguous(), k, self.rank, self._xchg[2],
+                                      self._xchg[3], self._epoch)
         if self._gather_s is None or self._gather_s.shape[1:] != s.shape or self._gather_s.device != s.device:
             self._gather_s = torch.empty((self.world, b, k), dtype=s.dtype, device=s.device)
             self._gather_i = torch.empty((self.world, b, k), dtype=i.dtype, device=i.device)

@@ -158,6 +158,34 @@ def test_merge_topk_matches_oracle(sqe):
         np.testing.assert_array_equal(gs.cpu().numpy(), ws)
 
 
+def test_exchange_merge_replayed_ranks_on_one_gpu(sqe):
+    """K4x on one GPU: the ranks are replayed one after the other against ONE buffer (all peer
+    pointers alias it); only the last call waits and its merge must equal the oracle's."""
+    rng = np.random.default_rng(31)
+    for world, b, k_in, k_out in [(1, 3, 10, 10), (4, 33, 10, 10), (8, 1, 10, 10), (8, 130, 100, 100), (2, 5, 7, 20)]:
+        cap = b * k_in + 5
+        buf = torch.zeros(sqe.ops.exchange_buffer_bytes(world, cap), dtype=torch.uint8, device=dev())
+        ptrs = [buf.data_ptr()] * world
+        for epoch in (1, 2, 3):                                # both parities, flags reused
+            s = np.sort(rng.standard_normal((world, b, k_in)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+            i = rng.permutation(world * b * k_in).reshape(world, b, k_in).astype(np.int64)
+            if world > 1:
+                s[1, 0, 3:] = -np.inf                          # short list
+                i[1, 0, 3:] = -1
+                s[0, -1, 0] = s[1, -1, 0] = 0.75               # cross-rank tie -> lower global row
+                s[0, -1] = np.sort(s[0, -1])[::-1]
+                s[1, -1] = np.sort(s[1, -1])[::-1]
+            out = None
+            for r in range(world):
+                out = sqe.ops.exchange_merge(torch.from_numpy(s[r]).to(dev()), torch.from_numpy(i[r]).to(dev()),
+                                             k_out, r, ptrs, cap, epoch,
+                                             wait_mask=((1 << world) - 1) if r == world - 1 else 0)
+            torch.cuda.synchronize()
+            ws, wi = oracle.merge_topk(s, i, k_out)
+            np.testing.assert_array_equal(out[1].cpu().numpy(), wi)
+            np.testing.assert_array_equal(out[0].cpu().numpy(), ws)
+
+
 # ------------------------------------------------------- drop-in classes, golden
 def test_corpus_index_reproduces_reference_search(sqe, golden_dir):
     g = np.load(os.path.join(golden_dir, "index_search.npz"))

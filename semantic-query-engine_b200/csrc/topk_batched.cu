@@ -79,18 +79,22 @@ constexpr int kQueriesPerLaunch = 1024;
 // R = 64-bit keys per lane of a query's sorted list (list length 32 R >= k).  For R = 1
 // (k <= 32) the 128 lists of the CTA live in shared memory (32 KB, one operand stage less)
 // and are written through to the global workspace; longer lists live in the workspace only.
-template <int CG, int R = 1>
+//
+// TOP1 = the k = 1 specialisation (cache lookup): no lists, no candidate buffers, one more
+// operand stage (this case is HBM-bound: more bytes in flight).
+template <int CG, int R = 1, bool TOP1 = false>
 struct Cfg {
     static constexpr int kQTile = kRowsPerCta * CG;          // queries per q-tile
     static constexpr int kBRows = kTileN / CG;               // D rows this CTA loads per chunk
     static constexpr int kBBytes = kBRows * kChunkK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB / 32 KB
-    static constexpr bool kSmemLists = (R == 1);
+    static constexpr bool kSmemLists = (R == 1) && !TOP1;
     static constexpr int kListBytes = kSmemLists ? kRowsPerCta * 32 * 8 : 0;
-    static constexpr int kStages = (CG == 1) ? (kSmemLists ? 3 : 4) : (kSmemLists ? 5 : 6);
+    static constexpr int kBufBytes = TOP1 ? 0 : kRowsPerCta * kBufStride * 8;
+    static constexpr int kStages = (CG == 1) ? (kSmemLists ? 3 : 4) : (kSmemLists ? 5 : (TOP1 ? 7 : 6));
     static constexpr int kOffLists = kStages * kStageBytes;
     static constexpr int kOffBuf = kOffLists + kListBytes;
-    static constexpr int kOffBar = kOffBuf + kRowsPerCta * kBufStride * 8;
+    static constexpr int kOffBar = kOffBuf + kBufBytes;
     static constexpr int kOffTmemPtr = kOffBar + 24 * 8;       // u32 tmem base, u32 epilogue-done counter
     static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
 };
@@ -343,7 +347,7 @@ __device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_
                                                int rows_in_qtile, int my_id, int n_ids,
                                                volatile uint32_t* done, int lane) {
     constexpr int L = 32 * R;
-    if (n_groups < 2 || k == 1) return;             // k = 1 keeps no lists (top1_strip)
+    if (n_groups < 2) return;
     unsigned sleep_ns = 500;        // the bound moves fast at the start, hardly at all later
     while (true) {
         for (int rl = my_id; rl < rows_in_qtile; rl += n_ids) {
@@ -377,7 +381,7 @@ __device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_
     }
 }
 
-template <int R, int CG>
+template <int R, int CG, bool TOP1>
 __global__ void __launch_bounds__(k2::kThreads, 1)
 topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const __grid_constant__ CUtensorMap tmap_d, uint32_t n, int b, int k,
@@ -385,7 +389,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau,
                     unsigned long long* __restrict__ dbg, int epi_mode) {
     using namespace k2;
-    using C = Cfg<CG, R>;
+    using C = Cfg<CG, R, TOP1>;
     constexpr int L = 32 * R;
     constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -511,6 +515,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
     } else if (warp == 6) {
         // ---------------------------------------------------------- threshold warp
+        if constexpr (!TOP1)                                 // k = 1 keeps no lists
         threshold_warp<R>(ws_lists, ws_tau, b, n_qt * C::kQTile, k, n_groups, q_tile * C::kQTile,
                           C::kQTile, group * CG + static_cast<int>(rank), n_groups * CG, epi_done, lane);
     } else {
@@ -539,7 +544,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         long long t_wtfull = 0, t_ld = 0;
         const long long t_begin = clock64();
 
-        if (k == 1) {
+        if constexpr (TOP1) {
             float best = __int_as_float(0xff800000);
             uint32_t best_col = 0u;
             for (int i = 0; i < my_tiles; ++i) {
@@ -737,14 +742,14 @@ int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
     return kTauBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8;
 }
 
-template <int R, int CG>
+template <int R, int CG, bool TOP1>
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
                             int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
                             uint32_t* ws_tau, float* out_score, int64_t* out_idx, int64_t idx_offset,
                             cudaStream_t stream) {
-    using C = k2::Cfg<CG, R>;
+    using C = k2::Cfg<CG, R, TOP1>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG>,
+    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("topk_batched: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     if (n_dtiles > 0) {
@@ -760,7 +765,7 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG>, tq, td, static_cast<uint32_t>(n), b, k,
+        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1>, tq, td, static_cast<uint32_t>(n), b, k,
                                n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau,
                                reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
@@ -812,10 +817,15 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         if (rc != 0) return rc;
         float* os = out_score + static_cast<int64_t>(q0) * k;
         int64_t* oi = out_idx + static_cast<int64_t>(q0) * k;
+        if (k == 1) {
+            rc = launch_batched_r<1, CG, true>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream);
+            if (rc != 0) return rc;
+            continue;
+        }
         switch (R) {
-            case 1: rc = launch_batched_r<1, CG>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-            case 2: rc = launch_batched_r<2, CG>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-            default: rc = launch_batched_r<4, CG>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+            case 1: rc = launch_batched_r<1, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+            case 2: rc = launch_batched_r<2, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+            default: rc = launch_batched_r<4, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
         }
         if (rc != 0) return rc;
     }

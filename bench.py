@@ -46,6 +46,9 @@ def parse_args():
                     choices=["b1024", "b1", "cache64"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=None,
+                    help="override the batch size of the b1024 workload (e.g. 256 with --k 100 "
+                         "--dtype fp16 --rows 12500000 = one rank's share of BASELINE configs[3])")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--k2-cta-group", type=int, default=0, choices=[0, 1, 2],
                     help="force the single-CTA (1) or CTA-pair (2) tensor-core kernel; 0 = library default")
@@ -192,7 +195,7 @@ def workload_config(args, world):
         return {"workload": "query cache 1Mx1024 bf16, streaming batch-64 top-1 + 0.95 threshold "
                             "(BASELINE configs[4])", "rows": 1_000_000, "batch": 64, "k": 1,
                 "dtype": "bf16", "l2": "inputs larger than L2"}
-    b = 1024 if args.workload == "b1024" else 1
+    b = (args.batch or 1024) if args.workload == "b1024" else 1
     return {"workload": f"{args.rows}x1024 {args.dtype} corpus, batch-{b} cosine top-{args.k} "
                         f"(BASELINE configs[2] / metric headline)",
             "rows": args.rows, "batch": b, "k": args.k, "dtype": args.dtype,
@@ -229,6 +232,8 @@ def main():
     peaks = load_peaks()
     is_cache = args.workload == "cache64"
     b = {"b1024": 1024, "b1": 1, "cache64": 64}[args.workload]
+    if args.batch and args.workload == "b1024":
+        b = args.batch
     k = 1 if is_cache else args.k
     dtype = "bf16" if is_cache else args.dtype
     total_rows = 1_000_000 if is_cache else args.rows

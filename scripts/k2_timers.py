@@ -10,26 +10,29 @@ nat = sqe_b200._native
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 b = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+DT = sys.argv[5] if len(sys.argv) > 5 else "bf16"
+TDT = {"bf16": torch.bfloat16, "fp16": torch.float16}[DT]
 dev = torch.device("cuda", 0)
-D = torch.empty((rows, 1024), dtype=torch.bfloat16, device=dev)
+D = torch.empty((rows, 1024), dtype=TDT, device=dev)
 gen = torch.Generator(device=dev)
 for lo in range(0, rows, 250_000):
     gen.manual_seed(lo)
     x = torch.randn((min(250_000, rows - lo), 1024), generator=gen, device=dev)
-    ops.normalize_cast(x, "bf16", out=D[lo:lo + x.shape[0]])
-Q = ops.normalize_cast(torch.randn((b, 1024), generator=gen, device=dev), "bf16")
+    ops.normalize_cast(x, DT, out=D[lo:lo + x.shape[0]])
+Q = ops.normalize_cast(torch.randn((b, 1024), generator=gen, device=dev), DT)
 names = ["prod_total", "prod_wait_empty", "mma_total", "mma_wait_full", "mma_wait_tempty", "epi_total", "epi_wait_tfull", "epi_flush"]
 import itertools
-for cg, mode in itertools.product(([int(sys.argv[3])] if len(sys.argv) > 3 else [1, 2]), (0,)):
+for cg, mode in itertools.product(([int(sys.argv[3])] if len(sys.argv) > 3 and int(sys.argv[3]) else [1, 2]), (0,)):
     nat.tuning_set(nat.SQE_TUNE_K2_CTA_GROUP, cg)
     nat.tuning_set(nat.SQE_TUNE_K2_EPILOGUE_MODE, mode)
     for _ in range(3):
-        ops.topk_batched(D, Q, 10)
+        ops.topk_batched(D, Q, K)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        ops.topk_batched(D, Q, 10)
+        ops.topk_batched(D, Q, K)
     e1.record()
     torch.cuda.synchronize()
     print(f"epilogue_mode={mode} cta_group={cg}: {e0.elapsed_time(e1) / 5:.3f} ms per call without timers "
@@ -38,11 +41,11 @@ for cg, mode in itertools.product(([int(sys.argv[3])] if len(sys.argv) > 3 else 
     nat.load().sqe_debug_k2_timers(buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.topk_batched(D, Q, 10)
+    ops.topk_batched(D, Q, K)
     e1.record()
     torch.cuda.synchronize()
     nat.load().sqe_debug_k2_timers(None)
-    grid = 144
+    grid = 148
     t = buf[: grid * 32].view(grid, 32).cpu().double()
     print(f"epilogue_mode={mode} cta_group={cg} rows={rows} b={b}: {e0.elapsed_time(e1):.3f} ms (timed with the timers on)")
     def stat(nm, col):

@@ -239,43 +239,26 @@ __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, 
     const bool want = row_valid && (m > st.thr);
     if (!__any_sync(kFull, want)) return;
 
-    // slow path.  Common case: every lane has room for all of its passing scores -> branch-free
-    // predicated appends, no votes.
+    // slow path, one half-strip (16 columns = one candidate buffer) at a time: make room where
+    // needed (merge the pending candidates of the lanes that would overflow), then branch-free
+    // predicated appends.  Works at any pass rate; normally neither half needs a merge.
     ++st.n_slow;
-    const float thr0 = st.thr;
-    int pc = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) pc += (want && f[j] > thr0) ? 1 : 0;
     uint64_t* mybuf = wbuf + lane * k2::kBufStride;
-    const unsigned over = __ballot_sync(kFull, st.cnt + pc > k2::kCap);
-    if (over) {
-        // make room: merge the pending candidates of the lanes that would overflow
-        const unsigned fl = over & __ballot_sync(kFull, st.cnt > 0);
-        if (fl) flush_lanes<R, SL>(fl, st, wbuf, slists, wlists, wtau, k, lane);
-    }
-    if (__any_sync(kFull, pc > k2::kCap)) {
-        // more than a buffer's worth in one strip (empty list without bootstrap, adversarial
-        // data): column by column with an overflow check after every append
-#pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
-            float fj = f[0];
 #pragma unroll
-            for (int jj = 1; jj < 32; ++jj)
-                if (jj == j) fj = f[jj];
-            if (want && fj > st.thr) {
-                mybuf[st.cnt] = make_key(fj, col0 + j);
+    for (int h = 0; h < 2; ++h) {
+        const float thr0 = st.thr;
+        int pc = 0;
+#pragma unroll
+        for (int j = 16 * h; j < 16 * h + 16; ++j) pc += (want && f[j] > thr0) ? 1 : 0;
+        if (!__any_sync(kFull, pc > 0)) continue;
+        const unsigned over = __ballot_sync(kFull, st.cnt + pc > k2::kCap);
+        if (over) flush_lanes<R, SL>(over, st, wbuf, slists, wlists, wtau, k, lane);   // their cnt > 0
+#pragma unroll
+        for (int j = 16 * h; j < 16 * h + 16; ++j) {
+            if (want && f[j] > thr0) {
+                mybuf[st.cnt] = make_key(f[j], col0 + j);
                 ++st.cnt;
             }
-            const unsigned full = __ballot_sync(kFull, st.cnt >= k2::kCap);
-            if (full) flush_lanes<R, SL>(full, st, wbuf, slists, wlists, wtau, k, lane);
-        }
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (want && f[j] > thr0) {
-            mybuf[st.cnt] = make_key(f[j], col0 + j);
-            ++st.cnt;
         }
     }
 }
@@ -303,6 +286,77 @@ __device__ __forceinline__ void bootstrap_strip(const uint32_t (&v)[32], uint32_
             top[i] = hi;
         }
     }
+}
+
+// Bootstrap for k > 16 (first d-tile of a CTA): the first 32*R columns become the query's
+// list as they are (unsorted), then the warp sorts each of its 32 lists once.  Without this
+// every one of those columns goes through the candidate buffers and k/16 full merges.
+template <int R, bool SL>
+__device__ __forceinline__ void direct_fill_strip(const uint32_t (&v)[32], uint32_t col0, uint32_t n,
+                                                  bool row_valid, int c, uint64_t* slists,
+                                                  uint64_t* dst, int lane) {
+    constexpr int L = 32 * R;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint64_t key = (row_valid && col0 + j < n) ? make_key(__uint_as_float(v[j]), col0 + j) : 0ull;
+        if constexpr (SL) slists[lane * 32 + j] = key;
+        else __stcg(dst + static_cast<size_t>(lane) * L + (c % R) * 32 + j, key);
+    }
+}
+
+// `src` = where the unsorted batch was written (the list itself for the first batch, the
+// scratch list afterwards); `merge` = fold the sorted batch into the existing list.
+template <int R, bool SL>
+__device__ __forceinline__ void sort_filled_lists(EpiState& st, uint64_t* slists, uint64_t* wlists,
+                                                  const uint64_t* src, bool merge, uint32_t* wtau,
+                                                  int k, int lane) {
+    constexpr int L = 32 * R;
+    __syncwarp();                                               // the owners' stores are visible
+    uint64_t nxt[R];
+    if constexpr (!SL) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) nxt[i] = __ldcg(src + i * 32 + lane);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+        WarpList<R> cur;
+        if constexpr (SL) {
+            cur.key[0] = slists[r * 32 + lane];
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) cur.key[i] = nxt[i];
+            if (r + 1 < 32) {
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    nxt[i] = __ldcg(src + static_cast<size_t>(r + 1) * L + i * 32 + lane);
+            }
+        }
+        cur.sort(lane);
+        if constexpr (!SL) {
+            if (merge) {
+                uint64_t old[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) old[i] = __ldcg(wlists + static_cast<size_t>(r) * L + i * 32 + lane);
+                cur.merge_sorted(old, lane);
+            }
+        }
+        if constexpr (SL) slists[r * 32 + lane] = cur.key[0];
+#pragma unroll
+        for (int i = 0; i < R; ++i) __stcg(wlists + static_cast<size_t>(r) * L + i * 32 + lane, cur.key[i]);
+        uint64_t kth_src = 0ull;
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            if (i == ((k - 1) >> 5)) kth_src = cur.key[i];
+        const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
+        if (lane == r && kth != 0ull) {
+            st.tau_l = key_score(kth);
+            const uint32_t o = static_cast<uint32_t>(kth >> 32);
+            atomicMax(wtau + r, o);
+            st.tau_g = max(st.tau_g, o);
+            st.thr = thr_of(st.tau_l, st.tau_g);
+        }
+    }
+    __syncwarp();
 }
 
 // k = 1 (the cache lookup, K5): no lists at all -- every thread keeps the running maximum of
@@ -532,6 +586,8 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             __syncwarp();
         }
         uint64_t* wlists = ws_lists + (static_cast<size_t>(group) * b_pad + row0) * L;
+        // scratch lists of the bootstrap (R > 1 only), behind the n_groups * b_pad real lists
+        uint64_t* wscratch = wlists + static_cast<size_t>(n_groups) * b_pad * L;
         uint32_t* wtau = ws_tau + row0;
 
         EpiState st;
@@ -627,6 +683,16 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 if (dbg) t_ld += clock64() - l0;
                 if (epi_mode == 1) {                                      // diagnostics: TMEM reads only
                     asm volatile("" ::"r"(v[0]), "r"(v[31]));
+                    continue;
+                }
+                if (i == 0 && k > 16 && (c < R || !SL)) {                 // bootstrap for k > 16
+                    // lists in smem (k <= 32): the first strip only; lists in the workspace:
+                    // the whole tile, in batches of 32*R columns through the scratch list
+                    uint64_t* dst = (c < R) ? wlists : wscratch;
+                    direct_fill_strip<R, SL>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid,
+                                             c, slists, dst, lane);
+                    if ((c % R) == R - 1)
+                        sort_filled_lists<R, SL>(st, slists, wlists, dst, c >= R, wtau, k, lane);
                     continue;
                 }
                 process_strip<R, SL>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
@@ -738,8 +804,10 @@ static inline int r_for_k_batched(int k) { return k <= 32 ? 1 : k <= 64 ? 2 : 4;
 static constexpr int64_t kTauBytes = 4096;        // kQueriesPerLaunch * 4
 
 int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
-    const int64_t L = 32 * r_for_k_batched(k);
-    return kTauBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8;
+    const int R = r_for_k_batched(k);
+    const int64_t L = 32 * R;
+    // R > 1: as many scratch lists again for the bootstrap of the first d-tile
+    return kTauBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8 * (R > 1 ? 2 : 1);
 }
 
 template <int R, int CG, bool TOP1>

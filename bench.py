@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SQE_BENCH_WORKLOAD", "b1024"),
-                    choices=["b1024", "b1", "cache64"])
+                    choices=["b1024", "b1", "cache64", "ingest"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=None,
@@ -230,6 +230,8 @@ def main():
         nat.tuning_set(nat.SQE_TUNE_K2_CTA_GROUP, args.k2_cta_group)
 
     peaks = load_peaks()
+    if args.workload == "ingest":
+        return run_ingest(args, torch, ops, nat, dev, peaks)
     is_cache = args.workload == "cache64"
     b = {"b1024": 1024, "b1": 1, "cache64": 64}[args.workload]
     if args.batch and args.workload == "b1024":
@@ -448,6 +450,46 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ingest(args, torch, ops, nat, dev, peaks):
+    """K1 alone (north_star subsystem 1): fused L2-normalise + cast of a 1M-row fp32 block into
+    the shard's storage type.  Algorithmic bytes per row = 4096 read + 1024*sizeof(out) written."""
+    rows = min(args.rows, 1_000_000)
+    steps = args.steps or 30
+    warmup = args.warmup if args.warmup is not None else 3
+    esize = {"bf16": 2, "fp16": 2, "fp32": 4}[args.dtype]
+    x = torch.randn((rows, DIM), device=dev, dtype=torch.float32)
+    out = torch.empty((rows, DIM), device=dev, dtype=ops.TORCH_DTYPES[args.dtype])
+    for _ in range(warmup):
+        ops.normalize_cast(x, args.dtype, out=out)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    time.sleep(1.0)
+    sampler.mark()
+    l0 = nat.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ops.normalize_cast(x, args.dtype, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    alg = rows * DIM * (4 + esize)
+    ach = alg / (ms * 1e-3) / 1e9
+    line = {"metric": "rows/sec fused L2-normalise + cast (ingest)", "value": rows / (ms * 1e-3), "unit": "rows/s",
+            "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{rows}x1024 fp32 -> {args.dtype} rows, x/(|x|+1e-9) (app/main.py:315-316)",
+                       "rows": rows, "l2": "6 GB per step, larger than L2"},
+            "clocks": sampler.stop(), "e2e": None, "gpu_launches": nat.launch_count - l0,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"], "kernel": "normalize_cast_kernel", "kernel_ms": ms,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peaks["source"], "traffic": None},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
 
 
 def load_traffic(kernel_name: str):

@@ -81,8 +81,20 @@ SQE_API int sqe_normalize_cast(const float *in, void *out, int64_t n, int dim, i
  * D [n, dim] stored unit rows (dtype), Q [nq, dim] stored unit queries (same dtype).
  * Each query streams the whole shard once.  out_score [nq, k] fp32, out_idx [nq, k] int64
  * (= idx_offset + local row).  1 <= k <= SQE_MAX_K_GEMV, n < 2^32 - 1.
+ *
+ * Workspace contract: the first 4096 bytes must be ZERO the first time a workspace is used
+ * (cudaMemset once after allocation); the library leaves them zero after every call, so no
+ * per-call memset is launched.
+ *
+ * sqe_search_gemv = K1 (query side) + K3 in ONE launch: Q_raw holds the RAW fp32 query
+ * embeddings [nq, dim]; every CTA normalises its query itself with the arithmetic of
+ * sqe_normalize_cast and rounds it to the shard's storage type.  Same results as
+ * sqe_normalize_cast followed by sqe_topk_gemv, bit for bit.
  */
 SQE_API int64_t sqe_topk_gemv_workspace_bytes(int nq, int k);
+SQE_API int sqe_search_gemv(const void *D, int dtype, int64_t n, int dim, const float *Q_raw, int nq,
+                    int k, float *out_score, int64_t *out_idx, int64_t idx_offset, void *workspace,
+                    int64_t workspace_bytes, void *stream);
 SQE_API int sqe_topk_gemv(const void *D, int dtype, int64_t n, int dim, const void *Q, int nq, int k,
                   float *out_score, int64_t *out_idx, int64_t idx_offset, void *workspace,
                   int64_t workspace_bytes, void *stream);

@@ -31,6 +31,8 @@ PROTOTYPES = [
     ("sqe_topk_gemv_workspace_bytes", c_int64, [c_int, c_int]),
     ("sqe_topk_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    ("sqe_search_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
+                                c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     ("sqe_topk_batched_workspace_bytes", c_int64, [c_int64, c_int, c_int]),
     ("sqe_topk_batched", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
@@ -64,6 +66,7 @@ launch_count = 0
 LAUNCHES_PER_CALL = {
     "sqe_normalize_cast": 1,
     "sqe_topk_gemv": 1,
+    "sqe_search_gemv": 1,
     "sqe_topk_batched": 2,
     "sqe_cache_top1": 2,      # +1 when it takes the tensor path (counted by the caller)
     "sqe_merge_topk": 1,

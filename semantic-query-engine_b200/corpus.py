@@ -60,6 +60,7 @@ class GpuCorpusIndex:
         self._docs: List[Dict[str, str]] = []   # payload table, row-aligned
         self._ids: List[str] = []
         self._pinned_q: Optional[torch.Tensor] = None
+        self._pinned_out: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ storage
     @property
@@ -189,19 +190,35 @@ class GpuCorpusIndex:
         q = self._as_rows(query_emb)
         with torch.cuda.device(self.device):
             qd = self._stage_queries(q)
-            s, i = self.search_device(qd, k)
-            s_h = s.cpu()
-            i_h = i.cpu()
-        return s_h.numpy(), i_h.numpy()
+            buf, s, i = ops.packed_topk_out(self.device, q.shape[0], k)
+            self.search_device(qd, k, out=(s, i))
+            return self._fetch_packed(buf, q.shape[0], k)
 
-    def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0
+    def _fetch_packed(self, buf: torch.Tensor, b: int, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """ONE device->host copy of a packed (rows, scores) buffer into reusable pinned memory."""
+        nbytes = buf.numel()
+        if self._pinned_out is None or self._pinned_out.numel() < nbytes:
+            self._pinned_out = torch.empty((max(nbytes, 4096),), dtype=torch.uint8).pin_memory()
+        host = self._pinned_out[:nbytes]
+        host.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        arr = host.numpy()
+        rows = arr[: b * k * 8].view(np.int64).reshape(b, k).copy()
+        scores = arr[b * k * 8:].view(np.float32).reshape(b, k).copy()
+        return scores, rows
+
+    def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0, out=None
                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Device-resident form: fp32 CUDA queries [B,1024] (un-normalised) -> CUDA
         (scores, rows).  No synchronisation."""
-        qn = ops.normalize_cast(q_dev.contiguous(), self.dtype)         # main.py:353-354
         rows = self._rows
         shard = self._shard if self._shard is not None else self.shard
-        return ops.topk(shard, qn, k, idx_offset=idx_offset, n=rows)
+        q_dev = q_dev.contiguous()
+        if q_dev.shape[0] == 1 and q_dev.dtype == torch.float32:
+            # the reference's own case (one query, main.py:355): normalise + scan in ONE launch
+            return ops.search_gemv(shard, q_dev, k, idx_offset=idx_offset, n=rows, out=out)
+        qn = ops.normalize_cast(q_dev, self.dtype)                       # main.py:353-354
+        return ops.topk(shard, qn, k, idx_offset=idx_offset, n=rows, out=out)
 
     def search(self, query_emb: np.ndarray, k: int = 3) -> List[Tuple[Dict[str, str], float]]:
         """main.py:347-373."""

@@ -143,7 +143,22 @@ int sqe_topk_gemv(const void* D, int dtype, int64_t n, int dim, const void* Q, i
     DevInfo d;
     rc = device_info(&d);
     if (rc != SQE_OK) return rc;
-    return launch_topk_gemv(D, dtype, n, Q, nq, k, out_score, out_idx, idx_offset, workspace,
+    return launch_topk_gemv(D, dtype, n, Q, false, nq, k, out_score, out_idx, idx_offset, workspace,
+                            workspace_bytes, d.sm_count, static_cast<cudaStream_t>(stream));
+}
+
+int sqe_search_gemv(const void* D, int dtype, int64_t n, int dim, const float* Q_raw, int nq, int k,
+                    float* out_score, int64_t* out_idx, int64_t idx_offset, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+    int rc = check_common("search_gemv", D, dtype, n, dim, Q_raw, nq);
+    if (rc != SQE_OK) return rc;
+    if (k < 1 || k > SQE_MAX_K_GEMV) { set_error("search_gemv: k=%d not in [1,%d]", k, SQE_MAX_K_GEMV); return SQE_E_ARG; }
+    if (nq == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("search_gemv: null output/workspace"); return SQE_E_ARG; }
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return launch_topk_gemv(D, dtype, n, Q_raw, true, nq, k, out_score, out_idx, idx_offset, workspace,
                             workspace_bytes, d.sm_count, static_cast<cudaStream_t>(stream));
 }
 

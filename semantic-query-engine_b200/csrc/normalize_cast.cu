@@ -22,7 +22,6 @@
 namespace sqe {
 
 constexpr int kNormWarps = 8;
-constexpr int kBlockStride = 136;            // 128 floats + 8 pad: conflict-free LDS.64 walk
 
 __device__ __forceinline__ void store_row_chunk(float* out, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out), "f"(v.x),
@@ -51,13 +50,11 @@ __device__ __forceinline__ void store_row_chunk(__half* out, float4 v) {
 template <typename OutT>
 __global__ void __launch_bounds__(kNormWarps * 32, 4)
 normalize_cast_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n) {
-    __shared__ __align__(16) float tile[kNormWarps][8 * kBlockStride];
+    __shared__ __align__(16) float tile[kNormWarps][8 * kNormBlockStride];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float* t = tile[warp];
     const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kNormWarps;
-    const int blk = lane >> 2;               // which 128-block this lane sums
-    const int jj = (lane & 3) * 2;           // accumulator pair (jj, jj+1) of that block
 
     for (int64_t row = static_cast<int64_t>(blockIdx.x) * kNormWarps + warp; row < n;
          row += warps_total) {
@@ -69,31 +66,8 @@ normalize_cast_kernel(const float* __restrict__ in, OutT* __restrict__ out, int6
             v[m] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
                                __uint_as_float(u.w));
         }
-#pragma unroll
-        for (int m = 0; m < 8; ++m)
-            *reinterpret_cast<float4*>(t + kBlockStride * m + 4 * lane) = v[m];
-        __syncwarp();
-
-        // chains r[jj], r[jj+1] of block blk: x[128*blk + 8*i + jj (+1)], i = 0..15
-        const float* c = t + kBlockStride * blk + jj;
-        float2 x0 = *reinterpret_cast<const float2*>(c);
-        float r0 = __fmul_rn(x0.x, x0.x);
-        float r1 = __fmul_rn(x0.y, x0.y);
-#pragma unroll
-        for (int i = 1; i < 16; ++i) {
-            float2 x = *reinterpret_cast<const float2*>(c + 8 * i);
-            r0 = __fadd_rn(r0, __fmul_rn(x.x, x.x));
-            r1 = __fadd_rn(r1, __fmul_rn(x.y, x.y));
-        }
-        float s = __fadd_rn(r0, r1);                                   // (r0+r1) | (r2+r3) | ...
-        s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 1));                // pairs of pairs
-        s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 2));                // one 128-block
-        s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 4));                // 256
-        s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 8));                // 512
-        s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 16));               // 1024
+        const float s = warp_row_sumsq_numpy(v, t, lane);
         const float den = __fadd_rn(__fsqrt_rn(s), 1e-9f);
-        __syncwarp();                                                   // tile reused next row
-
         OutT* dst = out + row * kDim;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {

@@ -191,6 +191,44 @@ struct WarpList {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Sum of squares of one 1024-float row in EXACTLY numpy's fp32 add.reduce order (pairwise
+// summation: blocks of 128, eight stride-8 accumulators per block combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), blocks combined by halving), squares rounded before
+// they are added (no FMA contraction).  The warp holds the row as v[m] = elements
+// 128 m + 4 lane .. +3; `t` is a per-warp smem tile of 8 * kNormBlockStride floats.  Used by
+// K1 and by the fused query normalisation of K3, so both are bit-identical to
+// np.linalg.norm(x)**2 of the reference expression (app/main.py:315-316, :353-354).
+// ---------------------------------------------------------------------------
+constexpr int kNormBlockStride = 136;        // 128 floats + 8 pad: conflict-free LDS.64 walk
+
+__device__ __forceinline__ float warp_row_sumsq_numpy(const float4 (&v)[8], float* t, int lane) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+        *reinterpret_cast<float4*>(t + kNormBlockStride * m + 4 * lane) = v[m];
+    __syncwarp();
+    const int blk = lane >> 2;               // which 128-block this lane sums
+    const int jj = (lane & 3) * 2;           // accumulator pair (jj, jj+1) of that block
+    const float* c = t + kNormBlockStride * blk + jj;
+    float2 x0 = *reinterpret_cast<const float2*>(c);
+    float r0 = __fmul_rn(x0.x, x0.x);
+    float r1 = __fmul_rn(x0.y, x0.y);
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+        float2 x = *reinterpret_cast<const float2*>(c + 8 * i);
+        r0 = __fadd_rn(r0, __fmul_rn(x.x, x.x));
+        r1 = __fadd_rn(r1, __fmul_rn(x.y, x.y));
+    }
+    float s = __fadd_rn(r0, r1);                                   // (r0+r1) | (r2+r3) | ...
+    s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 1));                // pairs of pairs
+    s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 2));                // one 128-block
+    s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 4));                // 256
+    s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 8));                // 512
+    s = __fadd_rn(s, __shfl_xor_sync(kFull, s, 16));               // 1024
+    __syncwarp();                                                   // tile may be reused
+    return s;
+}
+
 // Write the first k elements of a sorted list as (score, index) pairs.
 template <int R>
 __device__ __forceinline__ void emit_topk(const WarpList<R>& list, int k, int lane,

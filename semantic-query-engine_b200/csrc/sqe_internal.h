@@ -11,7 +11,7 @@ int launch_normalize_cast(const float* in, void* out, int64_t n, int out_dtype, 
 
 // K3
 int64_t gemv_workspace_bytes(int nq, int k, int sm_count);
-int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, int nq, int k,
+int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, bool raw_q, int nq, int k,
                      float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
                      int64_t ws_bytes, int sm_count, cudaStream_t stream);
 

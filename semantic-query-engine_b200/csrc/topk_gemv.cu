@@ -62,9 +62,21 @@ template <> struct Elem<__half> {
     }
 };
 
-template <typename T, int R>
+template <typename T> __device__ __forceinline__ float round_through(float x);
+template <> __device__ __forceinline__ float round_through<float>(float x) { return x; }
+template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float x) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+}
+template <> __device__ __forceinline__ float round_through<__half>(float x) {
+    return __half2float(__float2half_rn(x));
+}
+
+// RAWQ: `Qv` holds the RAW fp32 query embeddings; every CTA normalises its query itself
+// (x / (|x| + 1e-9), the K1 arithmetic bit for bit, app/main.py:353-354) and rounds it to the
+// shard's storage type -- the separate K1 launch for one query disappears.
+template <typename T, int R, bool RAWQ>
 __global__ void __launch_bounds__(kGemvWarps * 32, kGemvCtasPerSm)
-topk_gemv_kernel(const T* __restrict__ D, int64_t n, const T* __restrict__ Q, int k,
+topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv, int k,
                  uint64_t* __restrict__ ws_lists, unsigned* __restrict__ ws_counter,
                  float* __restrict__ out_score, int64_t* __restrict__ out_idx,
                  int64_t idx_offset) {
@@ -82,8 +94,33 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const T* __restrict__ Q, in
 
     // the query in registers, same element layout as a row's loads
     float q[32];
-    {
-        const T* qp = Q + static_cast<int64_t>(query) * kDim;
+    if constexpr (RAWQ) {
+        __shared__ __align__(16) float s_tile[8 * kNormBlockStride];
+        __shared__ __align__(16) float s_q[kDim];
+        if (warp == 0) {
+            const float* src = static_cast<const float*>(Qv) + static_cast<int64_t>(query) * kDim;
+            float4 v[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = *reinterpret_cast<const float4*>(src + 128 * m + 4 * lane);
+            const float ss = warp_row_sumsq_numpy(v, s_tile, lane);
+            const float den = __fadd_rn(__fsqrt_rn(ss), 1e-9f);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float4 o;
+                o.x = round_through<T>(__fdiv_rn(v[m].x, den));
+                o.y = round_through<T>(__fdiv_rn(v[m].y, den));
+                o.z = round_through<T>(__fdiv_rn(v[m].z, den));
+                o.w = round_through<T>(__fdiv_rn(v[m].w, den));
+                *reinterpret_cast<float4*>(s_q + 128 * m + 4 * lane) = o;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < LOADS; ++c)
+#pragma unroll
+            for (int e = 0; e < PER; ++e) q[c * PER + e] = s_q[c * (32 * PER) + lane * PER + e];
+    } else {
+        const T* qp = static_cast<const T*>(Qv) + static_cast<int64_t>(query) * kDim;
 #pragma unroll
         for (int c = 0; c < LOADS; ++c) {
             uint4 u = *reinterpret_cast<const uint4*>(qp + c * (32 * PER) + lane * PER);
@@ -205,47 +242,55 @@ static int gemv_grid_x(int64_t n, int sm_count, int rpw) {
     return static_cast<int>(want < need ? want : need);
 }
 
+// workspace = [counters: one u32 per query, padded to 4 KB][per-CTA lists].  The counters of
+// up to 1024 queries always sit in the first 4 KB; the kernel leaves them at zero, so they
+// need zeroing only once (header contract) -- no memset launch per call.
+static int64_t gemv_counter_bytes(int nq) { return ((static_cast<int64_t>(nq) * 4 + 4095) / 4096) * 4096; }
+
 int64_t gemv_workspace_bytes(int nq, int k, int sm_count) {
     const int64_t L = 32 * r_for_k(k);
     const int64_t lists = static_cast<int64_t>(nq) * sm_count * kGemvCtasPerSm * L * 8;
-    const int64_t counters = ((static_cast<int64_t>(nq) * 4 + 255) / 256) * 256;
-    return lists + counters;
+    return gemv_counter_bytes(nq) + lists;
 }
 
 template <typename T, int R>
-static int launch_gemv_t(const void* D, int64_t n, const void* Q, int nq, int k, float* out_score,
-                         int64_t* out_idx, int64_t idx_offset, void* ws, int sm_count,
+static int launch_gemv_t(const void* D, int64_t n, const void* Q, bool raw_q, int nq, int k,
+                         float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws, int sm_count,
                          cudaStream_t stream) {
     constexpr int RPW = 16 / Elem<T>::kLoads;
     const int gx = gemv_grid_x(n, sm_count, RPW);
-    const int64_t L = 32 * R;
-    const int64_t lists_bytes = static_cast<int64_t>(nq) * sm_count * kGemvCtasPerSm * L * 8;
-    uint64_t* ws_lists = static_cast<uint64_t*>(ws);
-    unsigned* ws_counter = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + lists_bytes);
-    cudaError_t e = cudaMemsetAsync(ws_counter, 0, static_cast<size_t>(nq) * 4, stream);
-    if (e != cudaSuccess) { set_error("gemv: memset: %s", cudaGetErrorString(e)); return -2; }
+    unsigned* ws_counter = static_cast<unsigned*>(ws);
+    uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + gemv_counter_bytes(nq));
+    cudaError_t e;
+    if (nq > 1024) {          // counters beyond the reserved 4 KB may hold an older call's lists
+        e = cudaMemsetAsync(ws_counter, 0, static_cast<size_t>(nq) * 4, stream);
+        if (e != cudaSuccess) { set_error("gemv: memset: %s", cudaGetErrorString(e)); return -2; }
+    }
     dim3 grid(gx, nq), block(kGemvWarps * 32);
-    topk_gemv_kernel<T, R><<<grid, block, 0, stream>>>(
-        static_cast<const T*>(D), n, static_cast<const T*>(Q), k, ws_lists, ws_counter, out_score,
-        out_idx, idx_offset);
+    if (raw_q)
+        topk_gemv_kernel<T, R, true><<<grid, block, 0, stream>>>(
+            static_cast<const T*>(D), n, Q, k, ws_lists, ws_counter, out_score, out_idx, idx_offset);
+    else
+        topk_gemv_kernel<T, R, false><<<grid, block, 0, stream>>>(
+            static_cast<const T*>(D), n, Q, k, ws_lists, ws_counter, out_score, out_idx, idx_offset);
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("gemv: launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
 }
 
 template <typename T>
-static int launch_gemv_r(const void* D, int64_t n, const void* Q, int nq, int k, float* out_score,
+static int launch_gemv_r(const void* D, int64_t n, const void* Q, bool raw_q, int nq, int k, float* out_score,
                          int64_t* out_idx, int64_t idx_offset, void* ws, int sm_count,
                          cudaStream_t stream) {
     switch (r_for_k(k)) {
-        case 1: return launch_gemv_t<T, 1>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 2: return launch_gemv_t<T, 2>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 4: return launch_gemv_t<T, 4>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        default: return launch_gemv_t<T, 8>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 1: return launch_gemv_t<T, 1>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 2: return launch_gemv_t<T, 2>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 4: return launch_gemv_t<T, 4>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        default: return launch_gemv_t<T, 8>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
     }
 }
 
-int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, int nq, int k,
+int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, bool raw_q, int nq, int k,
                      float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
                      int64_t ws_bytes, int sm_count, cudaStream_t stream) {
     if (ws_bytes < gemv_workspace_bytes(nq, k, sm_count)) {
@@ -254,9 +299,9 @@ int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, int nq,
         return -3;
     }
     switch (dtype) {
-        case 0: return launch_gemv_r<float>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 1: return launch_gemv_r<__nv_bfloat16>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 2: return launch_gemv_r<__half>(D, n, Q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 0: return launch_gemv_r<float>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 1: return launch_gemv_r<__nv_bfloat16>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 2: return launch_gemv_r<__half>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
         default: set_error("gemv: bad dtype %d", dtype); return -1;
     }
 }

@@ -51,6 +51,26 @@ def _workspace(dev: torch.device, kind: str, nbytes: int) -> torch.Tensor:
     return ws
 
 
+def packed_topk_out(dev: torch.device, b: int, k: int):
+    """One device buffer holding rows [b,k] int64 then scores [b,k] fp32 (a single D2H copy
+    brings both back).  Returns (buffer uint8, scores view, rows view)."""
+    buf = torch.empty((b * k * 12,), dtype=torch.uint8, device=dev)
+    idx = buf[: b * k * 8].view(torch.int64).view(b, k)
+    scores = buf[b * k * 8:].view(torch.float32).view(b, k)
+    return buf, scores, idx
+
+
+def _outputs(out, dev, b, k):
+    if out is None:
+        return (torch.empty((b, k), dtype=torch.float32, device=dev),
+                torch.empty((b, k), dtype=torch.int64, device=dev))
+    scores, idx = out
+    if scores.shape != (b, k) or idx.shape != (b, k) or scores.dtype != torch.float32 or \
+            idx.dtype != torch.int64 or not scores.is_contiguous() or not idx.is_contiguous():
+        raise ValueError("bad `out` tensors")
+    return scores, idx
+
+
 def normalize_cast(x: torch.Tensor, dtype: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K1: rows of fp32 `x` [n,1024] -> x/(||x||+1e-9) stored as `dtype`."""
     dev = _require_cuda(x)
@@ -81,11 +101,10 @@ def _check_dq(D: torch.Tensor, Q: torch.Tensor, n: Optional[int]) -> Tuple[torch
 
 
 def topk_gemv(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
-              n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+              n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K3: exact cosine top-k, one streaming pass over the shard per query."""
     dev, rows, b = _check_dq(D, Q, n)
-    scores = torch.empty((b, k), dtype=torch.float32, device=dev)
-    idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+    scores, idx = _outputs(out, dev, b, k)
     if b == 0:
         return scores, idx
     with torch.cuda.device(dev):
@@ -97,12 +116,35 @@ def topk_gemv(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
     return scores, idx
 
 
+def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 0,
+                n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1 (query side) + K3 in one launch: `q_raw` fp32 [nq,1024] un-normalised."""
+    dev = _require_cuda(D, q_raw)
+    if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
+        raise ValueError("q_raw must be fp32 [nq,1024]")
+    if D.dim() != 2 or D.shape[1] != nat.SQE_DIM:
+        raise ValueError("D must be [rows,1024]")
+    rows = D.shape[0] if n is None else int(n)
+    if rows > D.shape[0]:
+        raise ValueError("n exceeds shard rows")
+    b = q_raw.shape[0]
+    scores, idx = _outputs(out, dev, b, k)
+    if b == 0:
+        return scores, idx
+    with torch.cuda.device(dev):
+        need = nat.load().sqe_topk_gemv_workspace_bytes(b, k)
+        ws = _workspace(dev, "gemv", need)
+        nat.call("sqe_search_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
+                 q_raw.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+                 ws.data_ptr(), ws.numel(), _stream(dev))
+    return scores, idx
+
+
 def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
-                 n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                 n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K2: exact cosine top-k on the tensor cores (bf16/fp16 shards)."""
     dev, rows, b = _check_dq(D, Q, n)
-    scores = torch.empty((b, k), dtype=torch.float32, device=dev)
-    idx = torch.empty((b, k), dtype=torch.int64, device=dev)
+    scores, idx = _outputs(out, dev, b, k)
     if b == 0:
         return scores, idx
     with torch.cuda.device(dev):
@@ -115,11 +157,11 @@ def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
 
 
 def topk(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
-         n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+         n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Route: one query or an fp32 shard -> K3 (HBM-bound GEMV); else K2 (tensor cores)."""
     if Q.shape[0] <= 1 or D.dtype == torch.float32 or k > nat.SQE_MAX_K_BATCHED:
-        return topk_gemv(D, Q, k, idx_offset, n)
-    return topk_batched(D, Q, k, idx_offset, n)
+        return topk_gemv(D, Q, k, idx_offset, n, out=out)
+    return topk_batched(D, Q, k, idx_offset, n, out=out)
 
 
 def cache_top1(C: torch.Tensor, Q: torch.Tensor, threshold: float, path: int = 0,
@@ -142,7 +184,7 @@ def cache_top1(C: torch.Tensor, Q: torch.Tensor, threshold: float, path: int = 0
     return idx, score, hit
 
 
-def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int, out=None
                ) -> Tuple[torch.Tensor, torch.Tensor]:
     """K4: scores/idx [lists,b,k_in] -> best-first [b,k_out]."""
     dev = _require_cuda(scores, idx)
@@ -151,8 +193,7 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int
     if scores.dtype != torch.float32 or idx.dtype != torch.int64:
         raise TypeError("scores fp32, idx int64")
     lists, b, k_in = scores.shape
-    out_s = torch.empty((b, k_out), dtype=torch.float32, device=dev)
-    out_i = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+    out_s, out_i = _outputs(out, dev, b, k_out)
     if b == 0:
         return out_s, out_i
     with torch.cuda.device(dev):
@@ -169,8 +210,8 @@ def exchange_buffer_bytes(world: int, capacity_entries: int) -> int:
 
 
 def exchange_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int, rank: int,
-                   peer_ptrs, capacity_entries: int, epoch: int, wait_mask: Optional[int] = None
-                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+                   peer_ptrs, capacity_entries: int, epoch: int, wait_mask: Optional[int] = None,
+                   out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K4x: push this rank's [b,k] lists into every rank's peer-mapped buffer, wait for all
     ranks, merge.  `peer_ptrs`: device pointers (ints) of every rank's buffer as mapped here."""
     import ctypes
@@ -181,8 +222,7 @@ def exchange_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int, rank: in
         raise TypeError("scores fp32, idx int64")
     b, k_in = scores.shape
     world = len(peer_ptrs)
-    out_s = torch.empty((b, k_out), dtype=torch.float32, device=dev)
-    out_i = torch.empty((b, k_out), dtype=torch.int64, device=dev)
+    out_s, out_i = _outputs(out, dev, b, k_out)
     if b == 0:
         return out_s, out_i
     arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])

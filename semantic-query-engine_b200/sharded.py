@@ -124,18 +124,19 @@ class ShardedCorpusIndex:
             raise RuntimeError("exchange='p2p' requested but symmetric memory could not be set up")
 
     # ------------------------------------------------------------------ search
-    def search_device(self, q_dev: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search_device(self, q_dev: torch.Tensor, k: int, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """q_dev [B,1024] fp32 (replicated on every rank) -> merged (scores, global rows) on
         every rank: local scan, then ONE exchange + merge."""
         if self._local_topk is not None:
             s, i = self._local_topk(q_dev, k, self.row_offset)
         else:
-            s, i = self.local.search_device(q_dev, k, idx_offset=self.row_offset)
+            s, i = self.local.search_device(q_dev, k, idx_offset=self.row_offset,
+                                            out=out if self.world == 1 else None)
         if self.world == 1:
             return s, i
-        return self.exchange_lists(s, i, k)
+        return self.exchange_lists(s, i, k, out=out)
 
-    def exchange_lists(self, s: torch.Tensor, i: torch.Tensor, k: int
+    def exchange_lists(self, s: torch.Tensor, i: torch.Tensor, k: int, out=None
                        ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Collective: every rank passes its local [B,k] lists (global rows) and gets the merged
         top-k of all ranks."""
@@ -145,7 +146,7 @@ class ShardedCorpusIndex:
             from . import ops
             self._epoch += 1
             return ops.exchange_merge(s.contiguous(), i.contiguous(), k, self.rank, self._xchg[2],
-                                      self._xchg[3], self._epoch)
+                                      self._xchg[3], self._epoch, out=out)
         if self._gather_s is None or self._gather_s.shape[1:] != s.shape or self._gather_s.device != s.device:
             self._gather_s = torch.empty((self.world, b, k), dtype=s.dtype, device=s.device)
             self._gather_i = torch.empty((self.world, b, k), dtype=i.dtype, device=i.device)
@@ -155,12 +156,19 @@ class ShardedCorpusIndex:
         if self._merge is not None:
             return self._merge(self._gather_s, self._gather_i, k)
         from . import ops
-        return ops.merge_topk(self._gather_s, self._gather_i, k)
+        return ops.merge_topk(self._gather_s, self._gather_i, k, out=out)
 
     def search_batch(self, query_emb: np.ndarray, k: int = 3) -> Tuple[np.ndarray, np.ndarray]:
+        """Host fp32 [B,1024] in (the same batch on every rank), host (scores, global rows) out."""
         dev = self._comm_device()
-        q = torch.from_numpy(np.ascontiguousarray(query_emb, dtype=np.float32))
-        if dev.type == "cuda":
-            q = q.pin_memory().to(dev, non_blocking=True)
-        s, i = self.search_device(q, k)
-        return s.cpu().numpy(), i.cpu().numpy()
+        if dev.type != "cuda" or self.local is None:
+            q = torch.from_numpy(np.ascontiguousarray(query_emb, dtype=np.float32))
+            s, i = self.search_device(q, k)
+            return s.cpu().numpy(), i.cpu().numpy()
+        from . import ops
+        q = self.local._as_rows(query_emb)
+        with torch.cuda.device(dev):
+            qd = self.local._stage_queries(q)                  # reusable pinned staging
+            buf, s, i = ops.packed_topk_out(dev, q.shape[0], k)
+            self.search_device(qd, k, out=(s, i))
+            return self.local._fetch_packed(buf, q.shape[0], k)  # one D2H copy

@@ -118,6 +118,25 @@ def test_gemv_topk_matches_oracle(sqe, dtype, n):
     np.testing.assert_allclose(s.cpu().numpy()[0, :kk], so[0, :kk], atol=2e-6)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_search_gemv_fused_normalise_is_bit_identical(sqe, dtype):
+    """K1 + K3 in one launch == sqe_normalize_cast followed by sqe_topk_gemv, bit for bit."""
+    rng = np.random.default_rng(77)
+    x = make_corpus(rng, 30_000)
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    q = (rng.standard_normal((4, DIM)) * 10.0 ** rng.uniform(-6, 6, size=(4, 1))).astype(np.float32)
+    q[1] = x[7] * 0.25
+    q[2] = 0.0
+    qd = torch.from_numpy(q).to(dev())
+    for k in (1, 10, 100):
+        s0, i0 = sqe.ops.topk_gemv(D, sqe.ops.normalize_cast(qd, dtype), k)
+        s1, i1 = sqe.ops.search_gemv(D, qd, k)
+        s2, i2 = sqe.ops.search_gemv(D, qd, k)                 # counters were left at zero
+        torch.cuda.synchronize()
+        assert torch.equal(i0, i1) and torch.equal(s0, s1)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
 def test_gemv_idx_offset_and_partial_shard(sqe):
     rng = np.random.default_rng(5)
     x = make_corpus(rng, 3000)

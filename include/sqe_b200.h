@@ -118,14 +118,22 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
  * Returns the previous value, or SQE_E_ARG for an unknown knob / value.
  *   SQE_TUNE_K2_EPILOGUE_MODE: DIAGNOSTICS ONLY, results are invalid unless 0.  1 = the epilogue
  *                          only reads TMEM, 2 = no epilogue (isolates the TMA + MMA main loop).
+ *   SQE_TUNE_K2_D_HINT:    L2 cache policy attached to the shard-row TMA loads: 0 = none (default),
+ *                          1 = evict_normal, 2 = evict_first, 3 = evict_last.
+ *   SQE_TUNE_K2_WINDOW:    EXPERIMENT, default 0 = off.  How many d-tiles the units (CTAs / CTA pairs)
+ *                          that share d-tiles may drift apart before the one ahead waits.  Measured:
+ *                          it does bound the DRAM re-reads of pair mode (1.2-2x -> 1.05x the shard)
+ *                          but costs 8-12 % throughput at any window size (profiles/README.md).
  */
 #define SQE_TUNE_K2_CTA_GROUP 0
 #define SQE_TUNE_K2_EPILOGUE_MODE 1
+#define SQE_TUNE_K2_D_HINT 2
+#define SQE_TUNE_K2_WINDOW 3
 SQE_API int sqe_tuning_set(int knob, int value);
 
 /*
  * Diagnostics: when `device_buffer` is non-NULL, every later sqe_topk_batched launch writes
- * per-CTA role timers (clock64 cycles) and counters into it as u64 [grid][32]:
+ * per-CTA role timers (clock64 cycles) and counters into it as u64 [grid][40]:
  *   0 producer total, 1 producer waiting for a free stage, 2 MMA issuer total, 3 MMA issuer
  *   waiting for operands, 4 MMA issuer waiting for a drained accumulator; then for each of the
  *   four epilogue warps w at 8 + 6 w: total, waiting for an accumulator, inside list merges,

@@ -111,6 +111,8 @@ def call(name: str, *args) -> None:
 
 SQE_TUNE_K2_CTA_GROUP = 0
 SQE_TUNE_K2_EPILOGUE_MODE = 1      # diagnostics only
+SQE_TUNE_K2_D_HINT = 2
+SQE_TUNE_K2_WINDOW = 3
 
 
 def tuning_set(knob: int, value: int) -> int:

@@ -13,6 +13,8 @@ static thread_local char g_err[512] = "";
 int g_k2_cta_group = 0;
 void* g_k2_debug = nullptr;
 int g_k2_epilogue_mode = 0;
+int g_k2_d_hint = 0;
+int g_k2_window = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -90,6 +92,16 @@ int sqe_tuning_set(int knob, int value) {
     if (knob == SQE_TUNE_K2_EPILOGUE_MODE && value >= 0 && value <= 2) {
         const int old = g_k2_epilogue_mode;
         g_k2_epilogue_mode = value;
+        return old;
+    }
+    if (knob == SQE_TUNE_K2_WINDOW && value >= 0 && value <= 1024) {
+        const int old = g_k2_window;
+        g_k2_window = value;
+        return old;
+    }
+    if (knob == SQE_TUNE_K2_D_HINT && value >= 0 && value <= 4) {
+        const int old = g_k2_d_hint;
+        g_k2_d_hint = value;
         return old;
     }
     set_error("tuning_set: unknown knob %d / value %d", knob, value);

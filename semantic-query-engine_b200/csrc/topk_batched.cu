@@ -441,7 +441,8 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const __grid_constant__ CUtensorMap tmap_d, uint32_t n, int b, int k,
                     int n_qt, int n_groups, int n_dtiles, uint32_t idesc,
                     uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau,
-                    unsigned long long* __restrict__ dbg, int epi_mode) {
+                    uint32_t* __restrict__ ws_prog, unsigned long long* __restrict__ dbg, int epi_mode,
+                    int d_hint, int window) {
     using namespace k2;
     using C = Cfg<CG, R, TOP1>;
     constexpr int L = 32 * R;
@@ -490,14 +491,38 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             const uint64_t pol_q = ptx::policy_evict_last();   // 2 MB of queries: keep in L2
-            const uint64_t pol_d = ptx::policy_evict_normal();
+            // shard rows: no hint by default (an explicit evict_normal policy is classed
+            // "evict_normal_demote" by the L2 and doubled the DRAM reads, ncu r1i_k2)
+            const uint64_t pol_d = d_hint == 2 ? ptx::policy_evict_first()
+                                 : d_hint == 3 ? ptx::policy_evict_last() : ptx::policy_evict_normal();
             const int q_row = q_tile * C::kQTile + static_cast<int>(rank) * kRowsPerCta;
             int stage = 0;
             uint32_t phase = 0;
             long long t_wait = 0;
             const long long t_begin = clock64();
+            // Progress window (EXPERIMENT, off unless sqe_tuning_set(SQE_TUNE_K2_WINDOW, w > 0)).
+            // In pair mode the units of a group drift apart (start times ~15 us apart after 200
+            // tiles); a tile may then have left L2 when the laggards ask for it and is read from
+            // HBM again (ncu: 1.2-2x the shard).  With the window every unit publishes the tile
+            // it is loading and waits when it is more than `window` tiles ahead of a sibling.
+            // Measured: DRAM reads drop to 1.05x, but throughput drops 8-12 % at any window size
+            // and the units drift TO the limit instead of staying in their natural ~2-tile
+            // equilibrium (followers hit L2 and catch up with the DRAM-fetching leader).
+            const uint32_t kWindow = static_cast<uint32_t>(window);
+            uint32_t* my_prog = ws_prog + group * n_qt;
+            const bool sync_group = (rank == 0) && (n_qt > 1) && (window > 0);
+            uint32_t sib[8];
+            long long t_window = 0;
+            unsigned n_blocked = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int d_row = (group + i * n_groups) * kTileN + static_cast<int>(rank) * C::kBRows;
+                if (sync_group) {
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_prog + q_tile), "r"(static_cast<uint32_t>(i + 1)) : "memory");
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (u < n_qt)
+                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sib[u]) : "l"(my_prog + u) : "memory");
+                }
                 for (int kc = 0; kc < kNumChunks; ++kc) {
                     const long long w0 = dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
@@ -506,21 +531,48 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     if constexpr (CG == 1) {
                         const uint32_t fb = bar_full + 8 * stage;
                         ptx::mbar_expect_tx(fb, C::kStageBytes);
-                        ptx::tma_load_2d_hint(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
-                        ptx::tma_load_2d_hint(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
+                        if (d_hint == 4) ptx::tma_load_2d(sa, &tmap_q, kc * kChunkK, q_row, fb);
+                        else ptx::tma_load_2d_hint(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
+                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_2d(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb);
+                        else ptx::tma_load_2d_hint(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
                     } else {
                         // both CTAs' bytes are counted on the LEADER's barrier
                         if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
                         const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
-                        ptx::tma_load_2d_cg2(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
-                        ptx::tma_load_2d_cg2(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
+                        if (d_hint == 4) ptx::tma_load_2d_cg2_nohint(sa, &tmap_q, kc * kChunkK, q_row, fb);
+                        else ptx::tma_load_2d_cg2(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
+                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_2d_cg2_nohint(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb);
+                        else ptx::tma_load_2d_cg2(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+                if (sync_group && i + 1 < my_tiles) {
+                    // may tile i+1 start?  every sibling must have reached tile i+1-kWindow
+                    // (published value = tile index + 1; a finished unit publishes 0xffffffff)
+                    const long long t0 = clock64();
+                    while (true) {
+                        uint32_t lo = 0xffffffffu;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (u < n_qt) lo = min(lo, sib[u]);
+                        if (lo + kWindow >= static_cast<uint32_t>(i + 2) || lo == 0xffffffffu) break;
+                        ++n_blocked;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (u < n_qt)
+                                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sib[u]) : "l"(my_prog + u) : "memory");
+                        if (clock64() - t0 > 4000000000LL) __trap();
+                    }
+                    t_window += clock64() - t0;
+                }
             }
+            if (sync_group)       // done: never hold the others back
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_prog + q_tile), "r"(0xffffffffu) : "memory");
             if (dbg) {
-                dbg[blockIdx.x * 32 + 0] = clock64() - t_begin;
-                dbg[blockIdx.x * 32 + 1] = t_wait;
+                dbg[blockIdx.x * 40 + 0] = clock64() - t_begin;
+                dbg[blockIdx.x * 40 + 1] = t_wait;
+                dbg[blockIdx.x * 40 + 32] = t_window;
+                dbg[blockIdx.x * 40 + 33] = n_blocked;
             }
         }
     } else if (warp == 1) {
@@ -534,6 +586,11 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 const int acc = i & 1;
                 const uint32_t acc_phase = (i >> 1) & 1;
                 const long long w0 = dbg ? clock64() : 0;
+                if (dbg && (i == 8 || i == 64 || i == 200)) {            // skew between the units of a group
+                    unsigned long long gt;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    dbg[blockIdx.x * 40 + (i == 8 ? 5 : i == 64 ? 6 : 7)] = gt;
+                }
                 ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);   // epilogue(s) drained it
                 if (dbg) t_wtempty += clock64() - w0;
                 ptx::tc_fence_after();
@@ -562,9 +619,9 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 else ptx::umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
             }
             if (dbg) {
-                dbg[blockIdx.x * 32 + 2] = clock64() - t_begin;
-                dbg[blockIdx.x * 32 + 3] = t_wfull;
-                dbg[blockIdx.x * 32 + 4] = t_wtempty;
+                dbg[blockIdx.x * 40 + 2] = clock64() - t_begin;
+                dbg[blockIdx.x * 40 + 3] = t_wfull;
+                dbg[blockIdx.x * 40 + 4] = t_wtempty;
             }
         }
     } else if (warp == 6) {
@@ -710,7 +767,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const unsigned pending = __ballot_sync(kFull, st.cnt > 0);
             if (pending) flush_lanes<R, SL>(pending, st, wbuf, slists, wlists, wtau, k, lane);
             if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 64) {
-                unsigned long long* tr = dbg + gridDim.x * 32 + i * 4;
+                unsigned long long* tr = dbg + gridDim.x * 40 + i * 4;
                 tr[0] = w1 - w0;                 // waited for the accumulator
                 tr[1] = w2 - w1;                 // strips (until the accumulator was released)
                 tr[2] = clock64() - w2;          // tile-end list merges
@@ -721,7 +778,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         __syncwarp();
         if (lane == 0) atomicAdd(epi_done, 1u);
         if (dbg && lane == 0) {
-            unsigned long long* d = dbg + blockIdx.x * 32 + 8 + (warp - 2) * 6;
+            unsigned long long* d = dbg + blockIdx.x * 40 + 8 + (warp - 2) * 6;
             d[0] = clock64() - t_begin;
             d[1] = t_wtfull;
             d[2] = st.t_flush;
@@ -802,18 +859,20 @@ static int make_tile_map(CUtensorMap* map, const void* ptr, int dtype, uint64_t 
 static inline int r_for_k_batched(int k) { return k <= 32 ? 1 : k <= 64 ? 2 : 4; }
 
 static constexpr int64_t kTauBytes = 4096;        // kQueriesPerLaunch * 4
+static constexpr int64_t kProgBytes = 4096;       // one u32 of tile progress per unit (<= #SMs)
+static constexpr int64_t kHdrBytes = kTauBytes + kProgBytes;
 
 int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
     const int R = r_for_k_batched(k);
     const int64_t L = 32 * R;
     // R > 1: as many scratch lists again for the bootstrap of the first d-tile
-    return kTauBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8 * (R > 1 ? 2 : 1);
+    return kHdrBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8 * (R > 1 ? 2 : 1);
 }
 
 template <int R, int CG, bool TOP1>
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
                             int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
-                            uint32_t* ws_tau, float* out_score, int64_t* out_idx, int64_t idx_offset,
+                            uint32_t* ws_tau, uint32_t* ws_prog, float* out_score, int64_t* out_idx, int64_t idx_offset,
                             cudaStream_t stream) {
     using C = k2::Cfg<CG, R, TOP1>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
@@ -834,8 +893,8 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1>, tq, td, static_cast<uint32_t>(n), b, k,
-                               n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau,
-                               reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode);
+                               n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog,
+                               reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
     }
     batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, n_dtiles > 0 ? n_groups : 0, b,
@@ -854,7 +913,8 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
     const int R = r_for_k_batched(k);
     const int64_t L = 32 * R;
     uint32_t* ws_tau = static_cast<uint32_t*>(ws);
-    uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kTauBytes);
+    uint32_t* ws_prog = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + kTauBytes);
+    uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kHdrBytes);
     const int n_dtiles = static_cast<int>((n + k2::kTileN - 1) / k2::kTileN);
     const uint32_t fmt = (dtype == 1) ? 1u : 0u;               // BF16 = 1, F16 = 0
     // instruction descriptor: D fp32 [4,6)=1, A fmt [7,10), B fmt [10,13), K-major both,
@@ -876,7 +936,7 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         int n_groups = units / n_qt;
         if (n_groups < 1) n_groups = 1;
         if (n_dtiles > 0 && n_groups > n_dtiles) n_groups = n_dtiles;
-        const int64_t used = kTauBytes + static_cast<int64_t>(n_groups) * n_qt * C::kQTile * L * 8;
+        const int64_t used = kHdrBytes + static_cast<int64_t>(n_groups) * n_qt * C::kQTile * L * 8;
         cudaError_t e = cudaMemsetAsync(ws, 0, static_cast<size_t>(used), stream);
         if (e != cudaSuccess) { set_error("topk_batched: memset: %s", cudaGetErrorString(e)); return -2; }
         const char* qp = static_cast<const char*>(Q) + static_cast<int64_t>(q0) * kDim * 2;
@@ -886,14 +946,14 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         float* os = out_score + static_cast<int64_t>(q0) * k;
         int64_t* oi = out_idx + static_cast<int64_t>(q0) * k;
         if (k == 1) {
-            rc = launch_batched_r<1, CG, true>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream);
+            rc = launch_batched_r<1, CG, true>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream);
             if (rc != 0) return rc;
             continue;
         }
         switch (R) {
-            case 1: rc = launch_batched_r<1, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-            case 2: rc = launch_batched_r<2, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
-            default: rc = launch_batched_r<4, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, os, oi, idx_offset, stream); break;
+            case 1: rc = launch_batched_r<1, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream); break;
+            case 2: rc = launch_batched_r<2, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream); break;
+            default: rc = launch_batched_r<4, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream); break;
         }
         if (rc != 0) return rc;
     }

@@ -17,6 +17,8 @@ unpinned), rows live in HBM as bf16/fp16/fp32, and a batched entry point
 """
 from __future__ import annotations
 
+import json
+import os
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -253,3 +255,60 @@ class GpuCorpusIndex:
 
     def doc_id_of(self, row: int) -> str:
         return self._ids[row]
+
+    # -------------------------------------------------------------- persistence
+    # The reference's only "resume" is skipping ingest when the index already has data
+    # (main.py:300-307, :422-424); its persistence is whatever OpenSearch keeps.  Here the packed
+    # shard is written as it sits in HBM (stored rows, no re-normalisation on load) next to the
+    # payload table, so a restarted process answers `has_any_data()` the same way.
+    FORMAT_VERSION = 1
+
+    def save(self, path: str, chunk_rows: int = 1 << 17) -> None:
+        """Write `path`/shard.bin (raw stored rows), meta.json, payload.json."""
+        os.makedirs(path, exist_ok=True)
+        with self._lock:
+            rows = self._rows
+            esize = {"fp32": 4, "bf16": 2, "fp16": 2}[self.dtype]
+            with open(os.path.join(path, "shard.bin"), "wb") as f:
+                for lo in range(0, rows, chunk_rows):
+                    blk = self._shard[lo: min(rows, lo + chunk_rows)]
+                    raw = blk.contiguous().view(torch.uint8).cpu().numpy()
+                    f.write(raw.tobytes())
+            with open(os.path.join(path, "payload.json"), "w") as f:
+                json.dump({"docs": self._docs, "ids": self._ids}, f)
+            with open(os.path.join(path, "meta.json"), "w") as f:
+                json.dump({"format": self.FORMAT_VERSION, "rows": rows, "dim": EMBED_DIM,
+                           "dtype": self.dtype, "bytes": rows * EMBED_DIM * esize,
+                           "index_name": self.index_name, "normalised": True}, f)
+
+    @classmethod
+    def load(cls, path: str, *, device: Optional[torch.device] = None, chunk_rows: int = 1 << 17,
+             **kwargs) -> "GpuCorpusIndex":
+        """Rebuild an index from `save()` output: the stored rows go to HBM bit for bit."""
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != cls.FORMAT_VERSION or meta.get("dim") != EMBED_DIM:
+            raise ValueError(f"unsupported shard file {path}: {meta}")
+        index = cls(None, meta.get("index_name", ""), dtype=meta["dtype"], device=device, **kwargs)
+        rows = int(meta["rows"])
+        esize = {"fp32": 4, "bf16": 2, "fp16": 2}[index.dtype]
+        row_bytes = EMBED_DIM * esize
+        size = os.path.getsize(os.path.join(path, "shard.bin"))
+        if size != rows * row_bytes:
+            raise ValueError(f"shard.bin has {size} bytes, expected {rows * row_bytes}")
+        with index._lock:
+            index._grow_locked(max(rows, 1))
+            with open(os.path.join(path, "shard.bin"), "rb") as f:
+                for lo in range(0, rows, chunk_rows):
+                    n = min(chunk_rows, rows - lo)
+                    raw = np.frombuffer(f.read(n * row_bytes), dtype=np.uint8)
+                    dst = index._shard[lo: lo + n].view(torch.uint8)
+                    dst.copy_(torch.from_numpy(raw.copy()).view(n, row_bytes))
+            torch.cuda.current_stream(index.device).synchronize()
+            index._rows = rows
+            if index.keep_payload and os.path.isfile(os.path.join(path, "payload.json")):
+                with open(os.path.join(path, "payload.json")) as f:
+                    payload = json.load(f)
+                index._docs = payload["docs"]
+                index._ids = payload["ids"]
+        return index

@@ -67,6 +67,16 @@ def test_argument_errors_cross_the_abi_as_codes(sqe):
     assert lib.sqe_topk_gemv(8, 1, 10, 1024, 16, 1, 5, 16, 16, 0, 16, 1 << 20, None) == -1    # alignment
     assert lib.sqe_topk_batched(16, 0, 10, 1024, 16, 4, 5, 16, 16, 0, 16, 1 << 20, None) == -4  # fp32 shard
     assert lib.sqe_merge_topk(16, 16, 0, 1, 1, 1, 16, 16, None) == -1
+    assert lib.sqe_search_gemv(16, 1, 10, 1024, 16, 1, 0, 16, 16, 0, 16, 1 << 20, None) == -1  # k = 0
+    import ctypes
+    peers = (ctypes.c_void_p * 2)(16, 32)
+    assert lib.sqe_exchange_merge(16, 16, 4, 10, 10, 2, 2, peers, 100, 1, 3, 16, 16, None) == -1   # rank >= world
+    assert lib.sqe_exchange_merge(16, 16, 4, 10, 10, 0, 2, peers, 39, 1, 3, 16, 16, None) == -1    # capacity < b*k
+    assert lib.sqe_exchange_merge(16, 16, 4, 10, 10, 0, 17, peers, 100, 1, 3, 16, 16, None) == -1  # world > 16
+    assert lib.sqe_exchange_buffer_bytes(8, 1024 * 10) == 256 + 2 * 8 * 10240 * 16
+    assert lib.sqe_tuning_set(99, 0) == -1
+    old = lib.sqe_tuning_set(0, 2)
+    assert lib.sqe_tuning_set(0, old) == 2
     assert lib.sqe_topk_gemv_workspace_bytes(1, 10) > 0
     assert lib.sqe_topk_batched_workspace_bytes(1000, 8, 10) > 0
     assert lib.sqe_cache_top1_workspace_bytes(1000, 8) > 0

@@ -257,6 +257,82 @@ def test_query_cache_replays_reference_log(sqe, golden_dir, name, dtype):
     assert cache.freqs() == log["final_freqs"]
 
 
+class _FakeRedis:
+    """The five list commands the reference calls (main.py:69,95,117,125,128)."""
+
+    def __init__(self):
+        self.lists = {}
+
+    def _l(self, name):
+        return self.lists.setdefault(name, [])
+
+    def lrange(self, name, start, stop):
+        l = self._l(name)
+        return list(l[start: len(l) if stop == -1 else stop + 1])
+
+    def lset(self, name, index, value):
+        self._l(name)[index] = value
+
+    def llen(self, name):
+        return len(self._l(name))
+
+    def lpush(self, name, value):
+        self._l(name).insert(0, value)
+
+    def lrem(self, name, count, value):
+        l = self._l(name)
+        if value in l:
+            l.remove(value)
+
+
+@pytest.mark.parametrize("name", ["default", "evict8"])
+def test_query_cache_write_through_keeps_redis_in_the_reference_format(sqe, golden_dir, name):
+    """every mutation is mirrored into the Redis list in the reference's own
+    JSON entry format (main.py:123), so a reference process reading `query_cache_lfu` sees
+    exactly the list the reference's own run ends with (the oracle's LfuCacheModel replays it)."""
+    with open(os.path.join(golden_dir, f"cache_{name}.json")) as f:
+        log = json.load(f)
+    vecs = np.load(os.path.join(golden_dir, f"cache_{name}.npz"))["vecs"]
+    redis = _FakeRedis()
+    cache = sqe.GpuQueryCache(max_items=log["max_items"], threshold=log["threshold"], redis_client=redis)
+    model = no.LfuCacheModel(max_items=log["max_items"], threshold=log["threshold"])
+    for op in log["ops"]:
+        v = vecs[op["vec"]][None, :]
+        if op["op"] == "get":
+            assert cache.get(v) == op["result"] == model.get(v)
+        else:
+            cache.put(v, op["response"])
+            model.put(v, op["response"])
+    stored = redis.lrange(sqe.REDIS_CACHE_LIST, 0, -1)
+    assert stored == model.items                         # byte-identical JSON strings, same order
+    assert [json.loads(s)["freq"] for s in stored] == log["final_freqs"]
+    assert [json.loads(s)["response"] for s in stored] == log["final_responses"]
+
+
+def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
+    """the packed shard + payload survive a restart bit for bit."""
+    rng = np.random.default_rng(4)
+    emb = make_corpus(rng, 5000)
+    docs = [{"doc_id": f"doc{i // 7}", "text": f"chunk {i}"} for i in range(5000)]
+    q = rng.standard_normal((3, DIM)).astype(np.float32)
+    for dtype in ("bf16", "fp32"):
+        a = sqe.GpuCorpusIndex(None, "idx", dtype=dtype, strict=True)
+        assert a.has_any_data() is False
+        a.add_embeddings(emb[:3000], docs[:3000])
+        a.add_embeddings(emb[3000:], docs[3000:])        # incremental ingest into the shard tail
+        path = str(tmp_path / dtype)
+        a.save(path, chunk_rows=1024)
+        b = sqe.GpuCorpusIndex.load(path, strict=True, chunk_rows=777)
+        assert b.has_any_data() is True and b.num_rows == 5000 and b.dtype == dtype
+        assert torch.equal(a.shard.view(torch.uint8), b.shard.view(torch.uint8))
+        assert [b.doc_id_of(r) for r in (0, 2999, 3000, 4999)] == [a.doc_id_of(r) for r in (0, 2999, 3000, 4999)]
+        assert a.search(q[:1], k=5) == b.search(q[:1], k=5)
+        sa, ia = a.search_batch(q, 10)
+        sb, ib = b.search_batch(q, 10)
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_array_equal(sa, sb)
+
+
 def test_query_cache_edge_cases(sqe):
     rng = np.random.default_rng(3)
     cache = sqe.GpuQueryCache(max_items=4, threshold=0.96)

@@ -148,13 +148,15 @@ SQE_API void sqe_debug_k2_timers(void *device_buffer);
  * from -1.0 (first maximum = lowest row wins), miss iff best < threshold.
  * C [n, dim] stored unit cache rows, Q [b, dim] stored unit queries (same dtype).
  * out_idx [b] int32 (-1 when no row beats -1.0 or the cache is empty), out_score [b] fp32,
- * out_hit [b] uint8 (1 iff out_idx >= 0 and !(score < threshold)).
+ * out_hit [b] uint8 (1 iff out_idx >= 0 and !((double)score < threshold)): the comparison is done
+ * in double like the reference's Python floats (best_sim < CACHE_SIM_THRESHOLD, 0.96 is not an
+ * fp32 number).
  * `path`: 0 = choose (tensor cores when dtype is 16-bit and b > 1), 1 = force GEMV, 2 = force
  * tensor cores.
  */
 SQE_API int64_t sqe_cache_top1_workspace_bytes(int64_t n, int b);
 SQE_API int sqe_cache_top1(const void *C, int dtype, int64_t n, int dim, const void *Q, int b,
-                   float threshold, float *out_score, int32_t *out_idx, uint8_t *out_hit,
+                   double threshold, float *out_score, int32_t *out_idx, uint8_t *out_hit,
                    int path, void *workspace, int64_t workspace_bytes, void *stream);
 
 /*

@@ -215,7 +215,7 @@ def cache_lookup_batched(q_stored: np.ndarray, c_stored: np.ndarray, threshold: 
     s = s[:, 0]
     i = i[:, 0]
     valid = (i >= 0) & (s > np.float32(-1.0))
-    hit = valid & ~(s < np.float32(threshold))
+    hit = valid & ~(s.astype(np.float64) < float(threshold))     # Python-float compare, main.py:89
     return np.where(valid, i, -1).astype(np.int32), s.astype(np.float32), hit.astype(np.uint8)
 
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsqe_b200.so")
@@ -37,7 +37,7 @@ PROTOTYPES = [
     ("sqe_topk_batched", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     ("sqe_cache_top1_workspace_bytes", c_int64, [c_int64, c_int]),
-    ("sqe_cache_top1", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_float,
+    ("sqe_cache_top1", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_double,
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     ("sqe_merge_topk", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p]),

@@ -209,7 +209,7 @@ int64_t sqe_cache_top1_workspace_bytes(int64_t n, int b) {
 }
 
 int sqe_cache_top1(const void* C, int dtype, int64_t n, int dim, const void* Q, int b,
-                   float threshold, float* out_score, int32_t* out_idx, uint8_t* out_hit, int path,
+                   double threshold, float* out_score, int32_t* out_idx, uint8_t* out_hit, int path,
                    void* workspace, int64_t workspace_bytes, void* stream) {
     int rc = check_common("cache_top1", C, dtype, n, dim, Q, b);
     if (rc != SQE_OK) return rc;

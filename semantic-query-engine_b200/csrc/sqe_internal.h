@@ -33,7 +33,7 @@ int launch_exchange_merge(const float* scores, const int64_t* idx, int b, int k_
                           int sm_count, cudaStream_t stream);
 
 // K5 epilogue: (score,idx)[b] -> (score, idx32, hit)
-int launch_cache_finalize(const float* score, const int64_t* idx, int b, float threshold,
+int launch_cache_finalize(const float* score, const int64_t* idx, int b, double threshold,
                           float* out_score, int32_t* out_idx, uint8_t* out_hit,
                           cudaStream_t stream);
 

@@ -361,7 +361,7 @@ int launch_merge_topk(const float* scores, const int64_t* idx, int lists, int b,
 // K5 epilogue: threshold test of lfu_cache_get (app/main.py:74-75,84,89-90).
 // ---------------------------------------------------------------------------
 __global__ void cache_finalize_kernel(const float* __restrict__ score, const int64_t* __restrict__ idx,
-                                      int b, float threshold, float* __restrict__ out_score,
+                                      int b, double threshold, float* __restrict__ out_score,
                                       int32_t* __restrict__ out_idx, uint8_t* __restrict__ out_hit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b) return;
@@ -372,10 +372,10 @@ __global__ void cache_finalize_kernel(const float* __restrict__ score, const int
     const bool valid = (r >= 0) && (s > -1.0f);
     out_score[i] = valid ? s : -1.0f;
     out_idx[i] = valid ? static_cast<int32_t>(r) : -1;
-    out_hit[i] = (valid && !(s < threshold)) ? 1 : 0;
+    out_hit[i] = (valid && !(static_cast<double>(s) < threshold)) ? 1 : 0;   // Python-float compare
 }
 
-int launch_cache_finalize(const float* score, const int64_t* idx, int b, float threshold,
+int launch_cache_finalize(const float* score, const int64_t* idx, int b, double threshold,
                           float* out_score, int32_t* out_idx, uint8_t* out_hit,
                           cudaStream_t stream) {
     if (b == 0) return 0;

@@ -164,13 +164,25 @@ def topk(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
     return topk_batched(D, Q, k, idx_offset, n, out=out)
 
 
+def packed_cache_out(dev: torch.device, b: int):
+    """One device buffer for (idx int32 [b], score fp32 [b], hit uint8 [b]): a single D2H copy."""
+    buf = torch.empty((b * 9,), dtype=torch.uint8, device=dev)
+    idx = buf[: b * 4].view(torch.int32)
+    score = buf[b * 4: b * 8].view(torch.float32)
+    hit = buf[b * 8:]
+    return buf, idx, score, hit
+
+
 def cache_top1(C: torch.Tensor, Q: torch.Tensor, threshold: float, path: int = 0,
-               n: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """K5: (idx int32 [b], score fp32 [b], hit uint8 [b])."""
     dev, rows, b = _check_dq(C, Q, n)
-    score = torch.empty((b,), dtype=torch.float32, device=dev)
-    idx = torch.empty((b,), dtype=torch.int32, device=dev)
-    hit = torch.empty((b,), dtype=torch.uint8, device=dev)
+    if out is None:
+        score = torch.empty((b,), dtype=torch.float32, device=dev)
+        idx = torch.empty((b,), dtype=torch.int32, device=dev)
+        hit = torch.empty((b,), dtype=torch.uint8, device=dev)
+    else:
+        idx, score, hit = out
     if b == 0:
         return idx, score, hit
     with torch.cuda.device(dev):

@@ -458,6 +458,46 @@ def test_batched_idx_offset_and_partial_shard(sqe, cta_group):
     assert (i0.cpu().numpy() == -1).all() and np.isneginf(s0.cpu().numpy()).all()
 
 
+@pytest.mark.parametrize("path", ["gemv", "batched"])
+def test_adversarial_orderings(sqe, path):
+    """Worst cases for threshold filtering: (a) every row identical -> every score ties, the
+    result must be rows 0..k-1; (b) scores strictly increasing with the row number -> every
+    row beats everything before it (each one passes the running threshold), the result must be
+    the LAST k rows, best-first; (c) strictly decreasing -> the first k rows."""
+    rng = np.random.default_rng(99)
+    n, b = 6000, 5
+    base = rng.standard_normal(DIM).astype(np.float32)
+    fn = sqe.ops.topk_gemv if path == "gemv" else sqe.ops.topk_batched
+    # (a) identical rows
+    D = sqe.ops.normalize_cast(torch.from_numpy(np.tile(base, (n, 1))).to(dev()), "bf16")
+    Q = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((b, DIM)).astype(np.float32)).to(dev()), "bf16")
+    for k in (1, 10, 100):
+        s, i = fn(D, Q, k)
+        assert torch.equal(i.cpu(), torch.arange(k).repeat(b, 1)), k
+        assert (s == s[:, :1]).all()
+    # (b)/(c) monotone scores: row r = cos(t_r) q + sin(t_r) u, angle shrinking / growing with r
+    q = base / np.linalg.norm(base)
+    u = rng.standard_normal(DIM).astype(np.float32)
+    u -= (u @ q) * q
+    u /= np.linalg.norm(u)
+    ang = np.linspace(1.4, 0.05, n).astype(np.float32)            # increasing cosine
+    rows_inc = np.cos(ang)[:, None] * q[None, :] + np.sin(ang)[:, None] * u[None, :]
+    for rows, name in ((rows_inc, "increasing"), (rows_inc[::-1].copy(), "decreasing")):
+        D = sqe.ops.normalize_cast(torch.from_numpy(rows.astype(np.float32)).to(dev()), "fp16")
+        Q = sqe.ops.normalize_cast(torch.from_numpy(np.tile(q, (b, 1))).to(dev()), "fp16")
+        d_st = oracle.from_storage(stored_bits(D, "fp16"), "fp16")
+        q_st = oracle.from_storage(stored_bits(Q, "fp16"), "fp16")
+        for k in (1, 10, 100):
+            s, i = fn(D, Q, k)
+            torch.cuda.synchronize()
+            assert_topk_matches(s.cpu().numpy(), i.cpu().numpy(), d_st, q_st, k, score_tol=K2_TOL, tie_eps=K2_TOL)
+            got = i[0].cpu().numpy()
+            if name == "increasing":
+                assert got.min() >= n - k - 3, (name, k, got[:5])       # the last k rows (near-ties aside)
+            else:
+                assert got.max() <= k + 3, (name, k, got[:5])
+
+
 def test_batched_equals_gemv_and_is_deterministic(sqe, cta_group):
     rng = np.random.default_rng(11)
     D = sqe.ops.normalize_cast(torch.from_numpy(make_corpus(rng, 120_000)).to(dev()), "bf16")

@@ -42,13 +42,19 @@ struct __align__(16) XRecord {
     unsigned pad;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// One system-scope fence orders ALL the pushes before ALL the flag stores, and one after the
+// poll loop orders the flag reads before the data reads; the flag accesses themselves are
+// relaxed.  (st.release.sys per peer = one full fence per peer: measured ~3 us each.)
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 
 template <int R>
@@ -81,9 +87,9 @@ exchange_merge_kernel(const float* __restrict__ scores, const int64_t* __restric
         const unsigned t = atomicAdd(ticket, 1u);
         if (t == gridDim.x - 1) {
             *ticket = 0u;                                   // ready for the next call
-            __threadfence_system();
+            fence_acq_rel_sys();                            // every CTA's pushes (seen via the ticket) first
             for (int g = 0; g < world; ++g)
-                st_release_sys(reinterpret_cast<unsigned*>(peers.p[g]) + rank, epoch);
+                st_relaxed_sys(reinterpret_cast<unsigned*>(peers.p[g]) + rank, epoch);
         }
     }
     // ---- 3. wait for every rank's push into MY buffer
@@ -91,12 +97,12 @@ exchange_merge_kernel(const float* __restrict__ scores, const int64_t* __restric
     if (lane < world && ((wait_mask >> lane) & 1u)) {
         const long long t0 = clock64();
         unsigned spins = 0;
-        while (static_cast<int>(ld_acquire_sys(my_flags + lane) - epoch) < 0) {
-            __nanosleep(100);
+        while (static_cast<int>(ld_relaxed_sys(my_flags + lane) - epoch) < 0) {
             if ((++spins & 0xfffu) == 0 && clock64() - t0 > 8000000000LL) __trap();   // a peer died
         }
+        fence_acq_rel_sys();                                // flag reads before the data reads
     }
-    __syncwarp();                                           // the acquiring lanes order the rest of the warp
+    __syncwarp();                                           // the polling lanes order the rest of the warp
 
     // ---- 4. merge: one warp per query
     const int warps_per_cta = blockDim.x >> 5;

@@ -180,6 +180,9 @@ class GpuCorpusIndex:
         return np.ascontiguousarray(a, dtype=np.float32)
 
     def _stage_queries(self, q: np.ndarray) -> torch.Tensor:
+        t = torch.from_numpy(q)
+        if t.is_pinned():                                # caller already holds page-locked memory
+            return t.to(self.device, non_blocking=True)
         b = q.shape[0]
         if self._pinned_q is None or self._pinned_q.shape[0] < b:
             self._pinned_q = torch.empty((max(b, 64), EMBED_DIM), dtype=torch.float32).pin_memory()

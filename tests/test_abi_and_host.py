@@ -43,6 +43,21 @@ def test_library_contains_sm100a_code(sqe):
     assert "sm_100a" in out, out
 
 
+def test_header_is_plain_c_and_library_is_usable_from_c(sqe, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 with -pedantic and a C program can
+    link the library, call it and get error codes (no exceptions, no torch)."""
+    exe = str(tmp_path / "abi_smoke")
+    src = os.path.join(ROOT, "tests", "c", "abi_smoke.c")
+    libdir = os.path.dirname(sqe._native.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I",
+                         os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-lsqe_b200",
+                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "abi 1 ok" in run.stdout
+
+
 def test_no_cpu_fallback(sqe):
     import torch
     if torch.cuda.is_available():

@@ -82,7 +82,16 @@ constexpr int kQueriesPerLaunch = 1024;
 //
 // TOP1 = the k = 1 specialisation (cache lookup): no lists, no candidate buffers, one more
 // operand stage (this case is HBM-bound: more bytes in flight).
-template <int CG, int R = 1, bool TOP1 = false>
+//
+// DEEP (pair form only) = the deep operand ring.  When several q-tiles share d-tiles the ring is
+// kept SHALLOW (4 stages) on purpose: the unit that touches a d-tile first pays the DRAM
+// latency, and with only 4 stages that slows it down just enough for the followers (L2 hits) to
+// stay bunched behind it.  With 5+ stages the leaders never slow down, the units drift apart
+// (16 us after 200 tiles), tiles fall out of L2 before the laggards read them and 1.6x the shard
+// comes from DRAM -- measured 10M x 1024, b = 1024: 5 stages 32.5 GB / 55.6 k q/s, 4 stages
+// 21.5 GB / 60.2 k q/s, 3 stages 21.6 GB but a starved tensor pipe (73 % active).  A pair that
+// has its d-tiles to itself (one q-tile in flight) keeps the deep ring.
+template <int CG, int R = 1, bool TOP1 = false, bool DEEP = false>
 struct Cfg {
     static constexpr int kQTile = kRowsPerCta * CG;          // queries per q-tile
     static constexpr int kBRows = kTileN / CG;               // D rows this CTA loads per chunk
@@ -91,7 +100,9 @@ struct Cfg {
     static constexpr bool kSmemLists = (R == 1) && !TOP1;
     static constexpr int kListBytes = kSmemLists ? kRowsPerCta * 32 * 8 : 0;
     static constexpr int kBufBytes = TOP1 ? 0 : kRowsPerCta * kBufStride * 8;
-    static constexpr int kStages = (CG == 1) ? (kSmemLists ? 3 : 4) : (kSmemLists ? 5 : (TOP1 ? 7 : 6));
+    static constexpr int kStages = (CG == 1) ? (kSmemLists ? 3 : 4)
+                                   : !DEEP    ? 4
+                                              : (kSmemLists ? 5 : (TOP1 ? 7 : 6));
     static constexpr int kOffLists = kStages * kStageBytes;
     static constexpr int kOffBuf = kOffLists + kListBytes;
     static constexpr int kOffBar = kOffBuf + kBufBytes;
@@ -435,7 +446,7 @@ __device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_
     }
 }
 
-template <int R, int CG, bool TOP1>
+template <int R, int CG, bool TOP1, bool DEEP>
 __global__ void __launch_bounds__(k2::kThreads, 1)
 topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const __grid_constant__ CUtensorMap tmap_d, uint32_t n, int b, int k,
@@ -444,7 +455,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     uint32_t* __restrict__ ws_prog, unsigned long long* __restrict__ dbg, int epi_mode,
                     int d_hint, int window) {
     using namespace k2;
-    using C = Cfg<CG, R, TOP1>;
+    using C = Cfg<CG, R, TOP1, DEEP>;
     constexpr int L = 32 * R;
     constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -869,14 +880,14 @@ int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
     return kHdrBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8 * (R > 1 ? 2 : 1);
 }
 
-template <int R, int CG, bool TOP1>
+template <int R, int CG, bool TOP1, bool DEEP>
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
                             int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
                             uint32_t* ws_tau, uint32_t* ws_prog, float* out_score, int64_t* out_idx, int64_t idx_offset,
                             cudaStream_t stream) {
-    using C = k2::Cfg<CG, R, TOP1>;
+    using C = k2::Cfg<CG, R, TOP1, DEEP>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1>,
+    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1, DEEP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("topk_batched: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     if (n_dtiles > 0) {
@@ -892,7 +903,7 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1>, tq, td, static_cast<uint32_t>(n), b, k,
+        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1, DEEP>, tq, td, static_cast<uint32_t>(n), b, k,
                                n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog,
                                reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
@@ -945,16 +956,18 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         if (rc != 0) return rc;
         float* os = out_score + static_cast<int64_t>(q0) * k;
         int64_t* oi = out_idx + static_cast<int64_t>(q0) * k;
-        if (k == 1) {
-            rc = launch_batched_r<1, CG, true>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream);
-            if (rc != 0) return rc;
-            continue;
-        }
-        switch (R) {
-            case 1: rc = launch_batched_r<1, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream); break;
-            case 2: rc = launch_batched_r<2, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream); break;
-            default: rc = launch_batched_r<4, CG, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream); break;
-        }
+        // deep ring only when a pair has its d-tiles to itself (see Cfg)
+        const bool deep = (CG == 2) && (n_qt == 1);
+#define SQE_K2_LAUNCH(R_, TOP1_)                                                                        \
+    (deep ? launch_batched_r<R_, CG, TOP1_, (CG == 2)>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, \
+                                                       ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream) \
+          : launch_batched_r<R_, CG, TOP1_, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc,     \
+                                                   ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream))
+        if (k == 1) rc = SQE_K2_LAUNCH(1, true);
+        else if (R == 1) rc = SQE_K2_LAUNCH(1, false);
+        else if (R == 2) rc = SQE_K2_LAUNCH(2, false);
+        else rc = SQE_K2_LAUNCH(4, false);
+#undef SQE_K2_LAUNCH
         if (rc != 0) return rc;
     }
     return 0;

@@ -98,7 +98,9 @@ exchange_merge_kernel(const float* __restrict__ scores, const int64_t* __restric
         const long long t0 = clock64();
         unsigned spins = 0;
         while (static_cast<int>(ld_relaxed_sys(my_flags + lane) - epoch) < 0) {
-            if ((++spins & 0xfffu) == 0 && clock64() - t0 > 8000000000LL) __trap();   // a peer died
+            // a peer may legitimately arrive late (it is a collective: shard loading, a slow host);
+            // give up only after ~10 minutes, like a collective library's watchdog would
+            if ((++spins & 0xfffu) == 0 && clock64() - t0 > (1LL << 40)) __trap();
         }
         fence_acq_rel_sys();                                // flag reads before the data reads
     }

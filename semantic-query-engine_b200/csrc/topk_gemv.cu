@@ -211,11 +211,26 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
     __threadfence();
     const uint64_t* all = ws_lists + static_cast<int64_t>(query) * gridDim.x * L;
     list.clear();
-    for (int c = warp; c < static_cast<int>(gridDim.x); c += kGemvWarps) {
-        WarpList<R> other;
+    {
+        // each warp folds every 8th CTA list; the next list is fetched while the current merges
+        uint64_t nxt[R];
+        int c = warp;
+        if (c < static_cast<int>(gridDim.x)) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) other.key[r] = __ldcg(all + static_cast<int64_t>(c) * L + r * 32 + lane);
-        list.merge_sorted(other.key, lane);
+            for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(c) * L + r * 32 + lane);
+        }
+        while (c < static_cast<int>(gridDim.x)) {
+            WarpList<R> other;
+#pragma unroll
+            for (int r = 0; r < R; ++r) other.key[r] = nxt[r];
+            const int cn = c + kGemvWarps;
+            if (cn < static_cast<int>(gridDim.x)) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(cn) * L + r * 32 + lane);
+            }
+            list.merge_sorted(other.key, lane);
+            c = cn;
+        }
     }
     __syncthreads();                                   // s_lists reuse
     list.store(s_lists[warp], lane);

@@ -16,10 +16,12 @@ from ._native import NativeLibraryMissing, SqeError
 from .cache import CACHE_SIM_THRESHOLD, REDIS_CACHE_LIST, REDIS_MAX_ITEMS, GpuQueryCache
 from .corpus import EMBED_DIM, GpuCorpusIndex
 from .sharded import ShardedCorpusIndex, shard_bounds
+from .serving import MicroBatcher, UserIndexRegistry, build_context_text, group_hits_by_doc
 from . import ops, plugin
 
 __all__ = [
     "GpuCorpusIndex", "GpuQueryCache", "ShardedCorpusIndex", "shard_bounds", "ops", "plugin",
+    "MicroBatcher", "UserIndexRegistry", "build_context_text", "group_hits_by_doc",
     "NativeLibraryMissing", "SqeError", "EMBED_DIM", "CACHE_SIM_THRESHOLD", "REDIS_MAX_ITEMS",
     "REDIS_CACHE_LIST",
 ]

@@ -232,20 +232,24 @@ class GpuCorpusIndex:
         try:
             q = self._as_rows(query_emb)[:1]                             # main.py:355 sends row 0
             scores, rows = self.search_batch(q, k)
-            results = []
-            for s, r in zip(scores[0], rows[0]):
-                if r < 0:
-                    continue
-                s = float(s)
-                if self.score_mode == "opensearch":
-                    s = 1.0 / (2.0 - s)
-                results.append((self._source(int(r)), s))
-            return results
+            return self.hits_from_rows(scores[0], rows[0])
         except Exception as e:                                           # main.py:371-373
             if self.strict:
                 raise
             print(f"[GpuCorpusIndex] Search error: {e}")
             return []
+
+    def hits_from_rows(self, scores, rows) -> List[Tuple[Dict[str, str], float]]:
+        """(score, row) arrays of ONE query -> the reference's hit list (main.py:364-367)."""
+        results = []
+        for s, r in zip(scores, rows):
+            if r < 0:
+                continue
+            s = float(s)
+            if self.score_mode == "opensearch":
+                s = 1.0 / (2.0 - s)
+            results.append((self._source(int(r)), s))
+        return results
 
     def _source(self, row: int) -> Dict[str, str]:
         if self.keep_payload and row < len(self._docs):

@@ -42,3 +42,16 @@ def install(main_module, *, dtype: str = "bf16", cache_dtype: str = "fp32", devi
     main_module.lfu_cache_put = lfu_cache_put
     main_module._sqe_b200_cache = cache
     return cache
+
+
+def install_embedding_gen(module, *, dtype: str = "bf16", device=None, strict: bool = False):
+    """Patch a loaded reference `embedding_gen` module (the upload micro-service): its
+    `init_user_index(user_id)` and `bulk_index_embeddings(user_id, doc_id, embeddings, chunks)`
+    (embedding_gen.py:83, :196) then build / fill per-user `GpuCorpusIndex` objects."""
+    from .serving import UserIndexRegistry
+    base = getattr(module, "BASE_OPENSEARCH_INDEX_NAME", "docs")
+    reg = UserIndexRegistry(base, dtype=dtype, device=device, strict=strict)
+    module.init_user_index = lambda user_id: (reg.init_user_index(user_id), None)[1]
+    module.bulk_index_embeddings = reg.bulk_index_embeddings
+    module._sqe_b200_registry = reg
+    return reg

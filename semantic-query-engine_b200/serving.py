@@ -1,0 +1,169 @@
+"""Callers and data formats on either side of the path (SURVEY.md §8f "next" rows).
+
+* `UserIndexRegistry` -- the per-user index namespaces of the upload micro-service
+  (/root/reference/app/embedding_gen.py:83-122 `init_user_index`, :196-257
+  `bulk_index_embeddings`): one `GpuCorpusIndex` per `"{BASE}-{user_id}"`.
+* `MicroBatcher` -- handler-level micro-batching: the reference's handlers issue ONE query
+  per request (app/main.py:499, :684); under concurrent load those single queries are
+  coalesced into one batched search, i.e. one tensor-core launch (K2) instead of N streaming
+  passes over the shard (K3), and every request still gets exactly its own result.
+* `group_hits_by_doc` / `build_context_text` -- the step right after the path
+  (app/main.py:500-513): chunks of the same document are concatenated in hit order.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import time
+from concurrent.futures import Future
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .corpus import GpuCorpusIndex
+
+BASE_OPENSEARCH_INDEX_NAME = os.getenv("OPENSEARCH_INDEX_NAME", "")   # embedding_gen.py:38
+
+
+# --------------------------------------------------------------------- per-user indices
+class UserIndexRegistry:
+    """Drop-in for the module-level functions of embedding_gen.py."""
+
+    def __init__(self, base_name: str = BASE_OPENSEARCH_INDEX_NAME, **index_kwargs):
+        self.base_name = base_name
+        self.index_kwargs = index_kwargs
+        self._lock = threading.Lock()
+        self._indices: Dict[str, GpuCorpusIndex] = {}
+
+    def index_name(self, user_id: str) -> str:
+        return f"{self.base_name}-{user_id}"                      # embedding_gen.py:91, :211
+
+    def init_user_index(self, user_id: str) -> GpuCorpusIndex:
+        """embedding_gen.py:83-122: create the user's index if it does not exist yet."""
+        name = self.index_name(user_id)
+        with self._lock:
+            idx = self._indices.get(name)
+            if idx is None:
+                idx = GpuCorpusIndex(None, name, **self.index_kwargs)
+                self._indices[name] = idx
+            else:
+                print(f"[INFO] Index '{name}' already exists.")    # embedding_gen.py:93
+            return idx
+
+    def bulk_index_embeddings(self, user_id: str, doc_id: str, embeddings: np.ndarray,
+                              chunks: Sequence[str]) -> None:
+        """embedding_gen.py:196-257: all chunks of one document into the user's index,
+        `_id = f"{doc_id}_{chunk_index}"`; rows are normalised on the GPU (K1)."""
+        if embeddings is None or getattr(embeddings, "size", 0) == 0:
+            print("[ERROR] Missing OpenSearch client or embeddings => cannot index.")   # :207-209
+            return
+        idx = self.init_user_index(user_id)
+        idx.add_document_chunks(doc_id, embeddings, chunks)
+
+    def get(self, user_id: str) -> Optional[GpuCorpusIndex]:
+        return self._indices.get(self.index_name(user_id))
+
+    def search(self, user_id: str, query_emb: np.ndarray, k: int = 3):
+        idx = self.get(user_id)
+        return [] if idx is None else idx.search(query_emb, k)
+
+
+# ------------------------------------------------------------------- micro-batching
+class MicroBatcher:
+    """Coalesce concurrent single-query `search` calls into batched launches.
+
+    `search(query_emb, k)` blocks like `GpuCorpusIndex.search` and returns the same list;
+    `submit(query_emb, k)` returns a `concurrent.futures.Future` (wrap it with
+    `asyncio.wrap_future` inside the FastAPI handlers).  A background thread drains the queue:
+    it waits at most `max_wait_s` after the first request for more to arrive (or until
+    `max_batch` are queued), runs ONE `search_batch` with the largest k requested and slices
+    each request's rows out of it (a top-k list is a prefix of a longer top-k list)."""
+
+    def __init__(self, index: GpuCorpusIndex, max_batch: int = 256, max_wait_s: float = 200e-6):
+        self.index = index
+        self.max_batch = int(max_batch)
+        self.max_wait_s = float(max_wait_s)
+        self._cv = threading.Condition()
+        self._queue: List[Tuple[np.ndarray, int, Future]] = []
+        self._stop = False
+        self.batches = 0               # batched launches issued
+        self.requests = 0              # requests served
+        self._thread = threading.Thread(target=self._run, name="sqe-microbatcher", daemon=True)
+        self._thread.start()
+
+    # -- client side
+    def submit(self, query_emb: np.ndarray, k: int = 3) -> Future:
+        fut: Future = Future()
+        if query_emb is None or getattr(query_emb, "size", 0) == 0:     # main.py:350-351
+            fut.set_result([])
+            return fut
+        q = self.index._as_rows(query_emb)[:1]
+        with self._cv:
+            if self._stop:
+                raise RuntimeError("MicroBatcher is closed")
+            self._queue.append((q, int(k), fut))
+            self._cv.notify()
+        return fut
+
+    def search(self, query_emb: np.ndarray, k: int = 3):
+        return self.submit(query_emb, k).result()
+
+    def close(self) -> None:
+        with self._cv:
+            self._stop = True
+            self._cv.notify()
+        self._thread.join()
+
+    # -- server side
+    def _take(self) -> List[Tuple[np.ndarray, int, Future]]:
+        with self._cv:
+            while not self._queue and not self._stop:
+                self._cv.wait()
+            if not self._queue:
+                return []
+            deadline = time.perf_counter() + self.max_wait_s
+            while len(self._queue) < self.max_batch and not self._stop:
+                left = deadline - time.perf_counter()
+                if left <= 0:
+                    break
+                self._cv.wait(left)
+            batch, self._queue = self._queue[: self.max_batch], self._queue[self.max_batch:]
+            return batch
+
+    def _run(self) -> None:
+        while True:
+            batch = self._take()
+            if not batch:
+                if self._stop:
+                    return
+                continue
+            try:
+                q = np.concatenate([b[0] for b in batch], axis=0)
+                kmax = max(b[1] for b in batch)
+                scores, rows = self.index.search_batch(q, kmax)
+                self.batches += 1
+                self.requests += len(batch)
+                for i, (_, k, fut) in enumerate(batch):
+                    fut.set_result(self.index.hits_from_rows(scores[i, :k], rows[i, :k]))
+            except Exception as e:                                   # main.py:371-373 -> []
+                for _, _, fut in batch:
+                    if self.index.strict:
+                        fut.set_exception(e)
+                    else:
+                        fut.set_result([])
+
+
+# ------------------------------------------------------- the step right after the path
+def group_hits_by_doc(hits) -> Dict[str, str]:
+    """What main.py:500-507 builds: for every doc_id (first-seen order) the texts of its chunks
+    in hit order, joined by newlines."""
+    per_doc: Dict[str, List[str]] = {}
+    for source, _score in hits:
+        per_doc.setdefault(source["doc_id"], []).append(source["text"])
+    return {doc_id: "\n".join(texts) for doc_id, texts in per_doc.items()}
+
+
+def build_context_text(hits) -> str:
+    """The prompt context of main.py:509-513: one '--- Document ID: x ---' block per document."""
+    return "".join(f"--- Document ID: {doc_id} ---\n{text}\n\n"
+                   for doc_id, text in group_hits_by_doc(hits).items())

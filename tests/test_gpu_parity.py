@@ -333,6 +333,60 @@ def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
         np.testing.assert_array_equal(sa, sb)
 
 
+def test_user_index_registry_mirrors_embedding_gen(sqe):
+    """embedding_gen.py:83-122, :196-257: per-user indices, `_id = f"{doc_id}_{chunk_index}"`."""
+    import types
+    rng = np.random.default_rng(12)
+    mod = types.SimpleNamespace(BASE_OPENSEARCH_INDEX_NAME="docs")
+    reg = sqe.plugin.install_embedding_gen(mod, dtype="fp32", strict=True)
+    e1 = rng.standard_normal((7, DIM)).astype(np.float32)
+    e2 = rng.standard_normal((4, DIM)).astype(np.float32)
+    assert mod.init_user_index("alice") is None
+    mod.bulk_index_embeddings("alice", "PMC1", e1, [f"a{i}" for i in range(7)])
+    mod.bulk_index_embeddings("alice", "PMC2", e2, [f"b{i}" for i in range(4)])
+    mod.bulk_index_embeddings("bob", "PMC9", e2, [f"c{i}" for i in range(4)])
+    mod.bulk_index_embeddings("bob", "PMC9", np.array([]), [])             # :207-209 -> ignored
+    alice, bob = reg.get("alice"), reg.get("bob")
+    assert alice.index_name == "docs-alice" and alice.num_rows == 11 and bob.num_rows == 4
+    assert [alice.doc_id_of(r) for r in (0, 6, 7, 10)] == ["PMC1_0", "PMC1_6", "PMC2_0", "PMC2_3"]
+    np.testing.assert_array_equal(alice.shard.cpu().numpy().view(np.uint32),
+                                  oracle.normalize_rows(np.concatenate([e1, e2])).view(np.uint32))
+    hits = reg.search("alice", e2[2:3] * 4.0, k=2)
+    assert hits[0][0] == {"doc_id": "PMC2", "text": "b2"} and abs(hits[0][1] - 1.0) < 1e-5
+    assert reg.search("nobody", e2[:1]) == []
+
+
+def test_micro_batcher_coalesces_concurrent_requests(sqe):
+    """concurrent single-query requests are served by a few batched launches
+    and every request gets exactly the result of its own `search` call."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(13)
+    n = 50_000
+    emb = make_corpus(rng, n)
+    index = sqe.GpuCorpusIndex(dtype="bf16", strict=True)
+    index.add_embeddings(emb, [{"doc_id": f"doc{i // 9}", "text": f"chunk {i}"} for i in range(n)])
+    queries = rng.standard_normal((192, 1, DIM)).astype(np.float32)
+    queries[5, 0] = emb[7]                                   # planted duplicates 7 / 33 / n-1
+    ks = [3 + (i % 3) * 2 for i in range(len(queries))]      # mixed k: 3, 5, 7
+    want = [index.search(q, k=k) for q, k in zip(queries, ks)]
+    mb = sqe.MicroBatcher(index, max_batch=64, max_wait_s=2e-3)
+    try:
+        with ThreadPoolExecutor(max_workers=32) as pool:
+            got = list(pool.map(lambda a: mb.search(a[0], a[1]), zip(queries, ks)))
+        assert mb.search(np.array([]), 3) == []              # main.py:350-351
+    finally:
+        mb.close()
+    assert mb.requests == len(queries) and mb.batches < len(queries) // 2, (mb.batches, mb.requests)
+    for g, w, k in zip(got, want, ks):
+        assert len(g) == len(w) == k
+        assert [h[0] for h in g] == [h[0] for h in w]        # same chunks, same order
+        np.testing.assert_allclose([h[1] for h in g], [h[1] for h in w], atol=K2_TOL)
+    assert [h[0]["text"] for h in got[5][:3]] == ["chunk 7", "chunk 33", f"chunk {n - 1}"]
+    ctx = sqe.group_hits_by_doc(got[5])                      # main.py:500-507
+    assert ctx["doc0"].split("\n")[0] == "chunk 7" and "chunk 33" in ctx["doc3"]
+    assert sqe.build_context_text(got[5]).startswith("--- Document ID: doc0 ---\nchunk 7")
+
+
 def test_query_cache_edge_cases(sqe):
     rng = np.random.default_rng(3)
     cache = sqe.GpuQueryCache(max_items=4, threshold=0.96)

@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SQE_BENCH_WORKLOAD", "b1024"),
-                    choices=["b1024", "b1", "cache64", "ingest", "config1"])
+                    choices=["b1024", "b1", "cache64", "ingest", "config1", "serve"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=None,
@@ -250,6 +250,8 @@ def main():
         return run_ingest(args, torch, ops, nat, dev, peaks)
     if args.workload == "config1":
         return run_config1(args, torch, sqe_b200, nat, dev, peaks)
+    if args.workload == "serve":
+        return run_serve(args, torch, sqe_b200, nat, dev, peaks)
     is_cache = args.workload == "cache64"
     b = {"b1024": 1024, "b1": 1, "cache64": 64}[args.workload]
     if args.batch and args.workload == "b1024":
@@ -474,6 +476,72 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_serve(args, torch, sqe_b200, nat, dev, peaks):
+    """Handler-level micro-batching: `clients` threads each issue single-query
+    `search(q, k)` calls as the reference's handlers do (main.py:499, :684) against a resident
+    10M x 1024 bf16 corpus; a MicroBatcher coalesces what arrives within 0.5 ms into one batched
+    launch.  Reported: requests/s and latency, next to the same clients calling the index
+    directly (one streaming pass per request)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rows, k, clients = args.rows, args.k, 256
+    per_client = args.steps or 8
+    index = sqe_b200.GpuCorpusIndex(dtype=args.dtype, device=dev, keep_payload=False)
+    index.reserve(rows)
+    gen = torch.Generator(device=dev)
+    for blk in range((rows + GEN_BLOCK - 1) // GEN_BLOCK):
+        gen.manual_seed(1234 + blk)
+        n = min(GEN_BLOCK, rows - blk * GEN_BLOCK)
+        index.add_device_rows(torch.randn((n, DIM), generator=gen, device=dev, dtype=torch.float32))
+    qs = np.random.default_rng(3).standard_normal((clients, per_client, 1, DIM)).astype(np.float32)
+
+    def client(fn, c, lat):
+        for r in range(per_client):
+            t0 = time.perf_counter()
+            fn(qs[c, r], k)
+            lat.append(time.perf_counter() - t0)
+
+    def drive(fn, n_clients):
+        lat = []
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=n_clients) as pool:
+            list(pool.map(lambda c: client(fn, c, lat), range(n_clients)))
+        dt = time.perf_counter() - t0
+        lat.sort()
+        return n_clients * per_client / dt, lat[len(lat) // 2] * 1e3, lat[int(len(lat) * 0.99)] * 1e3
+
+    mb = sqe_b200.MicroBatcher(index, max_batch=256, max_wait_s=500e-6)
+    drive(mb.search, 64)                                               # warm-up
+    l0 = nat.launch_count
+    qps_mb, p50_mb, p99_mb = drive(mb.search, clients)
+    launches = nat.launch_count - l0
+    batches, served = mb.batches, mb.requests
+    mb.close()
+    lock = __import__("threading").Lock()
+
+    def direct(q, kk):
+        with lock:                                                     # one stream: requests serialise
+            return index.search(q, kk)
+    qps_direct, p50_d, p99_d = drive(direct, 16)
+    line = {"metric": "requests/sec, concurrent single-query clients, cosine top-10 @10Mx1024 (micro-batched)",
+            "value": qps_mb, "unit": "queries/s", "n_gpus": 1, "steps": per_client, "warmup": 1,
+            "ms_per_step": p50_mb, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{rows}x1024 {args.dtype} corpus, {clients} client threads x {per_client} "
+                                   f"single-query requests, top-{k}, MicroBatcher(max_batch=256, max_wait=0.5 ms)",
+                       "rows": rows, "clients": clients, "l2": "inputs larger than L2"},
+            "clocks": None,
+            "e2e": {"value": qps_mb, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": k * 12,
+                    "latency_ms_p50": p50_mb, "latency_ms_p99": p99_mb},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
+                         "kernel": "topk_batched_kernel", "traffic": None,
+                         "note": f"{served} requests in {batches} batched launches (mean batch {served / max(batches, 1):.0f})"},
+            "cpu_baseline": None,
+            "direct_b1": {"value": qps_direct, "unit": "queries/s", "clients": 16, "latency_ms_p50": p50_d,
+                          "latency_ms_p99": p99_d, "note": "same clients calling GpuCorpusIndex.search directly"}}
+    print(json.dumps(line), flush=True)
 
 
 def run_config1(args, torch, sqe_b200, nat, dev, peaks):

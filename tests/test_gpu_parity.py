@@ -381,7 +381,8 @@ def test_micro_batcher_coalesces_concurrent_requests(sqe):
         assert len(g) == len(w) == k
         assert [h[0] for h in g] == [h[0] for h in w]        # same chunks, same order
         np.testing.assert_allclose([h[1] for h in g], [h[1] for h in w], atol=K2_TOL)
-    assert [h[0]["text"] for h in got[5][:3]] == ["chunk 7", "chunk 33", f"chunk {n - 1}"]
+    texts = [h[0]["text"] for h in got[5]]                   # rows 7 / 33 / n-1 are bit-identical, 40 is 3x row 7
+    assert texts[0] == "chunk 7" and texts.index("chunk 7") < texts.index("chunk 33") < texts.index(f"chunk {n - 1}")
     ctx = sqe.group_hits_by_doc(got[5])                      # main.py:500-507
     assert ctx["doc0"].split("\n")[0] == "chunk 7" and "chunk 33" in ctx["doc3"]
     assert sqe.build_context_text(got[5]).startswith("--- Document ID: doc0 ---\nchunk 7")

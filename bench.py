@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--k2-window", type=int, default=None, help="progress window in d-tiles (tuning experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-yardstick", action="store_true",
+                    help="skip the cuBLAS GEMM of the same shape reported beside the tensor roofline")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the batch-1 measurement that rides along with the b1024 workload")
     return ap.parse_args()
@@ -368,6 +370,37 @@ def main():
                     "frac_of_sustained_peak": None}
         if peaks.get("bf16_tflops_sustained"):
             roofline["frac_of_sustained_peak"] = roofline["achieved"] / peaks["bf16_tflops_sustained"]
+    if roofline["bound"] == "tensor" and world == 1 and not args.no_yardstick:
+        # Yardstick, not the product path: a cuBLAS bf16 GEMM of the same shape (1M-row slices of
+        # the shard, no selection, bf16 output written) run back to back for the same number of
+        # launches -- what this box, at its power cap, gives a plain library GEMM right now.
+        try:
+            tdt = ops.TORCH_DTYPES[dtype]
+            chunk = min(local_rows, 1_000_000)
+            yout = torch.empty((b, chunk), dtype=tdt, device=dev)
+
+            def gemm_pass():
+                for lo in range(0, local_rows, chunk):
+                    hi = min(local_rows, lo + chunk)
+                    torch.matmul(qn, shard[lo:hi].T, out=yout[:, : hi - lo])
+            for _ in range(2):
+                gemm_pass()
+            torch.cuda.synchronize()
+            y0 = torch.cuda.Event(enable_timing=True)
+            y1 = torch.cuda.Event(enable_timing=True)
+            y0.record()
+            for _ in range(kiters):
+                gemm_pass()
+            y1.record()
+            torch.cuda.synchronize()
+            yms = y0.elapsed_time(y1) / kiters
+            roofline["yardstick"] = {"what": "cuBLAS GEMM of the same shape on this box in this run (torch.matmul, "
+                                             "no top-k, output written), same number of back-to-back passes",
+                                     "tflops": alg / (yms * 1e-3) / 1e12, "ms": yms,
+                                     "ours_over_yardstick": (alg / (kms * 1e-3)) / (alg / (yms * 1e-3))}
+            del yout
+        except Exception as e:                      # never let the yardstick break the bench line
+            roofline["yardstick"] = {"error": str(e)[:200]}
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
     roofline["kernel"] = kname
     roofline["kernel_ms"] = kms
@@ -448,9 +481,9 @@ def main():
         # the oracle port on this box's host cores, a bounded sample of about 10-20 s of CPU work
         cores = len(os.sched_getaffinity(0))
         if b > 1:
-            cb, crow, reps = (64, 250_000, 8) if is_cache else (512, 1_000_000, 2)
+            cb, crow, reps = (64, 250_000, 16) if is_cache else (512, 1_000_000, 8)
         else:
-            cb, crow, reps = 1, 1_000_000, 100                    # 100 single-query calls, as the reference issues them
+            cb, crow, reps = 1, 1_000_000, 400                    # single-query calls, as the reference issues them
         cpu_reference_sample(cb if b == 1 else 16, crow, k, total_rows)      # corpus + warm BLAS threads
         t_cpu, qps_acc = 0.0, []
         for r in range(reps):

@@ -55,6 +55,7 @@ class GpuCorpusIndex:
         self.keep_payload = keep_payload
         self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
         self._lock = threading.Lock()           # add_embeddings runs in an executor (main.py:454-455)
+        self._search_lock = threading.Lock()    # the pinned staging buffers are per index
         self._rows = 0                          # published row count
         self._capacity = 0
         self._shard: Optional[torch.Tensor] = None
@@ -193,7 +194,7 @@ class GpuCorpusIndex:
         """Batched form of `search`: host fp32 [B,1024] in, host (scores [B,k] fp32,
         rows [B,k] int64) out, best-first; empty slots are (-inf, -1)."""
         q = self._as_rows(query_emb)
-        with torch.cuda.device(self.device):
+        with self._search_lock, torch.cuda.device(self.device):
             qd = self._stage_queries(q)
             buf, s, i = ops.packed_topk_out(self.device, q.shape[0], k)
             self.search_device(qd, k, out=(s, i))

@@ -90,7 +90,12 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int query = blockIdx.y;
+    // grid = (queries, CTAs per query): the query is the FAST index, so the CTAs resident at any
+    // moment are the same row ranges for all queries -- a row leaves HBM once and the other
+    // queries' CTAs read it from L2 (one HBM pass for a small batch instead of one per query)
+    const int query = blockIdx.x;
+    const int cta = blockIdx.y;
+    const int nctas = gridDim.y;
 
     // the query in registers, same element layout as a row's loads
     float q[32];
@@ -135,8 +140,8 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
     list.clear();
     uint64_t worst = 0ull;
 
-    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kGemvWarps;
-    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kGemvWarps + warp;
+    const int64_t warps_total = static_cast<int64_t>(nctas) * kGemvWarps;
+    const int64_t gw = static_cast<int64_t>(cta) * kGemvWarps + warp;
     for (int64_t base = gw * RPW; base < n; base += warps_total * RPW) {
         uint4 raw[RPW][LOADS];
 #pragma unroll
@@ -188,7 +193,7 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
     // ---- CTA merge: 8 warp lists -> 1 ----
     list.store(s_lists[warp], lane);
     __syncthreads();
-    uint64_t* my_slot = ws_lists + (static_cast<int64_t>(query) * gridDim.x + blockIdx.x) * L;
+    uint64_t* my_slot = ws_lists + (static_cast<int64_t>(query) * nctas + cta) * L;
     if (warp == 0) {
 #pragma unroll 1
         for (int w = 1; w < kGemvWarps; ++w) {
@@ -201,7 +206,7 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
         __syncwarp();
         if (lane == 0) {
             const unsigned ticket = atomicAdd(ws_counter + query, 1u);
-            s_is_last = (ticket == gridDim.x - 1) ? 1 : 0;
+            s_is_last = (ticket == static_cast<unsigned>(nctas) - 1) ? 1 : 0;
         }
     }
     __syncthreads();
@@ -209,22 +214,22 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
 
     // ---- grid merge by the last CTA of this query ----
     __threadfence();
-    const uint64_t* all = ws_lists + static_cast<int64_t>(query) * gridDim.x * L;
+    const uint64_t* all = ws_lists + static_cast<int64_t>(query) * nctas * L;
     list.clear();
     {
         // each warp folds every 8th CTA list; the next list is fetched while the current merges
         uint64_t nxt[R];
         int c = warp;
-        if (c < static_cast<int>(gridDim.x)) {
+        if (c < nctas) {
 #pragma unroll
             for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(c) * L + r * 32 + lane);
         }
-        while (c < static_cast<int>(gridDim.x)) {
+        while (c < nctas) {
             WarpList<R> other;
 #pragma unroll
             for (int r = 0; r < R; ++r) other.key[r] = nxt[r];
             const int cn = c + kGemvWarps;
-            if (cn < static_cast<int>(gridDim.x)) {
+            if (cn < nctas) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(cn) * L + r * 32 + lane);
             }
@@ -281,7 +286,7 @@ static int launch_gemv_t(const void* D, int64_t n, const void* Q, bool raw_q, in
         e = cudaMemsetAsync(ws_counter, 0, static_cast<size_t>(nq) * 4, stream);
         if (e != cudaSuccess) { set_error("gemv: memset: %s", cudaGetErrorString(e)); return -2; }
     }
-    dim3 grid(gx, nq), block(kGemvWarps * 32);
+    dim3 grid(nq, gx), block(kGemvWarps * 32);
     if (raw_q)
         topk_gemv_kernel<T, R, true><<<grid, block, 0, stream>>>(
             static_cast<const T*>(D), n, Q, k, ws_lists, ws_counter, out_score, out_idx, idx_offset);

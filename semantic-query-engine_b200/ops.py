@@ -17,6 +17,12 @@ TORCH_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.flo
 _NAMES = {v: k for k, v in TORCH_DTYPES.items()}
 
 _workspaces = {}
+# A call = (memset +) kernels that share one workspace.  Two host threads launching on the same
+# stream must not interleave their launches (thread B's memset would land before thread A's
+# kernel and B would then see A's leftovers), so every workspace-using call is enqueued under
+# this lock.  It only covers the (asynchronous) enqueue, not the execution.
+import threading as _threading
+_launch_lock = _threading.Lock()
 
 
 def dtype_name(t: torch.Tensor) -> str:
@@ -107,7 +113,7 @@ def topk_gemv(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
     scores, idx = _outputs(out, dev, b, k)
     if b == 0:
         return scores, idx
-    with torch.cuda.device(dev):
+    with _launch_lock, torch.cuda.device(dev):
         need = nat.load().sqe_topk_gemv_workspace_bytes(b, k)
         ws = _workspace(dev, "gemv", need)
         nat.call("sqe_topk_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
@@ -131,7 +137,7 @@ def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 
     scores, idx = _outputs(out, dev, b, k)
     if b == 0:
         return scores, idx
-    with torch.cuda.device(dev):
+    with _launch_lock, torch.cuda.device(dev):
         need = nat.load().sqe_topk_gemv_workspace_bytes(b, k)
         ws = _workspace(dev, "gemv", need)
         nat.call("sqe_search_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
@@ -147,7 +153,7 @@ def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
     scores, idx = _outputs(out, dev, b, k)
     if b == 0:
         return scores, idx
-    with torch.cuda.device(dev):
+    with _launch_lock, torch.cuda.device(dev):
         need = nat.load().sqe_topk_batched_workspace_bytes(rows, b, k)
         ws = _workspace(dev, "batched", need)
         nat.call("sqe_topk_batched", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows,
@@ -185,7 +191,7 @@ def cache_top1(C: torch.Tensor, Q: torch.Tensor, threshold: float, path: int = 0
         idx, score, hit = out
     if b == 0:
         return idx, score, hit
-    with torch.cuda.device(dev):
+    with _launch_lock, torch.cuda.device(dev):
         need = nat.load().sqe_cache_top1_workspace_bytes(rows, b)
         ws = _workspace(dev, "cache", need)
         nat.call("sqe_cache_top1", C.data_ptr(), nat.DTYPE_CODES[dtype_name(C)], rows, nat.SQE_DIM,

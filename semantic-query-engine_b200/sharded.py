@@ -167,7 +167,7 @@ class ShardedCorpusIndex:
             return s.cpu().numpy(), i.cpu().numpy()
         from . import ops
         q = self.local._as_rows(query_emb)
-        with torch.cuda.device(dev):
+        with self.local._search_lock, torch.cuda.device(dev):
             qd = self.local._stage_queries(q)                  # reusable pinned staging
             buf, s, i = ops.packed_topk_out(dev, q.shape[0], k)
             self.search_device(qd, k, out=(s, i))

@@ -333,6 +333,23 @@ def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
         np.testing.assert_array_equal(sa, sb)
 
 
+def test_concurrent_searches_from_many_threads_are_safe(sqe):
+    """Unlike the reference (one event-loop thread) callers may search from several threads:
+    launches that share a workspace are enqueued atomically, staging buffers are per call."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(14)
+    emb = make_corpus(rng, 60_000)
+    index = sqe.GpuCorpusIndex(dtype="bf16", strict=True, keep_payload=False)
+    index.add_embeddings(emb, None)
+    qs = [rng.standard_normal((b, DIM)).astype(np.float32) for b in (1, 1, 5, 130, 1, 64, 300, 1) * 6]
+    want = [index.search_batch(q, 10) for q in qs]
+    with ThreadPoolExecutor(max_workers=12) as pool:
+        got = list(pool.map(lambda q: index.search_batch(q, 10), qs))
+    for (gs, gi), (ws_, wi) in zip(got, want):
+        np.testing.assert_array_equal(gi, wi)
+        np.testing.assert_array_equal(gs, ws_)
+
+
 def test_user_index_registry_mirrors_embedding_gen(sqe):
     """embedding_gen.py:83-122, :196-257: per-user indices, `_id = f"{doc_id}_{chunk_index}"`."""
     import types

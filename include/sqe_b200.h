@@ -50,6 +50,11 @@ extern "C" {
 #define SQE_F32 0
 #define SQE_BF16 1
 #define SQE_F16 2
+/* split bf16: every value stored as hi = bf16(x) and lo = bf16(x - hi); a row is
+ * [hi[1024] | lo[1024]] = 4096 bytes; the stored value hi + lo is exact in fp32 (16 significant
+ * bits).  Gives the fp32 tolerance class (1e-5) on the bf16 tensor cores: K2 accumulates
+ * Ql.Dl + Qh.Dl + Ql.Dh + Qh.Dh (small terms first), K3 reconstructs hi + lo exactly. */
+#define SQE_BF16X2 3
 
 /* error codes */
 #define SQE_OK 0

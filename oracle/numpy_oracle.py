@@ -86,6 +86,12 @@ def to_storage(x: np.ndarray, dtype: str) -> np.ndarray:
         rounded = (u + (0x7FFF + ((u >> 16) & 1))) >> 16
         rounded = np.where(nan, (u >> 16) | 0x0040, rounded)
         return rounded.astype(np.uint16)
+    if dtype == "bf16x2":
+        # split bf16 (new storage class): hi = bf16(x), lo = bf16(x - hi), row = [hi | lo]
+        hi = to_storage(x, "bf16")
+        rest = x - from_storage(hi, "bf16")
+        lo = to_storage(rest.astype(np.float32), "bf16")
+        return np.concatenate([hi, lo], axis=-1)
     raise ValueError(dtype)
 
 
@@ -97,6 +103,10 @@ def from_storage(s: np.ndarray, dtype: str) -> np.ndarray:
         return np.asarray(s, dtype=np.float16).astype(np.float32)
     if dtype == "bf16":
         return (np.asarray(s, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+    if dtype == "bf16x2":
+        s = np.asarray(s, dtype=np.uint16)
+        d = s.shape[-1] // 2
+        return from_storage(s[..., :d], "bf16") + from_storage(s[..., d:], "bf16")   # exact in fp32
     raise ValueError(dtype)
 
 

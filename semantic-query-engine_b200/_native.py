@@ -14,11 +14,11 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsqe_b200.so")
 
-SQE_F32, SQE_BF16, SQE_F16 = 0, 1, 2
+SQE_F32, SQE_BF16, SQE_F16, SQE_BF16X2 = 0, 1, 2, 3
 SQE_DIM = 1024
 SQE_MAX_K_GEMV = 256
 SQE_MAX_K_BATCHED = 128
-DTYPE_CODES = {"fp32": SQE_F32, "bf16": SQE_BF16, "fp16": SQE_F16}
+DTYPE_CODES = {"fp32": SQE_F32, "bf16": SQE_BF16, "fp16": SQE_F16, "bf16x2": SQE_BF16X2}
 
 # every symbol include/sqe_b200.h declares: (name, restype, argtypes)
 PROTOTYPES = [

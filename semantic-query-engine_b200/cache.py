@@ -45,7 +45,7 @@ class GpuQueryCache:
         # raw embeddings are only needed to write the reference's JSON entry
         self.keep_raw = (redis_client is not None) if keep_raw is None else keep_raw
         self._lock = threading.Lock()
-        self._buf = torch.zeros((self.max_items, nat.SQE_DIM), dtype=ops.TORCH_DTYPES[dtype],
+        self._buf = torch.zeros((self.max_items, ops.ROW_ELEMS[dtype]), dtype=ops.TORCH_DTYPES[dtype],
                                 device=self.device)
         self._head = self.max_items             # live rows are [_head, max_items)
         self._entries: List[dict] = []          # list order, index 0 = newest

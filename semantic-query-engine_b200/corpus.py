@@ -74,7 +74,7 @@ class GpuCorpusIndex:
     def shard(self) -> torch.Tensor:
         """The stored rows [num_rows,1024] (a view of the HBM shard)."""
         if self._shard is None:
-            return torch.empty((0, EMBED_DIM), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
+            return torch.empty((0, ops.ROW_ELEMS[self.dtype]), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
         return self._shard[: self._rows]
 
     def reserve(self, rows: int) -> None:
@@ -86,7 +86,7 @@ class GpuCorpusIndex:
         if need <= self._capacity:
             return
         cap = max(need, self._initial_capacity, self._capacity * 2)
-        new = torch.empty((cap, EMBED_DIM), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
+        new = torch.empty((cap, ops.ROW_ELEMS[self.dtype]), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
         if self._shard is not None and self._rows:
             new[: self._rows].copy_(self._shard[: self._rows])
         self._shard = new
@@ -258,7 +258,10 @@ class GpuCorpusIndex:
         else:
             src = {"doc_id": str(row), "text": ""}
         if self.return_embedding:                                        # main.py:326-330
-            src["embedding"] = self._shard[row].float().cpu().tolist()
+            stored = self._shard[row].float().cpu()
+            if self.dtype == "bf16x2":
+                stored = stored[:EMBED_DIM] + stored[EMBED_DIM:]          # hi + lo
+            src["embedding"] = stored.tolist()
         return src
 
     def doc_id_of(self, row: int) -> str:
@@ -276,7 +279,7 @@ class GpuCorpusIndex:
         os.makedirs(path, exist_ok=True)
         with self._lock:
             rows = self._rows
-            esize = {"fp32": 4, "bf16": 2, "fp16": 2}[self.dtype]
+            row_bytes = ops.ROW_BYTES[self.dtype]
             with open(os.path.join(path, "shard.bin"), "wb") as f:
                 for lo in range(0, rows, chunk_rows):
                     blk = self._shard[lo: min(rows, lo + chunk_rows)]
@@ -286,7 +289,7 @@ class GpuCorpusIndex:
                 json.dump({"docs": self._docs, "ids": self._ids}, f)
             with open(os.path.join(path, "meta.json"), "w") as f:
                 json.dump({"format": self.FORMAT_VERSION, "rows": rows, "dim": EMBED_DIM,
-                           "dtype": self.dtype, "bytes": rows * EMBED_DIM * esize,
+                           "dtype": self.dtype, "bytes": rows * row_bytes,
                            "index_name": self.index_name, "normalised": True}, f)
 
     @classmethod
@@ -299,8 +302,7 @@ class GpuCorpusIndex:
             raise ValueError(f"unsupported shard file {path}: {meta}")
         index = cls(None, meta.get("index_name", ""), dtype=meta["dtype"], device=device, **kwargs)
         rows = int(meta["rows"])
-        esize = {"fp32": 4, "bf16": 2, "fp16": 2}[index.dtype]
-        row_bytes = EMBED_DIM * esize
+        row_bytes = ops.ROW_BYTES[index.dtype]
         size = os.path.getsize(os.path.join(path, "shard.bin"))
         if size != rows * row_bytes:
             raise ValueError(f"shard.bin has {size} bytes, expected {rows * row_bytes}")

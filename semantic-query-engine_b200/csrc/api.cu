@@ -65,7 +65,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 static int check_common(const char* who, const void* D, int dtype, int64_t n, int dim, const void* Q,
                         int nq) {
     if (dim != SQE_DIM) { set_error("%s: dim must be %d (got %d)", who, SQE_DIM, dim); return SQE_E_ARG; }
-    if (dtype < SQE_F32 || dtype > SQE_F16) { set_error("%s: bad dtype %d", who, dtype); return SQE_E_ARG; }
+    if (dtype < SQE_F32 || dtype > SQE_BF16X2) { set_error("%s: bad dtype %d", who, dtype); return SQE_E_ARG; }
     if (n < 0 || n >= 0xffffffffLL) { set_error("%s: n=%lld out of range", who, (long long)n); return SQE_E_ARG; }
     if (nq < 0) { set_error("%s: negative query count", who); return SQE_E_ARG; }
     if ((n > 0 && D == nullptr) || (nq > 0 && Q == nullptr)) { set_error("%s: null pointer", who); return SQE_E_ARG; }
@@ -122,7 +122,7 @@ int sqe_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int sqe_normalize_cast(const float* in, void* out, int64_t n, int dim, int out_dtype, void* stream) {
     if (dim != SQE_DIM) { set_error("normalize_cast: dim must be %d (got %d)", SQE_DIM, dim); return SQE_E_ARG; }
-    if (out_dtype < SQE_F32 || out_dtype > SQE_F16) { set_error("normalize_cast: bad dtype %d", out_dtype); return SQE_E_ARG; }
+    if (out_dtype < SQE_F32 || out_dtype > SQE_BF16X2) { set_error("normalize_cast: bad dtype %d", out_dtype); return SQE_E_ARG; }
     if (n < 0) { set_error("normalize_cast: negative n"); return SQE_E_ARG; }
     if (n == 0) return SQE_OK;
     if (!in || !out || !aligned16(in) || !aligned16(out)) { set_error("normalize_cast: null or unaligned pointer"); return SQE_E_ARG; }
@@ -187,7 +187,7 @@ int sqe_topk_batched(const void* D, int dtype, int64_t n, int dim, const void* Q
                      int64_t workspace_bytes, void* stream) {
     int rc = check_common("topk_batched", D, dtype, n, dim, Q, b);
     if (rc != SQE_OK) return rc;
-    if (dtype == SQE_F32) { set_error("topk_batched: fp32 shards use sqe_topk_gemv (tensor path is bf16/fp16)"); return SQE_E_UNSUPPORTED; }
+    if (dtype == SQE_F32) { set_error("topk_batched: fp32 shards use sqe_topk_gemv (tensor path is bf16/fp16/split bf16)"); return SQE_E_UNSUPPORTED; }
     if (k < 1 || k > SQE_MAX_K_BATCHED) { set_error("topk_batched: k=%d not in [1,%d]", k, SQE_MAX_K_BATCHED); return SQE_E_ARG; }
     if (b == 0) return SQE_OK;
     if (!out_score || !out_idx || !workspace) { set_error("topk_batched: null output/workspace"); return SQE_E_ARG; }

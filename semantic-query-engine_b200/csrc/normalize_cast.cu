@@ -47,6 +47,24 @@ __device__ __forceinline__ void store_row_chunk(__half* out, float4 v) {
                  : "memory");
 }
 
+// split bf16 (SQE_BF16X2): hi into the first 1024 bf16 of the row, lo into the second 1024
+__device__ __forceinline__ void store_row_chunk(Bf16x2* out, float4 v) {
+    __nv_bfloat16 h[4], l[4];
+    split_bf16x2(v.x, h[0], l[0]);
+    split_bf16x2(v.y, h[1], l[1]);
+    split_bf16x2(v.z, h[2], l[2]);
+    split_bf16x2(v.w, h[3], l[3]);
+    uint2 uh, ul;
+    uh.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
+    uh.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16) | __bfloat16_as_ushort(h[2]);
+    ul.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
+    ul.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[3])) << 16) | __bfloat16_as_ushort(l[2]);
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(out), "r"(uh.x), "r"(uh.y) : "memory");
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(out + kDim), "r"(ul.x), "r"(ul.y) : "memory");
+}
+template <typename OutT> struct OutRow { static constexpr int kElems = kDim; };
+template <> struct OutRow<Bf16x2> { static constexpr int kElems = 2 * kDim; };
+
 template <typename OutT>
 __global__ void __launch_bounds__(kNormWarps * 32, 4)
 normalize_cast_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t n) {
@@ -68,7 +86,7 @@ normalize_cast_kernel(const float* __restrict__ in, OutT* __restrict__ out, int6
         }
         const float s = warp_row_sumsq_numpy(v, t, lane);
         const float den = __fadd_rn(__fsqrt_rn(s), 1e-9f);
-        OutT* dst = out + row * kDim;
+        OutT* dst = out + row * OutRow<OutT>::kElems;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             float4 o;
@@ -92,6 +110,7 @@ int launch_normalize_cast(const float* in, void* out, int64_t n, int out_dtype, 
         case 0: normalize_cast_kernel<float><<<g, b, 0, stream>>>(in, static_cast<float*>(out), n); break;
         case 1: normalize_cast_kernel<__nv_bfloat16><<<g, b, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), n); break;
         case 2: normalize_cast_kernel<__half><<<g, b, 0, stream>>>(in, static_cast<__half*>(out), n); break;
+        case 3: normalize_cast_kernel<Bf16x2><<<g, b, 0, stream>>>(in, static_cast<Bf16x2*>(out), n); break;
         default: return -1;
     }
     return 0;

@@ -19,6 +19,18 @@ namespace sqe {
 constexpr int kDim = 1024;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Storage type SQE_BF16X2: every value x is stored as TWO bf16 numbers, hi = bf16(x) and
+// lo = bf16(x - hi); a row is [hi[1024] | lo[1024]] = 4096 bytes (the size of an fp32 row).  The
+// stored value is hi + lo, which is exact in fp32 (16 significant bits) -- the fp32 tolerance
+// class on the bf16 tensor cores.  The tag type is 2 bytes so pointer arithmetic counts bf16s.
+struct Bf16x2 {
+    __nv_bfloat16 v;
+};
+__device__ __forceinline__ void split_bf16x2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(hi)));
+}
+
 __device__ __forceinline__ uint32_t orderable_u32(float s) {
     s = s + 0.0f;                                   // -0.0 -> +0.0 (numpy treats them as equal)
     uint32_t u = __float_as_uint(s);

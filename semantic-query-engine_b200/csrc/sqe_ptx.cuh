@@ -68,40 +68,41 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
-// 2-D tiled load, completion (bytes) signalled on an mbarrier of this CTA
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1,
+// 3-D tiled loads {element, plane, row}; completion (bytes) signalled on an mbarrier.  Plain
+// 16-bit shards have one plane; split-bf16 shards have two (hi, lo).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2,
                                             uint32_t bar) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
 // same, with an L2 cache policy
-__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void* tmap, int c0, int c1,
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const void* tmap, int c0, int c1, int c2,
                                                  uint32_t bar, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
         : "memory");
 }
-// 2-CTA form: data lands in this CTA's smem at `dst`, the bytes are signalled on the barrier
-// address `bar` interpreted in the cluster window (pass a mapa'd address of the leader CTA).
-__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, int c0, int c1,
+// 2-CTA forms: data lands in this CTA's smem at `dst`, the bytes are signalled on the barrier
+// address `bar_cluster` interpreted in the cluster window (a mapa'd address of the leader CTA).
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst, const void* tmap, int c0, int c1, int c2,
                                                 uint32_t bar_cluster, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        ".L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster), "l"(policy)
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster), "l"(policy)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_cg2_nohint(uint32_t dst, const void* tmap, int c0, int c1,
-                                                       uint32_t bar_cluster) {
+__device__ __forceinline__ void tma_load_3d_cg2_nohint(uint32_t dst, const void* tmap, int c0, int c1,
+                                                       int c2, uint32_t bar_cluster) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster)
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
         : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_last() {

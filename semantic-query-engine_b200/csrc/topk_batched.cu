@@ -453,7 +453,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     int n_qt, int n_groups, int n_dtiles, uint32_t idesc,
                     uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau,
                     uint32_t* __restrict__ ws_prog, unsigned long long* __restrict__ dbg, int epi_mode,
-                    int d_hint, int window) {
+                    int d_hint, int window, int passes) {
     using namespace k2;
     using C = Cfg<CG, R, TOP1, DEEP>;
     constexpr int L = 32 * R;
@@ -534,7 +534,16 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         if (u < n_qt)
                             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sib[u]) : "l"(my_prog + u) : "memory");
                 }
-                for (int kc = 0; kc < kNumChunks; ++kc) {
+                // split-bf16 shards: four passes over K into the same accumulator, smallest
+                // terms first -- (Q plane, D plane) = (lo, lo), (hi, lo), (lo, hi), (hi, hi).  The
+                // tensor core truncates when it aligns a product group to the accumulator, so the
+                // error grows with (#updates x |partial sum|): the cross terms are added while
+                // the sum is ~2^-9, and the big hi.hi pass costs what a plain bf16 shard costs.
+                for (int ch = 0; ch < kNumChunks * passes; ++ch) {
+                    const int kc = ch & (kNumChunks - 1);
+                    const int pass = ch / kNumChunks + (4 - passes);     // plain shards: only (hi, hi)
+                    const int q_plane = (pass == 0 || pass == 2) ? 1 : 0;
+                    const int d_plane = (pass == 0 || pass == 1) ? 1 : 0;
                     const long long w0 = dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                     if (dbg) t_wait += clock64() - w0;
@@ -542,18 +551,18 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     if constexpr (CG == 1) {
                         const uint32_t fb = bar_full + 8 * stage;
                         ptx::mbar_expect_tx(fb, C::kStageBytes);
-                        if (d_hint == 4) ptx::tma_load_2d(sa, &tmap_q, kc * kChunkK, q_row, fb);
-                        else ptx::tma_load_2d_hint(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
-                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_2d(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb);
-                        else ptx::tma_load_2d_hint(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
+                        if (d_hint == 4) ptx::tma_load_3d(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb);
+                        else ptx::tma_load_3d_hint(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb, pol_q);
+                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_3d(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb);
+                        else ptx::tma_load_3d_hint(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb, pol_d);
                     } else {
                         // both CTAs' bytes are counted on the LEADER's barrier
                         if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
                         const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
-                        if (d_hint == 4) ptx::tma_load_2d_cg2_nohint(sa, &tmap_q, kc * kChunkK, q_row, fb);
-                        else ptx::tma_load_2d_cg2(sa, &tmap_q, kc * kChunkK, q_row, fb, pol_q);
-                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_2d_cg2_nohint(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb);
-                        else ptx::tma_load_2d_cg2(sa + kABytes, &tmap_d, kc * kChunkK, d_row, fb, pol_d);
+                        if (d_hint == 4) ptx::tma_load_3d_cg2_nohint(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb);
+                        else ptx::tma_load_3d_cg2(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb, pol_q);
+                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_3d_cg2_nohint(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb);
+                        else ptx::tma_load_3d_cg2(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb, pol_d);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -606,7 +615,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 if (dbg) t_wtempty += clock64() - w0;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kTileN;
-                for (int kc = 0; kc < kNumChunks; ++kc) {
+                for (int kc = 0; kc < kNumChunks * passes; ++kc) {
                     const long long w1 = dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
                     if (dbg) t_wfull += clock64() - w1;
@@ -850,17 +859,18 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// [rows, 1024] 16-bit row-major matrix, box = 64 elements (128 B) x box_rows, 128-B swizzle,
-// out-of-range rows read as zeros.
+// [rows, planes, 1024] 16-bit matrix (planes = 1, or 2 for split bf16: hi | lo), box = 64 elements
+// (128 B) x 1 plane x box_rows, 128-B swizzle, out-of-range rows read as zeros.
 static int make_tile_map(CUtensorMap* map, const void* ptr, int dtype, uint64_t rows, uint32_t box_rows) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("topk_batched: cuTensorMapEncodeTiled not available from the driver"); return -2; }
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), rows};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(k2::kChunkK), box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = (dtype == 1) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    const cuuint64_t planes = (dtype == 3) ? 2 : 1;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kDim), planes, rows};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kDim) * 2, static_cast<cuuint64_t>(kDim) * 2 * planes};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(k2::kChunkK), 1, box_rows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = (dtype == 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = enc(map, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("topk_batched: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return -2; }
@@ -883,8 +893,8 @@ int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
 template <int R, int CG, bool TOP1, bool DEEP>
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
                             int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
-                            uint32_t* ws_tau, uint32_t* ws_prog, float* out_score, int64_t* out_idx, int64_t idx_offset,
-                            cudaStream_t stream) {
+                            uint32_t* ws_tau, uint32_t* ws_prog, int passes, float* out_score, int64_t* out_idx,
+                            int64_t idx_offset, cudaStream_t stream) {
     using C = k2::Cfg<CG, R, TOP1, DEEP>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1, DEEP>,
@@ -905,7 +915,7 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
         cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1, DEEP>, tq, td, static_cast<uint32_t>(n), b, k,
                                n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog,
-                               reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window);
+                               reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window, passes);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
     }
     batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, n_dtiles > 0 ? n_groups : 0, b,
@@ -927,7 +937,9 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
     uint32_t* ws_prog = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + kTauBytes);
     uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kHdrBytes);
     const int n_dtiles = static_cast<int>((n + k2::kTileN - 1) / k2::kTileN);
-    const uint32_t fmt = (dtype == 1) ? 1u : 0u;               // BF16 = 1, F16 = 0
+    const uint32_t fmt = (dtype == 2) ? 0u : 1u;               // F16 = 0; BF16 = 1 (also split bf16)
+    const int passes = (dtype == 3) ? 4 : 1;                   // split bf16: Ql.Dl + Qh.Dl + Ql.Dh + Qh.Dh
+    const int64_t q_row_bytes = (dtype == 3) ? 2 * kDim * 2 : kDim * 2;
     // instruction descriptor: D fp32 [4,6)=1, A fmt [7,10), B fmt [10,13), K-major both,
     // N>>3 [17,23), M>>4 [24,29)  (M = 128 per CTA, 256 for the pair)
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) |
@@ -950,7 +962,7 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         const int64_t used = kHdrBytes + static_cast<int64_t>(n_groups) * n_qt * C::kQTile * L * 8;
         cudaError_t e = cudaMemsetAsync(ws, 0, static_cast<size_t>(used), stream);
         if (e != cudaSuccess) { set_error("topk_batched: memset: %s", cudaGetErrorString(e)); return -2; }
-        const char* qp = static_cast<const char*>(Q) + static_cast<int64_t>(q0) * kDim * 2;
+        const char* qp = static_cast<const char*>(Q) + static_cast<int64_t>(q0) * q_row_bytes;
         CUtensorMap tq;
         int rc = make_tile_map(&tq, qp, dtype, static_cast<uint64_t>(bc), k2::kRowsPerCta);
         if (rc != 0) return rc;
@@ -960,9 +972,9 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         const bool deep = (CG == 2) && (n_qt == 1);
 #define SQE_K2_LAUNCH(R_, TOP1_)                                                                        \
     (deep ? launch_batched_r<R_, CG, TOP1_, (CG == 2)>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, \
-                                                       ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream) \
+                                                       ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream) \
           : launch_batched_r<R_, CG, TOP1_, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc,     \
-                                                   ws_lists, ws_tau, ws_prog, os, oi, idx_offset, stream))
+                                                   ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream))
         if (k == 1) rc = SQE_K2_LAUNCH(1, true);
         else if (R == 1) rc = SQE_K2_LAUNCH(1, false);
         else if (R == 2) rc = SQE_K2_LAUNCH(2, false);

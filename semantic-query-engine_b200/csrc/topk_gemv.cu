@@ -34,6 +34,9 @@ template <typename T> struct Elem;
 template <> struct Elem<float> {
     static constexpr int kLoads = 8;     // 128-bit loads per lane per row
     static constexpr int kPer = 4;       // elements per load
+    static constexpr int kQGroups = 8;   // groups of kPer logical elements per lane
+    static constexpr int kRowElems = kDim;
+    __device__ static __forceinline__ int load_off(int c) { return c * (32 * kPer); }
     __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[4]) {
         f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y);
         f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
@@ -42,6 +45,9 @@ template <> struct Elem<float> {
 template <> struct Elem<__nv_bfloat16> {
     static constexpr int kLoads = 4;
     static constexpr int kPer = 8;
+    static constexpr int kQGroups = 4;
+    static constexpr int kRowElems = kDim;
+    __device__ static __forceinline__ int load_off(int c) { return c * (32 * kPer); }
     __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[8]) {
         f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
         f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
@@ -52,6 +58,9 @@ template <> struct Elem<__nv_bfloat16> {
 template <> struct Elem<__half> {
     static constexpr int kLoads = 4;
     static constexpr int kPer = 8;
+    static constexpr int kQGroups = 4;
+    static constexpr int kRowElems = kDim;
+    __device__ static __forceinline__ int load_off(int c) { return c * (32 * kPer); }
     __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[8]) {
         float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
         float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
@@ -62,7 +71,41 @@ template <> struct Elem<__half> {
     }
 };
 
+// split bf16: loads 0-3 fetch the hi plane, loads 4-7 the lo plane of the same 8-element
+// groups; the value is hi + lo (exact in fp32)
+template <> struct Elem<Bf16x2> {
+    static constexpr int kLoads = 8;
+    static constexpr int kPer = 8;
+    static constexpr int kQGroups = 4;
+    static constexpr int kRowElems = 2 * kDim;
+    __device__ static __forceinline__ int load_off(int c) {
+        return (c & 3) * (32 * kPer) + (c < 4 ? 0 : kDim);          // hi plane | lo plane
+    }
+    __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[8]) {
+        Elem<__nv_bfloat16>::unpack(u, f);
+    }
+};
+
+// logical elements g*kPer .. +kPer-1 of a row held as raw 128-bit loads
+template <typename T>
+__device__ __forceinline__ void elem_group(const uint4* raw, int g, float (&f)[Elem<T>::kPer]) {
+    Elem<T>::unpack(raw[g], f);
+}
+template <>
+__device__ __forceinline__ void elem_group<Bf16x2>(const uint4* raw, int g, float (&f)[8]) {
+    float lo[8];
+    Elem<Bf16x2>::unpack(raw[g], f);
+    Elem<Bf16x2>::unpack(raw[g + 4], lo);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = __fadd_rn(f[e], lo[e]);
+}
+
 template <typename T> __device__ __forceinline__ float round_through(float x);
+template <> __device__ __forceinline__ float round_through<Bf16x2>(float x) {
+    __nv_bfloat16 hi, lo;
+    split_bf16x2(x, hi, lo);
+    return __fadd_rn(__bfloat162float(hi), __bfloat162float(lo));
+}
 template <> __device__ __forceinline__ float round_through<float>(float x) { return x; }
 template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float x) {
     return __bfloat162float(__float2bfloat16_rn(x));
@@ -83,6 +126,7 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
     using E = Elem<T>;
     constexpr int LOADS = E::kLoads;
     constexpr int PER = E::kPer;
+    constexpr int QG = E::kQGroups;
     constexpr int RPW = 16 / LOADS;              // rows in flight per warp
     constexpr int L = 32 * R;
     __shared__ uint64_t s_lists[kGemvWarps][L];
@@ -121,18 +165,20 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < LOADS; ++c)
+        for (int g = 0; g < QG; ++g)
 #pragma unroll
-            for (int e = 0; e < PER; ++e) q[c * PER + e] = s_q[c * (32 * PER) + lane * PER + e];
+            for (int e = 0; e < PER; ++e) q[g * PER + e] = s_q[g * (32 * PER) + lane * PER + e];
     } else {
-        const T* qp = static_cast<const T*>(Qv) + static_cast<int64_t>(query) * kDim;
+        const T* qp = static_cast<const T*>(Qv) + static_cast<int64_t>(query) * E::kRowElems + lane * PER;
+        uint4 qraw[LOADS];
 #pragma unroll
-        for (int c = 0; c < LOADS; ++c) {
-            uint4 u = *reinterpret_cast<const uint4*>(qp + c * (32 * PER) + lane * PER);
+        for (int c = 0; c < LOADS; ++c) qraw[c] = *reinterpret_cast<const uint4*>(qp + E::load_off(c));
+#pragma unroll
+        for (int g = 0; g < QG; ++g) {
             float f[PER];
-            E::unpack(u, f);
+            elem_group<T>(qraw, g, f);
 #pragma unroll
-            for (int e = 0; e < PER; ++e) q[c * PER + e] = f[e];
+            for (int e = 0; e < PER; ++e) q[g * PER + e] = f[e];
         }
     }
 
@@ -148,9 +194,9 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
         for (int j = 0; j < RPW; ++j) {
             const int64_t row = base + j;
             if (row < n) {
-                const T* rp = D + row * kDim + lane * PER;
+                const T* rp = D + row * E::kRowElems + lane * PER;
 #pragma unroll
-                for (int c = 0; c < LOADS; ++c) raw[j][c] = ldg_stream(rp + c * (32 * PER));
+                for (int c = 0; c < LOADS; ++c) raw[j][c] = ldg_stream(rp + E::load_off(c));
             } else {
 #pragma unroll
                 for (int c = 0; c < LOADS; ++c) raw[j][c] = make_uint4(0, 0, 0, 0);
@@ -161,13 +207,13 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
         for (int j = 0; j < RPW; ++j) {
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < LOADS; ++c) {
+            for (int g = 0; g < QG; ++g) {
                 float f[PER];
-                E::unpack(raw[j][c], f);
+                elem_group<T>(raw[j], g, f);
 #pragma unroll
                 for (int e = 0; e < PER; e += 2) {
-                    a0 = fmaf(f[e], q[c * PER + e], a0);
-                    a1 = fmaf(f[e + 1], q[c * PER + e + 1], a1);
+                    a0 = fmaf(f[e], q[g * PER + e], a0);
+                    a1 = fmaf(f[e + 1], q[g * PER + e + 1], a1);
                 }
             }
             s[j] = a0 + a1;
@@ -322,6 +368,7 @@ int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, bool ra
         case 0: return launch_gemv_r<float>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
         case 1: return launch_gemv_r<__nv_bfloat16>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
         case 2: return launch_gemv_r<__half>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 3: return launch_gemv_r<Bf16x2>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
         default: set_error("gemv: bad dtype %d", dtype); return -1;
     }
 }

@@ -13,8 +13,12 @@ import torch
 
 from . import _native as nat
 
-TORCH_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
-_NAMES = {v: k for k, v in TORCH_DTYPES.items()}
+TORCH_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16,
+                "bf16x2": torch.bfloat16}
+# elements of the torch dtype per stored row: split bf16 keeps hi[1024] | lo[1024]
+ROW_ELEMS = {"fp32": nat.SQE_DIM, "bf16": nat.SQE_DIM, "fp16": nat.SQE_DIM, "bf16x2": 2 * nat.SQE_DIM}
+ROW_BYTES = {"fp32": 4096, "bf16": 2048, "fp16": 2048, "bf16x2": 4096}
+_NAMES = {torch.float32: "fp32", torch.bfloat16: "bf16", torch.float16: "fp16"}
 
 _workspaces = {}
 # A call = (memset +) kernels that share one workspace.  Two host threads launching on the same
@@ -26,10 +30,14 @@ _launch_lock = _threading.Lock()
 
 
 def dtype_name(t: torch.Tensor) -> str:
+    """Storage class of a shard / query tensor: by torch dtype, split bf16 by its 2048-wide rows."""
     try:
-        return _NAMES[t.dtype]
+        name = _NAMES[t.dtype]
     except KeyError:
         raise TypeError(f"unsupported storage dtype {t.dtype}")
+    if name == "bf16" and t.dim() == 2 and t.shape[1] == 2 * nat.SQE_DIM:
+        return "bf16x2"
+    return name
 
 
 def _require_cuda(*tensors: torch.Tensor) -> torch.device:
@@ -82,11 +90,12 @@ def normalize_cast(x: torch.Tensor, dtype: str, out: Optional[torch.Tensor] = No
     dev = _require_cuda(x)
     if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != nat.SQE_DIM:
         raise ValueError(f"expected fp32 [n,{nat.SQE_DIM}], got {x.dtype} {tuple(x.shape)}")
+    shape = (x.shape[0], ROW_ELEMS[dtype])
     if out is None:
-        out = torch.empty(x.shape, dtype=TORCH_DTYPES[dtype], device=dev)
+        out = torch.empty(shape, dtype=TORCH_DTYPES[dtype], device=dev)
     else:
         _require_cuda(x, out)
-        if out.shape != x.shape or out.dtype != TORCH_DTYPES[dtype]:
+        if tuple(out.shape) != shape or out.dtype != TORCH_DTYPES[dtype]:
             raise ValueError("bad `out`")
     with torch.cuda.device(dev):
         nat.call("sqe_normalize_cast", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
@@ -96,10 +105,10 @@ def normalize_cast(x: torch.Tensor, dtype: str, out: Optional[torch.Tensor] = No
 
 def _check_dq(D: torch.Tensor, Q: torch.Tensor, n: Optional[int]) -> Tuple[torch.device, int, int]:
     dev = _require_cuda(D, Q)
-    if D.dim() != 2 or Q.dim() != 2 or D.shape[1] != nat.SQE_DIM or Q.shape[1] != nat.SQE_DIM:
-        raise ValueError("D and Q must be [rows,1024]")
-    if D.dtype != Q.dtype:
-        raise TypeError("queries must be stored in the shard's dtype (use normalize_cast)")
+    if D.dim() != 2 or Q.dim() != 2 or D.shape[1] not in (nat.SQE_DIM, 2 * nat.SQE_DIM):
+        raise ValueError("D and Q must be [rows,1024] (or [rows,2048] bf16 for split bf16)")
+    if D.dtype != Q.dtype or D.shape[1] != Q.shape[1] or ROW_ELEMS[dtype_name(D)] != D.shape[1]:
+        raise TypeError("queries must be stored in the shard's storage class (use normalize_cast)")
     rows = D.shape[0] if n is None else int(n)
     if rows > D.shape[0]:
         raise ValueError("n exceeds shard rows")
@@ -128,8 +137,8 @@ def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 
     dev = _require_cuda(D, q_raw)
     if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
         raise ValueError("q_raw must be fp32 [nq,1024]")
-    if D.dim() != 2 or D.shape[1] != nat.SQE_DIM:
-        raise ValueError("D must be [rows,1024]")
+    if D.dim() != 2 or D.shape[1] != ROW_ELEMS[dtype_name(D)]:
+        raise ValueError("D must be [rows,1024] (or [rows,2048] bf16 for split bf16)")
     rows = D.shape[0] if n is None else int(n)
     if rows > D.shape[0]:
         raise ValueError("n exceeds shard rows")

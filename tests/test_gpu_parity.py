@@ -14,7 +14,7 @@ from oracle import numpy_oracle as no
 from parity import assert_topk_matches, exact_scores
 
 DIM = 1024
-DTYPES = ["fp32", "bf16", "fp16"]
+DTYPES = ["fp32", "bf16", "fp16", "bf16x2"]      # bf16x2 = split bf16 (hi + lo), fp32 tolerance class
 K2_TOL = 1e-5          # score / near-tie tolerance of the tensor-core path (see _k2_case)
 
 
@@ -75,6 +75,7 @@ def test_normalize_cast_bit_exact_vs_oracle(sqe, dtype):
     if dtype == "fp32":
         np.testing.assert_array_equal(got_bits.view(np.uint32), want.view(np.uint32))
     else:
+        assert got_bits.shape == want.shape                  # bf16x2: [n, 2048] = hi | lo
         np.testing.assert_array_equal(got_bits.view(np.uint16), want.view(np.uint16))
 
 
@@ -333,6 +334,31 @@ def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
         np.testing.assert_array_equal(sa, sb)
 
 
+def test_split_bf16_index_is_in_the_fp32_tolerance_class(sqe, golden_dir):
+    """dtype="bf16x2": the reference's own search results (fp32 numpy path) are reproduced on the
+    TENSOR-CORE path within the 1e-5 the north star states for fp32 storage, batched, and the
+    b=1 path (K3 reconstructs hi + lo exactly) agrees with it."""
+    g = np.load(os.path.join(golden_dir, "index_search.npz"))
+    with open(os.path.join(golden_dir, "index_search.json")) as f:
+        meta = json.load(f)
+    index = sqe.GpuCorpusIndex(None, "golden-x2", dtype="bf16x2", strict=True)
+    index.add_embeddings(g["emb"], meta["docs"])
+    stored = oracle.from_storage(stored_bits(index.shard, "bf16x2"), "bf16x2")
+    assert np.abs(stored - g["stored"]).max() <= 2.0 ** -17               # 16 significant bits
+    kmax = int(max(g["ks"]))
+    sb, ib = index.search_batch(g["q"], kmax)                             # K1 + K2 (3 passes)
+    s64 = exact_scores(g["stored"], g["q_norm"])                          # the reference's fp32 rows
+    for qi in range(len(g["q"])):
+        s1, i1 = index.search_batch(g["q"][qi:qi + 1], kmax)              # K3, b = 1
+        np.testing.assert_allclose(s1[0], sb[qi], atol=1e-5)
+        for ki, k in enumerate(g["ks"]):
+            k = int(k)
+            np.testing.assert_allclose(sb[qi, :k], g["res_score"][qi, ki, :k], atol=1e-5)
+            top = np.sort(s64[qi])[::-1][: k + 1]
+            if np.min(-np.diff(top)) > 2e-5:                              # no near-tie at the boundary
+                assert ib[qi, :k].tolist() == g["res_idx"][qi, ki, :k].tolist(), (qi, k)
+
+
 def test_concurrent_searches_from_many_threads_are_safe(sqe):
     """Unlike the reference (one event-loop thread) callers may search from several threads:
     launches that share a workspace are enqueued atomically, staging buffers are per call."""
@@ -500,7 +526,7 @@ def _k2_case(sqe, dtype, n, b, ks, seed, idx_offset=0, n_used=None):
     return excused
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "bf16x2"])
 @pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 1000, 40037])
 def test_batched_topk_matches_oracle(sqe, cta_group, dtype, n):
     _k2_case(sqe, dtype, n, 5, (1, 3, 10, 32, 33, 100, 128), seed=2000 + n)
@@ -583,7 +609,7 @@ def test_batched_equals_gemv_and_is_deterministic(sqe, cta_group):
     np.testing.assert_allclose(sb.cpu().numpy(), sg.cpu().numpy(), atol=K2_TOL)
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "bf16x2"])
 def test_cache_top1_tensor_path(sqe, dtype):
     rng = np.random.default_rng(18)
     c = make_corpus(rng, 20_000)

@@ -175,3 +175,21 @@ def test_oracle_against_live_reference():
     assert oracle.CACHE_SIM_THRESHOLD == m.CACHE_SIM_THRESHOLD
     assert oracle.REDIS_MAX_ITEMS == m.REDIS_MAX_ITEMS
     assert oracle.EMBED_DIM == m.EMBED_DIM
+
+
+def test_split_bf16_storage_is_exact_to_16_bits():
+    """bf16x2 (new storage class): hi + lo reconstructs x to 2^-17 relative, the sum is exact in
+    fp32, and zeros / signs / tiny values survive."""
+    import oracle
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((64, 1024)) * 10.0 ** rng.uniform(-8, 0, size=(64, 1))).astype(np.float32)
+    x[0] = 0.0
+    st = oracle.to_storage(x, "bf16x2")
+    assert st.dtype == np.uint16 and st.shape == (64, 2048)
+    back = oracle.from_storage(st, "bf16x2")
+    assert back.dtype == np.float32 and back.shape == x.shape
+    assert np.all(np.abs(back - x) <= np.abs(x) * 2.0 ** -16 + 1e-38)
+    assert np.all(back[0] == 0.0)
+    hi = oracle.from_storage(st[:, :1024], "bf16").astype(np.float64)
+    lo = oracle.from_storage(st[:, 1024:], "bf16").astype(np.float64)
+    assert np.array_equal((hi + lo).astype(np.float32).astype(np.float64), hi + lo)    # exact in fp32

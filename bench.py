@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None,
                     help="override the batch size of the b1024 workload (e.g. 256 with --k 100 "
                          "--dtype fp16 --rows 12500000 = one rank's share of BASELINE configs[3])")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32", "bf16x2"])
     ap.add_argument("--k2-cta-group", type=int, default=0, choices=[0, 1, 2],
                     help="force the single-CTA (1) or CTA-pair (2) tensor-core kernel; 0 = library default")
     ap.add_argument("--k2-d-hint", type=int, default=None, choices=[0, 1, 2, 3, 4],
@@ -206,9 +206,10 @@ def run_reference_arm(args):
 
 def workload_config(args, world):
     if args.workload == "cache64":
-        return {"workload": "query cache 1Mx1024 bf16, streaming batch-64 top-1 + 0.95 threshold "
+        cdt = args.dtype if args.dtype in ("bf16x2", "fp16") else "bf16"
+        return {"workload": f"query cache 1Mx1024 {cdt}, streaming batch-64 top-1 + 0.95 threshold "
                             "(BASELINE configs[4])", "rows": 1_000_000, "batch": 64, "k": 1,
-                "dtype": "bf16", "l2": "inputs larger than L2"}
+                "dtype": cdt, "l2": "inputs larger than L2"}
     b = (args.batch or 1024) if args.workload == "b1024" else 1
     return {"workload": f"{args.rows}x1024 {args.dtype} corpus, batch-{b} cosine top-{args.k} "
                         f"(BASELINE configs[2] / metric headline)",
@@ -259,7 +260,7 @@ def main():
     if args.batch and args.workload == "b1024":
         b = args.batch
     k = 1 if is_cache else args.k
-    dtype = "bf16" if is_cache else args.dtype
+    dtype = args.dtype if (not is_cache or args.dtype in ("bf16x2", "fp16")) else "bf16"
     total_rows = 1_000_000 if is_cache else args.rows
     steps = args.steps or (20 if b > 1 else 50)
     warmup = args.warmup if args.warmup is not None else 3
@@ -357,7 +358,7 @@ def main():
     k1.record()
     torch.cuda.synchronize()
     kms = k0.elapsed_time(k1) / kiters
-    esize = {"bf16": 2, "fp16": 2, "fp32": 4}[dtype]
+    esize = {"bf16": 2, "fp16": 2, "fp32": 4, "bf16x2": 4}[dtype]
     if b == 1 or is_cache:
         alg = local_rows * DIM * esize
         roofline = {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
@@ -649,9 +650,9 @@ def run_ingest(args, torch, ops, nat, dev, peaks):
     rows = min(args.rows, 1_000_000)
     steps = args.steps or 30
     warmup = args.warmup if args.warmup is not None else 3
-    esize = {"bf16": 2, "fp16": 2, "fp32": 4}[args.dtype]
+    esize = {"bf16": 2, "fp16": 2, "fp32": 4, "bf16x2": 4}[args.dtype]
     x = torch.randn((rows, DIM), device=dev, dtype=torch.float32)
-    out = torch.empty((rows, DIM), device=dev, dtype=ops.TORCH_DTYPES[args.dtype])
+    out = torch.empty((rows, ops.ROW_ELEMS[args.dtype]), device=dev, dtype=ops.TORCH_DTYPES[args.dtype])
     for _ in range(warmup):
         ops.normalize_cast(x, args.dtype, out=out)
     torch.cuda.synchronize()

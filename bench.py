@@ -443,7 +443,8 @@ def main():
     secondary = None
     if args.workload == "b1024" and not args.no_secondary:
         q1 = q_dev[:1].contiguous()
-        for _ in range(3):
+        time.sleep(1.0)      # a separate measurement: let the clocks settle after the power-capped GEMM loops
+        for _ in range(5):
             sharded.search_device(q1, k)
         barrier()
         s0 = torch.cuda.Event(enable_timing=True)

@@ -40,7 +40,10 @@ __device__ __forceinline__ float from_orderable_u32(uint32_t o) {
     uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
     return __uint_as_float(u);
 }
+// A NaN score (a broken embedding) ranks below everything, like numpy's argsort puts NaN last
+// and like the reference's `sim > best_sim` (app/main.py:84), which is never true for NaN.
 __device__ __forceinline__ uint64_t make_key(float s, uint32_t row) {
+    s = (s == s) ? s : __int_as_float(0xff800000);
     return (static_cast<uint64_t>(orderable_u32(s)) << 32) | static_cast<uint64_t>(0xffffffffu - row);
 }
 __device__ __forceinline__ float key_score(uint64_t key) {

@@ -138,6 +138,26 @@ def test_search_gemv_fused_normalise_is_bit_identical(sqe, dtype):
         assert torch.equal(i1, i2) and torch.equal(s1, s2)
 
 
+def test_nan_rows_rank_last(sqe):
+    """A NaN embedding (broken embedder) never beats a real row: numpy's argsort puts NaN last and
+    the reference's `sim > best_sim` is False for NaN (main.py:84)."""
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((4000, DIM)).astype(np.float32)
+    x[5, 17] = np.nan
+    x[300] = np.nan
+    q = rng.standard_normal((3, DIM)).astype(np.float32)
+    for dtype in ("fp32", "bf16"):
+        D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+        Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+        s, i = sqe.ops.topk_gemv(D, Q, 10)
+        assert not torch.isnan(s).any() and not ((i == 5) | (i == 300)).any()
+        if dtype != "fp32":
+            s, i = sqe.ops.topk_batched(D, Q, 10)
+            assert not torch.isnan(s).any() and not ((i == 5) | (i == 300)).any()
+        idx, sc, hit = sqe.ops.cache_top1(D, Q, 0.96, path=1)
+        assert not ((idx == 5) | (idx == 300)).any()
+
+
 def test_gemv_idx_offset_and_partial_shard(sqe):
     rng = np.random.default_rng(5)
     x = make_corpus(rng, 3000)

@@ -818,25 +818,80 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
 }
 
-// Merge the per-group partial lists of each query: one warp per query.
+// Merge the per-group partial lists of each query.  Few groups (large batches): one warp per
+// query, four queries per CTA.  Many groups (small batches: up to one group per SM): one CTA
+// of eight warps per query -- each warp folds every 8th list (the next one is in flight while
+// the current one merges), warp 0 folds the eight partial lists.
 template <int R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 batched_merge_kernel(const uint64_t* __restrict__ ws_lists, int n_groups, int b, int b_pad, int k,
-                     float* __restrict__ out_score, int64_t* __restrict__ out_idx,
-                     int64_t idx_offset) {
+                     int warps_per_query, float* __restrict__ out_score,
+                     int64_t* __restrict__ out_idx, int64_t idx_offset) {
     constexpr int L = 32 * R;
+    __shared__ uint64_t s_part[8][L];
     const int lane = threadIdx.x & 31;
-    const int query = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (query >= b) return;
+    const int warp = threadIdx.x >> 5;
+    const int warps = blockDim.x >> 5;
+    const int query = (warps_per_query == 1) ? blockIdx.x * warps + warp : blockIdx.x;
+    const int sub = (warps_per_query == 1) ? 0 : warp;          // which share of the groups
+    const bool active = query < b;
     WarpList<R> list;
     list.clear();
-    for (int g = 0; g < n_groups; ++g) {
-        WarpList<R> other;
-        other.load(ws_lists + (static_cast<size_t>(g) * b_pad + query) * L, lane);
-        list.merge_sorted(other.key, lane);
+    if (active) {
+        uint64_t nxt[R];
+        int g = sub;
+        if (g < n_groups) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                nxt[r] = __ldcg(ws_lists + (static_cast<size_t>(g) * b_pad + query) * L + r * 32 + lane);
+        }
+        while (g < n_groups) {
+            WarpList<R> other;
+#pragma unroll
+            for (int r = 0; r < R; ++r) other.key[r] = nxt[r];
+            const int gn = g + warps_per_query;
+            if (gn < n_groups) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    nxt[r] = __ldcg(ws_lists + (static_cast<size_t>(gn) * b_pad + query) * L + r * 32 + lane);
+            }
+            list.merge_sorted(other.key, lane);
+            g = gn;
+        }
+    }
+    if (warps_per_query > 1) {
+        list.store(s_part[warp], lane);
+        __syncthreads();
+        if (warp != 0 || !active) return;
+#pragma unroll 1
+        for (int w = 1; w < warps_per_query; ++w) {
+            WarpList<R> other;
+            other.load(s_part[w], lane);
+            list.merge_sorted(other.key, lane);
+        }
+    } else if (!active) {
+        return;
     }
     emit_topk<R>(list, k, lane, out_score + static_cast<int64_t>(query) * k,
                  out_idx + static_cast<int64_t>(query) * k, idx_offset);
+}
+
+// k = 1: every group wrote at most one key (slot 0 of its list); the result is their maximum.
+__global__ void __launch_bounds__(128)
+top1_merge_kernel(const uint64_t* __restrict__ ws_lists, int n_groups, int b, int b_pad,
+                  float* __restrict__ out_score, int64_t* __restrict__ out_idx, int64_t idx_offset) {
+    const int lane = threadIdx.x & 31;
+    const int query = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (query >= b) return;
+    uint64_t best = 0ull;
+    for (int g = lane; g < n_groups; g += 32)
+        best = umax64(best, __ldcg(ws_lists + (static_cast<size_t>(g) * b_pad + query) * 32));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) best = umax64(best, shfl_xor_u64(best, d));
+    if (lane == 0) {
+        out_score[query] = best ? key_score(best) : __int_as_float(0xff800000);
+        out_idx[query] = best ? idx_offset + static_cast<int64_t>(key_row(best)) : -1;
+    }
 }
 
 // ------------------------------------------------------------------------------ host
@@ -918,9 +973,17 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
                                reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window, passes);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
     }
-    batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, n_dtiles > 0 ? n_groups : 0, b,
-                                                             n_qt * C::kQTile, k, out_score, out_idx,
-                                                             idx_offset);
+    const int mg = n_dtiles > 0 ? n_groups : 0;
+    if constexpr (TOP1) {
+        top1_merge_kernel<<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, mg, b, n_qt * C::kQTile, out_score,
+                                                           out_idx, idx_offset);
+    } else if (mg > 32) {
+        batched_merge_kernel<R><<<b, 256, 0, stream>>>(ws_lists, mg, b, n_qt * C::kQTile, k, 8, out_score,
+                                                       out_idx, idx_offset);
+    } else {
+        batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, mg, b, n_qt * C::kQTile, k, 1,
+                                                                 out_score, out_idx, idx_offset);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("topk_batched: merge launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;

@@ -91,16 +91,21 @@ constexpr int kQueriesPerLaunch = 1024;
 // comes from DRAM -- measured 10M x 1024, b = 1024: 5 stages 32.5 GB / 55.6 k q/s, 4 stages
 // 21.5 GB / 60.2 k q/s, 3 stages 21.6 GB but a starved tensor pipe (73 % active).  A pair that
 // has its d-tiles to itself (one q-tile in flight) keeps the deep ring.
-template <int CG, int R = 1, bool TOP1 = false, bool DEEP = false>
+//
+// NARROW (single-CTA form, k <= 16): the smem-resident lists keep only their best 16 keys, which
+// frees a fourth operand stage -- this form serves small batches and is HBM-bound, so bytes in
+// flight are what counts (3 stages: 5.7 TB/s, 4 stages: 6.5 TB/s).
+template <int CG, int R = 1, bool TOP1 = false, bool DEEP = false, bool NARROW = false>
 struct Cfg {
     static constexpr int kQTile = kRowsPerCta * CG;          // queries per q-tile
     static constexpr int kBRows = kTileN / CG;               // D rows this CTA loads per chunk
     static constexpr int kBBytes = kBRows * kChunkK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB / 32 KB
     static constexpr bool kSmemLists = (R == 1) && !TOP1;
-    static constexpr int kListBytes = kSmemLists ? kRowsPerCta * 32 * 8 : 0;
+    static constexpr int kListWidth = kSmemLists ? (NARROW ? 16 : 32) : 0;     // keys per list in smem
+    static constexpr int kListBytes = kRowsPerCta * kListWidth * 8;
     static constexpr int kBufBytes = TOP1 ? 0 : kRowsPerCta * kBufStride * 8;
-    static constexpr int kStages = (CG == 1) ? (kSmemLists ? 3 : 4)
+    static constexpr int kStages = (CG == 1) ? ((kSmemLists && !NARROW) ? 3 : 4)
                                    : !DEEP    ? 4
                                               : (kSmemLists ? 5 : (TOP1 ? 7 : 6));
     static constexpr int kOffLists = kStages * kStageBytes;
@@ -147,11 +152,12 @@ __device__ __forceinline__ float thr_of(float tau_l, uint32_t tau_g) {
 // SL = the master copy of the list is in shared memory (`slists`, this warp's 32 x 32 keys)
 // and the global copy is write-only here; otherwise the list of the next pending query is
 // fetched from L2 while the current one is sorted/merged.
-template <int R, bool SL>
+template <int R, int LW>
 __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const uint64_t* wbuf,
                                             uint64_t* slists, uint64_t* wlists, uint32_t* wtau,
                                             int k, int lane) {
     constexpr int L = 32 * R;
+    constexpr bool SL = LW > 0;          // LW = keys per list kept in smem (0: lists only in the workspace)
     const long long t_in = clock64();
     st.n_flush += __popc(mask);
     __syncwarp();                                               // owners' buffer stores are visible
@@ -167,7 +173,7 @@ __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const u
         const int r_next = mask ? (__ffs(mask) - 1) : -1;
         mask &= mask - 1;
         if constexpr (SL) {
-            cur.key[0] = slists[r * 32 + lane];
+            cur.key[0] = (lane < LW) ? slists[r * LW + lane] : 0ull;
         } else {
 #pragma unroll
             for (int i = 0; i < R; ++i) cur.key[i] = nxt[i];
@@ -197,7 +203,9 @@ __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const u
             for (int i = 0; i < R; ++i) other[i] = (i == 0) ? cand.key[0] : 0ull;
             cur.merge_sorted(other, lane);
         }
-        if constexpr (SL) slists[r * 32 + lane] = cur.key[0];
+        if constexpr (SL) {
+            if (lane < LW) slists[r * LW + lane] = cur.key[0];
+        }
         uint64_t* lp = wlists + static_cast<size_t>(r) * L;
 #pragma unroll
         for (int i = 0; i < R; ++i) __stcg(lp + i * 32 + lane, cur.key[i]);
@@ -226,7 +234,7 @@ __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const u
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // One 32-column strip of the accumulator: v[j] = score of (this thread's query, row col0+j).
-template <int R, bool SL>
+template <int R, int LW>
 __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, uint32_t n,
                                               bool row_valid, EpiState& st, uint64_t* wbuf,
                                               uint64_t* slists, uint64_t* wlists, uint32_t* wtau,
@@ -263,7 +271,7 @@ __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, 
         for (int j = 16 * h; j < 16 * h + 16; ++j) pc += (want && f[j] > thr0) ? 1 : 0;
         if (!__any_sync(kFull, pc > 0)) continue;
         const unsigned over = __ballot_sync(kFull, st.cnt + pc > k2::kCap);
-        if (over) flush_lanes<R, SL>(over, st, wbuf, slists, wlists, wtau, k, lane);   // their cnt > 0
+        if (over) flush_lanes<R, LW>(over, st, wbuf, slists, wlists, wtau, k, lane);   // their cnt > 0
 #pragma unroll
         for (int j = 16 * h; j < 16 * h + 16; ++j) {
             if (want && f[j] > thr0) {
@@ -446,7 +454,7 @@ __device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_
     }
 }
 
-template <int R, int CG, bool TOP1, bool DEEP>
+template <int R, int CG, bool TOP1, bool DEEP, bool NARROW>
 __global__ void __launch_bounds__(k2::kThreads, 1)
 topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const __grid_constant__ CUtensorMap tmap_d, uint32_t n, int b, int k,
@@ -455,7 +463,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     uint32_t* __restrict__ ws_prog, unsigned long long* __restrict__ dbg, int epi_mode,
                     int d_hint, int window, int passes) {
     using namespace k2;
-    using C = Cfg<CG, R, TOP1, DEEP>;
+    using C = Cfg<CG, R, TOP1, DEEP, NARROW>;
     constexpr int L = 32 * R;
     constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -656,10 +664,11 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const bool row_valid = row0 + lane < b;
         const int b_pad = n_qt * C::kQTile;
         constexpr bool SL = C::kSmemLists;
+        constexpr int LW = C::kListWidth;
         uint64_t* wbuf = reinterpret_cast<uint64_t*>(sm + C::kOffBuf) + quarter * 32 * kBufStride;
-        uint64_t* slists = reinterpret_cast<uint64_t*>(sm + C::kOffLists) + quarter * 32 * 32;
+        uint64_t* slists = reinterpret_cast<uint64_t*>(sm + C::kOffLists) + quarter * 32 * LW;
         if constexpr (SL) {
-            for (int i = lane; i < 32 * 32; i += 32) slists[i] = 0ull;
+            for (int i = lane; i < 32 * LW; i += 32) slists[i] = 0ull;
             __syncwarp();
         }
         uint64_t* wlists = ws_lists + (static_cast<size_t>(group) * b_pad + row0) * L;
@@ -762,7 +771,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     asm volatile("" ::"r"(v[0]), "r"(v[31]));
                     continue;
                 }
-                if (i == 0 && k > 16 && (c < R || !SL)) {                 // bootstrap for k > 16
+                if (!NARROW && i == 0 && k > 16 && (c < R || !SL)) {      // bootstrap for k > 16
                     // lists in smem (k <= 32): the first strip only; lists in the workspace:
                     // the whole tile, in batches of 32*R columns through the scratch list
                     uint64_t* dst = (c < R) ? wlists : wscratch;
@@ -772,7 +781,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                         sort_filled_lists<R, SL>(st, slists, wlists, dst, c >= R, wtau, k, lane);
                     continue;
                 }
-                process_strip<R, SL>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
+                process_strip<R, LW>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
                                      wbuf, slists, wlists, wtau, k, lane);
             }
             ptx::tc_fence_before();
@@ -785,7 +794,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             // the threshold warps see them
             const long long w2 = dbg ? clock64() : 0;
             const unsigned pending = __ballot_sync(kFull, st.cnt > 0);
-            if (pending) flush_lanes<R, SL>(pending, st, wbuf, slists, wlists, wtau, k, lane);
+            if (pending) flush_lanes<R, LW>(pending, st, wbuf, slists, wlists, wtau, k, lane);
             if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 64) {
                 unsigned long long* tr = dbg + gridDim.x * 40 + i * 4;
                 tr[0] = w1 - w0;                 // waited for the accumulator
@@ -945,14 +954,14 @@ int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
     return kHdrBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8 * (R > 1 ? 2 : 1);
 }
 
-template <int R, int CG, bool TOP1, bool DEEP>
+template <int R, int CG, bool TOP1, bool DEEP, bool NARROW = false>
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
                             int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
                             uint32_t* ws_tau, uint32_t* ws_prog, int passes, float* out_score, int64_t* out_idx,
                             int64_t idx_offset, cudaStream_t stream) {
-    using C = k2::Cfg<CG, R, TOP1, DEEP>;
+    using C = k2::Cfg<CG, R, TOP1, DEEP, NARROW>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1, DEEP>,
+    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1, DEEP, NARROW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("topk_batched: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     if (n_dtiles > 0) {
@@ -968,7 +977,7 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1, DEEP>, tq, td, static_cast<uint32_t>(n), b, k,
+        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1, DEEP, NARROW>, tq, td, static_cast<uint32_t>(n), b, k,
                                n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog,
                                reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window, passes);
         if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
@@ -1039,6 +1048,9 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
           : launch_batched_r<R_, CG, TOP1_, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc,     \
                                                    ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream))
         if (k == 1) rc = SQE_K2_LAUNCH(1, true);
+        else if (CG == 1 && k <= 16)         // narrow smem lists + a fourth stage (see Cfg)
+            rc = launch_batched_r<1, CG, false, false, (CG == 1)>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc,
+                                                                  ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream);
         else if (R == 1) rc = SQE_K2_LAUNCH(1, false);
         else if (R == 2) rc = SQE_K2_LAUNCH(2, false);
         else rc = SQE_K2_LAUNCH(4, false);

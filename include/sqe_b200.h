@@ -73,9 +73,9 @@ SQE_API int sqe_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * K1  fused L2-normalise + cast (ingest and query side).
  * Replaces   norms = np.linalg.norm(E, axis=1, keepdims=True); E = E / (norms + 1e-9)
  *            app/main.py:315-316 (corpus), :353-354 (query), app/embedding_gen.py:215-216.
- * in  [n, dim] fp32;  out [n, dim] of `out_dtype`.  The fp32 result is bit-identical
- * to the numpy expression (same pairwise summation order, IEEE sqrt and divide);
- * bf16 / fp16 are that value rounded to nearest even.
+ * in  [n, dim] fp32;  out [n, dim] of `out_dtype` ([n, 2 dim] bf16 for SQE_BF16X2).  The fp32
+ * result is bit-identical to the numpy expression (same pairwise summation order, IEEE sqrt and
+ * divide); bf16 / fp16 are that value rounded to nearest even; SQE_BF16X2 is its hi/lo split.
  */
 SQE_API int sqe_normalize_cast(const float *in, void *out, int64_t n, int dim, int out_dtype,
                        void *stream);
@@ -107,9 +107,11 @@ SQE_API int sqe_topk_gemv(const void *D, int dtype, int64_t n, int dim, const vo
 /*
  * K2  batched exact cosine top-k on the tensor cores (tcgen05 + TMA), with the
  * per-tile top-k selection fused into the accumulator epilogue so the score matrix
- * never reaches HBM.  Same contract as sqe_topk_gemv; dtype must be SQE_BF16 or SQE_F16;
- * 1 <= k <= SQE_MAX_K_BATCHED; any b >= 1 (queries are processed in groups of 128).
- * D and Q must be 16-byte aligned device pointers.
+ * never reaches HBM.  Same contract as sqe_topk_gemv; dtype must be SQE_BF16, SQE_F16 or
+ * SQE_BF16X2 (fp32 shards: SQE_E_UNSUPPORTED, use sqe_topk_gemv); 1 <= k <= SQE_MAX_K_BATCHED;
+ * any b >= 1 (128 queries per CTA, CTA pairs of 256 when b > 128; more than 1024 queries are
+ * processed in several launches).  D and Q must be 16-byte aligned device pointers.  The
+ * workspace needs no initialisation (it is cleared by the call).
  */
 SQE_API int64_t sqe_topk_batched_workspace_bytes(int64_t n, int b, int k);
 SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const void *Q, int b, int k,
@@ -117,10 +119,11 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
                      int64_t workspace_bytes, void *stream);
 
 /*
- * Tuning knobs (process-wide, for tests and benchmarks; results never depend on them).
+ * Tuning knobs (process-wide, for tests and benchmarks; results never depend on them, except the
+ * diagnostics-only epilogue mode).  sqe_tuning_set returns the previous value, or SQE_E_ARG for
+ * an unknown knob / value.
  *   SQE_TUNE_K2_CTA_GROUP: 0 = choose (CTA pairs when more than 128 queries are in flight),
  *                          1 = single-CTA UMMA (M = 128), 2 = CTA-pair UMMA (cta_group::2, M = 256).
- * Returns the previous value, or SQE_E_ARG for an unknown knob / value.
  *   SQE_TUNE_K2_EPILOGUE_MODE: DIAGNOSTICS ONLY, results are invalid unless 0.  1 = the epilogue
  *                          only reads TMEM, 2 = no epilogue (isolates the TMA + MMA main loop).
  *   SQE_TUNE_K2_D_HINT:    L2 cache policy attached to the shard-row TMA loads: 0 = none (default),

@@ -44,7 +44,7 @@ class GpuQueryCache:
         self.list_name = list_name
         # raw embeddings are only needed to write the reference's JSON entry
         self.keep_raw = (redis_client is not None) if keep_raw is None else keep_raw
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()          # also guards the pinned staging buffers
         self._buf = torch.zeros((self.max_items, ops.ROW_ELEMS[dtype]), dtype=ops.TORCH_DTYPES[dtype],
                                 device=self.device)
         self._head = self.max_items             # live rows are [_head, max_items)
@@ -81,7 +81,7 @@ class GpuQueryCache:
         vec = self._row0(query_emb)
         if vec is None or not self._entries:
             return -1, -1.0, False
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             # ONE launch: normalise the query + scan + top-1 (sqe_search_gemv, k = 1); one 12-byte
             # copy back; the threshold rule is then the reference's own Python-float arithmetic
             buf, s, i = ops.packed_topk_out(self.device, 1, 1)
@@ -107,7 +107,6 @@ class GpuQueryCache:
             if not hit:                                              # main.py:89-90
                 return None
             e = self._entries[idx]
-            old_json = self._entry_json(e) if self.redis is not None else None
             e["freq"] = e.get("freq", 1) + 1                         # main.py:94
             if self.redis is not None:
                 self.redis.lset(self.list_name, idx, self._entry_json(e))   # main.py:95
@@ -121,7 +120,7 @@ class GpuQueryCache:
         if q.ndim != 2 or q.shape[1] != nat.SQE_DIM:
             raise ValueError("expected [B,1024] queries")
         b = q.shape[0]
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             if self._pinned_qb is None or self._pinned_qb.shape[0] < b:
                 self._pinned_qb = torch.empty((max(b, 64), nat.SQE_DIM), dtype=torch.float32).pin_memory()
             self._pinned_qb[:b].copy_(torch.from_numpy(q))

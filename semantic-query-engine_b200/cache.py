@@ -33,7 +33,8 @@ CACHE_SIM_THRESHOLD = 0.96      # main.py:44
 class GpuQueryCache:
     def __init__(self, max_items: int = REDIS_MAX_ITEMS, threshold: float = CACHE_SIM_THRESHOLD,
                  *, dtype: str = "fp32", device: Optional[torch.device] = None,
-                 redis_client=None, list_name: str = REDIS_CACHE_LIST, keep_raw: bool = None):
+                 redis_client=None, list_name: str = REDIS_CACHE_LIST, keep_raw: bool = None,
+                 use_graphs: bool = True):
         if dtype not in ops.TORCH_DTYPES:
             raise ValueError(f"dtype must be one of {sorted(ops.TORCH_DTYPES)}")
         self.max_items = int(max_items)
@@ -49,6 +50,8 @@ class GpuQueryCache:
                                 device=self.device)
         self._head = self.max_items             # live rows are [_head, max_items)
         self._entries: List[dict] = []          # list order, index 0 = newest
+        self.use_graphs = use_graphs
+        self._graph = None                       # captured single-query lookup; dropped on every mutation
         self._pinned = torch.empty((1, nat.SQE_DIM), dtype=torch.float32).pin_memory()
         self._pinned_out = torch.empty((4096,), dtype=torch.uint8).pin_memory()
         self._pinned_qb: Optional[torch.Tensor] = None
@@ -82,21 +85,36 @@ class GpuQueryCache:
         if vec is None or not self._entries:
             return -1, -1.0, False
         with self._lock, torch.cuda.device(self.device):
-            # ONE launch: normalise the query + scan + top-1 (sqe_search_gemv, k = 1); one 12-byte
-            # copy back; the threshold rule is then the reference's own Python-float arithmetic
-            buf, s, i = ops.packed_topk_out(self.device, 1, 1)
-            ops.search_gemv(self._buf[self._head:], self._to_device(vec), 1, n=len(self._entries),
-                            out=(s, i))
-            self._pinned_out[:12].copy_(buf, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            raw = self._pinned_out[:12].numpy()
-            row = int(raw[:8].view(np.int64)[0])
-            sim = float(raw[8:12].view(np.float32)[0])
+            row, sim = self._top1(vec)
         best_sim, best_index = -1.0, -1                  # main.py:74-75
         if row >= 0 and sim > best_sim:                  # main.py:84 (strict '>')
             best_sim, best_index = sim, row
         hit = best_index >= 0 and not (best_sim < self.threshold)    # main.py:89
         return best_index, best_sim, hit
+
+    def _top1(self, vec: np.ndarray) -> Tuple[int, float]:
+        """(row, similarity) of the best live entry for one raw query.  ONE kernel: normalise the
+        query + scan + top-1 (sqe_search_gemv, k = 1) -- replayed from a captured CUDA graph
+        (H2D, kernel, D2H) when possible."""
+        live = self._buf[self._head:]
+        if self.use_graphs:
+            g = self._graph
+            if g is None or g.rows != len(self._entries) or g.shard_ptr != live.data_ptr():
+                try:
+                    g = self._graph = ops.SingleQueryGraph(live, len(self._entries), 1)
+                except Exception as e:                       # capture not possible here: stay eager
+                    print(f"[GpuQueryCache] CUDA graph capture failed ({e}); using eager launches")
+                    self.use_graphs = False
+                    g = None
+            if g is not None:
+                s_, r_ = g.run(vec)
+                return int(r_[0]), float(s_[0])
+        buf, s, i = ops.packed_topk_out(self.device, 1, 1)
+        ops.search_gemv(live, self._to_device(vec), 1, n=len(self._entries), out=(s, i))
+        self._pinned_out[:12].copy_(buf, non_blocking=True)     # one 12-byte copy back
+        torch.cuda.current_stream(self.device).synchronize()
+        raw = self._pinned_out[:12].numpy()
+        return int(raw[:8].view(np.int64)[0]), float(raw[8:12].view(np.float32)[0])
 
     def get(self, query_emb) -> Optional[str]:
         """lfu_cache_get, main.py:67-98."""

@@ -35,7 +35,8 @@ class GpuCorpusIndex:
     def __init__(self, client=None, index_name: str = "", *, dtype: str = "bf16",
                  device: Optional[torch.device] = None, initial_capacity: int = 65536,
                  score_mode: str = "cosine", strict: bool = False,
-                 return_embedding: bool = False, keep_payload: bool = True):
+                 return_embedding: bool = False, keep_payload: bool = True,
+                 use_graphs: bool = True):
         """`client` / `index_name` are accepted for signature compatibility
         (main.py:296-298) and ignored: there is no OpenSearch behind this index.
 
@@ -62,6 +63,9 @@ class GpuCorpusIndex:
         self._initial_capacity = int(initial_capacity)
         self._docs: List[Dict[str, str]] = []   # payload table, row-aligned
         self._ids: List[str] = []
+        # CUDA graphs of the single-query step, keyed by k; dropped whenever rows are added
+        self.use_graphs = use_graphs
+        self._graphs: Dict[int, "ops.SingleQueryGraph"] = {}
         self._pinned_q: Optional[torch.Tensor] = None
         self._pinned_out: Optional[torch.Tensor] = None
 
@@ -169,6 +173,7 @@ class GpuCorpusIndex:
                 ops.normalize_cast(blk, self.dtype, out=self._shard[base + lo: base + hi])
             torch.cuda.current_stream(self.device).synchronize()
         self._rows = base + n                            # publish
+        self._graphs.clear()                             # captured row count / shard pointer are stale
 
     # ------------------------------------------------------------------- search
     @staticmethod
@@ -232,13 +237,32 @@ class GpuCorpusIndex:
             return []
         try:
             q = self._as_rows(query_emb)[:1]                             # main.py:355 sends row 0
-            scores, rows = self.search_batch(q, k)
-            return self.hits_from_rows(scores[0], rows[0])
+            scores, rows = self._search_one(q, k)
+            return self.hits_from_rows(scores, rows)
         except Exception as e:                                           # main.py:371-373
             if self.strict:
                 raise
             print(f"[GpuCorpusIndex] Search error: {e}")
             return []
+
+    def _search_one(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """The reference's call shape (one query): replay a captured CUDA graph (H2D, fused
+        normalise + scan + top-k, D2H) when possible, else the eager path."""
+        if self.use_graphs and self._rows > 0 and 1 <= k <= nat.SQE_MAX_K_GEMV:
+            with self._search_lock:
+                g = self._graphs.get(k)
+                if g is None or g.rows != self._rows or g.shard_ptr != self._shard.data_ptr():
+                    try:
+                        g = ops.SingleQueryGraph(self._shard, self._rows, k)
+                        self._graphs[k] = g
+                    except Exception as e:                   # capture not possible here: stay eager
+                        print(f"[GpuCorpusIndex] CUDA graph capture failed ({e}); using eager launches")
+                        self.use_graphs = False
+                        g = None
+                if g is not None:
+                    return g.run(q[0])
+        scores, rows = self.search_batch(q, k)
+        return scores[0], rows[0]
 
     def hits_from_rows(self, scores, rows) -> List[Tuple[Dict[str, str], float]]:
         """(score, row) arrays of ONE query -> the reference's hit list (main.py:364-367)."""

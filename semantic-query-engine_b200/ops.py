@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _native as nat
@@ -260,3 +261,48 @@ def exchange_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int, rank: in
                  arr, capacity_entries, epoch & 0xFFFFFFFF, wait_mask, out_s.data_ptr(),
                  out_i.data_ptr(), _stream(dev))
     return out_s, out_i
+
+
+class SingleQueryGraph:
+    """A captured CUDA graph of the launch-bound single-query step:
+    pinned host query -> device, `sqe_search_gemv` (normalise + scan + top-k), device -> pinned host.
+    Replaying it costs one graph launch instead of several Python-level copies and launches.
+    The shard pointer, row count, k and row offset are baked in: build a new one when they change."""
+
+    def __init__(self, shard: torch.Tensor, rows: int, k: int, idx_offset: int = 0):
+        dev = shard.device
+        self.device = dev
+        self.k = int(k)
+        self.rows = int(rows)
+        self.shard_ptr = shard.data_ptr()
+        self._shard = shard                                    # keep the storage alive
+        self.host_q = torch.empty((1, nat.SQE_DIM), dtype=torch.float32).pin_memory()
+        self.host_out = torch.empty((self.k * 12,), dtype=torch.uint8).pin_memory()
+        self.dev_q = torch.empty((1, nat.SQE_DIM), dtype=torch.float32, device=dev)
+        self.dev_out, self.scores, self.idx = packed_topk_out(dev, 1, self.k)
+        self.host_q.zero_()
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                      # warm-up on the side stream (allocates its workspace)
+                self._body()
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._body()
+        self._np_q = self.host_q.numpy()
+        self._np_out = self.host_out.numpy()
+
+    def _body(self) -> None:
+        self.dev_q.copy_(self.host_q, non_blocking=True)
+        search_gemv(self._shard, self.dev_q, self.k, idx_offset=0, n=self.rows, out=(self.scores, self.idx))
+        self.host_out.copy_(self.dev_out, non_blocking=True)
+
+    def run(self, q_row: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """q_row: fp32 [1024] (raw).  Returns (scores [k] fp32, rows [k] int64) as fresh arrays."""
+        self._np_q[0, :] = q_row
+        self.graph.replay()
+        nat.launch_count += 1                                  # the replayed sqe_search_gemv
+        torch.cuda.current_stream(self.device).synchronize()
+        k = self.k
+        return self._np_out[k * 8:].view(np.float32).copy(), self._np_out[: k * 8].view(np.int64).copy()

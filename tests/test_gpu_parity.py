@@ -379,6 +379,35 @@ def test_split_bf16_index_is_in_the_fp32_tolerance_class(sqe, golden_dir):
                 assert ib[qi, :k].tolist() == g["res_idx"][qi, ki, :k].tolist(), (qi, k)
 
 
+def test_cuda_graph_replay_equals_eager_single_query_path(sqe):
+    """`search` / cache `get` replay a captured CUDA graph (H2D, fused kernel, D2H); results must be
+    identical to the eager launches, across ingest (re-capture) and cache mutations."""
+    rng = np.random.default_rng(15)
+    emb = make_corpus(rng, 9000)
+    docs = [{"doc_id": f"d{i // 5}", "text": f"t{i}"} for i in range(9000)]
+    qs = rng.standard_normal((6, 1, DIM)).astype(np.float32)
+    qs[1, 0] = emb[7] * 2
+    g = sqe.GpuCorpusIndex(dtype="bf16", strict=True, use_graphs=True)
+    e = sqe.GpuCorpusIndex(dtype="bf16", strict=True, use_graphs=False)
+    for lo, hi in ((0, 4000), (4000, 9000)):                 # second ingest invalidates the graphs
+        g.add_embeddings(emb[lo:hi], docs[lo:hi])
+        e.add_embeddings(emb[lo:hi], docs[lo:hi])
+        for q in qs:
+            for k in (3, 10):
+                assert g.search(q, k=k) == e.search(q, k=k)
+    assert g.use_graphs and len(g._graphs) == 2
+    cg = sqe.GpuQueryCache(max_items=4, threshold=0.96, use_graphs=True)
+    ce = sqe.GpuQueryCache(max_items=4, threshold=0.96, use_graphs=False)
+    for step in range(12):                                   # puts, hits, LFU evictions
+        q = qs[step % 6]
+        assert cg.get(q) == ce.get(q)
+        if step % 2 == 0:
+            cg.put(q * (1.0 + step), f"r{step}")
+            ce.put(q * (1.0 + step), f"r{step}")
+        assert cg.get(q) == ce.get(q)
+    assert cg.responses() == ce.responses() and cg.freqs() == ce.freqs() and cg.use_graphs
+
+
 def test_concurrent_searches_from_many_threads_are_safe(sqe):
     """Unlike the reference (one event-loop thread) callers may search from several threads:
     launches that share a workspace are enqueued atomically, staging buffers are per call."""

@@ -172,3 +172,16 @@ class ShardedCorpusIndex:
             buf, s, i = ops.packed_topk_out(dev, q.shape[0], k)
             self.search_device(qd, k, out=(s, i))
             return self.local._fetch_packed(buf, q.shape[0], k)  # one D2H copy
+
+    def search_batches(self, batches, k: int = 3, depth: int = 2):
+        """Streaming form of `search_batch` (every rank passes the same sequence of batches):
+        yields one `(scores, global rows)` per batch, in order, while the copies of the
+        neighbouring batches overlap the scan + exchange of the current one
+        (GpuCorpusIndex.search_batches)."""
+        dev = self._comm_device()
+        if dev.type != "cuda" or self.local is None:
+            for qb in batches:
+                yield self.search_batch(qb, k)
+            return
+        yield from self.local.search_batches(
+            batches, k, depth, device_fn=lambda qd, kk, out: self.search_device(qd, kk, out=out))

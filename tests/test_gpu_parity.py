@@ -408,6 +408,34 @@ def test_cuda_graph_replay_equals_eager_single_query_path(sqe):
     assert cg.responses() == ce.responses() and cg.freqs() == ce.freqs() and cg.use_graphs
 
 
+def test_streaming_search_batches_equal_per_batch_calls(sqe):
+    """`search_batches` overlaps the copies of neighbouring batches with the scan; every yielded
+    result must be identical to `search_batch` of that batch -- ragged batch sizes (b = 1 takes the
+    GEMV form, larger ones the tensor-core form), pinned and pageable inputs, any depth."""
+    import torch
+    rng = np.random.default_rng(16)
+    emb = make_corpus(rng, 20000)
+    index = sqe.GpuCorpusIndex(dtype="bf16", strict=True, keep_payload=False)
+    index.add_embeddings(emb, None)
+    sizes = [64, 1, 200, 64, 7, 300, 64, 64, 129]
+    batches = [rng.standard_normal((n, DIM)).astype(np.float32) for n in sizes]
+    batches[3][5] = emb[11] * 3
+    pinned = torch.from_numpy(batches[4].copy()).pin_memory()
+    batches[4] = pinned.numpy()
+    want = [index.search_batch(q, 10) for q in batches]
+    for depth in (1, 2, 3):
+        got = list(index.search_batches(iter(batches), 10, depth=depth))
+        assert len(got) == len(want)
+        for (ws, wi), (gs, gi) in zip(want, got):
+            assert np.array_equal(wi, gi) and np.array_equal(ws, gs)
+    sharded = sqe.ShardedCorpusIndex(index)
+    sharded.finalize()
+    got = list(sharded.search_batches(batches, 10))
+    for (ws, wi), (gs, gi) in zip(want, got):
+        assert np.array_equal(wi, gi) and np.array_equal(ws, gs)
+    assert list(index.search_batches([], 10)) == []
+
+
 def test_concurrent_searches_from_many_threads_are_safe(sqe):
     """Unlike the reference (one event-loop thread) callers may search from several threads:
     launches that share a workspace are enqueued atomically, staging buffers are per call."""

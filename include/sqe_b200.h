@@ -111,7 +111,9 @@ SQE_API int sqe_topk_gemv(const void *D, int dtype, int64_t n, int dim, const vo
  * SQE_BF16X2 (fp32 shards: SQE_E_UNSUPPORTED, use sqe_topk_gemv); 1 <= k <= SQE_MAX_K_BATCHED;
  * any b >= 1 (128 queries per CTA, CTA pairs of 256 when b > 128; more than 1024 queries are
  * processed in several launches).  D and Q must be 16-byte aligned device pointers.  The
- * workspace needs no initialisation (it is cleared by the call).
+ * workspace needs no initialisation (it is cleared by the call) and its first 4096 bytes are
+ * ZERO again when the call has finished, so the same workspace may afterwards be passed to
+ * sqe_topk_gemv / sqe_search_gemv (sqe_cache_top1 relies on this).
  */
 SQE_API int64_t sqe_topk_batched_workspace_bytes(int64_t n, int b, int k);
 SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const void *Q, int b, int k,
@@ -161,6 +163,8 @@ SQE_API void sqe_debug_k2_timers(void *device_buffer);
  * fp32 number).
  * `path`: 0 = choose (tensor cores when dtype is 16-bit and b > 1), 1 = force GEMV, 2 = force
  * tensor cores.
+ * Workspace: same contract as sqe_topk_gemv (first 4096 bytes zero on first use; every call, on
+ * either path and for any b, leaves them zero), so one workspace serves all lookups of a cache.
  */
 SQE_API int64_t sqe_cache_top1_workspace_bytes(int64_t n, int b);
 SQE_API int sqe_cache_top1(const void *C, int dtype, int64_t n, int dim, const void *Q, int b,

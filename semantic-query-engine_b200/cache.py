@@ -154,6 +154,28 @@ class GpuQueryCache:
             return (raw[: b * 4].view(np.int32).copy(), raw[b * 4: b * 8].view(np.float32).copy(),
                     raw[b * 8:].copy())
 
+    def lookup_batches(self, batches, path: int = 0, depth: int = 2):
+        """`lookup_batch` for a stream of query batches (BASELINE config 5 is exactly this):
+        a generator yielding `(idx, score, hit)` per batch, in order, identical to `lookup_batch`;
+        the copies of neighbouring batches overlap the scan (ops.stream_pipeline).  The cache must
+        not be mutated while the generator is being consumed."""
+        def as_rows(x) -> np.ndarray:
+            q = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+            if q.ndim != 2 or q.shape[1] != nat.SQE_DIM:
+                raise ValueError("expected [B,1024] queries")
+            return q
+
+        def launch(qd: torch.Tensor, buf: torch.Tensor) -> None:
+            b = qd.shape[0]
+            self.lookup_device(qd, path, out=(buf[: b * 4].view(torch.int32),
+                                              buf[b * 4: b * 8].view(torch.float32), buf[b * 8:]))
+
+        def unpack(raw: np.ndarray, b: int):
+            return (raw[: b * 4].view(np.int32).copy(), raw[b * 4: b * 8].view(np.float32).copy(),
+                    raw[b * 8:].copy())
+
+        return ops.stream_pipeline(self.device, batches, as_rows, lambda b: b * 9, launch, unpack, depth)
+
     def lookup_device(self, q_dev: torch.Tensor, path: int = 0, out=None):
         qn = ops.normalize_cast(q_dev.contiguous(), self.dtype)
         return ops.cache_top1(self._buf[self._head:], qn, self.threshold, path=path,

@@ -31,35 +31,6 @@ from . import ops
 EMBED_DIM = nat.SQE_DIM          # main.py:38
 
 
-class _StreamSlot:
-    """Buffers and events of one in-flight batch of `search_batches` (reused round robin)."""
-
-    def __init__(self):
-        self.host_q: Optional[torch.Tensor] = None      # pinned staging for unpinned inputs
-        self.dev_q: Optional[torch.Tensor] = None
-        self.dev_out: Optional[torch.Tensor] = None     # packed rows int64 | scores fp32
-        self.host_out: Optional[torch.Tensor] = None    # pinned
-        self.ev_h2d = torch.cuda.Event()
-        self.ev_done = torch.cuda.Event()
-        self.ev_d2h = torch.cuda.Event()
-
-    def stage(self, q: np.ndarray, b: int, k: int, dev: torch.device) -> torch.Tensor:
-        """Size the buffers for a [b,1024] batch with k results per query; returns the
-        page-locked source of the host->device copy (the caller's array when it is pinned)."""
-        if self.dev_q is None or self.dev_q.shape[0] < b:
-            self.dev_q = torch.empty((b, EMBED_DIM), dtype=torch.float32, device=dev)
-        if self.dev_out is None or self.dev_out.numel() < b * k * 12:
-            self.dev_out = torch.empty((b * k * 12,), dtype=torch.uint8, device=dev)
-            self.host_out = torch.empty((b * k * 12,), dtype=torch.uint8).pin_memory()
-        t = torch.from_numpy(q)
-        if t.is_pinned():
-            return t
-        if self.host_q is None or self.host_q.shape[0] < b:
-            self.host_q = torch.empty((b, EMBED_DIM), dtype=torch.float32).pin_memory()
-        self.host_q[:b].copy_(t)
-        return self.host_q[:b]
-
-
 class GpuCorpusIndex:
     def __init__(self, client=None, index_name: str = "", *, dtype: str = "bf16",
                  device: Optional[torch.device] = None, initial_capacity: int = 65536,
@@ -252,56 +223,22 @@ class GpuCorpusIndex:
         each): a generator that yields one `(scores [B,k], rows [B,k])` per input batch, in
         order, with identical contents.  The host->device copy of batch j+1 and the
         device->host copy of batch j-1 run on copy streams while batch j is being scored, so the
-        GPU never waits for PCIe or for Python; at most `depth` batches are in flight and result
-        j-depth is handed out when batch j is submitted.  `device_fn(q_dev, k, out)` replaces the
-        local scan (ShardedCorpusIndex passes scan + exchange)."""
-        if depth < 1:
-            raise ValueError("depth must be >= 1")
+        GPU never waits for PCIe or for Python (ops.stream_pipeline).  `device_fn(q_dev, k, out)`
+        replaces the local scan (ShardedCorpusIndex passes scan + exchange)."""
         fn = device_fn if device_fn is not None else (lambda qd, kk, out: self.search_device(qd, kk, out=out))
-        dev = self.device
-        with torch.cuda.device(dev):
-            compute = torch.cuda.current_stream(dev)
-            h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        slots = [_StreamSlot() for _ in range(depth)]
-        pending: List[Tuple[int, int]] = []             # (slot index, batch rows), oldest first
 
-        def collect(si: int, b: int):
-            s = slots[si]
-            s.ev_d2h.synchronize()
-            arr = s.host_out[: b * k * 12].numpy()
+        def launch(qd: torch.Tensor, buf: torch.Tensor) -> None:
+            b = qd.shape[0]
+            fn(qd, k, (buf[b * k * 8:].view(torch.float32).view(b, k),
+                       buf[: b * k * 8].view(torch.int64).view(b, k)))
+
+        def unpack(arr: np.ndarray, b: int):
             rows = arr[: b * k * 8].view(np.int64).reshape(b, k).copy()
             scores = arr[b * k * 8:].view(np.float32).reshape(b, k).copy()
             return scores, rows
 
-        j = 0
-        for batch in batches:
-            q = self._as_rows(batch)
-            b = q.shape[0]
-            si = j % depth
-            done = None
-            if len(pending) == depth:                    # the slot's previous occupant
-                done = collect(*pending.pop(0))
-            s = slots[si]
-            with torch.cuda.device(dev):
-                src = s.stage(q, b, k, dev)
-                with torch.cuda.stream(h2d):
-                    s.dev_q[:b].copy_(src, non_blocking=True)
-                    s.ev_h2d.record(h2d)
-                compute.wait_event(s.ev_h2d)
-                buf = s.dev_out[: b * k * 12]
-                out = (buf[b * k * 8:].view(torch.float32).view(b, k), buf[: b * k * 8].view(torch.int64).view(b, k))
-                fn(s.dev_q[:b], k, out)
-                s.ev_done.record(compute)
-                with torch.cuda.stream(d2h):
-                    d2h.wait_event(s.ev_done)
-                    s.host_out[: b * k * 12].copy_(buf, non_blocking=True)
-                    s.ev_d2h.record(d2h)
-            pending.append((si, b))
-            j += 1
-            if done is not None:
-                yield done
-        while pending:
-            yield collect(*pending.pop(0))
+        return ops.stream_pipeline(self.device, batches, self._as_rows, lambda b: b * k * 12,
+                                   launch, unpack, depth)
 
     def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0, out=None
                       ) -> Tuple[torch.Tensor, torch.Tensor]:

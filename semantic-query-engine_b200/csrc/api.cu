@@ -205,7 +205,7 @@ int64_t sqe_cache_top1_workspace_bytes(int64_t n, int b) {
     if (b < 1) b = 1;
     int64_t g = sqe_topk_gemv_workspace_bytes(b, 1);
     int64_t t = sqe_topk_batched_workspace_bytes(n, b, 1);
-    return cache_stage_bytes(b) + (g > t ? g : t);
+    return cache_stage_bytes(b) + 256 + (g > t ? g : t);      // + alignment slack for the staging area
 }
 
 int sqe_cache_top1(const void* C, int dtype, int64_t n, int dim, const void* Q, int b,
@@ -218,15 +218,20 @@ int sqe_cache_top1(const void* C, int dtype, int64_t n, int dim, const void* Q, 
     if (path < 0 || path > 2) { set_error("cache_top1: bad path %d", path); return SQE_E_ARG; }
     const int64_t stage = cache_stage_bytes(b);
     if (workspace_bytes < stage) { set_error("cache_top1: workspace too small"); return SQE_E_WORKSPACE; }
+    // Layout: [kernel workspace (zeroed 4 KB header first) ... | staging (idx, score) at the END].
+    // The header must sit at the same address for every b and every path: it is shared state
+    // between calls (GEMV ticket counters; both kernels leave it zero).
     char* ws = static_cast<char*>(workspace);
-    int64_t* st_idx = reinterpret_cast<int64_t*>(ws);
-    float* st_score = reinterpret_cast<float*>(ws + static_cast<int64_t>(b) * 8);
+    char* st = ws + ((workspace_bytes - stage) & ~static_cast<int64_t>(255));
+    int64_t* st_idx = reinterpret_cast<int64_t*>(st);
+    float* st_score = reinterpret_cast<float*>(st + static_cast<int64_t>(b) * 8);
+    const int64_t kernel_bytes = st - ws;
     const bool tensor = (path == 2) || (path == 0 && dtype != SQE_F32 && b > 1);
     if (tensor && dtype == SQE_F32) { set_error("cache_top1: tensor path needs a bf16/fp16 cache"); return SQE_E_UNSUPPORTED; }
     if (tensor)
-        rc = sqe_topk_batched(C, dtype, n, dim, Q, b, 1, st_score, st_idx, 0, ws + stage, workspace_bytes - stage, stream);
+        rc = sqe_topk_batched(C, dtype, n, dim, Q, b, 1, st_score, st_idx, 0, ws, kernel_bytes, stream);
     else
-        rc = sqe_topk_gemv(C, dtype, n, dim, Q, b, 1, st_score, st_idx, 0, ws + stage, workspace_bytes - stage, stream);
+        rc = sqe_topk_gemv(C, dtype, n, dim, Q, b, 1, st_score, st_idx, 0, ws, kernel_bytes, stream);
     if (rc != SQE_OK) return rc;
     rc = launch_cache_finalize(st_score, st_idx, b, threshold, out_score, out_idx, out_hit,
                                static_cast<cudaStream_t>(stream));

@@ -827,17 +827,27 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
 }
 
+// The first 4 KB of a workspace double as the ticket counters of the GEMV kernel when a caller
+// shares one workspace between entry points (sqe_cache_top1 does); the header contract
+// (include/sqe_b200.h) is that every call leaves them ZERO.  The main kernel has finished
+// (stream order) when the merge kernel runs, so the published bounds are dead by now.
+__device__ __forceinline__ void clear_header(uint32_t* ws_tau) {
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < k2::kQueriesPerLaunch; i += blockDim.x) ws_tau[i] = 0u;
+}
+
 // Merge the per-group partial lists of each query.  Few groups (large batches): one warp per
 // query, four queries per CTA.  Many groups (small batches: up to one group per SM): one CTA
 // of eight warps per query -- each warp folds every 8th list (the next one is in flight while
 // the current one merges), warp 0 folds the eight partial lists.
 template <int R>
 __global__ void __launch_bounds__(256)
-batched_merge_kernel(const uint64_t* __restrict__ ws_lists, int n_groups, int b, int b_pad, int k,
-                     int warps_per_query, float* __restrict__ out_score,
+batched_merge_kernel(const uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau, int n_groups,
+                     int b, int b_pad, int k, int warps_per_query, float* __restrict__ out_score,
                      int64_t* __restrict__ out_idx, int64_t idx_offset) {
     constexpr int L = 32 * R;
     __shared__ uint64_t s_part[8][L];
+    clear_header(ws_tau);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps = blockDim.x >> 5;
@@ -887,8 +897,10 @@ batched_merge_kernel(const uint64_t* __restrict__ ws_lists, int n_groups, int b,
 
 // k = 1: every group wrote at most one key (slot 0 of its list); the result is their maximum.
 __global__ void __launch_bounds__(128)
-top1_merge_kernel(const uint64_t* __restrict__ ws_lists, int n_groups, int b, int b_pad,
-                  float* __restrict__ out_score, int64_t* __restrict__ out_idx, int64_t idx_offset) {
+top1_merge_kernel(const uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau, int n_groups,
+                  int b, int b_pad, float* __restrict__ out_score, int64_t* __restrict__ out_idx,
+                  int64_t idx_offset) {
+    clear_header(ws_tau);
     const int lane = threadIdx.x & 31;
     const int query = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (query >= b) return;
@@ -984,13 +996,13 @@ static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_
     }
     const int mg = n_dtiles > 0 ? n_groups : 0;
     if constexpr (TOP1) {
-        top1_merge_kernel<<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, mg, b, n_qt * C::kQTile, out_score,
+        top1_merge_kernel<<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, ws_tau, mg, b, n_qt * C::kQTile, out_score,
                                                            out_idx, idx_offset);
     } else if (mg > 32) {
-        batched_merge_kernel<R><<<b, 256, 0, stream>>>(ws_lists, mg, b, n_qt * C::kQTile, k, 8, out_score,
+        batched_merge_kernel<R><<<b, 256, 0, stream>>>(ws_lists, ws_tau, mg, b, n_qt * C::kQTile, k, 8, out_score,
                                                        out_idx, idx_offset);
     } else {
-        batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, mg, b, n_qt * C::kQTile, k, 1,
+        batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, ws_tau, mg, b, n_qt * C::kQTile, k, 1,
                                                                  out_score, out_idx, idx_offset);
     }
     e = cudaGetLastError();

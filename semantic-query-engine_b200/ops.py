@@ -133,8 +133,11 @@ def topk_gemv(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
 
 
 def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 0,
-                n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """K1 (query side) + K3 in one launch: `q_raw` fp32 [nq,1024] un-normalised."""
+                n: Optional[int] = None, out=None, ws: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1 (query side) + K3 in one launch: `q_raw` fp32 [nq,1024] un-normalised.  `ws`: a private
+    workspace (zero-initialised uint8 tensor) instead of the per-stream one -- a captured CUDA
+    graph must own the memory its kernel uses."""
     dev = _require_cuda(D, q_raw)
     if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
         raise ValueError("q_raw must be fp32 [nq,1024]")
@@ -149,7 +152,10 @@ def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 
         return scores, idx
     with _launch_lock, torch.cuda.device(dev):
         need = nat.load().sqe_topk_gemv_workspace_bytes(b, k)
-        ws = _workspace(dev, "gemv", need)
+        if ws is None:
+            ws = _workspace(dev, "gemv", need)
+        elif ws.numel() < need or ws.device != dev or ws.dtype != torch.uint8:
+            raise ValueError("bad private workspace")
         nat.call("sqe_search_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
                  q_raw.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
                  ws.data_ptr(), ws.numel(), _stream(dev))
@@ -273,6 +279,7 @@ class SingleQueryGraph:
         dev = shard.device
         self.device = dev
         self.k = int(k)
+        self.idx_offset = int(idx_offset)
         self.rows = int(rows)
         self.shard_ptr = shard.data_ptr()
         self._shard = shard                                    # keep the storage alive
@@ -280,6 +287,10 @@ class SingleQueryGraph:
         self.host_out = torch.empty((self.k * 12,), dtype=torch.uint8).pin_memory()
         self.dev_q = torch.empty((1, nat.SQE_DIM), dtype=torch.float32, device=dev)
         self.dev_out, self.scores, self.idx = packed_topk_out(dev, 1, self.k)
+        # private workspace: the per-stream ones are shared by everything launched on that stream
+        # and replaced when they grow, neither of which a captured pointer survives
+        self._ws = torch.zeros((int(nat.load().sqe_topk_gemv_workspace_bytes(1, self.k)),),
+                               dtype=torch.uint8, device=dev)
         self.host_q.zero_()
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
@@ -295,7 +306,8 @@ class SingleQueryGraph:
 
     def _body(self) -> None:
         self.dev_q.copy_(self.host_q, non_blocking=True)
-        search_gemv(self._shard, self.dev_q, self.k, idx_offset=0, n=self.rows, out=(self.scores, self.idx))
+        search_gemv(self._shard, self.dev_q, self.k, idx_offset=self.idx_offset, n=self.rows, out=(self.scores, self.idx),
+                    ws=self._ws)
         self.host_out.copy_(self.dev_out, non_blocking=True)
 
     def run(self, q_row: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
@@ -306,3 +318,81 @@ class SingleQueryGraph:
         torch.cuda.current_stream(self.device).synchronize()
         k = self.k
         return self._np_out[k * 8:].view(np.float32).copy(), self._np_out[: k * 8].view(np.int64).copy()
+
+
+class _StreamSlot:
+    """Buffers and events of one in-flight batch of `stream_pipeline` (reused round robin)."""
+
+    def __init__(self):
+        self.host_q: Optional[torch.Tensor] = None      # pinned staging for pageable inputs
+        self.dev_q: Optional[torch.Tensor] = None
+        self.dev_out: Optional[torch.Tensor] = None     # packed result bytes
+        self.host_out: Optional[torch.Tensor] = None    # pinned
+        self.ev_h2d = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        self.ev_d2h = torch.cuda.Event()
+
+    def stage(self, q: np.ndarray, b: int, out_bytes: int, dev: torch.device) -> torch.Tensor:
+        """Size the buffers for a [b,1024] batch; returns the page-locked source of the
+        host->device copy (the caller's own array when it is already pinned)."""
+        if self.dev_q is None or self.dev_q.shape[0] < b:
+            self.dev_q = torch.empty((b, nat.SQE_DIM), dtype=torch.float32, device=dev)
+        if self.dev_out is None or self.dev_out.numel() < out_bytes:
+            self.dev_out = torch.empty((out_bytes,), dtype=torch.uint8, device=dev)
+            self.host_out = torch.empty((out_bytes,), dtype=torch.uint8).pin_memory()
+        t = torch.from_numpy(q)
+        if t.is_pinned():
+            return t
+        if self.host_q is None or self.host_q.shape[0] < b:
+            self.host_q = torch.empty((b, nat.SQE_DIM), dtype=torch.float32).pin_memory()
+        self.host_q[:b].copy_(t)
+        return self.host_q[:b]
+
+
+def stream_pipeline(dev: torch.device, batches, as_rows, out_bytes, launch, unpack, depth: int = 2):
+    """Generator behind `GpuCorpusIndex.search_batches` / `GpuQueryCache.lookup_batches`.
+
+    For every host batch: `as_rows(batch)` -> fp32 [b,1024]; its host->device copy runs on a copy
+    stream, `launch(q_dev [b,1024], packed_out uint8 [out_bytes(b)])` enqueues the kernels on the
+    caller's current stream, the packed result returns on a second copy stream, and
+    `unpack(host uint8 array, b)` turns it into fresh host arrays.  At most `depth` batches are in
+    flight; the result of batch j-depth is yielded when batch j has been submitted, so the copies
+    of the neighbouring batches overlap the kernels of the current one."""
+    if depth < 1:
+        raise ValueError("depth must be >= 1")
+    with torch.cuda.device(dev):
+        compute = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    slots = [_StreamSlot() for _ in range(depth)]
+    pending = []                                       # (slot index, batch rows, bytes), oldest first
+
+    def collect(si: int, b: int, nbytes: int):
+        s = slots[si]
+        s.ev_d2h.synchronize()
+        return unpack(s.host_out[:nbytes].numpy(), b)
+
+    j = 0
+    for batch in batches:
+        q = as_rows(batch)
+        b = q.shape[0]
+        nbytes = out_bytes(b)
+        done = collect(*pending.pop(0)) if len(pending) == depth else None   # frees slot j % depth
+        s = slots[j % depth]
+        with torch.cuda.device(dev):
+            src = s.stage(q, b, nbytes, dev)
+            with torch.cuda.stream(h2d):
+                s.dev_q[:b].copy_(src, non_blocking=True)
+                s.ev_h2d.record(h2d)
+            compute.wait_event(s.ev_h2d)
+            launch(s.dev_q[:b], s.dev_out[:nbytes])
+            s.ev_done.record(compute)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(s.ev_done)
+                s.host_out[:nbytes].copy_(s.dev_out[:nbytes], non_blocking=True)
+                s.ev_d2h.record(d2h)
+        pending.append((j % depth, b, nbytes))
+        j += 1
+        if done is not None:
+            yield done
+    while pending:
+        yield collect(*pending.pop(0))

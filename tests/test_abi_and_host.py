@@ -144,6 +144,9 @@ ws, wi = oracle.topk_cosine(d, oracle.normalize_rows(q), k)
 assert np.array_equal(i, wi), (rank, i, wi)
 assert np.allclose(s, ws, atol=1e-6)
 assert list(i[0][:2]) == [3, 900]
+outs = list(idx.search_batches([q, q[:2], q[1:]], k))          # streaming form: same lists, in order
+assert len(outs) == 3 and np.array_equal(outs[0][1], wi) and np.array_equal(outs[1][1], wi[:2])
+assert np.array_equal(outs[2][1], wi[1:])
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -434,6 +434,17 @@ def test_streaming_search_batches_equal_per_batch_calls(sqe):
     for (ws, wi), (gs, gi) in zip(want, got):
         assert np.array_equal(wi, gi) and np.array_equal(ws, gs)
     assert list(index.search_batches([], 10)) == []
+    # the query-cache stream (BASELINE config 5): same contract
+    cache = sqe.GpuQueryCache(max_items=6000, threshold=0.95, dtype="bf16")
+    cache.bulk_load(emb[:6000])
+    qb = [rng.standard_normal((n, DIM)).astype(np.float32) for n in (64, 64, 1, 33, 64)]
+    qb[1][3] = emb[42] * 0.5                               # a certain hit
+    want_c = [cache.lookup_batch(q) for q in qb]
+    got_c = list(cache.lookup_batches(qb))
+    assert len(got_c) == len(want_c) and got_c[1][2][3] == 1 and got_c[1][0][3] == 42
+    for w, g in zip(want_c, got_c):
+        for a, b_ in zip(w, g):
+            assert np.array_equal(a, b_)
 
 
 def test_concurrent_searches_from_many_threads_are_safe(sqe):
@@ -544,6 +555,30 @@ def test_cache_top1_batched_gemv_path(sqe, dtype):
     np.testing.assert_allclose(score.cpu().numpy(), ws, atol=2e-6)
     np.testing.assert_array_equal(hit.cpu().numpy(), wh)
     assert idx[0].item() == 42 and hit[0].item() == 1 and idx[1].item() in (7, 40) and hit[2].item() == 0
+
+
+def test_cache_paths_share_one_workspace(sqe):
+    """sqe_cache_top1 gives the SAME workspace to the tensor-core form (which publishes bounds in
+    the first 4 KB) and to the GEMV form (whose ticket counters live there and must start at
+    zero): every call has to leave that header zeroed.  Regression: a tensor-path lookup followed
+    by a GEMV-path lookup returned garbage rows."""
+    rng = np.random.default_rng(18)
+    c = make_corpus(rng, 7000)
+    q = rng.standard_normal((64, DIM)).astype(np.float32)
+    q[0] = c[42] * 2
+    C = sqe.ops.normalize_cast(torch.from_numpy(c).to(dev()), "bf16")
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), "bf16")
+    ref = [t.cpu().numpy() for t in sqe.ops.cache_top1(C, Q, 0.96, path=1)]
+    for path in (2, 1, 2, 2, 1, 0, 1):
+        got = [t.cpu().numpy() for t in sqe.ops.cache_top1(C, Q, 0.96, path=path)]
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2]), path
+        np.testing.assert_allclose(got[1], ref[1], atol=1e-5)
+        for nb in (1, 5):                                       # other batch sizes, GEMV form
+            few = [t.cpu().numpy() for t in sqe.ops.cache_top1(C, Q[:nb], 0.96, path=0 if nb == 1 else 1)]
+            assert np.array_equal(few[0], ref[0][:nb]) and few[2][0] == 1
+    ws = sqe.ops._workspaces[(dev().index, "cache", torch.cuda.current_stream(dev()).cuda_stream)]
+    torch.cuda.synchronize()
+    assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0
 
 
 def test_plugin_install_patches_reference_names(sqe):

@@ -581,6 +581,59 @@ def test_cache_paths_share_one_workspace(sqe):
     assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0
 
 
+def test_random_call_sequences_leave_no_state_behind(sqe):
+    """Seeded random sequence of entry points (GEMV, fused GEMV, tensor-core, cache lookup on each
+    path) over shards of every storage class with changing b, k and row counts -- they share the
+    per-stream workspaces, so anything a call leaves behind shows up as a wrong answer in a
+    later one.  Every result is checked against the oracle on the stored rows."""
+    rng = np.random.default_rng(2026)
+    shards = {}
+    for dtype, n in (("fp32", 3000), ("bf16", 9000), ("fp16", 5003), ("bf16x2", 4100)):
+        c = make_corpus(rng, n)
+        C = sqe.ops.normalize_cast(torch.from_numpy(c).to(dev()), dtype)
+        shards[dtype] = (c, C, oracle.from_storage(stored_bits(C, dtype), dtype))
+    ops_ = ["gemv", "search_gemv", "batched", "cache0", "cache1", "cache2"]
+    for step in range(200):
+        dtype = DTYPES[int(rng.integers(len(DTYPES)))]
+        c, C, c_st = shards[dtype]
+        op = ops_[int(rng.integers(len(ops_)))]
+        if dtype == "fp32" and op in ("batched", "cache2"):
+            op = "gemv"
+        b = int(rng.choice([1, 1, 2, 7, 33, 64, 130, 257]))
+        if op in ("gemv", "search_gemv", "cache1") or dtype == "fp32":
+            b = min(b, 33)                                   # one streaming pass per query
+        k = int(rng.choice([1, 3, 10, 32, 33, 100]))
+        n = int(rng.choice([C.shape[0], C.shape[0] - 1, 257, 1000]))
+        q = rng.standard_normal((b, DIM)).astype(np.float32)
+        q[0] = c[int(rng.integers(50, n))] * 1.5             # a certain cache hit / clear top-1
+        qd = torch.from_numpy(q).to(dev())
+        Q = sqe.ops.normalize_cast(qd, dtype)
+        q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+        tol = K2_TOL if op in ("batched", "cache2", "cache0") else 2e-6
+        tag = (step, op, dtype, b, k, n)
+        if op.startswith("cache"):
+            idx, score, hit = sqe.ops.cache_top1(C, Q, 0.96, path=int(op[-1]), n=n)
+            wi, ws, wh = no.cache_lookup_batched(q_st, c_st[:n], 0.96)
+            s64 = exact_scores(c_st[:n], q_st)
+            gi = idx.cpu().numpy()
+            for r in range(b):
+                assert gi[r] == wi[r] or abs(s64[r, gi[r]] - s64[r, wi[r]]) <= tol, (tag, r, gi[r], wi[r])
+            np.testing.assert_allclose(score.cpu().numpy(), ws, atol=tol, err_msg=str(tag))
+            assert hit[0].item() == 1, tag
+            continue
+        if op == "gemv":
+            gs, gi = sqe.ops.topk_gemv(C, Q, k, n=n)
+        elif op == "search_gemv":
+            gs, gi = sqe.ops.search_gemv(C, qd, k, n=n)
+        else:
+            gs, gi = sqe.ops.topk_batched(C, Q, k, n=n)
+        try:
+            assert_topk_matches(gs.cpu().numpy(), gi.cpu().numpy(), c_st[:n], q_st, k,
+                                score_tol=tol, tie_eps=tol)
+        except AssertionError as e:
+            raise AssertionError(f"{tag}: {e}")
+
+
 def test_plugin_install_patches_reference_names(sqe):
     import types
     main = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=1000,

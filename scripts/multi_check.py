@@ -48,6 +48,12 @@ for b, k in [(1, 10), (64, 10), (1024, 10), (256, 100)]:
         e1.record(); torch.cuda.synchronize()
         res[mode + "_x"] = e0.elapsed_time(e1) / 200
     assert want_i[0, 0].item() == 11 and want_i[0, 1].item() == n - 7
+    # the streaming host API over the sharded index: every batch identical to the single shard
+    sh = sqe_b200.ShardedCorpusIndex(local, exchange="p2p"); sh.finalize()
+    qh = q.cpu().numpy()
+    outs = list(sh.search_batches([qh, qh[: max(1, b // 2)], qh, qh], k))
+    wi = want_i.cpu().numpy()
+    assert len(outs) == 4 and all(np.array_equal(o[1], wi[: o[1].shape[0]]) for o in outs), "streaming mismatch"
     if rank == 0:
         print(f"world={world} b={b} k={k}: identical to single shard; step p2p {res['p2p']*1e3:.1f} us, nccl {res['nccl']*1e3:.1f} us; "
               f"exchange alone p2p {res['p2p_x']*1e3:.1f} us, nccl {res['nccl_x']*1e3:.1f} us", flush=True)

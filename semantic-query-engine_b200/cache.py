@@ -250,6 +250,33 @@ class GpuQueryCache:
             self._entries = [{"response": (responses[i] if responses is not None else str(i)),
                               "freq": 1} for i in range(n)]
 
+    def load_from_redis(self, redis_client=None, list_name: Optional[str] = None) -> int:
+        """Warm start from the list a reference process has been writing: LRANGE the whole list
+        (main.py:69), parse every entry the way lfu_cache_get does (main.py:79-82:
+        `{"embedding": [1024 floats], "response": str, "freq": int}`), keep the list order (index 0
+        = newest) and the `freq` counters.  The cache must be empty; nothing is written back.
+        Returns the number of entries loaded."""
+        client = redis_client if redis_client is not None else self.redis
+        if client is None:
+            raise ValueError("no Redis client")
+        name = list_name if list_name is not None else self.list_name
+        items = client.lrange(name, 0, -1)
+        if not items:
+            return 0
+        if len(items) > self.max_items:
+            raise ValueError(f"Redis list holds {len(items)} entries, max_items is {self.max_items}")
+        parsed = [json.loads(it) for it in items]
+        emb = np.asarray([e["embedding"] for e in parsed], dtype=np.float32)     # main.py:80
+        if emb.ndim != 2 or emb.shape[1] != nat.SQE_DIM:
+            raise ValueError(f"cache entries must hold {nat.SQE_DIM}-d embeddings, got {emb.shape}")
+        self.bulk_load(emb, [e["response"] for e in parsed])
+        with self._lock:
+            for mine, theirs in zip(self._entries, parsed):
+                mine["freq"] = theirs.get("freq", 1)                             # main.py:107
+                if self.keep_raw:
+                    mine["raw"] = theirs["embedding"]
+        return len(parsed)
+
     # ------------------------------------------------------------- inspection
     def responses(self) -> List[str]:
         return [e["response"] for e in self._entries]

@@ -313,6 +313,57 @@ class GpuCorpusIndex:
     def doc_id_of(self, row: int) -> str:
         return self._ids[row]
 
+    # ------------------------------------------- the reference's OpenSearch documents
+    def export_bulk_actions(self, chunk_rows: int = 4096):
+        """Yield one OpenSearch bulk action per stored row in the reference's own format
+        (main.py:318-331): `{"_op_type": "index", "_index", "_id", "_source": {"doc_id", "text",
+        "embedding": [1024 floats]}}` -- what `helpers.bulk` needs to rebuild the reference's
+        k-NN index from this shard.  The embedding is the STORED (normalised, rounded) row."""
+        rows = self._rows
+        for lo in range(0, rows, chunk_rows):
+            blk = self._shard[lo: min(rows, lo + chunk_rows)].float().cpu()
+            if self.dtype == "bf16x2":
+                blk = blk[:, :EMBED_DIM] + blk[:, EMBED_DIM:]
+            blk = blk.numpy()
+            for j in range(blk.shape[0]):
+                r = lo + j
+                have = self.keep_payload and r < len(self._docs)
+                yield {"_op_type": "index", "_index": self.index_name,
+                       "_id": self._ids[r] if have else str(r),
+                       "_source": {"doc_id": self._docs[r]["doc_id"] if have else str(r),
+                                   "text": self._docs[r]["text"] if have else "",
+                                   "embedding": blk[j].tolist()}}
+
+    def import_bulk_actions(self, actions, batch_rows: int = 4096) -> int:
+        """Ingest documents in the reference's OpenSearch format -- bulk actions (main.py:318-331)
+        or search/scroll hits (`{"_id", "_source": {...}}`) -- e.g. to move an index the reference
+        built into HBM.  `_id` is kept as it is.  Embeddings go through K1 like any other ingest
+        (re-normalising a unit row changes it by at most one rounding).  Returns the row count."""
+        total = 0
+        emb, docs, ids = [], [], []
+
+        def flush():
+            nonlocal total
+            if not emb:
+                return
+            base = self._rows
+            self._add(np.asarray(emb, dtype=np.float32), docs, id_from_global_row=True)
+            if self.keep_payload:
+                with self._lock:
+                    self._ids[base: base + len(ids)] = ids
+            total += len(emb)
+            emb.clear(); docs.clear(); ids.clear()
+
+        for a in actions:
+            src = a["_source"]
+            emb.append(src["embedding"])
+            docs.append({"doc_id": src["doc_id"], "text": src["text"]})
+            ids.append(a.get("_id", f"{src['doc_id']}_{len(ids)}"))
+            if len(emb) >= batch_rows:
+                flush()
+        flush()
+        return total
+
     # -------------------------------------------------------------- persistence
     # The reference's only "resume" is skipping ingest when the index already has data
     # (main.py:300-307, :422-424); its persistence is whatever OpenSearch keeps.  Here the packed

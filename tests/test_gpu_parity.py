@@ -330,6 +330,68 @@ def test_query_cache_write_through_keeps_redis_in_the_reference_format(sqe, gold
     assert [json.loads(s)["response"] for s in stored] == log["final_responses"]
 
 
+def test_query_cache_warm_start_from_the_reference_redis_list(sqe, golden_dir):
+    """A GPU cache started next to a Redis list the REFERENCE has been writing (entries in its
+    JSON format, main.py:123) takes over list order, responses and freq counters, then behaves
+    like the reference from there on -- and keeps the list byte-identical through write-through."""
+    with open(os.path.join(golden_dir, "cache_evict8.json")) as f:
+        log = json.load(f)
+    vecs = np.load(os.path.join(golden_dir, "cache_evict8.npz"))["vecs"]
+    model = no.LfuCacheModel(max_items=log["max_items"], threshold=log["threshold"])
+    half = len(log["ops"]) // 2
+    for op in log["ops"][:half]:                          # the reference's life so far
+        v = vecs[op["vec"]][None, :]
+        model.get(v) if op["op"] == "get" else model.put(v, op["response"])
+    redis = _FakeRedis()
+    redis.lists[sqe.REDIS_CACHE_LIST] = list(model.items)
+    cache = sqe.GpuQueryCache(max_items=log["max_items"], threshold=log["threshold"], redis_client=redis)
+    assert cache.load_from_redis() == len(model.items)
+    assert cache.responses() == [json.loads(s)["response"] for s in model.items]
+    assert cache.freqs() == [json.loads(s)["freq"] for s in model.items]
+    for op in log["ops"][half:]:                          # ... and the rest of it on the GPU
+        v = vecs[op["vec"]][None, :]
+        if op["op"] == "get":
+            assert cache.get(v) == op["result"] == model.get(v)
+        else:
+            cache.put(v, op["response"])
+            model.put(v, op["response"])
+    assert redis.lrange(sqe.REDIS_CACHE_LIST, 0, -1) == model.items
+    assert cache.freqs() == log["final_freqs"] and cache.responses() == log["final_responses"]
+    empty = sqe.GpuQueryCache(max_items=4, redis_client=_FakeRedis())
+    assert empty.load_from_redis() == 0 and len(empty) == 0
+
+
+def test_corpus_index_speaks_the_reference_opensearch_bulk_format(sqe):
+    """export_bulk_actions yields the reference's own bulk actions (main.py:318-331); feeding them
+    (or search hits of the same shape) to import_bulk_actions rebuilds an equivalent index."""
+    rng = np.random.default_rng(21)
+    emb = make_corpus(rng, 3000)
+    docs = [{"doc_id": f"PMC{i // 9}", "text": f"chunk {i}"} for i in range(3000)]
+    a = sqe.GpuCorpusIndex(None, "medical-search-index", dtype="fp32", strict=True)
+    a.add_embeddings(emb[:1000], docs[:1000])
+    a.add_embeddings(emb[1000:], docs[1000:])
+    actions = list(a.export_bulk_actions(chunk_rows=700))
+    assert len(actions) == 3000
+    first = actions[1001]
+    assert set(first) == {"_op_type", "_index", "_id", "_source"} and first["_op_type"] == "index"
+    assert first["_index"] == "medical-search-index" and first["_id"] == "PMC111_1"      # main.py:325
+    assert set(first["_source"]) == {"doc_id", "text", "embedding"} and len(first["_source"]["embedding"]) == DIM
+    stored = a.shard.cpu().numpy()
+    np.testing.assert_array_equal(np.asarray(first["_source"]["embedding"], dtype=np.float32), stored[1001])
+    b = sqe.GpuCorpusIndex(None, "copy", dtype="fp32", strict=True)
+    hits = [{"_id": x["_id"], "_score": 1.0, "_source": x["_source"]} for x in actions]    # scroll-hit shape
+    assert b.import_bulk_actions(iter(hits), batch_rows=512) == 3000
+    assert b.num_rows == 3000 and [b.doc_id_of(r) for r in (0, 1001, 2999)] == [a.doc_id_of(r) for r in (0, 1001, 2999)]
+    np.testing.assert_allclose(b.shard.cpu().numpy(), stored, atol=1.2e-7)     # unit rows re-normalised: <= 1 ulp
+    q = rng.standard_normal((4, DIM)).astype(np.float32)
+    q[0] = emb[77]
+    sa, ia = a.search_batch(q, 5)
+    sb, ib = b.search_batch(q, 5)
+    np.testing.assert_array_equal(ia, ib)
+    np.testing.assert_allclose(sa, sb, atol=1e-6)
+    assert [h[0] for h in a.search(q[:1], k=3)] == [h[0] for h in b.search(q[:1], k=3)]
+
+
 def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
     """the packed shard + payload survive a restart bit for bit."""
     rng = np.random.default_rng(4)

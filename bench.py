@@ -700,14 +700,38 @@ def run_ingest(args, torch, ops, nat, dev, peaks):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    launches = nat.launch_count - l0
+    clocks = sampler.stop()
     alg = rows * DIM * (4 + esize)
     ach = alg / (ms * 1e-3) / 1e9
+    # end to end: pinned host fp32 rows -> add_device_rows (H2D on a copy stream overlapped with K1)
+    e2e = None
+    if not args.no_e2e:
+        import sqe_b200
+        hrows = min(rows, 262_144)                                   # 1 GiB of pinned host rows
+        xh = torch.randn((hrows, DIM), dtype=torch.float32).pin_memory()
+        index = sqe_b200.GpuCorpusIndex(dtype=args.dtype, device=dev, keep_payload=False)
+        index.reserve(hrows)
+        esteps = max(3, min(steps, 10))
+        for _ in range(2):
+            index.clear()
+            index.add_device_rows(xh)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            index.clear()
+            index.add_device_rows(xh)                                # synchronises before publishing the rows
+        dt = (time.perf_counter() - t0) / esteps
+        e2e = {"value": hrows / dt, "unit": "rows/s", "h2d_bytes_per_step": hrows * DIM * 4,
+               "d2h_bytes_per_step": 0, "ms_per_step": dt * 1e3,
+               "api": "GpuCorpusIndex.add_device_rows(pinned host fp32 rows)",
+               "h2d_gbs": hrows * DIM * 4 / dt / 1e9}
     line = {"metric": "rows/sec fused L2-normalise + cast (ingest)", "value": rows / (ms * 1e-3), "unit": "rows/s",
             "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{rows}x1024 fp32 -> {args.dtype} rows, x/(|x|+1e-9) (app/main.py:315-316)",
                        "rows": rows, "l2": "6 GB per step, larger than L2"},
-            "clocks": sampler.stop(), "e2e": None, "gpu_launches": nat.launch_count - l0,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / peaks["hbm_gbs"], "kernel": "normalize_cast_kernel", "kernel_ms": ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peaks["source"], "traffic": None},

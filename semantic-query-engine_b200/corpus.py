@@ -162,18 +162,54 @@ class GpuCorpusIndex:
         if n == 0:
             return
         base = self._rows
-        step = 1 << 18                                   # 1 GiB of fp32 staging at most
         with torch.cuda.device(self.device):
-            for lo in range(0, n, step):
-                hi = min(n, lo + step)
-                blk = emb[lo:hi]
-                if not blk.is_cuda:
-                    blk = blk.to(self.device, non_blocking=False)
-                blk = blk.contiguous()
-                ops.normalize_cast(blk, self.dtype, out=self._shard[base + lo: base + hi])
+            if emb.is_cuda:
+                step = 1 << 18
+                for lo in range(0, n, step):
+                    hi = min(n, lo + step)
+                    ops.normalize_cast(emb[lo:hi].contiguous(), self.dtype, out=self._shard[base + lo: base + hi])
+            else:
+                self._ingest_host_rows(emb, base, n)
             torch.cuda.current_stream(self.device).synchronize()
         self._rows = base + n                            # publish
         self._graphs.clear()                             # captured row count / shard pointer are stale
+
+    def _ingest_host_rows(self, emb: torch.Tensor, base: int, n: int, chunk: int = 1 << 15) -> None:
+        """Host rows -> shard: two fp32 staging blocks on the device (128 MB each); the copy of
+        block i+1 runs on a copy stream while K1 normalises block i into the shard tail, so a
+        pinned source is ingested at PCIe speed (a pageable one at the host's memcpy speed)."""
+        dev = self.device
+        emb = emb.contiguous()
+        if emb.dtype != torch.float32:
+            emb = emb.float()
+        compute = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(device=dev)
+        m = min(chunk, n)
+        stage = [torch.empty((m, EMBED_DIM), dtype=torch.float32, device=dev) for _ in range(2 if n > m else 1)]
+        ev_cp = [torch.cuda.Event() for _ in stage]
+        ev_k1 = [torch.cuda.Event() for _ in stage]
+        copy.wait_stream(compute)
+        for i, lo in enumerate(range(0, n, m)):
+            hi = min(n, lo + m)
+            s = i % len(stage)
+            with torch.cuda.stream(copy):
+                if i >= len(stage):
+                    copy.wait_event(ev_k1[s])            # K1 has consumed this block's previous content
+                stage[s][: hi - lo].copy_(emb[lo:hi], non_blocking=True)
+                ev_cp[s].record(copy)
+            compute.wait_event(ev_cp[s])
+            ops.normalize_cast(stage[s][: hi - lo], self.dtype, out=self._shard[base + lo: base + hi])
+            ev_k1[s].record(compute)
+        for t in stage:                                  # freed on `compute`, last used there too
+            t.record_stream(copy)
+
+    def clear(self) -> None:
+        """Drop every row (capacity is kept): the index is empty again, `has_any_data()` False."""
+        with self._lock:
+            self._rows = 0
+            self._docs.clear()
+            self._ids.clear()
+            self._graphs.clear()
 
     # ------------------------------------------------------------------- search
     @staticmethod

@@ -392,6 +392,26 @@ def test_corpus_index_speaks_the_reference_opensearch_bulk_format(sqe):
     assert [h[0] for h in a.search(q[:1], k=3)] == [h[0] for h in b.search(q[:1], k=3)]
 
 
+def test_host_ingest_pipeline_is_bit_identical_to_one_k1_pass(sqe):
+    """Host rows are ingested block by block (copy stream + K1 double buffering); the shard must
+    be bit-identical to one K1 pass over the whole matrix -- ragged last block, pageable and
+    pinned sources, appended after existing rows; clear() empties the index."""
+    rng = np.random.default_rng(23)
+    n = 2 * 32768 + 4097                                   # three blocks, ragged tail
+    x = rng.standard_normal((n, DIM)).astype(np.float32) * rng.uniform(0.01, 50, size=(n, 1)).astype(np.float32)
+    x[5] = 0.0
+    for dtype in ("bf16", "fp32"):
+        want = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+        index = sqe.GpuCorpusIndex(dtype=dtype, strict=True, keep_payload=False)
+        index.add_device_rows(x[:1000])                    # small append first
+        index.add_device_rows(x[1000:])                    # pageable, three blocks
+        assert index.num_rows == n and torch.equal(index.shard.view(torch.uint8), want.view(torch.uint8))
+        index.clear()
+        assert index.num_rows == 0 and index.has_any_data() is False and index.search(x[:1], k=3) == []
+        index.add_device_rows(torch.from_numpy(x).pin_memory())      # pinned source
+        assert index.num_rows == n and torch.equal(index.shard.view(torch.uint8), want.view(torch.uint8))
+
+
 def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
     """the packed shard + payload survive a restart bit for bit."""
     rng = np.random.default_rng(4)

@@ -52,6 +52,7 @@ class GpuQueryCache:
         self._entries: List[dict] = []          # list order, index 0 = newest
         self.use_graphs = use_graphs
         self._graph = None                       # captured single-query lookup; dropped on every mutation
+        self._graph_key = None                   # cache state seen by the last eager lookup
         self._pinned = torch.empty((1, nat.SQE_DIM), dtype=torch.float32).pin_memory()
         self._pinned_out = torch.empty((4096,), dtype=torch.uint8).pin_memory()
         self._pinned_qb: Optional[torch.Tensor] = None
@@ -99,7 +100,14 @@ class GpuQueryCache:
         live = self._buf[self._head:]
         if self.use_graphs:
             g = self._graph
-            if g is None or g.rows != len(self._entries) or g.shard_ptr != live.data_ptr():
+            stale = g is None or g.rows != len(self._entries) or g.shard_ptr != live.data_ptr()
+            if stale and self._graph_key != (len(self._entries), live.data_ptr()):
+                # first lookup of this cache state: launch eagerly.  The reference's handler
+                # alternates get (miss) -> put (main.py:493, :547); capturing a graph per state
+                # would cost more than it saves.  A second lookup of the same state captures.
+                self._graph_key = (len(self._entries), live.data_ptr())
+                g = self._graph = None
+            elif stale:
                 try:
                     g = self._graph = ops.SingleQueryGraph(live, len(self._entries), 1)
                 except Exception as e:                       # capture not possible here: stay eager

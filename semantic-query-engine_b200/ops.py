@@ -349,50 +349,76 @@ class _StreamSlot:
         return self.host_q[:b]
 
 
-def stream_pipeline(dev: torch.device, batches, as_rows, out_bytes, launch, unpack, depth: int = 2):
-    """Generator behind `GpuCorpusIndex.search_batches` / `GpuQueryCache.lookup_batches`.
+class StreamPipeline:
+    """Copy/compute overlap for a stream of host query batches (behind
+    `GpuCorpusIndex.search_batches`, `GpuQueryCache.lookup_batches` and the MicroBatcher).
 
-    For every host batch: `as_rows(batch)` -> fp32 [b,1024]; its host->device copy runs on a copy
-    stream, `launch(q_dev [b,1024], packed_out uint8 [out_bytes(b)])` enqueues the kernels on the
-    caller's current stream, the packed result returns on a second copy stream, and
-    `unpack(host uint8 array, b)` turns it into fresh host arrays.  At most `depth` batches are in
-    flight; the result of batch j-depth is yielded when batch j has been submitted, so the copies
-    of the neighbouring batches overlap the kernels of the current one."""
-    if depth < 1:
-        raise ValueError("depth must be >= 1")
-    with torch.cuda.device(dev):
-        compute = torch.cuda.current_stream(dev)
-        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    slots = [_StreamSlot() for _ in range(depth)]
-    pending = []                                       # (slot index, batch rows, bytes), oldest first
+    `submit(batch, ctx)`: `as_rows(batch)` -> fp32 [b,1024]; its host->device copy runs on a copy
+    stream, `launch(q_dev [b,1024], packed_out uint8 [out_bytes(b, ctx)], ctx)` enqueues the
+    kernels on the compute stream (the constructing thread's current stream), the packed result
+    returns on a second copy stream.  `collect()` waits for the OLDEST in-flight batch and returns
+    `unpack(host uint8 array, b, ctx)` (fresh host arrays).  At most `depth` batches are in flight;
+    `submit` blocks while all slots are taken, so a second thread may do the collecting."""
 
-    def collect(si: int, b: int, nbytes: int):
-        s = slots[si]
-        s.ev_d2h.synchronize()
-        return unpack(s.host_out[:nbytes].numpy(), b)
-
-    j = 0
-    for batch in batches:
-        q = as_rows(batch)
-        b = q.shape[0]
-        nbytes = out_bytes(b)
-        done = collect(*pending.pop(0)) if len(pending) == depth else None   # frees slot j % depth
-        s = slots[j % depth]
+    def __init__(self, dev: torch.device, as_rows, out_bytes, launch, unpack, depth: int = 2):
+        import queue
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.dev, self.depth = dev, depth
+        self._as_rows, self._out_bytes, self._launch, self._unpack = as_rows, out_bytes, launch, unpack
         with torch.cuda.device(dev):
-            src = s.stage(q, b, nbytes, dev)
-            with torch.cuda.stream(h2d):
-                s.dev_q[:b].copy_(src, non_blocking=True)
-                s.ev_h2d.record(h2d)
-            compute.wait_event(s.ev_h2d)
-            launch(s.dev_q[:b], s.dev_out[:nbytes])
-            s.ev_done.record(compute)
-            with torch.cuda.stream(d2h):
-                d2h.wait_event(s.ev_done)
-                s.host_out[:nbytes].copy_(s.dev_out[:nbytes], non_blocking=True)
-                s.ev_d2h.record(d2h)
-        pending.append((j % depth, b, nbytes))
-        j += 1
+            self.compute = torch.cuda.current_stream(dev)
+            self.h2d, self.d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._free = queue.Queue()
+        for _ in range(depth):
+            self._free.put(_StreamSlot())
+        self._pending = queue.Queue()
+
+    def in_flight(self) -> int:
+        return self._pending.qsize()
+
+    def submit(self, batch, ctx=None) -> None:
+        q = self._as_rows(batch)
+        b = q.shape[0]
+        nbytes = self._out_bytes(b, ctx)
+        s = self._free.get()
+        try:
+            with torch.cuda.device(self.dev), torch.cuda.stream(self.compute):
+                src = s.stage(q, b, nbytes, self.dev)
+                with torch.cuda.stream(self.h2d):
+                    s.dev_q[:b].copy_(src, non_blocking=True)
+                    s.ev_h2d.record(self.h2d)
+                self.compute.wait_event(s.ev_h2d)
+                self._launch(s.dev_q[:b], s.dev_out[:nbytes], ctx)
+                s.ev_done.record(self.compute)
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(s.ev_done)
+                    s.host_out[:nbytes].copy_(s.dev_out[:nbytes], non_blocking=True)
+                    s.ev_d2h.record(self.d2h)
+        except BaseException:
+            self._free.put(s)
+            raise
+        self._pending.put((s, b, nbytes, ctx))
+
+    def collect(self):
+        s, b, nbytes, ctx = self._pending.get()
+        try:
+            s.ev_d2h.synchronize()
+            return self._unpack(s.host_out[:nbytes].numpy(), b, ctx)
+        finally:
+            self._free.put(s)
+
+
+def stream_pipeline(dev: torch.device, batches, as_rows, out_bytes, launch, unpack, depth: int = 2):
+    """Single-threaded generator over a StreamPipeline: the result of batch j-depth is yielded when
+    batch j has been submitted, so the copies of the neighbouring batches overlap the kernels of
+    the current one.  The callbacks take no ctx here."""
+    pipe = StreamPipeline(dev, as_rows, lambda b, _c: out_bytes(b), lambda qd, buf, _c: launch(qd, buf),
+                          lambda arr, b, _c: unpack(arr, b), depth)
+    for batch in batches:
+        done = pipe.collect() if pipe.in_flight() == depth else None      # frees a slot
+        pipe.submit(batch)
         if done is not None:
             yield done
-    while pending:
-        yield collect(*pending.pop(0))
+    while pipe.in_flight():
+        yield pipe.collect()

@@ -19,7 +19,9 @@ from concurrent.futures import Future
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
+import torch
 
+from . import ops
 from .corpus import GpuCorpusIndex
 
 BASE_OPENSEARCH_INDEX_NAME = os.getenv("OPENSEARCH_INDEX_NAME", "")   # embedding_gen.py:38
@@ -74,12 +76,17 @@ class MicroBatcher:
 
     `search(query_emb, k)` blocks like `GpuCorpusIndex.search` and returns the same list;
     `submit(query_emb, k)` returns a `concurrent.futures.Future` (wrap it with
-    `asyncio.wrap_future` inside the FastAPI handlers).  A background thread drains the queue:
+    `asyncio.wrap_future` inside the FastAPI handlers).  A launcher thread drains the queue:
     it waits at most `max_wait_s` after the first request for more to arrive (or until
-    `max_batch` are queued), runs ONE `search_batch` with the largest k requested and slices
-    each request's rows out of it (a top-k list is a prefix of a longer top-k list)."""
+    `max_batch` are queued) and enqueues ONE batched search with the largest k requested (copies
+    and kernels are asynchronous, ops.StreamPipeline).  A delivery thread waits for the oldest
+    batch in flight and slices each request's rows out of it (a top-k list is a prefix of a longer
+    top-k list) -- so the GPU scores batch j+1 while the results of batch j are being handed out
+    (`depth` batches in flight)."""
 
-    def __init__(self, index: GpuCorpusIndex, max_batch: int = 256, max_wait_s: float = 200e-6):
+    def __init__(self, index: GpuCorpusIndex, max_batch: int = 256, max_wait_s: float = 200e-6,
+                 depth: int = 2):
+        import queue
         self.index = index
         self.max_batch = int(max_batch)
         self.max_wait_s = float(max_wait_s)
@@ -88,8 +95,23 @@ class MicroBatcher:
         self._stop = False
         self.batches = 0               # batched launches issued
         self.requests = 0              # requests served
+
+        def launch(qd, buf, k):
+            b = qd.shape[0]
+            index.search_device(qd, k, out=(buf[b * k * 8:].view(torch.float32).view(b, k),
+                                            buf[: b * k * 8].view(torch.int64).view(b, k)))
+
+        def unpack(arr, b, k):
+            return (arr[b * k * 8:].view(np.float32).reshape(b, k).copy(),
+                    arr[: b * k * 8].view(np.int64).reshape(b, k).copy())
+
+        self._pipe = ops.StreamPipeline(index.device, lambda q: q, lambda b, k: b * k * 12, launch, unpack, depth)
+        self._handoff: "queue.Queue" = queue.Queue()
         self._thread = threading.Thread(target=self._run, name="sqe-microbatcher", daemon=True)
+        self._deliverer = threading.Thread(target=self._deliver, name="sqe-microbatcher-out", daemon=True)
         self._thread.start()
+        if depth > 1:
+            self._deliverer.start()
 
     # -- client side
     def submit(self, query_emb: np.ndarray, k: int = 3) -> Future:
@@ -113,6 +135,8 @@ class MicroBatcher:
             self._stop = True
             self._cv.notify()
         self._thread.join()
+        if self._pipe.depth > 1:
+            self._deliverer.join()
 
     # -- server side
     def _take(self) -> List[Tuple[np.ndarray, int, Future]]:
@@ -130,27 +154,48 @@ class MicroBatcher:
             batch, self._queue = self._queue[: self.max_batch], self._queue[self.max_batch:]
             return batch
 
+    def _fail(self, batch, e: Exception) -> None:
+        for _, _, fut in batch:                                      # main.py:371-373 -> []
+            if self.index.strict:
+                fut.set_exception(e)
+            else:
+                fut.set_result([])
+
     def _run(self) -> None:
         while True:
             batch = self._take()
             if not batch:
                 if self._stop:
+                    self._handoff.put(None)
                     return
                 continue
             try:
                 q = np.concatenate([b[0] for b in batch], axis=0)
                 kmax = max(b[1] for b in batch)
-                scores, rows = self.index.search_batch(q, kmax)
+                self._pipe.submit(q, kmax)                           # blocks while `depth` are in flight
                 self.batches += 1
                 self.requests += len(batch)
-                for i, (_, k, fut) in enumerate(batch):
-                    fut.set_result(self.index.hits_from_rows(scores[i, :k], rows[i, :k]))
-            except Exception as e:                                   # main.py:371-373 -> []
-                for _, _, fut in batch:
-                    if self.index.strict:
-                        fut.set_exception(e)
-                    else:
-                        fut.set_result([])
+                if self._pipe.depth > 1:
+                    self._handoff.put(batch)
+                else:
+                    self._deliver_one(batch)                         # depth 1: one thread does it all
+            except Exception as e:
+                self._fail([b for b in batch if not b[2].done()], e)
+
+    def _deliver_one(self, batch) -> None:
+        scores, rows = self._pipe.collect()
+        for i, (_, k, fut) in enumerate(batch):
+            fut.set_result(self.index.hits_from_rows(scores[i, :k], rows[i, :k]))
+
+    def _deliver(self) -> None:
+        while True:
+            batch = self._handoff.get()
+            if batch is None:
+                return
+            try:
+                self._deliver_one(batch)
+            except Exception as e:
+                self._fail([b for b in batch if not b[2].done()], e)
 
 
 # ------------------------------------------------------- the step right after the path

@@ -587,9 +587,19 @@ def test_micro_batcher_coalesces_concurrent_requests(sqe):
         with ThreadPoolExecutor(max_workers=32) as pool:
             got = list(pool.map(lambda a: mb.search(a[0], a[1]), zip(queries, ks)))
         assert mb.search(np.array([]), 3) == []              # main.py:350-351
+        import asyncio                                        # the handlers' way: one event loop
+
+        async def many():
+            return await asyncio.gather(*[asyncio.wrap_future(mb.submit(q, k)) for q, k in zip(queries, ks)])
+        assert asyncio.run(many()) == got
     finally:
         mb.close()
-    assert mb.requests == len(queries) and mb.batches < len(queries) // 2, (mb.batches, mb.requests)
+    empty = sqe.MicroBatcher(sqe.GpuCorpusIndex(dtype="bf16"), max_batch=8)
+    try:
+        assert empty.search(queries[0], 3) == []             # nothing indexed yet: no hits, no error
+    finally:
+        empty.close()
+    assert mb.requests == 2 * len(queries) and mb.batches < len(queries), (mb.batches, mb.requests)
     for g, w, k in zip(got, want, ks):
         assert len(g) == len(w) == k
         assert [h[0] for h in g] == [h[0] for h in w]        # same chunks, same order

@@ -184,8 +184,9 @@ class MicroBatcher:
 
     def _deliver_one(self, batch) -> None:
         scores, rows = self._pipe.collect()
+        scores, rows = scores.tolist(), rows.tolist()                # one conversion per batch
         for i, (_, k, fut) in enumerate(batch):
-            fut.set_result(self.index.hits_from_rows(scores[i, :k], rows[i, :k]))
+            fut.set_result(self.index.hits_from_rows(scores[i][:k], rows[i][:k]))
 
     def _deliver(self) -> None:
         while True:

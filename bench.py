@@ -402,6 +402,38 @@ def main():
             del yout
         except Exception as e:                      # never let the yardstick break the bench line
             roofline["yardstick"] = {"error": str(e)[:200]}
+    if roofline["bound"] == "tensor" and dtype != "bf16x2" and b <= 1024:
+        # In-kernel evidence for the clock the tensor pipes really ran at: K2's own clock64 role
+        # timers (sqe_debug_k2_timers) over ONE extra launch, against CUDA events around it.
+        # cycles per d-tile vs the issue floor (8192 cycles: 128 x 256 x 1024 MACs per SM at 8192
+        # FLOP/clk) says how busy the pipe is; cycles / time says how fast the SMs were clocked --
+        # nvidia-smi's samples lag on sub-second runs.
+        try:
+            grid = 148
+            tbuf = torch.zeros((160 * 40 + 64 * 4,), dtype=torch.int64, device=dev)
+            for _ in range(2):
+                kern()
+            nat.load().sqe_debug_k2_timers(tbuf.data_ptr())
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            kern()
+            t1e.record()
+            torch.cuda.synchronize()
+            nat.load().sqe_debug_k2_timers(None)
+            tms = t0e.elapsed_time(t1e)
+            mma = tbuf[: grid * 40].view(grid, 40)[:, 2].double()
+            mma = mma[mma > 0]
+            cg = 2 if b > 128 else 1
+            n_qt = (min(b, 1024) + 128 * cg - 1) // (128 * cg)
+            n_groups = max(1, (grid // cg) // n_qt)
+            tiles = ((local_rows + 255) // 256 + n_groups - 1) // n_groups
+            cyc = float(mma.mean().item())
+            roofline["in_kernel"] = {"mma_issuer_cycles": cyc, "d_tiles_per_unit": tiles,
+                                     "cycles_per_tile": cyc / tiles, "issue_floor_cycles_per_tile": 8192,
+                                     "frac_of_issue_floor": 8192.0 * tiles / cyc,
+                                     "sm_mhz": cyc / (tms * 1e-3) / 1e6, "launch_ms_with_timers": tms}
+        except Exception as e:
+            roofline["in_kernel"] = {"error": str(e)[:200]}
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
     roofline["kernel"] = kname
     roofline["kernel_ms"] = kms

@@ -105,7 +105,14 @@ class FakeOpenSearch:
 
 def _fake_bulk(client, actions):
     for a in actions:
-        client.docs.append((a["_id"], a["_source"]))
+        # an "index" action REPLACES the document that already has this _id (OpenSearch bulk API);
+        # the replaced document keeps its position, so tie order does not change
+        for j, (known, _) in enumerate(client.docs):
+            if known == a["_id"]:
+                client.docs[j] = (a["_id"], a["_source"])
+                break
+        else:
+            client.docs.append((a["_id"], a["_source"]))
     return len(actions), []
 
 

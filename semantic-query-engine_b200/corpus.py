@@ -63,6 +63,7 @@ class GpuCorpusIndex:
         self._initial_capacity = int(initial_capacity)
         self._docs: List[Dict[str, str]] = []   # payload table, row-aligned
         self._ids: List[str] = []
+        self._row_of_id: Dict[str, int] = {}    # `_id` -> row: an "index" action with a known _id overwrites
         # CUDA graphs of the single-query step, keyed by k; dropped whenever rows are added
         self.use_graphs = use_graphs
         self._graphs: Dict[int, "ops.SingleQueryGraph"] = {}
@@ -130,7 +131,12 @@ class GpuCorpusIndex:
                 raise
             print(f"[GpuCorpusIndex] Bulk error (doc_id={doc_id}): {e}")
 
-    def _add(self, embeddings, docs, id_from_global_row: bool) -> None:
+    def _add(self, embeddings, docs, id_from_global_row: bool, ids: Optional[Sequence[str]] = None) -> None:
+        """Append rows -- or overwrite them: the reference sends `_op_type: "index"` actions with
+        `_id = f"{doc_id}_{i}"` (main.py:321-325, embedding_gen.py:221-233), and OpenSearch REPLACES
+        a document whose `_id` already exists (re-uploading a document replaces its chunks instead
+        of duplicating them).  A row whose `_id` is known is therefore rewritten in place (it keeps
+        its row number, so the tie order does not change); the others go to the shard tail."""
         emb = self._as_rows(embeddings)
         n = emb.shape[0]
         if docs is not None and self.keep_payload and len(docs) != n:
@@ -138,15 +144,34 @@ class GpuCorpusIndex:
             n = min(n, len(docs))
             emb = emb[:n]
         with self._lock:
-            base = self._rows
-            self._grow_locked(base + n)
-            self.add_device_rows(emb, _locked=True)
-            if self.keep_payload and docs is not None:
-                for i in range(n):
+            if not (self.keep_payload and docs is not None):
+                self._grow_locked(self._rows + n)
+                self.add_device_rows(emb, _locked=True)
+                return
+            # main.py:325: i enumerates the rows of THIS call
+            new_ids = list(ids[:n]) if ids is not None else [f"{docs[i]['doc_id']}_{i}" for i in range(n)]
+            last = {}                                    # the same _id twice in one call: the last one wins
+            for i, _id in enumerate(new_ids):
+                last[_id] = i
+            fresh = [i for i, _id in enumerate(new_ids) if last[_id] == i and _id not in self._row_of_id]
+            over = [i for i, _id in enumerate(new_ids) if last[_id] == i and _id in self._row_of_id]
+            if over:
+                rows = torch.tensor([self._row_of_id[new_ids[i]] for i in over], dtype=torch.int64, device=self.device)
+                with torch.cuda.device(self.device):
+                    src = torch.from_numpy(np.ascontiguousarray(emb[over])).to(self.device)
+                    self._shard.index_copy_(0, rows, ops.normalize_cast(src, self.dtype))
+                    torch.cuda.current_stream(self.device).synchronize()
+                for i in over:
+                    self._docs[self._row_of_id[new_ids[i]]] = {"doc_id": docs[i]["doc_id"], "text": docs[i]["text"]}
+            if fresh:
+                base = self._rows
+                self._grow_locked(base + len(fresh))
+                self.add_device_rows(emb if len(fresh) == n else np.ascontiguousarray(emb[fresh]), _locked=True)
+                for j, i in enumerate(fresh):
                     d = docs[i]
                     self._docs.append({"doc_id": d["doc_id"], "text": d["text"]})
-                    # main.py:325: i enumerates the rows of THIS call
-                    self._ids.append(f"{d['doc_id']}_{i}")
+                    self._ids.append(new_ids[i])
+                    self._row_of_id[new_ids[i]] = base + j
 
     def add_device_rows(self, emb, _locked: bool = False) -> None:
         """Append rows without payload.  `emb`: host ndarray / CPU tensor / CUDA fp32 tensor
@@ -209,6 +234,7 @@ class GpuCorpusIndex:
             self._rows = 0
             self._docs.clear()
             self._ids.clear()
+            self._row_of_id.clear()
             self._graphs.clear()
 
     # ------------------------------------------------------------------- search
@@ -373,8 +399,9 @@ class GpuCorpusIndex:
     def import_bulk_actions(self, actions, batch_rows: int = 4096) -> int:
         """Ingest documents in the reference's OpenSearch format -- bulk actions (main.py:318-331)
         or search/scroll hits (`{"_id", "_source": {...}}`) -- e.g. to move an index the reference
-        built into HBM.  `_id` is kept as it is.  Embeddings go through K1 like any other ingest
-        (re-normalising a unit row changes it by at most one rounding).  Returns the row count."""
+        built into HBM.  `_id` is kept as it is (a known `_id` overwrites its row, as in OpenSearch).
+        Embeddings go through K1 like any other ingest (re-normalising a unit row changes it by at
+        most one rounding).  Returns the number of documents processed."""
         total = 0
         emb, docs, ids = [], [], []
 
@@ -382,11 +409,7 @@ class GpuCorpusIndex:
             nonlocal total
             if not emb:
                 return
-            base = self._rows
-            self._add(np.asarray(emb, dtype=np.float32), docs, id_from_global_row=True)
-            if self.keep_payload:
-                with self._lock:
-                    self._ids[base: base + len(ids)] = ids
+            self._add(np.asarray(emb, dtype=np.float32), docs, id_from_global_row=True, ids=list(ids))
             total += len(emb)
             emb.clear(); docs.clear(); ids.clear()
 
@@ -454,4 +477,5 @@ class GpuCorpusIndex:
                     payload = json.load(f)
                 index._docs = payload["docs"]
                 index._ids = payload["ids"]
+                index._row_of_id = {_id: r for r, _id in enumerate(index._ids)}
         return index

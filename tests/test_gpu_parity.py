@@ -412,6 +412,40 @@ def test_host_ingest_pipeline_is_bit_identical_to_one_k1_pass(sqe):
         assert index.num_rows == n and torch.equal(index.shard.view(torch.uint8), want.view(torch.uint8))
 
 
+def test_reuploading_a_document_replaces_its_chunks_like_an_opensearch_index_action(sqe):
+    """The reference's bulk actions are `_op_type: "index"` with `_id = f"{doc_id}_{i}"`
+    (main.py:321-325, embedding_gen.py:221-233): OpenSearch replaces a document whose _id exists.
+    Re-uploading a document therefore rewrites its chunk rows in place (same row numbers), leaves
+    chunks the new version no longer has, and appends what is new."""
+    rng = np.random.default_rng(31)
+    a_old = rng.standard_normal((5, DIM)).astype(np.float32)
+    b_doc = rng.standard_normal((3, DIM)).astype(np.float32)
+    a_new = rng.standard_normal((4, DIM)).astype(np.float32)
+    index = sqe.GpuCorpusIndex(None, "medical-search-index-u1", dtype="fp32", strict=True)
+    index.add_document_chunks("A", a_old, [f"A old {i}" for i in range(5)])
+    index.add_document_chunks("B", b_doc, [f"B {i}" for i in range(3)])
+    before = index.shard.cpu().numpy().copy()
+    index.add_document_chunks("A", a_new, [f"A new {i}" for i in range(4)])      # the re-upload
+    assert index.num_rows == 8
+    after = index.shard.cpu().numpy()
+    np.testing.assert_array_equal(after[:4].view(np.uint32), oracle.normalize_rows(a_new).view(np.uint32))
+    np.testing.assert_array_equal(after[4:], before[4:])                         # stale chunk 4 and doc B untouched
+    hit = index.search(a_new[2:3], k=1)[0]
+    assert hit[0] == {"doc_id": "A", "text": "A new 2"} and abs(hit[1] - 1.0) < 1e-5
+    assert index.search(a_old[1:2], k=1)[0][1] < 0.5                             # the old chunk is gone
+    assert index.search(a_old[4:5], k=1)[0][0]["text"] == "A old 4"              # OpenSearch keeps it too
+    index.add_document_chunks("A", np.concatenate([a_new, a_old[:2]]), [f"A v3 {i}" for i in range(6)])
+    assert index.num_rows == 9 and index.doc_id_of(8) == "A_5"                   # chunk 5 is new: appended
+    texts = [x["_source"]["text"] for x in index.export_bulk_actions()]
+    assert texts == ["A v3 0", "A v3 1", "A v3 2", "A v3 3", "A v3 4", "B 0", "B 1", "B 2", "A v3 5"]
+    # the main-app form numbers rows per call (main.py:325): a second call with the same doc ids collides too
+    m = sqe.GpuCorpusIndex(dtype="fp32", strict=True)
+    docs = [{"doc_id": "PMC1.txt", "text": f"c{i}"} for i in range(3)]
+    m.add_embeddings(b_doc, docs)
+    m.add_embeddings(b_doc[::-1].copy(), [{"doc_id": "PMC1.txt", "text": f"d{i}"} for i in range(3)])
+    assert m.num_rows == 3 and m.search(b_doc[:1], k=1)[0][0]["text"] == "d2"
+
+
 def test_corpus_index_save_and_load_round_trip(sqe, tmp_path):
     """the packed shard + payload survive a restart bit for bit."""
     rng = np.random.default_rng(4)

@@ -177,6 +177,30 @@ def test_oracle_against_live_reference():
     assert oracle.EMBED_DIM == m.EMBED_DIM
 
 
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+def test_reference_bulk_actions_collide_on_id_when_a_document_is_indexed_again():
+    """Pins the `_id` claim behind GpuCorpusIndex's overwrite-in-place: the reference's OWN
+    add_embeddings numbers `_id = f"{doc_id}_{i}"` per call (main.py:318-325) with
+    `_op_type: "index"`, so indexing the same document again sends the same _ids -- which an
+    OpenSearch index replaces (the stand-in bulk does what the bulk API documents)."""
+    from oracle.ref_loader import FakeOpenSearch
+    m = load_reference_main()
+    client = FakeOpenSearch()
+    idx = m.OpenSearchIndexer(client, "medical-search-index")
+    rng = np.random.default_rng(9)
+    e = rng.standard_normal((3, 1024)).astype(np.float32)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        idx.add_embeddings(e, [{"doc_id": "PMC1.txt", "text": f"c{i}"} for i in range(3)])
+        idx.add_embeddings(e[::-1].copy(), [{"doc_id": "PMC1.txt", "text": f"d{i}"} for i in range(3)])
+        idx.add_embeddings(e[:1], [{"doc_id": "PMC2.txt", "text": "x"}])
+    assert [d[0] for d in client.docs] == ["PMC1.txt_0", "PMC1.txt_1", "PMC1.txt_2", "PMC2.txt_0"]
+    assert [d[1]["text"] for d in client.docs] == ["d0", "d1", "d2", "x"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        hits = idx.search(e[:1], k=1)
+    assert hits[0][0]["text"] == "d2"                    # what the GPU index returns in the same scenario
+
+
 def test_split_bf16_storage_is_exact_to_16_bits():
     """bf16x2 (new storage class): hi + lo reconstructs x to 2^-17 relative, the sum is exact in
     fp32, and zeros / signs / tiny values survive."""

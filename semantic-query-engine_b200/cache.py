@@ -77,7 +77,16 @@ class GpuQueryCache:
         return self._pinned.to(self.device, non_blocking=True)
 
     def _entry_json(self, e: dict) -> str:
-        return json.dumps({"embedding": e["raw"], "response": e["response"], "freq": e["freq"]})
+        raw = e.get("raw")
+        if raw is None:
+            # entry without its raw embedding (bulk_load): write the stored unit row -- the same
+            # cosine for every reader, the reference normalises at lookup (main.py:59-64)
+            i = next(j for j, x in enumerate(self._entries) if x is e)
+            row = self._buf[self._head + i].float().cpu()
+            if self.dtype == "bf16x2":
+                row = row[: nat.SQE_DIM] + row[nat.SQE_DIM:]
+            raw = e["raw"] = row.tolist()
+        return json.dumps({"embedding": raw, "response": e["response"], "freq": e["freq"]})
 
     # ------------------------------------------------------------------- get
     def lookup(self, query_emb) -> Tuple[int, float, bool]:
@@ -203,9 +212,10 @@ class GpuQueryCache:
                 min_index = i
         if min_index < 0:
             return
-        e = self._entries.pop(min_index)
+        e = self._entries[min_index]
         if self.redis is not None:
             self.redis.lrem(self.list_name, 1, self._entry_json(e))  # main.py:117
+        self._entries.pop(min_index)
         h = self._head
         if min_index > 0:
             # rows [h, h+min_index) slide to [h+1, h+min_index+1): list order is kept

@@ -165,6 +165,9 @@ class GpuCorpusIndex:
                     self._docs[self._row_of_id[new_ids[i]]] = {"doc_id": docs[i]["doc_id"], "text": docs[i]["text"]}
             if fresh:
                 base = self._rows
+                while len(self._docs) < base:            # rows added without payload (add_device_rows)
+                    self._docs.append({"doc_id": str(len(self._docs)), "text": ""})
+                    self._ids.append(str(len(self._ids)))
                 self._grow_locked(base + len(fresh))
                 self.add_device_rows(emb if len(fresh) == n else np.ascontiguousarray(emb[fresh]), _locked=True)
                 for j, i in enumerate(fresh):

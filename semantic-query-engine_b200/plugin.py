@@ -18,14 +18,37 @@ from .cache import GpuQueryCache
 from .corpus import GpuCorpusIndex
 
 
+class GpuIndexStandIn:
+    """Truthy placeholder for `main.os_client` when no OpenSearch server is running:
+    `RAGModel.__init__` only builds its indexer `if os_client` (main.py:408-411), and the reason to
+    install this plugin is that there is no such server any more."""
+
+    def __repr__(self) -> str:
+        return "<sqe_b200: GPU index, no OpenSearch client>"
+
+
 def install(main_module, *, dtype: str = "bf16", cache_dtype: str = "fp32", device=None,
             write_through_redis: bool = False, strict: bool = False):
+    """`write_through_redis`: mirror every cache mutation into `main.redis_client` in the
+    reference's entry format and take over what that list already holds (warm start)."""
     threshold = getattr(main_module, "CACHE_SIM_THRESHOLD", 0.96)
     max_items = getattr(main_module, "REDIS_MAX_ITEMS", 1000)
     list_name = getattr(main_module, "REDIS_CACHE_LIST", "query_cache_lfu")
     redis_client = getattr(main_module, "redis_client", None) if write_through_redis else None
     cache = GpuQueryCache(max_items=max_items, threshold=threshold, dtype=cache_dtype,
                           device=device, redis_client=redis_client, list_name=list_name)
+
+    if redis_client is not None:
+        try:
+            n = cache.load_from_redis()
+            if n:
+                print(f"[sqe_b200] query cache warm-started with {n} entries from Redis list {list_name!r}")
+        except Exception as e:                           # a broken entry must not stop the service
+            if strict:
+                raise
+            print(f"[sqe_b200] could not warm-start the query cache from Redis: {e}")
+    if getattr(main_module, "os_client", None) is None:
+        main_module.os_client = GpuIndexStandIn()
 
     class OpenSearchIndexer(GpuCorpusIndex):
         def __init__(self, client=None, index_name: str = ""):

@@ -776,6 +776,33 @@ def test_plugin_install_patches_reference_names(sqe):
     main.lfu_cache_put(q, "hello")
     assert main.lfu_cache_get(q) == "hello"
 
+    # no OpenSearch server (main.py:286-288 leaves os_client = None): RAGModel.__init__ builds its
+    # indexer only `if os_client` (main.py:408-411) -- install() must make that happen; and with
+    # write-through the cache takes over what the reference left in Redis
+    redis = _FakeRedis()
+    redis.lpush("query_cache_lfu", json.dumps({"embedding": q[0].tolist(), "response": "from redis", "freq": 7}))
+    main2 = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=1000, REDIS_CACHE_LIST="query_cache_lfu",
+                                  os_client=None, redis_client=redis)
+    cache = sqe.plugin.install(main2, dtype="bf16", write_through_redis=True)
+
+    class RAGModel:                                       # main.py:408-411, :458-465
+        def __init__(self):
+            self.os_indexer = None
+            if main2.os_client:
+                self.os_indexer = main2.OpenSearchIndexer(main2.os_client, "medical-search-index")
+
+        def os_search(self, query_emb, top_k=3):
+            if not self.os_indexer:
+                return []
+            return self.os_indexer.search(query_emb, k=top_k)
+    rag = RAGModel()
+    assert rag.os_indexer is not None and rag.os_indexer.has_any_data() is False
+    assert rag.os_search(q) == []
+    rag.os_indexer.add_embeddings(emb, [{"doc_id": f"d{i}", "text": f"t{i}"} for i in range(300)])
+    assert rag.os_search(emb[5:6], top_k=2)[0][0]["doc_id"] == "d5"
+    assert main2.lfu_cache_get(q) == "from redis" and cache.freqs() == [8]
+    assert json.loads(redis.lrange("query_cache_lfu", 0, -1)[0])["freq"] == 8          # main.py:94-95
+
 
 # ------------------------------------------------------------------------- K2
 @pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_pair"])

@@ -194,7 +194,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),     # our arm's config at this N
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0,

@@ -1,8 +1,10 @@
 """CPU oracle for the retrieval hot path.  TEST INFRASTRUCTURE ONLY.
 
 This package is a numpy restatement of the reference's similarity path
-(`/root/reference/app/main.py`, `app/embedding_gen.py`).  It exists so the
-CUDA path can be checked; it is never the thing shipped or measured.
+(`/root/reference/app/main.py`, `app/embedding_gen.py`) plus an independent plain-C
+twin of it (`c_oracle.c`, compiled with gcc by `__graft_entry__.build()`, wrapped by
+`c_oracle.py`).  It exists so the CUDA path can be checked; it is never the thing
+shipped or measured.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py` (its `cpu_baseline`
 leg and `--impl reference` arm) may import it.  Nothing under
@@ -12,7 +14,7 @@ the CUDA library is missing rather than falling back to this code.
 Parity pin: PINNED.  `oracle/make_golden.py` imports the reference's own
 functions (with absent third-party services stubbed, see `ref_loader.py`),
 runs them on seeded inputs and commits inputs+outputs under `tests/golden/`;
-`tests/test_oracle_golden.py` checks every function here against those
+`tests/test_oracle_golden.py` checks every function here -- numpy and C -- against those
 vectors.  The one leg with no reference arithmetic to pin is corpus
 scoring/top-k: the reference delegates it to an external, unpinned
 OpenSearch HNSW index (`app/main.py:356-361`); `numpy_oracle.topk_cosine`

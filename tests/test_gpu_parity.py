@@ -60,6 +60,36 @@ def test_normalize_fp32_bit_identical_to_reference_vectors(sqe, golden_dir):
     np.testing.assert_array_equal(qn.view(np.uint32), g["q_norm"].view(np.uint32))
 
 
+def test_cuda_path_against_the_plain_c_oracle(sqe):
+    """The second, independent checker (oracle/c_oracle.c, plain C): K1 fp32 output is its output
+    bit for bit; K3 / K2 index sets equal its exact-scoring top-k on the stored rows; the cache
+    lookup agrees with its restatement of lfu_cache_get's scan."""
+    from oracle import c_oracle as co
+    if not co.available():
+        pytest.skip("no gcc and no prebuilt C oracle")
+    rng = np.random.default_rng(41)
+    x = make_corpus(rng, 6000)
+    q = rng.standard_normal((9, DIM)).astype(np.float32)
+    q[0] = x[7] * 3
+    got = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), "fp32")
+    np.testing.assert_array_equal(got.cpu().numpy().view(np.uint32), co.normalize_rows(x).view(np.uint32))
+    for dtype, fn, tol in (("fp32", sqe.ops.topk_gemv, 2e-6), ("bf16", sqe.ops.topk_batched, K2_TOL)):
+        D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+        Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+        d_st = oracle.from_storage(stored_bits(D, dtype), dtype)
+        q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+        gs, gi = fn(D, Q, 10)
+        ws, wi = co.topk_cosine(d_st, q_st, 10)
+        gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
+        for r in range(len(q)):
+            if list(gi[r]) != list(wi[r]):                   # only fp32-reorder near-ties may differ
+                assert set(gi[r]) ^ set(wi[r]) == set() or np.abs(np.sort(gs[r]) - np.sort(ws[r])).max() <= tol, r
+        np.testing.assert_allclose(gs, ws, atol=tol)
+        assert list(gi[0][:3]) == [7, 33, 5999] or 40 in gi[0][:4]          # planted duplicates, lower row first
+        idx, score, hit = sqe.ops.cache_top1(D, Q[:1], 0.96, path=1)
+        assert (int(idx[0]), bool(hit[0])) == co.cache_lookup(d_st, q_st[0], 0.96)[::2]
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_normalize_cast_bit_exact_vs_oracle(sqe, dtype):
     rng = np.random.default_rng(123)

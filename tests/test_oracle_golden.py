@@ -201,6 +201,69 @@ def test_reference_bulk_actions_collide_on_id_when_a_document_is_indexed_again()
     assert hits[0][0]["text"] == "d2"                    # what the GPU index returns in the same scenario
 
 
+# ---------------------------------------------------------------- the plain-C restatement
+def _c():
+    from oracle import c_oracle
+    if not c_oracle.available():
+        pytest.skip("no gcc and no prebuilt oracle/_build/libsqe_oracle.so")
+    return c_oracle
+
+
+def test_c_oracle_normalise_is_bit_identical_to_the_reference_vectors(golden_dir):
+    """oracle/c_oracle.c spells out numpy's pairwise fp32 reduction in plain C; its output must be
+    the reference's own stored rows bit for bit (main.py:315-316) -- an independent statement of
+    the order the CUDA ingest kernel reproduces."""
+    co = _c()
+    g = _load(golden_dir, "index_search.npz")
+    np.testing.assert_array_equal(co.normalize_rows(g["emb"]).view(np.uint32), g["stored"].view(np.uint32))
+    np.testing.assert_array_equal(co.normalize_rows(g["q"]).view(np.uint32), g["q_norm"].view(np.uint32))
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((300, 1024)) * 10.0 ** rng.uniform(-12, 12, (300, 1))).astype(np.float32)
+    x[0] = 0.0
+    x[1] = 1e-30
+    np.testing.assert_array_equal(co.row_sumsq(x).view(np.uint32), np.add.reduce(x * x, axis=1).view(np.uint32))
+    np.testing.assert_array_equal(co.normalize_rows(x).view(np.uint32), oracle.normalize_rows(x).view(np.uint32))
+
+
+def test_c_oracle_cosine_search_and_cache_match_the_reference_vectors(golden_dir):
+    co = _c()
+    g = _load(golden_dir, "cosine.npz")
+    got = np.array([co.cosine_similarity(a, b) for a, b in zip(g["a"], g["b"])])
+    np.testing.assert_allclose(got, g["out"], rtol=0, atol=1e-6)
+    assert got[4] == 0.0 and got[5] == 0.0 and got[6] == 0.0       # zero-norm guard, main.py:62-63
+    g = _load(golden_dir, "index_search.npz")
+    for ki, k in enumerate(g["ks"]):
+        s, i = co.topk_cosine(g["stored"], g["q_norm"], int(k))
+        np.testing.assert_array_equal(i, g["res_idx"][:, ki, :k])   # the reference run's own hit order
+        np.testing.assert_allclose(s, g["res_score"][:, ki, :k], atol=1e-6)
+    # and against the numpy restatement on fresh data: ties (7 / 50 / last) by lower row, NaN last
+    rng = np.random.default_rng(12)
+    d = oracle.normalize_rows(rng.standard_normal((2000, 1024)).astype(np.float32))
+    d[50] = d[7]
+    d[1999] = d[7]
+    q = oracle.normalize_rows(rng.standard_normal((5, 1024)).astype(np.float32))
+    q[0] = d[7]
+    s1, i1 = co.topk_cosine(d, q, 12)
+    s2, i2 = oracle.topk_cosine(d, q, 12)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_allclose(s1, s2, atol=1e-6)
+    assert list(i1[0][:3]) == [7, 50, 1999]
+    sc = np.array([[0.5, np.nan, 0.5, -0.0, 0.0, 0.7]], dtype=np.float32)
+    _, i = co.topk_from_scores(sc, 6)
+    assert list(i[0]) == [5, 0, 2, 3, 4, 1]
+    _, i = co.topk_from_scores(sc[:, :2], 4)
+    assert list(i[0]) == [0, 1, -1, -1]
+    # lfu_cache_get's scan (main.py:73-90): first maximum, strict '>', double threshold compare
+    idx, sim, hit = co.cache_lookup(d, q[0], 0.96)
+    assert (idx, hit) == (7, True) and abs(sim - 1.0) < 1e-6
+    idx, sim, hit = co.cache_lookup(d, q[1], 0.96)
+    wi, ws, wh = no.cache_lookup_batched(q[1:2], d, 0.96)
+    assert idx == wi[0] and hit == bool(wh[0]) and abs(sim - ws[0]) < 1e-6 and hit is False
+    idx, sim, hit = co.cache_lookup(-q[2:3], q[2], 0.96)                  # similarity -1 (to rounding)
+    assert hit is False and (idx == -1 or sim <= -1.0 + 1e-6)             # only a sim > -1.0 replaces the start value
+    assert co.cache_lookup(np.zeros((0, 1024), np.float32), q[2], 0.96) == (-1, -1.0, False)
+
+
 def test_split_bf16_storage_is_exact_to_16_bits():
     """bf16x2 (new storage class): hi + lo reconstructs x to 2^-17 relative, the sum is exact in
     fp32, and zeros / signs / tiny values survive."""

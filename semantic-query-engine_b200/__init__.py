@@ -13,14 +13,15 @@ patch a loaded reference `main` module, and `csrc/` (the sm_100a kernels + C ABI
 """
 from . import _native
 from ._native import NativeLibraryMissing, SqeError
-from .cache import CACHE_SIM_THRESHOLD, REDIS_CACHE_LIST, REDIS_MAX_ITEMS, GpuQueryCache
+from .cache import (CACHE_SIM_THRESHOLD, REDIS_CACHE_LIST, REDIS_MAX_ITEMS, GpuQueryCache,
+                    cosine_similarity)
 from .corpus import EMBED_DIM, GpuCorpusIndex
 from .sharded import ShardedCorpusIndex, shard_bounds
 from .serving import MicroBatcher, UserIndexRegistry, build_context_text, group_hits_by_doc
 from . import ops, plugin
 
 __all__ = [
-    "GpuCorpusIndex", "GpuQueryCache", "ShardedCorpusIndex", "shard_bounds", "ops", "plugin",
+    "GpuCorpusIndex", "GpuQueryCache", "cosine_similarity", "ShardedCorpusIndex", "shard_bounds", "ops", "plugin",
     "MicroBatcher", "UserIndexRegistry", "build_context_text", "group_hits_by_doc",
     "NativeLibraryMissing", "SqeError", "EMBED_DIM", "CACHE_SIM_THRESHOLD", "REDIS_MAX_ITEMS",
     "REDIS_CACHE_LIST",

@@ -6,7 +6,7 @@
 
 After `install`, `main.OpenSearchIndexer(client, index_name)` builds a
 `GpuCorpusIndex`, and `main.lfu_cache_get` / `main.lfu_cache_put` /
-`main.cosine_similarity` are served by a `GpuQueryCache` -- the names, arguments and
+`main.cosine_similarity` are served by a `GpuQueryCache` / the same kernels -- the names, arguments and
 return values RAGModel.ask (main.py:493,499,547) and the websocket handler
 (main.py:676,684,727) already use.  See INTEGRATION.md.
 """
@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .cache import GpuQueryCache
+from .cache import GpuQueryCache, cosine_similarity as gpu_cosine_similarity
 from .corpus import GpuCorpusIndex
 
 
@@ -60,7 +60,11 @@ def install(main_module, *, dtype: str = "bf16", cache_dtype: str = "fp32", devi
     def lfu_cache_put(query_emb: np.ndarray, response: str):
         cache.put(query_emb, response)
 
+    def cosine_similarity(a: np.ndarray, b: np.ndarray) -> float:
+        return gpu_cosine_similarity(a, b, device=device)
+
     main_module.OpenSearchIndexer = OpenSearchIndexer
+    main_module.cosine_similarity = cosine_similarity
     main_module.lfu_cache_get = lfu_cache_get
     main_module.lfu_cache_put = lfu_cache_put
     main_module._sqe_b200_cache = cache

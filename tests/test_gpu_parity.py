@@ -790,6 +790,24 @@ def test_random_call_sequences_leave_no_state_behind(sqe):
             raise AssertionError(f"{tag}: {e}")
 
 
+def test_cosine_similarity_drop_in_matches_reference_golden(sqe, golden_dir):
+    """main.py:59-64 on the GPU against the outputs of the reference's own function
+    (tests/golden/cosine.npz, made by oracle/make_golden.py): fp32 tolerance 1e-5 (north_star);
+    a zero-norm argument gives exactly 0.0 (main.py:62-63); [1,1024] inputs use row 0."""
+    import types
+    g = np.load(os.path.join(golden_dir, "cosine.npz"))
+    got = np.array([sqe.cosine_similarity(a, b) for a, b in zip(g["a"], g["b"])])
+    assert np.abs(got - g["out"]).max() < 1e-5
+    zero_pairs = [i for i in range(len(got)) if not g["a"][i].any() or not g["b"][i].any()]
+    assert zero_pairs and all(got[i] == 0.0 for i in zero_pairs)
+    assert np.abs(got - np.array([no.cosine_similarity(a, b) for a, b in zip(g["a"], g["b"])])).max() < 1e-5
+    main = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=10, REDIS_CACHE_LIST="x")
+    sqe.plugin.install(main)
+    v = main.cosine_similarity(g["a"][3], g["b"][3])
+    assert isinstance(v, float) and abs(v - g["out"][3]) < 1e-5
+    assert abs(sqe.cosine_similarity(g["a"][3:4], g["b"][3:4]) - g["out"][3]) < 1e-5
+
+
 def test_plugin_install_patches_reference_names(sqe):
     import types
     main = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=1000,

@@ -153,6 +153,22 @@ def cpu_reference_corpus(rows: int):
     return _CPU_CORPUS[rows]
 
 
+def cpu_use_all_cores() -> int:
+    """Give numpy's BLAS every core this process may run on and return how many it now uses.
+    torchrun exports OMP_NUM_THREADS=1 into its workers, which would silently make the CPU legs
+    single-threaded (10x slower on this box) while `cores` still said 16."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores, user_api="blas")
+        used = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") == "blas"]
+        if used:
+            return int(max(used))
+    except Exception:
+        pass
+    return int(os.environ.get("OMP_NUM_THREADS", cores)) if "OMP_NUM_THREADS" in os.environ else cores
+
+
 def cpu_reference_sample(b: int, rows: int, k: int, total_rows: int, seed: int = 1):
     """One bounded sample of the reference's CPU path (oracle port): fp32 unit rows,
     `Q @ D.T` + stable top-k, every host thread numpy's BLAS can use.  Returns
@@ -178,7 +194,7 @@ def run_reference_arm(args):
     k = args.k if args.workload != "cache64" else 1
     steps = args.steps or 3
     warmup = args.warmup if args.warmup is not None else 1
-    cores = len(os.sched_getaffinity(0))
+    cores = cpu_use_all_cores()
     for _ in range(warmup):
         cpu_reference_sample(b, sample_rows, k, total_rows)
     times, qps = [], []
@@ -556,7 +572,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the oracle port on this box's host cores, a bounded sample of about 10-20 s of CPU work
-        cores = len(os.sched_getaffinity(0))
+        cores = cpu_use_all_cores()
         if b > 1:
             cb, crow, reps = (64, 250_000, 16) if is_cache else (512, 1_000_000, 8)
         else:

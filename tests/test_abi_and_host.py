@@ -165,7 +165,8 @@ def test_sharded_search_two_ranks_gloo(tmp_path):
 
 
 def test_bench_reference_arm_runs_on_cpu():
-    env = dict(os.environ)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use every core
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
                            "--steps", "1", "--warmup", "0", "--workload", "b1"],
                           capture_output=True, text=True, env=env, timeout=300)
@@ -173,3 +174,4 @@ def test_bench_reference_arm_runs_on_cpu():
     import json
     line = json.loads(proc.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))

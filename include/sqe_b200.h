@@ -105,6 +105,31 @@ SQE_API int sqe_topk_gemv(const void *D, int dtype, int64_t n, int dim, const vo
                   int64_t workspace_bytes, void *stream);
 
 /*
+ * K3p  the same exact top-k as sqe_topk_gemv at about half the HBM traffic: an int8 prefilter
+ * with a rigorous error bound + exact rescoring of the rows the bound cannot rule out.
+ * Results are BIT-IDENTICAL to sqe_topk_gemv (scores, rows, tie order) for every input; only
+ * the number of bytes read differs (10.5 GB instead of 20.5 GB per query on a 10M x 1024 bf16
+ * shard).  Replaces the same reference lines as K3 (app/main.py:356-367).
+ *
+ * sqe_quantize_rows (ingest side, after sqe_normalize_cast): stored rows D [n, dim] (dtype) ->
+ *   D8   int8 [n, 1024]: rint(d / sd), sd = max|d| / 127 per row, and
+ *   meta float [n, 4] = {sd, eps >= |d - sd d8|_2, nd >= |sd d8|_2, 0} (16-byte aligned).
+ * sqe_topk_gemv_prefiltered: D, Q, k, outputs and idx_offset as in sqe_topk_gemv; D8 / meta as
+ *   written by sqe_quantize_rows for the same rows; 1 <= nq <= SQE_MAX_NQ_PREFILTER;
+ *   out_rescored (may be NULL) uint32 [nq]: how many rows went through the exact pass.
+ *   Workspace: sqe_topk_gemv_prefiltered_workspace_bytes(n, nq, k) (it holds one fp32 upper
+ *   bound per row and query); first 4096 bytes zero on first use, left zero by every call.
+ */
+#define SQE_MAX_NQ_PREFILTER 64
+SQE_API int sqe_quantize_rows(const void *D, int dtype, int64_t n, int dim, void *D8, void *meta,
+                      void *stream);
+SQE_API int64_t sqe_topk_gemv_prefiltered_workspace_bytes(int64_t n, int nq, int k);
+SQE_API int sqe_topk_gemv_prefiltered(const void *D, int dtype, int64_t n, int dim, const void *D8,
+                              const void *meta, const void *Q, int nq, int k, float *out_score,
+                              int64_t *out_idx, int64_t idx_offset, uint32_t *out_rescored,
+                              void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
  * K2  batched exact cosine top-k on the tensor cores (tcgen05 + TMA), with the
  * per-tile top-k selection fused into the accumulator epilogue so the score matrix
  * never reaches HBM.  Same contract as sqe_topk_gemv; dtype must be SQE_BF16, SQE_F16 or

@@ -36,4 +36,6 @@ from .numpy_oracle import (  # noqa: F401
     merge_topk,
     LfuCacheModel,
     opensearch_score,
+    quantize_rows_int8,
+    prefilter_bounds,
 )

@@ -284,3 +284,54 @@ class LfuCacheModel:
 
     def responses(self) -> List[str]:
         return [json.loads(s)["response"] for s in self.items]
+
+
+# ----------------------------------------------------------------------------
+# K3p  int8 prefilter: the bound that makes it exact (no reference line: the reference scores
+# every row, main.py:59-64; this is the checker of the device-side error bound)
+# ----------------------------------------------------------------------------
+PREFILTER_SLACK = np.float32(4e-6)
+PREFILTER_INFLATE = np.float32(1.001)
+
+
+def quantize_rows_int8(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-row max-abs int8 quantisation as `sqe_quantize_rows` does it (fp32 arithmetic):
+    d8 = clip(rint(x * (127 / max|x|))), meta = [sd, eps, nd, 0] with sd = max|x| / 127,
+    eps >= |x - sd d8|_2, nd >= |sd d8|_2.  Non-finite rows: d8 = 0, eps = +inf."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = x.shape[0]
+    with np.errstate(all="ignore"):
+        finite = np.isfinite((x.astype(np.float64) ** 2).sum(axis=1).astype(np.float32))
+        mx = np.nanmax(np.abs(np.where(np.isnan(x), np.float32(0), x)), axis=1).astype(np.float32)
+        live = finite & (mx > 0)
+        sd = np.where(live, mx / np.float32(127), np.float32(0)).astype(np.float32)
+        inv = np.where(live, np.float32(127) / np.where(live, mx, np.float32(1)), np.float32(0)).astype(np.float32)
+        xs = np.where(live[:, None], x, np.float32(0))
+        r = np.clip(np.rint(xs * inv[:, None]), -127, 127).astype(np.float32)
+        back = (sd[:, None] * r).astype(np.float64)
+        err = xs.astype(np.float64) - back
+        eps = (np.sqrt((err ** 2).sum(axis=1)).astype(np.float32) * PREFILTER_INFLATE + np.float32(1e-12))
+        nd = np.sqrt((back ** 2).sum(axis=1)).astype(np.float32) * PREFILTER_INFLATE
+    meta = np.zeros((n, 4), dtype=np.float32)
+    meta[:, 0] = sd
+    meta[:, 1] = np.where(finite, eps, np.float32(np.inf))
+    meta[:, 2] = np.where(finite, nd, np.float32(0))
+    return r.astype(np.int8), meta
+
+
+def prefilter_bounds(d_stored: np.ndarray, q_stored: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """(L, U) [B,N]: the lower / upper bounds the int8 prefilter puts on every exact score
+    `q_stored . d_stored`:  s8 = sd sq (q8 . d8),  m = |eq| nd + |q| eps + slack,  L = s8 - m,
+    U = s8 + m (Cauchy-Schwarz on q = sq q8 + eq, d = sd d8 + ed)."""
+    d8, dm = quantize_rows_int8(d_stored)
+    q8, qm = quantize_rows_int8(q_stored)
+    q = np.ascontiguousarray(q_stored, dtype=np.float32)
+    qn = np.sqrt((q.astype(np.float64) ** 2).sum(axis=1)).astype(np.float32) * PREFILTER_INFLATE
+    qe = qm[:, 1]
+    acc = q8.astype(np.int32) @ d8.astype(np.int32).T                      # exact integers
+    s8 = (dm[None, :, 0] * qm[:, None, 0]).astype(np.float32) * acc.astype(np.float32)
+    with np.errstate(all="ignore"):
+        m = ((qe[:, None] * dm[None, :, 2] + qn[:, None] * dm[None, :, 1]
+              + PREFILTER_SLACK * qn[:, None] * (dm[None, :, 2] + dm[None, :, 1])) * PREFILTER_INFLATE
+             + np.float32(1e-30)).astype(np.float32)
+        return (s8 - m).astype(np.float32), (s8 + m).astype(np.float32)

@@ -18,6 +18,7 @@ SQE_F32, SQE_BF16, SQE_F16, SQE_BF16X2 = 0, 1, 2, 3
 SQE_DIM = 1024
 SQE_MAX_K_GEMV = 256
 SQE_MAX_K_BATCHED = 128
+SQE_MAX_NQ_PREFILTER = 64
 DTYPE_CODES = {"fp32": SQE_F32, "bf16": SQE_BF16, "fp16": SQE_F16, "bf16x2": SQE_BF16X2}
 
 # every symbol include/sqe_b200.h declares: (name, restype, argtypes)
@@ -33,6 +34,11 @@ PROTOTYPES = [
                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     ("sqe_search_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    ("sqe_quantize_rows", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    ("sqe_topk_gemv_prefiltered_workspace_bytes", c_int64, [c_int64, c_int, c_int]),
+    ("sqe_topk_gemv_prefiltered", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                          c_void_p, c_int64, c_void_p]),
     ("sqe_topk_batched_workspace_bytes", c_int64, [c_int64, c_int, c_int]),
     ("sqe_topk_batched", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
@@ -67,6 +73,8 @@ LAUNCHES_PER_CALL = {
     "sqe_normalize_cast": 1,
     "sqe_topk_gemv": 1,
     "sqe_search_gemv": 1,
+    "sqe_quantize_rows": 1,
+    "sqe_topk_gemv_prefiltered": 2,
     "sqe_topk_batched": 2,
     "sqe_cache_top1": 2,      # +1 when it takes the tensor path (counted by the caller)
     "sqe_merge_topk": 1,

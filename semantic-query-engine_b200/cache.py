@@ -16,6 +16,7 @@ process can keep reading the same list.
 from __future__ import annotations
 
 import json
+import math
 import threading
 from typing import List, Optional, Tuple
 
@@ -42,6 +43,15 @@ def cosine_similarity(a, b, *, device: Optional[torch.device] = None) -> float:
     va, vb = GpuQueryCache._row0(a), GpuQueryCache._row0(b)
     if va is None or vb is None:
         raise ValueError(f"expected two [{nat.SQE_DIM}] embeddings")
+    na, nb = float(np.linalg.norm(va)), float(np.linalg.norm(vb))
+    if na == 0.0 or nb == 0.0:                           # main.py:62-63
+        return 0.0
+    # The reference divides by the norms themselves, the kernels by (norm + 1e-9): bring both
+    # norms into [0.5, 1) with an exact power-of-two scaling so that the 1e-9 is immaterial for
+    # tiny (or huge) vectors too; the cosine is scale-invariant.
+    if np.isfinite(na) and np.isfinite(nb):
+        va = np.ldexp(va, -math.frexp(na)[1]).astype(np.float32)
+        vb = np.ldexp(vb, -math.frexp(nb)[1]).astype(np.float32)
     with torch.cuda.device(dev):
         row = ops.normalize_cast(torch.from_numpy(vb[None, :]).to(dev), "fp32")
         scores, _ = ops.search_gemv(row, torch.from_numpy(va[None, :]).to(dev), 1)

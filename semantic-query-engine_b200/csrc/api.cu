@@ -174,6 +174,54 @@ int sqe_search_gemv(const void* D, int dtype, int64_t n, int dim, const float* Q
                             workspace_bytes, d.sm_count, static_cast<cudaStream_t>(stream));
 }
 
+int sqe_quantize_rows(const void* D, int dtype, int64_t n, int dim, void* D8, void* meta, void* stream) {
+    if (dim != SQE_DIM) { set_error("quantize_rows: dim must be %d (got %d)", SQE_DIM, dim); return SQE_E_ARG; }
+    if (dtype < SQE_F32 || dtype > SQE_BF16X2) { set_error("quantize_rows: bad dtype %d", dtype); return SQE_E_ARG; }
+    if (n < 0 || n >= 0xffffffffLL) { set_error("quantize_rows: n=%lld out of range", (long long)n); return SQE_E_ARG; }
+    if (n == 0) return SQE_OK;
+    if (!D || !D8 || !meta || !aligned16(D) || !aligned16(D8) || !aligned16(meta)) {
+        set_error("quantize_rows: null or unaligned pointer");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_quantize_rows(D, dtype, n, D8, meta, d.sm_count, static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : SQE_E_CUDA);
+}
+
+int64_t sqe_topk_gemv_prefiltered_workspace_bytes(int64_t n, int nq, int k) {
+    DevInfo d;
+    if (device_info(&d) != SQE_OK) d.sm_count = 160;
+    if (nq < 1) nq = 1;
+    if (k < 1) k = 1;
+    if (n < 0) n = 0;
+    return prefilter_workspace_bytes(n, nq, k, d.sm_count);
+}
+
+int sqe_topk_gemv_prefiltered(const void* D, int dtype, int64_t n, int dim, const void* D8,
+                              const void* meta, const void* Q, int nq, int k, float* out_score,
+                              int64_t* out_idx, int64_t idx_offset, uint32_t* out_rescored,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_common("topk_gemv_prefiltered", D, dtype, n, dim, Q, nq);
+    if (rc != SQE_OK) return rc;
+    if (k < 1 || k > SQE_MAX_K_GEMV) { set_error("topk_gemv_prefiltered: k=%d not in [1,%d]", k, SQE_MAX_K_GEMV); return SQE_E_ARG; }
+    if (nq > SQE_MAX_NQ_PREFILTER) { set_error("topk_gemv_prefiltered: nq=%d > %d", nq, SQE_MAX_NQ_PREFILTER); return SQE_E_ARG; }
+    if (nq == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("topk_gemv_prefiltered: null output/workspace"); return SQE_E_ARG; }
+    if (n > 0 && (!D8 || !meta || !aligned16(D8) || !aligned16(meta))) {
+        set_error("topk_gemv_prefiltered: null or unaligned coarse rows");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_topk_prefiltered(D, dtype, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset,
+                                 out_rescored, workspace, workspace_bytes, d.sm_count,
+                                 static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : rc == -3 ? SQE_E_WORKSPACE : SQE_E_CUDA);
+}
+
 int64_t sqe_topk_batched_workspace_bytes(int64_t n, int b, int k) {
     DevInfo d;
     if (device_info(&d) != SQE_OK) d.sm_count = 160;

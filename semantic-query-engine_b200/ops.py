@@ -162,6 +162,68 @@ def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 
     return scores, idx
 
 
+def quantize_rows(D: torch.Tensor, n: Optional[int] = None, out=None, row0: int = 0
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1q: the coarse copy of stored rows for the prefiltered scan: (int8 [n,1024], fp32 [n,4] =
+    {scale, |d - scale d8| bound, |scale d8| bound, 0}).  `out=(D8, meta)` + `row0`: write rows
+    [row0, row0+n) of preallocated buffers (ingest into a shard tail)."""
+    dev = _require_cuda(D)
+    if D.dim() != 2 or D.shape[1] != ROW_ELEMS[dtype_name(D)]:
+        raise ValueError("D must be [rows,1024] (or [rows,2048] bf16 for split bf16)")
+    rows = D.shape[0] if n is None else int(n)
+    if rows > D.shape[0]:
+        raise ValueError("n exceeds shard rows")
+    if out is None:
+        d8 = torch.empty((rows, nat.SQE_DIM), dtype=torch.int8, device=dev)
+        meta = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        row0 = 0
+    else:
+        d8, meta = out
+        _require_cuda(D, d8, meta)
+        if d8.dtype != torch.int8 or meta.dtype != torch.float32 or d8.dim() != 2 or meta.dim() != 2 or \
+                d8.shape[1] != nat.SQE_DIM or meta.shape[1] != 4 or \
+                d8.shape[0] < row0 + rows or meta.shape[0] < row0 + rows:
+            raise ValueError("bad `out` buffers")
+    if rows:
+        with torch.cuda.device(dev):
+            nat.call("sqe_quantize_rows", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
+                     d8.data_ptr() + row0 * nat.SQE_DIM, meta.data_ptr() + row0 * 16, _stream(dev))
+    return d8, meta
+
+
+def topk_gemv_prefiltered(D: torch.Tensor, D8: torch.Tensor, meta: torch.Tensor, Q: torch.Tensor,
+                          k: int, idx_offset: int = 0, n: Optional[int] = None, out=None,
+                          rescored: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None
+                          ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K3p: the results of `topk_gemv`, bit for bit, at about half the HBM traffic: int8 scan of
+    the coarse copy (`quantize_rows`) with a rigorous error bound, then exact rescoring of the
+    rows the bound cannot rule out.  `rescored`: optional int32 CUDA tensor [nq] that receives the
+    number of rows rescored per query.  `ws`: a private zero-initialised workspace (CUDA graphs)."""
+    dev, rows, b = _check_dq(D, Q, n)
+    _require_cuda(D, D8, meta)
+    if D8.dtype != torch.int8 or meta.dtype != torch.float32 or D8.dim() != 2 or meta.dim() != 2 or \
+            D8.shape[1] != nat.SQE_DIM or meta.shape[1] != 4 or D8.shape[0] < rows or meta.shape[0] < rows:
+        raise ValueError("coarse rows must be int8 [rows,1024] + fp32 [rows,4] (ops.quantize_rows)")
+    if b > nat.SQE_MAX_NQ_PREFILTER:
+        raise ValueError(f"at most {nat.SQE_MAX_NQ_PREFILTER} queries per call")
+    scores, idx = _outputs(out, dev, b, k)
+    if b == 0:
+        return scores, idx
+    if rescored is not None and (rescored.dtype != torch.int32 or rescored.numel() < b or not rescored.is_cuda):
+        raise ValueError("`rescored` must be an int32 CUDA tensor [nq]")
+    with _launch_lock, torch.cuda.device(dev):
+        need = nat.load().sqe_topk_gemv_prefiltered_workspace_bytes(rows, b, k)
+        if ws is None:
+            ws = _workspace(dev, "prefilter", need)
+        elif ws.numel() < need or ws.device != dev or ws.dtype != torch.uint8:
+            raise ValueError("bad private workspace")
+        nat.call("sqe_topk_gemv_prefiltered", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows,
+                 nat.SQE_DIM, D8.data_ptr(), meta.data_ptr(), Q.data_ptr(), b, k, scores.data_ptr(),
+                 idx.data_ptr(), idx_offset, rescored.data_ptr() if rescored is not None else None,
+                 ws.data_ptr(), ws.numel(), _stream(dev))
+    return scores, idx
+
+
 def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
                  n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K2: exact cosine top-k on the tensor cores (bf16/fp16 shards)."""
@@ -275,8 +337,11 @@ class SingleQueryGraph:
     Replaying it costs one graph launch instead of several Python-level copies and launches.
     The shard pointer, row count, k and row offset are baked in: build a new one when they change."""
 
-    def __init__(self, shard: torch.Tensor, rows: int, k: int, idx_offset: int = 0):
+    def __init__(self, shard: torch.Tensor, rows: int, k: int, idx_offset: int = 0, coarse=None):
+        """`coarse = (D8, meta, dtype name)`: capture the prefiltered scan (K1 + K3p) instead of the
+        fused exact scan; same results, about half the bytes per replay."""
         dev = shard.device
+        self.coarse = coarse
         self.device = dev
         self.k = int(k)
         self.idx_offset = int(idx_offset)
@@ -289,8 +354,12 @@ class SingleQueryGraph:
         self.dev_out, self.scores, self.idx = packed_topk_out(dev, 1, self.k)
         # private workspace: the per-stream ones are shared by everything launched on that stream
         # and replaced when they grow, neither of which a captured pointer survives
-        self._ws = torch.zeros((int(nat.load().sqe_topk_gemv_workspace_bytes(1, self.k)),),
-                               dtype=torch.uint8, device=dev)
+        if coarse is None:
+            need = nat.load().sqe_topk_gemv_workspace_bytes(1, self.k)
+        else:
+            need = nat.load().sqe_topk_gemv_prefiltered_workspace_bytes(self.rows, 1, self.k)
+            self.dev_qn = torch.empty((1, ROW_ELEMS[coarse[2]]), dtype=TORCH_DTYPES[coarse[2]], device=dev)
+        self._ws = torch.zeros((int(need),), dtype=torch.uint8, device=dev)
         self.host_q.zero_()
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
@@ -306,15 +375,20 @@ class SingleQueryGraph:
 
     def _body(self) -> None:
         self.dev_q.copy_(self.host_q, non_blocking=True)
-        search_gemv(self._shard, self.dev_q, self.k, idx_offset=self.idx_offset, n=self.rows, out=(self.scores, self.idx),
-                    ws=self._ws)
+        if self.coarse is not None:
+            normalize_cast(self.dev_q, self.coarse[2], out=self.dev_qn)
+            topk_gemv_prefiltered(self._shard, self.coarse[0], self.coarse[1], self.dev_qn, self.k,
+                                  idx_offset=self.idx_offset, n=self.rows, out=(self.scores, self.idx), ws=self._ws)
+        else:
+            search_gemv(self._shard, self.dev_q, self.k, idx_offset=self.idx_offset, n=self.rows,
+                        out=(self.scores, self.idx), ws=self._ws)
         self.host_out.copy_(self.dev_out, non_blocking=True)
 
     def run(self, q_row: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """q_row: fp32 [1024] (raw).  Returns (scores [k] fp32, rows [k] int64) as fresh arrays."""
         self._np_q[0, :] = q_row
         self.graph.replay()
-        nat.launch_count += 1                                  # the replayed sqe_search_gemv
+        nat.launch_count += 1 if self.coarse is None else 3    # the replayed sqe_search_gemv | K1 + K3p
         torch.cuda.current_stream(self.device).synchronize()
         k = self.k
         return self._np_out[k * 8:].view(np.float32).copy(), self._np_out[: k * 8].view(np.int64).copy()

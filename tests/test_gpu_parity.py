@@ -149,6 +149,155 @@ def test_gemv_topk_matches_oracle(sqe, dtype, n):
     np.testing.assert_allclose(s.cpu().numpy()[0, :kk], so[0, :kk], atol=2e-6)
 
 
+# ------------------------------------------------------------------------ K3p
+def test_index_with_prefilter_answers_exactly_like_the_plain_index(sqe, tmp_path):
+    """GpuCorpusIndex(prefilter=True): same hits as the plain index through every entry point that
+    takes one or two queries (graph replay, eager, search_batch, search_device), across
+    incremental ingest with regrowth, an in-place overwrite by _id, and save / load."""
+    rng = np.random.default_rng(321)
+    n = 9000
+    emb = rng.standard_normal((n, DIM)).astype(np.float32)
+    emb[4000] = emb[17]
+    docs = [{"doc_id": f"d{i // 4}", "text": f"t{i}"} for i in range(n)]
+    plain = sqe.GpuCorpusIndex(dtype="bf16", device=dev(), strict=True, initial_capacity=1024)
+    fast = sqe.GpuCorpusIndex(dtype="bf16", device=dev(), strict=True, initial_capacity=1024, prefilter=True)
+    for lo in range(0, n, 2500):                       # several appends -> the shard regrows
+        for ix in (plain, fast):
+            ix.add_embeddings(emb[lo: lo + 2500], docs[lo: lo + 2500])
+    assert fast.num_rows == plain.num_rows == n
+    w8, wm = oracle.quantize_rows_int8(oracle.from_storage(stored_bits(fast.shard, "bf16"), "bf16"))
+    np.testing.assert_array_equal(fast._coarse8[:n].cpu().numpy(), w8)
+    qs = rng.standard_normal((6, DIM)).astype(np.float32)
+    qs[0] = emb[17] * 2
+    for k in (1, 3, 10, 40):
+        for qi in range(3):
+            assert fast.search(qs[qi: qi + 1], k) == plain.search(qs[qi: qi + 1], k)      # graph replay (2nd call on)
+        for b in (1, 2, 5):
+            fs, fi = fast.search_batch(qs[:b], k)
+            ps, pi = plain.search_batch(qs[:b], k)
+            np.testing.assert_array_equal(fi, pi)
+            if b <= 2:                                   # K3p vs K3: the same bits (b=5: both take K2)
+                es, ei = sqe.ops.topk_gemv(plain.shard, sqe.ops.normalize_cast(torch.from_numpy(qs[:b]).to(dev()), "bf16"), k)
+                np.testing.assert_array_equal(fs.view(np.uint32), es.cpu().numpy().view(np.uint32))
+            np.testing.assert_allclose(fs, ps, atol=K2_TOL)
+    assert [h[0]["text"] for h in fast.search(qs[:1], 2)] == ["t17", "t4000"]
+    # re-upload of the first 8 chunks with new vectors: rows rewritten in place, coarse copy too
+    new = rng.standard_normal((8, DIM)).astype(np.float32)
+    for ix in (plain, fast):
+        ix.add_embeddings(new, docs[:8])
+    assert fast.num_rows == n
+    w8, _ = oracle.quantize_rows_int8(oracle.from_storage(stored_bits(fast.shard, "bf16"), "bf16"))
+    np.testing.assert_array_equal(fast._coarse8[:n].cpu().numpy(), w8)
+    assert fast.search(new[3:4], 3) == plain.search(new[3:4], 3)
+    assert fast.search(new[3:4], 3)[0][0]["text"] == "t3"
+    fast.save(str(tmp_path / "ix"))
+    back = sqe.GpuCorpusIndex.load(str(tmp_path / "ix"), device=dev(), prefilter=True, strict=True)
+    np.testing.assert_array_equal(back._coarse8[:n].cpu().numpy(), w8)
+    assert back.search(qs[1:2], 10) == plain.search(qs[1:2], 10)
+    nogr = sqe.GpuCorpusIndex.load(str(tmp_path / "ix"), device=dev(), prefilter=True, strict=True, use_graphs=False)
+    assert nogr.search(qs[1:2], 10) == plain.search(qs[1:2], 10)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_quantize_rows_matches_the_oracle_quantiser(sqe, dtype):
+    """K1q: int8 rows equal the numpy restatement bit for bit; the row constants (scale, error
+    bound, norm bound) agree and ARE upper bounds of what they bound."""
+    rng = np.random.default_rng(77)
+    x = make_corpus(rng, 1500)
+    x[20, 3] = 55.0                                    # an outlier dimension
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    d_st = oracle.from_storage(stored_bits(D, dtype), dtype)
+    d8, meta = sqe.ops.quantize_rows(D)
+    torch.cuda.synchronize()
+    w8, wmeta = oracle.quantize_rows_int8(d_st)
+    np.testing.assert_array_equal(d8.cpu().numpy(), w8)
+    got = meta.cpu().numpy()
+    np.testing.assert_array_equal(got[:, 0], wmeta[:, 0])
+    np.testing.assert_allclose(got[:, 1:3], wmeta[:, 1:3], rtol=1e-5, atol=1e-12)
+    back = got[:, :1].astype(np.float64) * w8.astype(np.float64)
+    assert np.all(np.linalg.norm(d_st.astype(np.float64) - back, axis=1) <= got[:, 1])
+    assert np.all(np.linalg.norm(back, axis=1) <= got[:, 2])
+    assert not w8[10].any() and got[10, 0] == 0.0      # the zero row
+    # into the tail of preallocated buffers (the ingest path)
+    buf8 = torch.zeros((2000, DIM), dtype=torch.int8, device=dev())
+    bufm = torch.zeros((2000, 4), dtype=torch.float32, device=dev())
+    sqe.ops.quantize_rows(D[100:400], out=(buf8, bufm), row0=700)
+    np.testing.assert_array_equal(buf8[700:1000].cpu().numpy(), w8[100:400])
+    assert not buf8[:700].any() and not buf8[1000:].any()
+    np.testing.assert_array_equal(bufm[700:1000].cpu().numpy(), got[100:400])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 7, 63, 1000, 40000])
+def test_prefiltered_gemv_is_bit_identical_to_the_exact_scan(sqe, dtype, n):
+    """K3p returns what K3 returns -- scores, rows, tie order, empty slots -- bit for bit, and
+    matches the oracle; on random rows it rescans only a small part of the shard."""
+    rng = np.random.default_rng(2000 + n)
+    x = make_corpus(rng, n)
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    d8, meta = sqe.ops.quantize_rows(D)
+    q = rng.standard_normal((3, DIM)).astype(np.float32)
+    if n >= 64:
+        q[1] = x[7] * 0.25                               # the planted duplicates: ties
+        q[2] = 0.0                                       # zero query: every score 0 -> rows 0..k-1
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+    d_st = oracle.from_storage(stored_bits(D, dtype), dtype)
+    q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+    s64 = exact_scores(d_st, q_st)
+    resc = torch.zeros((3,), dtype=torch.int32, device=dev())
+    for k in (1, 10, 33, 100, 256):
+        ws, wi = sqe.ops.topk_gemv(D, Q, k, idx_offset=5)
+        gs, gi = sqe.ops.topk_gemv_prefiltered(D, d8, meta, Q, k, idx_offset=5, rescored=resc)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(gi.cpu().numpy(), wi.cpu().numpy())
+        np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), ws.cpu().numpy().view(np.uint32))
+        assert_topk_matches(gs.cpu().numpy(), gi.cpu().numpy(), d_st, q_st, k, idx_offset=5, s64=s64)
+        r = resc.cpu().numpy()
+        assert (r >= min(k, n)).all() and (r <= n).all(), r
+        if n == 40000 and k == 10:
+            assert r[0] < n // 20, r                      # ~1 % at this size, 1e-4 at 10M rows
+            assert r[2] == n                              # zero query: nothing can be ruled out
+    one_s, one_i = sqe.ops.topk_gemv_prefiltered(D, d8, meta, Q[:1], 10)      # a single query
+    ws, wi = sqe.ops.topk_gemv(D, Q[:1], 10)
+    np.testing.assert_array_equal(one_i.cpu().numpy(), wi.cpu().numpy())
+    np.testing.assert_array_equal(one_s.cpu().numpy().view(np.uint32), ws.cpu().numpy().view(np.uint32))
+
+
+def test_prefiltered_gemv_on_hostile_data(sqe):
+    """Where the bound is loose or useless the result is still the exact scan's: clustered rows
+    (thousands within the margin of the k-th best), non-finite rows, a non-finite query, a
+    partial shard (n < allocated rows), a private workspace shared with the exact kernel."""
+    rng = np.random.default_rng(99)
+    n = 30000
+    x = rng.standard_normal((n, DIM)).astype(np.float32)
+    centre = rng.standard_normal(DIM).astype(np.float32)
+    x[1000:9000] = centre + 0.02 * rng.standard_normal((8000, DIM)).astype(np.float32)   # one tight cluster
+    x[9000:9100] = x[1000]                                                            # 100-way exact tie
+    q = np.stack([centre, x[1000], rng.standard_normal(DIM).astype(np.float32), centre]).astype(np.float32)
+    for dtype in ("bf16", "fp32"):
+        D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+        Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+        if dtype == "fp32":
+            D[123, 4] = float("nan")
+            D[124, 5] = float("inf")
+            Q[3, 0] = float("nan")                                                    # NaN query
+        d8, meta = sqe.ops.quantize_rows(D)
+        private = torch.zeros((int(sqe._native.load().sqe_topk_gemv_prefiltered_workspace_bytes(n, 4, 100)),),
+                              dtype=torch.uint8, device=dev())
+        for k, rows in ((10, n), (100, n), (10, 20001)):
+            ws, wi = sqe.ops.topk_gemv(D, Q, k, n=rows)
+            gs, gi = sqe.ops.topk_gemv_prefiltered(D, d8, meta, Q, k, n=rows, ws=private)
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(gi.cpu().numpy(), wi.cpu().numpy())
+            a, b = gs.cpu().numpy(), ws.cpu().numpy()
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) or \
+                (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]))
+            # the same memory then serves the exact kernel: its 4 KB header was left zero
+            es, ei = sqe.ops.search_gemv(D, torch.from_numpy(q[:1]).to(dev()), k, n=rows, ws=private)
+            fs, fi = sqe.ops.search_gemv(D, torch.from_numpy(q[:1]).to(dev()), k, n=rows)
+            np.testing.assert_array_equal(ei.cpu().numpy(), fi.cpu().numpy())
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_search_gemv_fused_normalise_is_bit_identical(sqe, dtype):
     """K1 + K3 in one launch == sqe_normalize_cast followed by sqe_topk_gemv, bit for bit."""

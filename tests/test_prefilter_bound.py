@@ -1,0 +1,88 @@
+"""CPU checks of the error bound that makes the int8-prefiltered scan (K3p) exact: for every
+row, L <= exact score <= U, whatever the data -- so a row with U below the k-th best L can be
+skipped without changing the result.  The device kernels are checked against the exact scan bit
+for bit in tests/test_gpu_parity.py; this file checks the mathematics (oracle restatement)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import numpy_oracle as no
+
+DIM = 1024
+
+
+def _stored(x, dtype):
+    return oracle.from_storage(oracle.to_storage(oracle.normalize_rows(x), dtype), dtype)
+
+
+def _check(d, q, k=10):
+    L, U = oracle.prefilter_bounds(d, q)
+    s64 = q.astype(np.float64) @ d.astype(np.float64).T
+    s32 = q @ d.T                                        # an fp32 summation order (BLAS)
+    for s in (s64, s32.astype(np.float64)):
+        ok = np.isfinite(s)
+        with np.errstate(invalid="ignore"):
+            assert not (s[ok] < L.astype(np.float64)[ok]).any()          # NaN bounds never exclude
+            assert not (U.astype(np.float64)[ok] < s[ok]).any()
+    # the selection argument: every row of the exact top-k survives the filter U >= tau
+    kk = min(k, d.shape[0])
+    with np.errstate(invalid="ignore"):
+        tau = -np.sort(-np.where(np.isnan(L), -np.inf, L), axis=1)[:, kk - 1]
+        keep = ~(U < tau[:, None])
+    _, idx = oracle.topk_from_scores(s32, kk)
+    for b in range(q.shape[0]):
+        assert keep[b, idx[b][idx[b] >= 0]].all()
+    return keep.sum(axis=1)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
+def test_bounds_hold_on_random_unit_rows(dtype):
+    rng = np.random.default_rng(5)
+    d = _stored(rng.standard_normal((3000, DIM)).astype(np.float32), dtype)
+    q = _stored(rng.standard_normal((5, DIM)).astype(np.float32), dtype)
+    kept = _check(d, q)
+    assert kept.max() < 600                              # the filter does filter (3000 rows, k = 10)
+
+
+def test_bounds_hold_in_the_cauchy_schwarz_worst_case():
+    """Queries aligned with a row's own quantisation error (the direction in which the bound is
+    tight), rows with outliers, near-duplicates of the query, scaled (non-unit) rows."""
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((400, DIM)).astype(np.float32)
+    x[5, 17] = 40.0                                      # outlier -> coarse scale
+    x[6] = 0.0
+    d = _stored(x, "bf16")
+    d[7] *= np.float32(3.5)                              # not unit norm
+    d8, meta = oracle.quantize_rows_int8(d)
+    err = d - meta[:, :1] * d8.astype(np.float32)
+    q = np.stack([err[3], -err[4], d[9] + 0.01 * err[9], d[5], d[7], np.zeros(DIM, np.float32)]).astype(np.float32)
+    q[:5] = oracle.normalize_rows(q[:5])
+    _check(d, q, k=3)
+    near = oracle.normalize_rows(d[9][None, :] + 1e-3 * rng.standard_normal((200, DIM)).astype(np.float32))
+    _check(np.concatenate([d, near]), q, k=10)
+
+
+def test_non_finite_rows_and_queries_are_never_filtered_out():
+    rng = np.random.default_rng(7)
+    d = _stored(rng.standard_normal((64, DIM)).astype(np.float32), "fp32")
+    d[3, 5] = np.nan
+    d[4, 6] = np.inf
+    q = _stored(rng.standard_normal((3, DIM)).astype(np.float32), "fp32")
+    q[2, 0] = np.nan
+    L, U = oracle.prefilter_bounds(d, q)
+    with np.errstate(invalid="ignore"):
+        assert not (U[:, 3] < np.inf).any() and not (U[:, 4] < np.inf).any()      # +inf or NaN
+        assert not (U[2] < np.inf).any()                                          # NaN query: all rows
+    d8, meta = oracle.quantize_rows_int8(d)
+    assert not d8[3].any() and not d8[4].any() and np.isinf(meta[3, 1]) and np.isinf(meta[4, 1])
+
+
+def test_quantiser_is_max_abs_round_to_nearest():
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((16, DIM)).astype(np.float32)
+    d8, meta = oracle.quantize_rows_int8(x)
+    assert np.abs(d8).max(axis=1).tolist() == [127] * 16
+    back = meta[:, :1] * d8.astype(np.float32)
+    assert np.abs(x - back).max() <= meta[:, 0].max() * 0.5001
+    assert np.all(np.linalg.norm((x - back).astype(np.float64), axis=1) <= meta[:, 1])
+    assert np.all(np.linalg.norm(back.astype(np.float64), axis=1) <= meta[:, 2])

@@ -110,6 +110,23 @@ class GpuCorpusIndex:
             self._coarse8, self._coarse_meta = c8, cm
         self._capacity = cap
 
+    def enable_prefilter(self) -> None:
+        """Turn the prefiltered scan on for an index that was built without it: allocate the int8
+        copy for the current capacity and quantise the rows already stored (K1q, one pass)."""
+        with self._lock:
+            if self.prefilter and self._coarse8 is not None:
+                return
+            self.prefilter = True
+            if self._shard is None:
+                return
+            self._coarse8 = torch.empty((self._capacity, EMBED_DIM), dtype=torch.int8, device=self.device)
+            self._coarse_meta = torch.empty((self._capacity, 4), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                if self._rows:
+                    ops.quantize_rows(self._shard[: self._rows], out=(self._coarse8, self._coarse_meta))
+                torch.cuda.current_stream(self.device).synchronize()
+            self._graphs.clear()
+
     def has_any_data(self) -> bool:                      # main.py:300-307
         try:
             return self._rows > 0

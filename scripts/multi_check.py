@@ -14,11 +14,14 @@ gen = torch.Generator(device=dev); gen.manual_seed(5)
 full = torch.randn((n, 1024), generator=gen, device=dev)          # same on every rank (same seed)
 full[n - 7] = full[11]                                            # tie across shards
 lo, hi = sqe_b200.shard_bounds(n, world, rank)
-local = sqe_b200.GpuCorpusIndex(dtype="bf16", device=dev, keep_payload=False)
+# SQE_PREFILTER=1: the shards answer one- and two-query searches through the int8-prefiltered scan
+# (K3p); the single-shard reference below stays on the exact scan
+local = sqe_b200.GpuCorpusIndex(dtype="bf16", device=dev, keep_payload=False,
+                                prefilter=bool(os.environ.get("SQE_PREFILTER")))
 local.add_device_rows(full[lo:hi])
 whole = sqe_b200.GpuCorpusIndex(dtype="bf16", device=dev, keep_payload=False)
 whole.add_device_rows(full)
-for b, k in [(1, 10), (64, 10), (1024, 10), (256, 100)]:
+for b, k in [(1, 10), (2, 40), (64, 10), (1024, 10), (256, 100)]:
     q = torch.randn((b, 1024), generator=gen, device=dev); q[0] = full[11] * 2
     want_s, want_i = whole.search_device(q, k)
     res = {}

@@ -28,9 +28,12 @@ class GpuIndexStandIn:
 
 
 def install(main_module, *, dtype: str = "bf16", cache_dtype: str = "fp32", device=None,
-            write_through_redis: bool = False, strict: bool = False):
+            write_through_redis: bool = False, strict: bool = False, prefilter: bool = True):
     """`write_through_redis`: mirror every cache mutation into `main.redis_client` in the
-    reference's entry format and take over what that list already holds (warm start)."""
+    reference's entry format and take over what that list already holds (warm start).
+    `prefilter`: the handlers issue ONE query per request (main.py:499, :684), the shape the
+    int8-prefiltered scan (K3p) serves: the same hits as the exact scan, bit for bit, at about half
+    the HBM bytes per request, for +1 KB of HBM per stored row.  False keeps only the shard."""
     threshold = getattr(main_module, "CACHE_SIM_THRESHOLD", 0.96)
     max_items = getattr(main_module, "REDIS_MAX_ITEMS", 1000)
     list_name = getattr(main_module, "REDIS_CACHE_LIST", "query_cache_lfu")
@@ -52,7 +55,8 @@ def install(main_module, *, dtype: str = "bf16", cache_dtype: str = "fp32", devi
 
     class OpenSearchIndexer(GpuCorpusIndex):
         def __init__(self, client=None, index_name: str = ""):
-            super().__init__(client, index_name, dtype=dtype, device=device, strict=strict)
+            super().__init__(client, index_name, dtype=dtype, device=device, strict=strict,
+                             prefilter=prefilter)
 
     def lfu_cache_get(query_emb: np.ndarray):
         return cache.get(query_emb)

@@ -1,0 +1,49 @@
+"""The JSON lines bench.py has printed on B200 (committed under profiles/) carry every key the
+driver contract names -- a cheap guard against a bench edit dropping one."""
+import glob
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+             "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def _lines(pattern):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern))):
+        with open(path) as f:
+            txt = f.read().strip()
+        if txt:
+            yield path, json.loads(txt.splitlines()[-1])
+
+
+def test_latest_default_line_has_the_contract_keys():
+    found = list(_lines("r1_pf_bench_default.json")) + list(_lines("r1_pf_scale_default_n2.json"))
+    assert found
+    for path, line in found:
+        assert BASE_KEYS <= set(line), (path, BASE_KEYS - set(line))
+        assert line["metric"].startswith("queries/sec exact cosine top-10 @10M") and line["unit"] == "queries/s"
+        assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+        assert line["config"]["workload"].startswith("10000000x1024 bf16 corpus, batch-1024") and "model" not in line["config"]
+        assert line["clocks"]["sm_mhz"] and "reasons" in line["clocks"]
+        e2e = line["e2e"]
+        assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 1024 * 1024 * 4 and e2e["d2h_bytes_per_step"] == 1024 * 10 * 12
+        roof = line["roofline"]
+        assert roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+        assert roof["traffic"] > 0 and line["gpu_launches"] > 0
+        if line["n_gpus"] == 1:
+            cpu = line["cpu_baseline"]
+            assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0 and cpu["sample"]
+        pf = line["secondary_prefiltered"]
+        assert pf["identical_to_exact_scan"] is True and pf["value"] > line["secondary"]["value"]
+
+
+def test_reference_arm_line():
+    found = list(_lines("r1_final2_bench_reference.json"))
+    assert found
+    for _, line in found:
+        assert line["impl"] == "reference" and line["gpu_launches"] == 0
+        assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert line["cpu_baseline"]["value"] == line["value"]

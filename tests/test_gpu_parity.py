@@ -263,6 +263,34 @@ def test_prefiltered_gemv_is_bit_identical_to_the_exact_scan(sqe, dtype, n):
     np.testing.assert_array_equal(one_s.cpu().numpy().view(np.uint32), ws.cpu().numpy().view(np.uint32))
 
 
+def test_prefiltered_gemv_on_a_2m_row_shard(sqe):
+    """Closer to the benchmarked size (2M x 1024 bf16 = 4 GB + 2 GB int8): identical to the exact
+    scan for several queries and k, and only ~1e-3 of the rows go through the exact pass."""
+    n = 2_000_000
+    gen = torch.Generator(device=dev())
+    D = torch.empty((n, DIM), dtype=torch.bfloat16, device=dev())
+    for lo in range(0, n, 250_000):
+        gen.manual_seed(700 + lo)
+        sqe.ops.normalize_cast(torch.randn((250_000, DIM), generator=gen, device=dev()), "bf16", out=D[lo: lo + 250_000])
+    D[1_999_999] = D[5]                                  # a tie between the two ends of the shard
+    d8, meta = sqe.ops.quantize_rows(D)
+    q = torch.randn((4, DIM), generator=gen, device=dev())
+    q[0] = D[5].float() * 3
+    Q = sqe.ops.normalize_cast(q, "bf16")
+    resc = torch.zeros((4,), dtype=torch.int32, device=dev())
+    for k in (10, 100):
+        ws, wi = sqe.ops.topk_gemv(D, Q, k)
+        gs, gi = sqe.ops.topk_gemv_prefiltered(D, d8, meta, Q, k, rescored=resc)
+        torch.cuda.synchronize()
+        assert torch.equal(gi, wi) and torch.equal(gs.view(torch.int32), ws.view(torch.int32))
+        assert gi[0, :2].tolist() == [5, 1_999_999]
+        assert int(resc.max()) < n // 200, resc.tolist()
+    for j in range(4):                                   # one query per call, the reference's shape
+        ws, wi = sqe.ops.topk_gemv(D, Q[j: j + 1], 10)
+        gs, gi = sqe.ops.topk_gemv_prefiltered(D, d8, meta, Q[j: j + 1], 10)
+        assert torch.equal(gi, wi) and torch.equal(gs.view(torch.int32), ws.view(torch.int32))
+
+
 def test_prefiltered_gemv_on_hostile_data(sqe):
     """Where the bound is loose or useless the result is still the exact scan's: clustered rows
     (thousands within the margin of the k-th best), non-finite rows, a non-finite query, a

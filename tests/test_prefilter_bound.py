@@ -86,3 +86,26 @@ def test_quantiser_is_max_abs_round_to_nearest():
     assert np.abs(x - back).max() <= meta[:, 0].max() * 0.5001
     assert np.all(np.linalg.norm((x - back).astype(np.float64), axis=1) <= meta[:, 1])
     assert np.all(np.linalg.norm(back.astype(np.float64), axis=1) <= meta[:, 2])
+
+
+def test_bounds_hold_for_arbitrary_rows_hypothesis():
+    """Property test: any mixture of scales, sparsity, outliers and sign patterns, unit or not."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), scale_exp=st.integers(-30, 12), sparsity=st.floats(0.0, 0.99),
+           outliers=st.integers(0, 5), dtype=st.sampled_from(["fp32", "bf16", "fp16"]))
+    def prop(seed, scale_exp, sparsity, outliers, dtype):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((48, DIM)).astype(np.float32)
+        x[rng.random(x.shape) < sparsity] = 0.0
+        for _ in range(outliers):
+            x[rng.integers(48), rng.integers(DIM)] = np.float32(rng.choice([-1, 1]) * 10.0 ** rng.integers(1, 4))
+        d = oracle.from_storage(oracle.to_storage(oracle.normalize_rows(x), dtype), dtype)
+        d[:8] *= np.float32(2.0 ** scale_exp)            # some rows far from unit norm
+        q = rng.standard_normal((3, DIM)).astype(np.float32)
+        q[1] = d[9] + 1e-3 * q[1]
+        q = oracle.from_storage(oracle.to_storage(q if dtype == "fp32" else oracle.normalize_rows(q), dtype), dtype)
+        _check(d, q, k=5)
+    prop()

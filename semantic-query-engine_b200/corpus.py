@@ -396,15 +396,18 @@ class GpuCorpusIndex:
 
     def hits_from_rows(self, scores, rows) -> List[Tuple[Dict[str, str], float]]:
         """(score, row) arrays of ONE query -> the reference's hit list (main.py:364-367)."""
-        results = []
-        for s, r in zip(scores, rows):
-            if r < 0:
-                continue
-            s = float(s)
-            if self.score_mode == "opensearch":
-                s = 1.0 / (2.0 - s)
-            results.append((self._source(int(r)), s))
-        return results
+        if not isinstance(scores, list):                 # numpy in, Python floats / ints out
+            scores, rows = np.asarray(scores).tolist(), np.asarray(rows).tolist()
+        if self.return_embedding:
+            src = self._source
+        elif self.keep_payload:                          # a fresh dict per hit, like hit["_source"]
+            docs, n_docs = self._docs, len(self._docs)
+            src = lambda r: dict(docs[r]) if r < n_docs else {"doc_id": str(r), "text": ""}
+        else:
+            src = lambda r: {"doc_id": str(r), "text": ""}
+        if self.score_mode == "opensearch":
+            return [(src(r), 1.0 / (2.0 - s)) for s, r in zip(scores, rows) if r >= 0]
+        return [(src(r), s) for s, r in zip(scores, rows) if r >= 0]
 
     def _source(self, row: int) -> Dict[str, str]:
         if self.keep_payload and row < len(self._docs):

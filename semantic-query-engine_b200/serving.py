@@ -71,6 +71,27 @@ class UserIndexRegistry:
 
 
 # ------------------------------------------------------------------- micro-batching
+class _LoopFuture:
+    """A request that waits on an event loop: its asyncio future and the loop that owns it."""
+    __slots__ = ("loop", "afut")
+
+    def __init__(self, loop, afut):
+        self.loop, self.afut = loop, afut
+
+    def done(self) -> bool:
+        return self.afut.done()
+
+
+def _resolve_on_loop(group) -> None:
+    for afut, value, is_exc in group:                                # runs ON the loop thread
+        if afut.done():                                              # cancelled by its handler
+            continue
+        if is_exc:
+            afut.set_exception(value)
+        else:
+            afut.set_result(value)
+
+
 class MicroBatcher:
     """Coalesce concurrent single-query `search` calls into batched launches.
 
@@ -82,7 +103,13 @@ class MicroBatcher:
     and kernels are asynchronous, ops.StreamPipeline).  A delivery thread waits for the oldest
     batch in flight and slices each request's rows out of it (a top-k list is a prefix of a longer
     top-k list) -- so the GPU scores batch j+1 while the results of batch j are being handed out
-    (`depth` batches in flight)."""
+    (`depth` batches in flight).
+
+    `await mb.asearch(query_emb, k)` is the form for `async def` handlers on an event loop
+    (main.py:587, :650): the request carries an asyncio future of the CALLER's loop and the delivery
+    thread resolves all requests of a batch with ONE `call_soon_threadsafe` per loop -- one
+    loop wake-up per batch instead of one per request (`asyncio.wrap_future(mb.submit(...))` costs a
+    concurrent future, a chained asyncio future and a self-pipe write per request)."""
 
     def __init__(self, index: GpuCorpusIndex, max_batch: int = 256, max_wait_s: float = 200e-6,
                  depth: int = 2):
@@ -130,6 +157,25 @@ class MicroBatcher:
     def search(self, query_emb: np.ndarray, k: int = 3):
         return self.submit(query_emb, k).result()
 
+    def asubmit(self, query_emb: np.ndarray, k: int = 3):
+        """Called ON an event loop: returns an asyncio future of that loop (await it)."""
+        import asyncio
+        loop = asyncio.get_running_loop()
+        afut = loop.create_future()
+        if query_emb is None or getattr(query_emb, "size", 0) == 0:     # main.py:350-351
+            afut.set_result([])
+            return afut
+        q = self.index._as_rows(query_emb)[:1]
+        with self._cv:
+            if self._stop:
+                raise RuntimeError("MicroBatcher is closed")
+            self._queue.append((q, int(k), _LoopFuture(loop, afut)))
+            self._cv.notify()
+        return afut
+
+    async def asearch(self, query_emb: np.ndarray, k: int = 3):
+        return await self.asubmit(query_emb, k)
+
     def close(self) -> None:
         with self._cv:
             self._stop = True
@@ -155,11 +201,26 @@ class MicroBatcher:
             return batch
 
     def _fail(self, batch, e: Exception) -> None:
-        for _, _, fut in batch:                                      # main.py:371-373 -> []
-            if self.index.strict:
-                fut.set_exception(e)
+        strict = self.index.strict
+        self._resolve([(fut, e if strict else [], strict) for _, _, fut in batch])   # main.py:371-373 -> []
+
+    @staticmethod
+    def _resolve(items) -> None:
+        """items: (future, value, is_exception).  Thread futures are completed here; asyncio
+        futures are handed to their loop in ONE call per loop."""
+        per_loop = {}
+        for fut, value, is_exc in items:
+            if isinstance(fut, _LoopFuture):
+                per_loop.setdefault(fut.loop, []).append((fut.afut, value, is_exc))
+            elif is_exc:
+                fut.set_exception(value)
             else:
-                fut.set_result([])
+                fut.set_result(value)
+        for loop, group in per_loop.items():
+            try:
+                loop.call_soon_threadsafe(_resolve_on_loop, group)
+            except RuntimeError:                                     # that loop is closed: nobody waits
+                pass
 
     def _run(self) -> None:
         while True:
@@ -185,8 +246,8 @@ class MicroBatcher:
     def _deliver_one(self, batch) -> None:
         scores, rows = self._pipe.collect()
         scores, rows = scores.tolist(), rows.tolist()                # one conversion per batch
-        for i, (_, k, fut) in enumerate(batch):
-            fut.set_result(self.index.hits_from_rows(scores[i][:k], rows[i][:k]))
+        hits = self.index.hits_from_rows
+        self._resolve([(fut, hits(scores[i][:k], rows[i][:k]), False) for i, (_, k, fut) in enumerate(batch)])
 
     def _deliver(self) -> None:
         while True:

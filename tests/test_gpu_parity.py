@@ -833,6 +833,10 @@ def test_micro_batcher_coalesces_concurrent_requests(sqe):
         async def many():
             return await asyncio.gather(*[asyncio.wrap_future(mb.submit(q, k)) for q, k in zip(queries, ks)])
         assert asyncio.run(many()) == got
+
+        async def many_native():                              # one loop wake-up per batch
+            return await asyncio.gather(*[mb.asearch(q, k) for q, k in zip(queries, ks)])
+        assert asyncio.run(many_native()) == got
     finally:
         mb.close()
     empty = sqe.MicroBatcher(sqe.GpuCorpusIndex(dtype="bf16"), max_batch=8)
@@ -840,7 +844,7 @@ def test_micro_batcher_coalesces_concurrent_requests(sqe):
         assert empty.search(queries[0], 3) == []             # nothing indexed yet: no hits, no error
     finally:
         empty.close()
-    assert mb.requests == 2 * len(queries) and mb.batches < len(queries), (mb.batches, mb.requests)
+    assert mb.requests == 3 * len(queries) and mb.batches < len(queries), (mb.batches, mb.requests)
     for g, w, k in zip(got, want, ks):
         assert len(g) == len(w) == k
         assert [h[0] for h in g] == [h[0] for h in w]        # same chunks, same order

@@ -698,7 +698,7 @@ def run_serve(args, torch, sqe_b200, nat, dev, peaks):
     streaming pass per request)."""
     from concurrent.futures import ThreadPoolExecutor
     rows, k, clients = args.rows, args.k, 256
-    per_client = args.steps or 8
+    per_client = args.steps or 24
     index = sqe_b200.GpuCorpusIndex(dtype=args.dtype, device=dev, keep_payload=False)
     index.reserve(rows)
     gen = torch.Generator(device=dev)

@@ -114,17 +114,17 @@ class GpuCorpusIndex:
         """Turn the prefiltered scan on for an index that was built without it: allocate the int8
         copy for the current capacity and quantise the rows already stored (K1q, one pass)."""
         with self._lock:
-            if self.prefilter and self._coarse8 is not None:
+            if self.prefilter and (self._coarse8 is not None or self._shard is None):
                 return
-            self.prefilter = True
-            if self._shard is None:
-                return
-            self._coarse8 = torch.empty((self._capacity, EMBED_DIM), dtype=torch.int8, device=self.device)
-            self._coarse_meta = torch.empty((self._capacity, 4), dtype=torch.float32, device=self.device)
-            with torch.cuda.device(self.device):
-                if self._rows:
-                    ops.quantize_rows(self._shard[: self._rows], out=(self._coarse8, self._coarse_meta))
-                torch.cuda.current_stream(self.device).synchronize()
+            if self._shard is not None:
+                c8 = torch.empty((self._capacity, EMBED_DIM), dtype=torch.int8, device=self.device)
+                cm = torch.empty((self._capacity, 4), dtype=torch.float32, device=self.device)
+                with torch.cuda.device(self.device):
+                    if self._rows:
+                        ops.quantize_rows(self._shard[: self._rows], out=(c8, cm))
+                    torch.cuda.current_stream(self.device).synchronize()
+                self._coarse8, self._coarse_meta = c8, cm
+            self.prefilter = True                        # last: searches may run concurrently
             self._graphs.clear()
 
     def has_any_data(self) -> bool:                      # main.py:300-307
@@ -349,11 +349,11 @@ class GpuCorpusIndex:
         rows = self._rows
         shard = self._shard if self._shard is not None else self.shard
         q_dev = q_dev.contiguous()
-        if self.prefilter and 1 <= q_dev.shape[0] <= 2 and rows > 0:
+        c8, cm = self._coarse8, self._coarse_meta
+        if self.prefilter and c8 is not None and 1 <= q_dev.shape[0] <= 2 and 0 < rows <= c8.shape[0]:
             # K3p: int8 prefilter + exact rescoring -- the exact scan's results at half its bytes
             qn = ops.normalize_cast(q_dev, self.dtype)
-            return ops.topk_gemv_prefiltered(shard, self._coarse8, self._coarse_meta, qn, k,
-                                             idx_offset=idx_offset, n=rows, out=out)
+            return ops.topk_gemv_prefiltered(shard, c8, cm, qn, k, idx_offset=idx_offset, n=rows, out=out)
         if q_dev.shape[0] == 1 and q_dev.dtype == torch.float32:
             # the reference's own case (one query, main.py:355): normalise + scan in ONE launch
             return ops.search_gemv(shard, q_dev, k, idx_offset=idx_offset, n=rows, out=out)

@@ -175,10 +175,12 @@ def test_index_with_prefilter_answers_exactly_like_the_plain_index(sqe, tmp_path
         for b in (1, 2, 5):
             fs, fi = fast.search_batch(qs[:b], k)
             ps, pi = plain.search_batch(qs[:b], k)
-            np.testing.assert_array_equal(fi, pi)
-            if b <= 2:                                   # K3p vs K3: the same bits (b=5: both take K2)
+            if b <= 2:                                   # K3p vs the exact scan K3: the same bits
                 es, ei = sqe.ops.topk_gemv(plain.shard, sqe.ops.normalize_cast(torch.from_numpy(qs[:b]).to(dev()), "bf16"), k)
+                np.testing.assert_array_equal(fi, ei.cpu().numpy())
                 np.testing.assert_array_equal(fs.view(np.uint32), es.cpu().numpy().view(np.uint32))
+            else:                                        # b = 5: both indices take the tensor-core path
+                np.testing.assert_array_equal(fi, pi)
             np.testing.assert_allclose(fs, ps, atol=K2_TOL)
     assert [h[0]["text"] for h in fast.search(qs[:1], 2)] == ["t17", "t4000"]
     # re-upload of the first 8 chunks with new vectors: rows rewritten in place, coarse copy too

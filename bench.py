@@ -492,7 +492,10 @@ def main():
     roofline["kernel_ms"] = kms
     roofline["peak_source"] = peaks["source"] + (" (burst)" if roofline["bound"] == "tensor" else "")
     ratio = load_traffic(kname)
-    if ratio is not None:
+    if ratio is not None and kname == "coarse_scan_kernel":
+        roofline["traffic"] = ratio["dram_bytes_per_algorithmic_byte"] * alg     # both passes of K3p
+        roofline["traffic_source"] = ratio["source"]
+    elif ratio is not None:
         unit_bytes = local_rows * DIM * esize            # shard bytes one launch must stream
         roofline["traffic"] = ratio["dram_bytes_per_algorithmic_byte"] * unit_bytes
         roofline["traffic_source"] = ratio["source"]

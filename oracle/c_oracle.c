@@ -121,3 +121,71 @@ void sqe_oracle_cache_lookup(const float *C, int64_t n, const float *q, double t
     *out_sim = (float)best;
     *out_hit = (best_i >= 0 && !(best < threshold)) ? 1 : 0; /* main.py:89 */
 }
+
+/* ------------------------------------------------------------------------------------------
+ * The int8 prefilter (K3p).  No reference line: the reference scores every row (main.py:59-64);
+ * this restates the quantiser and the Cauchy-Schwarz bound that lets the device skip rows
+ * without changing the answer:  L <= exact score <= U  for every row.
+ *   d8 = clip(rint(x * (127 / max|x|))), sd = max|x| / 127, eps >= |x - sd d8|_2, nd >= |sd d8|_2
+ *   s8 = sd sq (q8 . d8)  (exact integer dot product),  m = |eq| nd + |q| eps + slack
+ * Norms are accumulated in double and inflated by 0.1 % like the device does in fp32.
+ * ------------------------------------------------------------------------------------------ */
+#define SQE_PF_INFLATE 1.001f
+#define SQE_PF_SLACK 4e-6f
+
+void sqe_oracle_quantize_row(const float *x, int8_t *d8, float *meta /* [4] */) {
+    float mx = 0.0f;
+    double ss = 0.0;
+    for (int j = 0; j < SQE_ORACLE_DIM; ++j) {
+        const float a = fabsf(x[j]);
+        if (a > mx) mx = a;                                  /* NaN never wins, like fmaxf */
+        ss += (double)x[j] * (double)x[j];
+    }
+    const int finite = isfinite((float)ss);
+    const int live = finite && mx > 0.0f;
+    const float sd = live ? mx / 127.0f : 0.0f;
+    const float inv = live ? 127.0f / mx : 0.0f;
+    double e2 = 0.0, n2 = 0.0;
+    for (int j = 0; j < SQE_ORACLE_DIM; ++j) {
+        const float v = live ? x[j] : 0.0f;
+        float r = rintf(v * inv);
+        if (r > 127.0f) r = 127.0f;
+        if (r < -127.0f) r = -127.0f;
+        const double back = (double)(sd * r), err = (double)v - back;
+        e2 += err * err;
+        n2 += back * back;
+        d8[j] = (int8_t)r;
+    }
+    meta[0] = sd;
+    meta[1] = finite ? (float)sqrt(e2) * SQE_PF_INFLATE + 1e-12f : INFINITY;
+    meta[2] = finite ? (float)sqrt(n2) * SQE_PF_INFLATE : 0.0f;
+    meta[3] = 0.0f;
+}
+
+/* L[q, r], U[q, r] for stored rows D [n, 1024] and stored queries Q [b, 1024] */
+void sqe_oracle_prefilter_bounds(const float *D, int64_t n, const float *Q, int b, float *L, float *U) {
+    int8_t *d8 = (int8_t *)malloc((size_t)n * SQE_ORACLE_DIM);
+    float *dm = (float *)malloc((size_t)n * 4 * sizeof(float));
+    for (int64_t r = 0; r < n; ++r) sqe_oracle_quantize_row(D + r * SQE_ORACLE_DIM, d8 + r * SQE_ORACLE_DIM, dm + r * 4);
+    for (int q = 0; q < b; ++q) {
+        const float *y = Q + (int64_t)q * SQE_ORACLE_DIM;
+        int8_t q8[SQE_ORACLE_DIM];
+        float qm[4];
+        sqe_oracle_quantize_row(y, q8, qm);
+        double ss = 0.0;
+        for (int j = 0; j < SQE_ORACLE_DIM; ++j) ss += (double)y[j] * (double)y[j];
+        const float qn = (float)sqrt(ss) * SQE_PF_INFLATE, qe = qm[1], sq = qm[0];
+        for (int64_t r = 0; r < n; ++r) {
+            int32_t acc = 0;
+            const int8_t *x = d8 + r * SQE_ORACLE_DIM;
+            for (int j = 0; j < SQE_ORACLE_DIM; ++j) acc += (int32_t)x[j] * (int32_t)q8[j];
+            const float sd = dm[r * 4], eps = dm[r * 4 + 1], nd = dm[r * 4 + 2];
+            const float s8 = (sd * sq) * (float)acc;
+            const float m = ((qe * nd + qn * eps) + SQE_PF_SLACK * qn * (nd + eps)) * SQE_PF_INFLATE + 1e-30f;
+            L[(int64_t)q * n + r] = s8 - m;
+            U[(int64_t)q * n + r] = s8 + m;
+        }
+    }
+    free(d8);
+    free(dm);
+}

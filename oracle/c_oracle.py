@@ -52,6 +52,8 @@ def _load():
         lib.sqe_oracle_cache_lookup.argtypes = [f32p, ctypes.c_int64, f32p, ctypes.c_double,
                                                 ctypes.POINTER(ctypes.c_int32), f32p,
                                                 ctypes.POINTER(ctypes.c_uint8)]
+        lib.sqe_oracle_quantize_row.argtypes = [f32p, ctypes.POINTER(ctypes.c_int8), f32p]
+        lib.sqe_oracle_prefilter_bounds.argtypes = [f32p, ctypes.c_int64, f32p, ctypes.c_int, f32p, f32p]
         _lib = lib
     return _lib
 
@@ -111,3 +113,24 @@ def cache_lookup(c_stored, q_stored_row, threshold: float) -> Tuple[int, float, 
     _load().sqe_oracle_cache_lookup(_f32(c), c.shape[0], _f32(q), float(threshold),
                                     ctypes.byref(idx), ctypes.byref(sim), ctypes.byref(hit))
     return int(idx.value), float(sim.value), bool(hit.value)
+
+
+def quantize_rows_int8(x) -> Tuple[np.ndarray, np.ndarray]:
+    """The K3p quantiser in plain C: (int8 [n,1024], fp32 [n,4] = {sd, eps, nd, 0})."""
+    a = _rows(x)
+    d8 = np.empty(a.shape, dtype=np.int8)
+    meta = np.empty((a.shape[0], 4), dtype=np.float32)
+    lib = _load()
+    for i in range(a.shape[0]):
+        lib.sqe_oracle_quantize_row(_f32(a[i]), d8[i].ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _f32(meta[i]))
+    return d8, meta
+
+
+def prefilter_bounds(d_stored, q_stored) -> Tuple[np.ndarray, np.ndarray]:
+    """(L, U) [B,N]: lower / upper bounds of every exact score, as the int8 prefilter derives them."""
+    d, q = _rows(d_stored), _rows(q_stored)
+    n, b = d.shape[0], q.shape[0]
+    L = np.empty((b, n), dtype=np.float32)
+    U = np.empty((b, n), dtype=np.float32)
+    _load().sqe_oracle_prefilter_bounds(_f32(d), n, _f32(q), b, _f32(L), _f32(U))
+    return L, U

@@ -109,3 +109,33 @@ def test_bounds_hold_for_arbitrary_rows_hypothesis():
         q = oracle.from_storage(oracle.to_storage(q if dtype == "fp32" else oracle.normalize_rows(q), dtype), dtype)
         _check(d, q, k=5)
     prop()
+
+
+def test_plain_c_twin_agrees_with_the_numpy_restatement():
+    """oracle/c_oracle.c states the quantiser and the bound a second time, independently: same
+    int8 rows and scales bit for bit, same bounds up to the rounding of the norms, and its bounds
+    hold as well."""
+    from oracle import c_oracle as co
+    if not co.available():
+        pytest.skip("no gcc and no prebuilt C oracle")
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((300, DIM)).astype(np.float32)
+    x[3] = 0.0
+    x[4, 9] = 30.0
+    d = _stored(x, "bf16")
+    d[5, 1] = np.nan
+    q = _stored(rng.standard_normal((4, DIM)).astype(np.float32), "bf16")
+    w8, wm = oracle.quantize_rows_int8(d)
+    c8, cm = co.quantize_rows_int8(d)
+    np.testing.assert_array_equal(c8, w8)
+    np.testing.assert_array_equal(cm[:, 0], wm[:, 0])
+    np.testing.assert_allclose(cm[:, 1:3], wm[:, 1:3], rtol=1e-6)
+    Ln, Un = oracle.prefilter_bounds(d, q)
+    Lc, Uc = co.prefilter_bounds(d, q)
+    ok = np.isfinite(Un)
+    np.testing.assert_allclose(Lc[ok], Ln[ok], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(Uc[ok], Un[ok], rtol=0, atol=1e-6)
+    assert not np.isfinite(Uc[:, 5]).any()                 # the NaN row can never be ruled out
+    s = q.astype(np.float64) @ np.where(np.isnan(d), 0, d).astype(np.float64).T
+    fin = np.isfinite(Uc)
+    assert not (s[fin] < Lc[fin]).any() and not (Uc[fin] < s[fin]).any()

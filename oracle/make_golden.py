@@ -6,7 +6,8 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
 
 Inputs are seeded; outputs are what `/root/reference/app/main.py`'s unmodified
 `cosine_similarity`, `lfu_cache_get`, `lfu_cache_put`,
-`_remove_least_frequent_item`, `OpenSearchIndexer.add_embeddings/.search`
+`_remove_least_frequent_item`, `OpenSearchIndexer.add_embeddings/.search`, and the websocket
+handler `ask_websocket_endpoint` (a whole request sequence, `gen_ws_session`)
 return (external services stubbed as in ref_loader.py).  Two module constants
 are overridden for some scenarios -- `REDIS_MAX_ITEMS` (1000 -> 8, so LFU
 eviction is reachable with a small fixture) and `CACHE_SIM_THRESHOLD`
@@ -159,6 +160,95 @@ def run_cache_scenario(m, rng, max_items, threshold, n_ops, name):
                    "final_freqs": [e["freq"] for e in final]}, f)
 
 
+def gen_ws_session(m, seed):
+    """The reference's OWN websocket handler (`ask_websocket_endpoint`, main.py:650-735), driven
+    request by request with a fake socket: embed_query (main.py:172-180, its Ollama call stubbed
+    with fixed vectors) -> lfu_cache_get -> RAGModel.os_search -> the doc-id grouping and prompt
+    building of main.py:685-717 -> generation (stubbed: records the prompt, streams two tokens) ->
+    lfu_cache_put.  Recorded: every message sent to the client and the prompt handed to the LLM --
+    what a drop-in for the retrieval path must reproduce.  Uses its own rng so the older fixtures
+    stay byte-identical."""
+    import asyncio
+    rng = np.random.default_rng(seed)
+    n, per_doc = 240, 6
+    emb = (rng.standard_normal((n, DIM)) * rng.uniform(0.2, 5.0, size=(n, 1))).astype(np.float32)
+    docs = [{"doc_id": f"PMC{2000 + i // per_doc}", "text": f"passage {i} of PMC{2000 + i // per_doc}"}
+            for i in range(n)]
+    unit = emb / np.linalg.norm(emb, axis=1, keepdims=True)
+
+    def mix(rows):
+        w = np.array([1.0, 0.85, 0.7, 0.58, 0.48, 0.4, 0.33, 0.27][: len(rows)], dtype=np.float32)
+        return ((w[:, None] * unit[rows]).sum(axis=0) * np.float32(2.5)).astype(np.float32)
+
+    qvec = {
+        "what does passage thirteen say": mix([13, 14, 15, 90, 91, 200, 17, 33]),      # doc 2002 three times
+        "tell me about document 2001": mix([7, 6, 8, 9, 10, 11, 100, 150]),          # six chunks of one doc
+        "a different question": mix([120, 5, 121, 60, 122, 61, 62, 123]),
+    }
+    base = qvec["what does passage thirteen say"]
+    qvec["what does passage 13 say?"] = (with_cosine(rng, base, 0.97) * 1.3).astype(np.float32)    # cache hit
+    qvec["what might passage thirteen say"] = (with_cosine(rng, base, 0.95) * 0.8).astype(np.float32)  # miss
+    requests = [
+        {"query": "what does passage thirteen say", "top_k": 8},
+        {"query": "tell me about document 2001"},                       # default top_k = 3 (main.py:667)
+        {"query": "what does passage 13 say?", "top_k": 8},             # >= 0.96 to request 0: cached answer
+        {"query": "   "},                                               # blank -> "[ERROR] Empty query."
+        {"query": "what might passage thirteen say", "top_k": 5},       # 0.95 < 0.96: a miss, retrieval again
+        {"query": "tell me about document 2001", "top_k": 6},           # exact repeat: cached answer
+        {"query": "a different question", "top_k": 7},
+    ]
+
+    m.REDIS_MAX_ITEMS, m.CACHE_SIM_THRESHOLD = 1000, 0.96
+    m.redis_client.lists.clear()
+    m.os_client = FakeOpenSearch()
+    m.rag_model = m.RAGModel()                                          # main.py:408-411
+    m.rag_model.os_indexer.add_embeddings(emb, docs)                    # main.py:309-338
+
+    async def fake_ollama(text, model=None):                            # main.py:134-153's result
+        return qvec[text].tolist()
+    m.ollama_embed_text = fake_ollama
+    prompts = []
+
+    async def fake_stream(prompt, system_msg=""):                       # main.py:615-647's interface
+        prompts.append(prompt)
+        yield "Answer "
+        yield f"#{len(prompts)}"
+    m.openai_generate_text_stream = fake_stream
+
+    class FakeWebSocket:
+        def __init__(self, payload):
+            self.payload, self.sent, self.closed = payload, [], False
+
+        async def accept(self):
+            pass
+
+        async def receive_text(self):
+            return self.payload
+
+        async def send_text(self, text):
+            self.sent.append(text)
+
+        async def close(self):
+            self.closed = True
+
+    results = []
+    for req in requests:
+        ws = FakeWebSocket(json.dumps(req))
+        before = len(prompts)
+        asyncio.run(m.ask_websocket_endpoint(ws))
+        assert ws.closed
+        results.append({"sent": ws.sent, "prompt": prompts[before] if len(prompts) > before else None})
+    cache = [json.loads(x) for x in m.redis_client.lrange(m.REDIS_CACHE_LIST, 0, -1)]
+    assert [bool(r["prompt"]) for r in results] == [True, True, False, False, True, False, True]
+    names = sorted(qvec)
+    np.savez_compressed(os.path.join(GOLDEN, "ws_session.npz"), emb=emb,
+                        qvecs=np.stack([qvec[t] for t in names]))
+    with open(os.path.join(GOLDEN, "ws_session.json"), "w") as f:
+        json.dump({"docs": docs, "query_texts": names, "requests": requests, "results": results,
+                   "final_cache_responses": [e["response"] for e in cache],
+                   "final_cache_freqs": [e["freq"] for e in cache]}, f)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     m = load_reference_main()
@@ -170,6 +260,7 @@ def main():
         run_cache_scenario(m, rng, max_items=1000, threshold=0.96, n_ops=40, name="default")
         run_cache_scenario(m, rng, max_items=8, threshold=0.96, n_ops=60, name="evict8")
         run_cache_scenario(m, rng, max_items=8, threshold=0.95, n_ops=40, name="thr095")
+        gen_ws_session(m, 20261019)
     print("golden vectors written to", GOLDEN)
 
 

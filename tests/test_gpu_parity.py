@@ -991,6 +991,27 @@ def test_cosine_similarity_drop_in_matches_reference_golden(sqe, golden_dir):
     assert abs(sqe.cosine_similarity(g["a"][3:4], g["b"][3:4]) - g["out"][3]) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_ws_session_recorded_from_the_reference_handler_replays_on_the_gpu_path(sqe, golden_dir, dtype):
+    """tests/golden/ws_session.* is the reference's OWN websocket handler (main.py:650-735) run on a
+    request sequence.  With `plugin.install` the same sequence -- cache lookups, retrieval (through
+    the prefiltered scan, the plugin's default), doc-id grouping, cache inserts -- gives the same
+    client messages and the same prompts, character for character."""
+    import types
+    from ws_replay import load_session, replay
+    meta, emb, qvec = load_session(golden_dir)
+    main = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=1000, REDIS_CACHE_LIST="query_cache_lfu",
+                                 os_client=None)
+    cache = sqe.plugin.install(main, dtype=dtype, strict=True)
+    indexer = main.OpenSearchIndexer(main.os_client, "medical-search-index")       # main.py:411
+    assert indexer.prefilter
+    indexer.add_embeddings(emb, meta["docs"])                                       # main.py:455
+    got = replay(meta, qvec, main.lfu_cache_get, main.lfu_cache_put,
+                 lambda q, k: indexer.search(q, k=k), sqe.build_context_text)
+    assert got == meta["results"]
+    assert cache.responses() == meta["final_cache_responses"] and cache.freqs() == meta["final_cache_freqs"]
+
+
 def test_plugin_install_patches_reference_names(sqe):
     import types
     main = types.SimpleNamespace(CACHE_SIM_THRESHOLD=0.96, REDIS_MAX_ITEMS=1000,

@@ -280,3 +280,27 @@ def test_split_bf16_storage_is_exact_to_16_bits():
     hi = oracle.from_storage(st[:, :1024], "bf16").astype(np.float64)
     lo = oracle.from_storage(st[:, 1024:], "bf16").astype(np.float64)
     assert np.array_equal((hi + lo).astype(np.float32).astype(np.float64), hi + lo)    # exact in fp32
+
+
+def test_ws_session_replay_with_the_oracle_and_the_product_context_builder(golden_dir):
+    """The reference's own websocket handler was recorded on a request sequence (hits, near
+    misses, repeats, a blank query; tests/golden/ws_session.*).  Replaying it with the oracle for
+    the retrieval path and the PRODUCT's host-side grouping (`serving.build_context_text`, the
+    step right after the path, main.py:685-698) must give the same client messages and the same
+    prompts, character for character."""
+    import sqe_b200
+    from ws_replay import load_session, replay
+    meta, emb, qvec = load_session(golden_dir)
+    stored = oracle.normalize_rows(emb)
+    cache = oracle.LfuCacheModel()
+
+    def os_search(query_emb, k):
+        qn = oracle.normalize_rows(query_emb)
+        s, i = oracle.topk_cosine(stored, qn, k)
+        return [(dict(meta["docs"][r]), float(v)) for v, r in zip(s[0], i[0]) if r >= 0]
+    got = replay(meta, qvec, cache.get, cache.put, os_search, sqe_b200.build_context_text)
+    assert got == meta["results"]
+    assert cache.responses() == meta["final_cache_responses"] and cache.freqs() == meta["final_cache_freqs"]
+    # the recording exercises what it should: multi-chunk documents, cache hits, a blank query
+    assert sum(r["prompt"] is None for r in got) == 3
+    assert "passage 13 of PMC2002\npassage 14 of PMC2002" in got[0]["prompt"]

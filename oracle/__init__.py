@@ -13,7 +13,9 @@ the CUDA library is missing rather than falling back to this code.
 
 Parity pin: PINNED.  `oracle/make_golden.py` imports the reference's own
 functions (with absent third-party services stubbed, see `ref_loader.py`),
-runs them on seeded inputs and commits inputs+outputs under `tests/golden/`;
+runs them on seeded inputs -- single functions, a whole websocket request sequence through the
+reference's handler, and the upload service's `bulk_index_embeddings` (`embedding_gen.py`) -- and
+commits inputs+outputs under `tests/golden/`;
 `tests/test_oracle_golden.py` checks every function here -- numpy and C -- against those
 vectors.  The one leg with no reference arithmetic to pin is corpus
 scoring/top-k: the reference delegates it to an external, unpinned

@@ -22,7 +22,7 @@ import os
 
 import numpy as np
 
-from .ref_loader import FakeOpenSearch, load_reference_main
+from .ref_loader import FakeOpenSearch, load_reference_embedding_gen, load_reference_main
 
 DIM = 1024
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -249,6 +249,48 @@ def gen_ws_session(m, seed):
                    "final_cache_freqs": [e["freq"] for e in cache]}, f)
 
 
+def gen_upload_service(seed):
+    """The reference's upload micro-service (`app/embedding_gen.py`): its own
+    `bulk_index_embeddings(user_id, doc_id, embeddings, chunks)` (:196-257, normalise :215-216,
+    `_id = f"{doc_id}_{i}"` :221, batches of 64 :236) and `init_user_index` (:83-122) on a call
+    sequence with two users, a document longer than one bulk batch, a zero chunk embedding
+    (:147-148 returns one on an embedding error), the same doc_id under two users, a re-upload
+    with fewer chunks (ids _0.._2 replaced, _3 and _4 stay) and an empty call (:207-209).
+    Recorded per user index: the documents in stored order and the stored vectors."""
+    g = load_reference_embedding_gen("docs")
+    rng = np.random.default_rng(seed)
+    calls = []
+
+    def call(user, doc_id, n_chunks, tag):
+        e = (rng.standard_normal((n_chunks, DIM)) * rng.uniform(0.3, 4.0, size=(max(n_chunks, 1), 1))[:n_chunks]).astype(np.float32)
+        if n_chunks > 10:
+            e[9] = 0.0
+        chunks = [f"{tag} chunk {i}" for i in range(n_chunks)]
+        g.bulk_index_embeddings(user, doc_id, e if n_chunks else np.array([]), chunks)
+        calls.append({"user": user, "doc_id": doc_id, "chunks": chunks, "emb": e})
+    g.init_user_index("alice")
+    g.init_user_index("alice")                                          # :92-94: already exists
+    call("alice", "notes_1700000000", 70, "notes v1")
+    call("alice", "paper_1700000001", 5, "paper v1")
+    call("bob", "notes_1700000000", 3, "bob notes")
+    call("alice", "paper_1700000001", 3, "paper v2")
+    call("bob", "empty_1700000002", 0, "nothing")
+    indices = {}
+    stored = {}
+    for name, docs in g.os_client.by_index.items():
+        indices[name] = [{"_id": i, "doc_id": s["doc_id"], "text": s["text"]} for i, s in docs]
+        stored[name] = np.asarray([s["embedding"] for _, s in docs], dtype=np.float32).reshape(len(docs), DIM)
+    mapping = g.os_client.bodies["docs-alice"]["mappings"]["properties"]["embedding"]
+    assert mapping["dimension"] == 1024 and mapping["method"]["space_type"] == "cosinesimil"
+    arrays = {f"emb_{i}": c["emb"] for i, c in enumerate(calls)}
+    arrays.update({f"stored_{k}": v for k, v in stored.items()})
+    np.savez_compressed(os.path.join(GOLDEN, "upload_service.npz"), **arrays)
+    with open(os.path.join(GOLDEN, "upload_service.json"), "w") as f:
+        json.dump({"base_index_name": "docs",
+                   "calls": [{"user": c["user"], "doc_id": c["doc_id"], "chunks": c["chunks"]} for c in calls],
+                   "indices": indices}, f)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     m = load_reference_main()
@@ -261,6 +303,7 @@ def main():
         run_cache_scenario(m, rng, max_items=8, threshold=0.96, n_ops=60, name="evict8")
         run_cache_scenario(m, rng, max_items=8, threshold=0.95, n_ops=40, name="thr095")
         gen_ws_session(m, 20261019)
+        gen_upload_service(20261020)
     print("golden vectors written to", GOLDEN)
 
 

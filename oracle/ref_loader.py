@@ -150,3 +150,83 @@ def load_reference_main(quiet: bool = True):
             else:
                 sys.modules[k] = v
     return m
+
+
+class FakeMultiIndexOpenSearch:
+    """Per-index document store for the upload micro-service (embedding_gen.py): `bulk` actions
+    carry `_index`; an "index" action replaces the document with the same `_id` in place."""
+
+    def __init__(self, **kw):
+        self.by_index = {}
+        outer = self
+
+        class _Indices:
+            def exists(self, index=None, **k):
+                return index in outer.by_index
+
+            def create(self, index=None, body=None, **k):
+                outer.by_index.setdefault(index, [])
+                outer.bodies = getattr(outer, "bodies", {})
+                outer.bodies[index] = body
+                return {}
+
+        self.indices = _Indices()
+
+
+def _fake_multi_bulk(client, actions):
+    for a in actions:
+        docs = client.by_index.setdefault(a["_index"], [])
+        for j, (known, _) in enumerate(docs):
+            if known == a["_id"]:
+                docs[j] = (a["_id"], a["_source"])
+                break
+        else:
+            docs.append((a["_id"], a["_source"]))
+    return len(actions), []
+
+
+def load_reference_embedding_gen(base_index_name: str = "docs", quiet: bool = True):
+    """Return the reference's `app/embedding_gen.py` (the upload micro-service) with Postgres and
+    OpenSearch stubbed; `os_client` is a FakeMultiIndexOpenSearch.  Loaded from a scratch working
+    directory because the module creates `uploads/` relative to the cwd at import."""
+    import tempfile
+    if not reference_available():
+        raise FileNotFoundError(REFERENCE_ROOT)
+
+    def mod(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    names = ("opensearchpy", "opensearchpy.helpers", "psycopg2", "psycopg2.extras", "asyncpg")
+    saved = {k: sys.modules.get(k) for k in names}
+    osp = mod("opensearchpy", OpenSearch=lambda **kw: FakeMultiIndexOpenSearch(**kw), RequestsHttpConnection=object)
+    osp.helpers = mod("opensearchpy.helpers", bulk=_fake_multi_bulk)
+    pg = mod("psycopg2")
+    pg.extras = mod("psycopg2.extras")
+    mod("asyncpg")
+    cwd = os.getcwd()
+    old_env = os.environ.get("OPENSEARCH_INDEX_NAME")
+    os.environ["OPENSEARCH_INDEX_NAME"] = base_index_name
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            spec = importlib.util.spec_from_file_location(
+                "sqe_reference_embedding_gen", os.path.join(REFERENCE_ROOT, "app", "embedding_gen.py"))
+            m = importlib.util.module_from_spec(spec)
+            with contextlib.redirect_stdout(io.StringIO() if quiet else sys.stdout):
+                spec.loader.exec_module(m)
+            os.chdir(cwd)
+    finally:
+        os.chdir(cwd)
+        if old_env is None:
+            os.environ.pop("OPENSEARCH_INDEX_NAME", None)
+        else:
+            os.environ["OPENSEARCH_INDEX_NAME"] = old_env
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return m

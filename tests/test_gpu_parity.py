@@ -812,6 +812,34 @@ def test_user_index_registry_mirrors_embedding_gen(sqe):
     assert reg.search("nobody", e2[:1]) == []
 
 
+def test_upload_service_recorded_from_the_reference_replays_on_the_gpu_registry(sqe, golden_dir):
+    """tests/golden/upload_service.* is the reference's own `init_user_index` /
+    `bulk_index_embeddings` (embedding_gen.py:83-122, :196-257) on a call sequence: two users, a
+    document longer than one bulk batch, a zero chunk vector, a re-upload with fewer chunks, an
+    empty call.  `plugin.install_embedding_gen` on the same sequence ends with the same documents
+    in the same order per user index and the same stored vectors, bit for bit (fp32 shards)."""
+    import types
+    with open(os.path.join(golden_dir, "upload_service.json")) as f:
+        meta = json.load(f)
+    arr = np.load(os.path.join(golden_dir, "upload_service.npz"))
+    mod = types.SimpleNamespace(BASE_OPENSEARCH_INDEX_NAME=meta["base_index_name"])
+    reg = sqe.plugin.install_embedding_gen(mod, dtype="fp32", strict=True)
+    mod.init_user_index("alice")
+    mod.init_user_index("alice")
+    for ci, c in enumerate(meta["calls"]):
+        emb = arr[f"emb_{ci}"]
+        mod.bulk_index_embeddings(c["user"], c["doc_id"], emb if emb.size else np.array([]), c["chunks"])
+    for name, docs in meta["indices"].items():
+        idx = reg.get(name[len(meta["base_index_name"]) + 1:])
+        assert idx is not None and idx.index_name == name and idx.num_rows == len(docs)
+        assert [idx.doc_id_of(r) for r in range(idx.num_rows)] == [d["_id"] for d in docs]
+        assert [idx._source(r) for r in range(idx.num_rows)] == [{"doc_id": d["doc_id"], "text": d["text"]} for d in docs]
+        np.testing.assert_array_equal(idx.shard.cpu().numpy().view(np.uint32), arr[f"stored_{name}"].view(np.uint32))
+    q = arr["emb_3"][1:2] * 2.0                                 # the re-uploaded paper, chunk 1
+    hit = reg.search("alice", q, k=1)[0]
+    assert hit[0] == {"doc_id": "paper_1700000001", "text": "paper v2 chunk 1"} and abs(hit[1] - 1.0) < 1e-5
+
+
 def test_micro_batcher_coalesces_concurrent_requests(sqe):
     """concurrent single-query requests are served by a few batched launches
     and every request gets exactly the result of its own `search` call."""

@@ -304,3 +304,41 @@ def test_ws_session_replay_with_the_oracle_and_the_product_context_builder(golde
     # the recording exercises what it should: multi-chunk documents, cache hits, a blank query
     assert sum(r["prompt"] is None for r in got) == 3
     assert "passage 13 of PMC2002\npassage 14 of PMC2002" in got[0]["prompt"]
+
+
+def _upload_fixture(golden_dir):
+    with open(os.path.join(golden_dir, "upload_service.json")) as f:
+        meta = json.load(f)
+    arr = np.load(os.path.join(golden_dir, "upload_service.npz"))
+    return meta, arr
+
+
+def test_upload_service_golden_is_what_the_oracle_predicts(golden_dir):
+    """tests/golden/upload_service.* = the reference's own `bulk_index_embeddings`
+    (embedding_gen.py:196-257) on a call sequence.  The oracle's normalise gives the stored
+    vectors bit for bit (:215-216 is the expression of main.py:315-316), `_id = f"{doc_id}_{i}"`
+    with i the chunk index of THAT call (:221), an index action on a known _id replaces the
+    document in place, and each user has an index of their own (:211)."""
+    meta, arr = _upload_fixture(golden_dir)
+    model = {}                                               # index name -> list of [_id, doc_id, text, vec]
+    for ci, c in enumerate(meta["calls"]):
+        emb = arr[f"emb_{ci}"]
+        if emb.size == 0:                                    # :207-209
+            continue
+        docs = model.setdefault(f"{meta['base_index_name']}-{c['user']}", [])
+        vecs = oracle.normalize_rows(emb)
+        for i, (chunk, v) in enumerate(zip(c["chunks"], vecs)):
+            entry = [f"{c['doc_id']}_{i}", c["doc_id"], chunk, v]
+            for j, known in enumerate(docs):
+                if known[0] == entry[0]:
+                    docs[j] = entry
+                    break
+            else:
+                docs.append(entry)
+    assert set(model) == set(meta["indices"])
+    for name, docs in model.items():
+        assert [{"_id": d[0], "doc_id": d[1], "text": d[2]} for d in docs] == meta["indices"][name]
+        np.testing.assert_array_equal(np.stack([d[3] for d in docs]).view(np.uint32),
+                                      arr[f"stored_{name}"].view(np.uint32))
+    alice = meta["indices"]["docs-alice"]
+    assert len(alice) == 75 and alice[-1]["text"] == "paper v1 chunk 4" and alice[-3]["text"] == "paper v2 chunk 2"

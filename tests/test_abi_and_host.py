@@ -175,3 +175,22 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(proc.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line_and_uses_every_core():
+    """The driver launches the reference arm like our own arm: under torchrun for N > 1.  Rank 0
+    alone works and prints; torchrun's OMP_NUM_THREADS=1 must not make it single-threaded."""
+    import json
+    env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "bench.py"),
+         "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--workload", "b1"],
+        capture_output=True, text=True, env=env, timeout=400)
+    assert proc.returncode == 0, proc.stdout[-1500:] + proc.stderr[-1500:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert "rows split over 2 rank(s)" in line["config"]["sharding"]

@@ -7,6 +7,9 @@ CUDA tensors without synchronising.
 """
 from __future__ import annotations
 
+import ctypes
+import queue
+import threading as _threading
 from typing import Optional, Tuple
 
 import numpy as np
@@ -26,7 +29,6 @@ _workspaces = {}
 # stream must not interleave their launches (thread B's memset would land before thread A's
 # kernel and B would then see A's leftovers), so every workspace-using call is enqueued under
 # this lock.  It only covers the (asynchronous) enqueue, not the execution.
-import threading as _threading
 _launch_lock = _threading.Lock()
 
 
@@ -310,7 +312,6 @@ def exchange_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int, rank: in
                    out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K4x: push this rank's [b,k] lists into every rank's peer-mapped buffer, wait for all
     ranks, merge.  `peer_ptrs`: device pointers (ints) of every rank's buffer as mapped here."""
-    import ctypes
     dev = _require_cuda(scores, idx)
     if scores.dim() != 2 or scores.shape != idx.shape:
         raise ValueError("scores/idx must be [b,k]")
@@ -435,7 +436,6 @@ class StreamPipeline:
     `submit` blocks while all slots are taken, so a second thread may do the collecting."""
 
     def __init__(self, dev: torch.device, as_rows, out_bytes, launch, unpack, depth: int = 2):
-        import queue
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.dev, self.depth = dev, depth

@@ -14,6 +14,18 @@ int main(void) {
     if (strstr(sqe_last_error(), "dim") == NULL) return 7;
     if (sqe_topk_gemv_workspace_bytes(1, 10) <= 0) return 8;
     if (sqe_exchange_buffer_bytes(8, 10240) != 256 + 2 * 8 * 10240 * 16) return 10;
+    /* the prefiltered scan: k out of range, too many queries, unaligned coarse rows */
+    if (sqe_topk_gemv_prefiltered_workspace_bytes(1000, 1, 10) < 1000 * 4) return 11;
+    if (sqe_quantize_rows((const void *)16, SQE_BF16, 4, SQE_DIM / 2, (void *)16, (void *)16, NULL) != SQE_E_ARG) return 12;
+    if (sqe_topk_gemv_prefiltered((const void *)16, SQE_BF16, 10, SQE_DIM, (const void *)16, (const void *)16,
+                                  (const void *)16, 1, 0, (float *)16, (int64_t *)16, 0, NULL, (void *)16,
+                                  1 << 20, NULL) != SQE_E_ARG) return 13;
+    if (sqe_topk_gemv_prefiltered((const void *)16, SQE_BF16, 10, SQE_DIM, (const void *)16, (const void *)16,
+                                  (const void *)16, SQE_MAX_NQ_PREFILTER + 1, 5, (float *)16, (int64_t *)16, 0,
+                                  NULL, (void *)16, 1 << 20, NULL) != SQE_E_ARG) return 14;
+    if (sqe_topk_gemv_prefiltered((const void *)16, SQE_BF16, 10, SQE_DIM, (const void *)8, (const void *)16,
+                                  (const void *)16, 1, 5, (float *)16, (int64_t *)16, 0, NULL, (void *)16,
+                                  1 << 20, NULL) != SQE_E_ARG) return 15;
     rc = sqe_device_info(&sms, &major, &minor);
     if (rc == 1) {
         printf("device sm_%d%d with %d SMs\n", major, minor, sms);

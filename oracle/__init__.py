@@ -40,4 +40,5 @@ from .numpy_oracle import (  # noqa: F401
     opensearch_score,
     quantize_rows_int8,
     prefilter_bounds,
+    k3_score_emulation,
 )

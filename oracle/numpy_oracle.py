@@ -335,3 +335,29 @@ def prefilter_bounds(d_stored: np.ndarray, q_stored: np.ndarray) -> Tuple[np.nda
               + PREFILTER_SLACK * qn[:, None] * (dm[None, :, 2] + dm[None, :, 1])) * PREFILTER_INFLATE
              + np.float32(1e-30)).astype(np.float32)
         return (s8 - m).astype(np.float32), (s8 + m).astype(np.float32)
+
+
+def k3_score_emulation(d_row: np.ndarray, q_row: np.ndarray, per: int = 8) -> np.float32:
+    """The fp32 operation order of the exact GEMV scan (topk_gemv.cu, also the rescoring pass of
+    K3p) for ONE row: lane l of a warp holds elements g*(32*per) + l*per + e (per = 8 for 16-bit
+    storage, 4 for fp32), accumulates the even e into one FMA chain and the odd e into another
+    (g outer, e inner), adds the two chains, then a 5-step xor butterfly over the 32 lanes.
+    Each FMA rounds once (the product is formed exactly in float64).  Used to check the rounding
+    allowance of the prefilter bound: |this - exact| <= 22 * 2^-24 * |q| |d|."""
+    d = np.asarray(d_row, dtype=np.float32).astype(np.float64)
+    q = np.asarray(q_row, dtype=np.float32).astype(np.float64)
+    groups = EMBED_DIM // (32 * per)
+    lanes = np.zeros(32, dtype=np.float32)
+    for l in range(32):
+        a0 = np.float32(0.0)
+        a1 = np.float32(0.0)
+        for g in range(groups):
+            base = g * 32 * per + l * per
+            for e in range(0, per, 2):
+                a0 = np.float32(d[base + e] * q[base + e] + np.float64(a0))
+                a1 = np.float32(d[base + e + 1] * q[base + e + 1] + np.float64(a1))
+        lanes[l] = np.float32(a0 + a1)
+    idx = np.arange(32)
+    for step in (16, 8, 4, 2, 1):
+        lanes = (lanes + lanes[idx ^ step]).astype(np.float32)
+    return lanes[0]

@@ -139,3 +139,29 @@ def test_plain_c_twin_agrees_with_the_numpy_restatement():
     s = q.astype(np.float64) @ np.where(np.isnan(d), 0, d).astype(np.float64).T
     fin = np.isfinite(Uc)
     assert not (s[fin] < Lc[fin]).any() and not (Uc[fin] < s[fin]).any()
+
+
+def test_rounding_allowance_covers_the_exact_scan_s_own_summation_order():
+    """The bound is on the real-number dot product; what the device compares against is the fp32
+    score of the exact scan.  Its summation tree (two FMA chains of 16 per lane, one add, a 5-step
+    butterfly) has at most 22 roundings on any path, i.e. an error <= 22 * 2^-24 * sum|q_i d_i|
+    <= 1.3e-6 |q||d|; the bound reserves 4e-6 |q|(|d8| + eps) for it.  Checked here on an emulation
+    of that order, including all-positive vectors where the rounding errors do not cancel."""
+    rng = np.random.default_rng(21)
+    worst = 0.0
+    for trial in range(24):
+        per = 8 if trial % 2 == 0 else 4
+        x = rng.standard_normal((2, DIM)).astype(np.float32)
+        if trial % 3 == 0:
+            x = np.abs(x)                                   # no cancellation
+        if trial % 4 == 1:
+            x[1] = x[0] + 1e-3 * x[1]                       # score near 1
+        d, q = _stored(x[:1], "bf16" if per == 8 else "fp32")[0], _stored(x[1:], "bf16" if per == 8 else "fp32")[0]
+        s = float(no.k3_score_emulation(d, q, per))
+        exact = float(d.astype(np.float64) @ q.astype(np.float64))
+        scale = float(np.linalg.norm(d.astype(np.float64)) * np.linalg.norm(q.astype(np.float64)))
+        worst = max(worst, abs(s - exact) / scale)
+        L, U = oracle.prefilter_bounds(d[None, :], q[None, :])
+        assert L[0, 0] <= s <= U[0, 0]
+    assert worst <= 22 * 2.0 ** -24, worst                  # the analytical allowance ...
+    assert worst < 4e-6 / 3                                 # ... and the reserved slack is 3x that

@@ -21,11 +21,15 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsqe_b200.so")
 
 SOURCES = ["api.cu", "normalize_cast.cu", "topk_gemv.cu", "topk_prefilter.cu", "topk_batched.cu", "exchange.cu"]
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
+]
+LINK_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "--shared", "-Xcompiler", "-fPIC",
     "-cudart", "static",
 ]
 
@@ -46,18 +50,46 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_one(nvcc: str, src: str, obj: str, extra, verbose: bool):
+    cmd = [nvcc] + COMPILE_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return proc.returncode, proc.stdout, cmd
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per source, compiled in parallel and only when the source (or any header) is
+    newer than its object; then one link.  Objects live in lib/obj/ (git-ignored)."""
     if not force and not _stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = find_nvcc()
     extra = os.environ.get("SQE_NVCC_EXTRA", "").split()      # extra nvcc flags for experiments
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + \
+              [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)] + [os.path.abspath(__file__)]
+    t_hdr = max(os.path.getmtime(h) for h in headers)
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(obj_dir, s[:-3] + ".o")
+        if force or extra or verbose or not os.path.isfile(obj) or \
+                os.path.getmtime(obj) < max(t_hdr, os.path.getmtime(src)):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], extra, verbose), jobs))
+    for rc, out, cmd in results:
+        if verbose or rc != 0:
+            sys.stderr.write(out)
+        if rc != 0:
+            raise RuntimeError("nvcc failed (exit %d): %s" % (rc, " ".join(cmd)))
+    cmd = [nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + [os.path.join(obj_dir, s[:-3] + ".o") for s in SOURCES]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed (exit %d): %s" % (proc.returncode, " ".join(cmd)))
+        raise RuntimeError("nvcc link failed (exit %d): %s" % (proc.returncode, " ".join(cmd)))
     return LIB_PATH
 
 

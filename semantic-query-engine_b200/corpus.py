@@ -20,6 +20,7 @@ from __future__ import annotations
 import json
 import os
 import threading
+import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -32,6 +33,8 @@ EMBED_DIM = nat.SQE_DIM          # main.py:38
 
 
 class GpuCorpusIndex:
+    _GRAPH_RETRY_S = 5.0
+
     def __init__(self, client=None, index_name: str = "", *, dtype: str = "bf16",
                  device: Optional[torch.device] = None, initial_capacity: int = 65536,
                  score_mode: str = "cosine", strict: bool = False,
@@ -73,6 +76,8 @@ class GpuCorpusIndex:
         # CUDA graphs of the single-query step, keyed by k; dropped whenever rows are added
         self.use_graphs = use_graphs
         self._graphs: Dict[int, "ops.SingleQueryGraph"] = {}
+        self._graph_seen: Dict[int, tuple] = {}   # index state at the last eager single-query search, per k
+        self._graph_retry_at = 0.0               # monotonic time before which no capture is attempted
         self._pinned_q: Optional[torch.Tensor] = None
         self._pinned_out: Optional[torch.Tensor] = None
 
@@ -204,21 +209,29 @@ class GpuCorpusIndex:
                     self._docs.append({"doc_id": str(len(self._docs)), "text": ""})
                     self._ids.append(str(len(self._ids)))
                 self._grow_locked(base + len(fresh))
-                self.add_device_rows(emb if len(fresh) == n else np.ascontiguousarray(emb[fresh]), _locked=True)
+                # rows first into the shard tail (not yet visible), then the payload tables, and the
+                # row count LAST: a concurrent search never returns a row whose payload is missing
+                self.add_device_rows(emb if len(fresh) == n else np.ascontiguousarray(emb[fresh]),
+                                     _locked=True, _publish=False)
                 for j, i in enumerate(fresh):
                     d = docs[i]
                     self._docs.append({"doc_id": d["doc_id"], "text": d["text"]})
                     self._ids.append(new_ids[i])
                     self._row_of_id[new_ids[i]] = base + j
+                self._publish_rows(base + len(fresh))
 
-    def add_device_rows(self, emb, _locked: bool = False) -> None:
+    def _publish_rows(self, rows: int) -> None:
+        self._rows = rows
+        self._graphs.clear()                             # captured row count / shard pointer are stale
+
+    def add_device_rows(self, emb, _locked: bool = False, _publish: bool = True) -> None:
         """Append rows without payload.  `emb`: host ndarray / CPU tensor / CUDA fp32 tensor
         [n,1024], un-normalised.  K1 writes straight into the shard tail, then the new row
         count is published."""
         if not _locked:
             with self._lock:
                 self._grow_locked(self._rows + int(emb.shape[0]))
-                return self.add_device_rows(emb, _locked=True)
+                return self.add_device_rows(emb, _locked=True, _publish=_publish)
         if isinstance(emb, np.ndarray):
             emb = torch.from_numpy(emb)
         n = int(emb.shape[0])
@@ -236,8 +249,8 @@ class GpuCorpusIndex:
             if self.prefilter:                           # the coarse copy of the new rows (K1q)
                 ops.quantize_rows(self._shard[base: base + n], out=(self._coarse8, self._coarse_meta), row0=base)
             torch.cuda.current_stream(self.device).synchronize()
-        self._rows = base + n                            # publish
-        self._graphs.clear()                             # captured row count / shard pointer are stale
+        if _publish:
+            self._publish_rows(base + n)
 
     def _ingest_host_rows(self, emb: torch.Tensor, base: int, n: int, chunk: int = 1 << 15) -> None:
         """Host rows -> shard: two fp32 staging blocks on the device (128 MB each); the copy of
@@ -376,19 +389,35 @@ class GpuCorpusIndex:
 
     def _search_one(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
         """The reference's call shape (one query): replay a captured CUDA graph (H2D, fused
-        normalise + scan + top-k, D2H) when possible, else the eager path."""
+        normalise + scan + top-k, D2H) when possible, else the eager path.
+
+        Capture policy: a graph is captured at the SECOND search of an unchanged index state (the
+        first one runs eagerly -- while rows are still arriving every search would otherwise pay a
+        warm-up scan + a capture), under the ingest lock (no rows are added, no shard is regrown
+        while the capture is open) and in thread-local capture mode.  A failed capture is retried
+        after `_GRAPH_RETRY_S`, not never."""
         if self.use_graphs and self._rows > 0 and 1 <= k <= nat.SQE_MAX_K_GEMV:
             with self._search_lock:
                 g = self._graphs.get(k)
-                if g is None or g.rows != self._rows or g.shard_ptr != self._shard.data_ptr():
-                    try:
-                        g = ops.SingleQueryGraph(self._shard, self._rows, k, coarse=(
-                            (self._coarse8, self._coarse_meta, self.dtype) if self.prefilter else None))
-                        self._graphs[k] = g
-                    except Exception as e:                   # capture not possible here: stay eager
-                        print(f"[GpuCorpusIndex] CUDA graph capture failed ({e}); using eager launches")
-                        self.use_graphs = False
+                state = (self._rows, self._shard.data_ptr(), self.prefilter)
+                if g is not None and (g.rows, g.shard_ptr) != state[:2]:
+                    g = None
+                    self._graphs.pop(k, None)
+                if g is None and self._graph_seen.get(k) != state:
+                    self._graph_seen[k] = state          # first search of this state: eager
+                elif g is None and time.monotonic() >= self._graph_retry_at and self._lock.acquire(blocking=False):
+                    try:                                  # ingest in progress -> lock busy -> stay eager
+                        if (self._rows, self._shard.data_ptr(), self.prefilter) == state:
+                            g = ops.SingleQueryGraph(self._shard, self._rows, k, coarse=(
+                                (self._coarse8, self._coarse_meta, self.dtype) if self.prefilter else None))
+                            self._graphs[k] = g
+                    except Exception as e:               # capture not possible right now: eager, retry later
+                        print(f"[GpuCorpusIndex] CUDA graph capture failed ({e}); eager launches for "
+                              f"{self._GRAPH_RETRY_S:.0f} s")
+                        self._graph_retry_at = time.monotonic() + self._GRAPH_RETRY_S
                         g = None
+                    finally:
+                        self._lock.release()
                 if g is not None:
                     return g.run(q[0])
         scores, rows = self.search_batch(q, k)

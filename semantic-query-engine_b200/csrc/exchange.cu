@@ -147,12 +147,28 @@ int launch_exchange_merge(const float* scores, const int64_t* idx, int b, int k_
     if (world < 1 || world > kMaxWorld) { set_error("exchange: world=%d not in [1,%d]", world, kMaxWorld); return -1; }
     PeerBufs peers;
     for (int g = 0; g < kMaxWorld; ++g) peers.p[g] = (g < world) ? static_cast<char*>(peer_buffers[g]) : nullptr;
-    int grid = (b + 3) / 4;
-    const int max_grid = sm_count * 8;                     // every CTA must be resident (they wait on flags)
-    if (grid > max_grid) grid = max_grid;
-    if (grid < 1) grid = 1;
     const int kmax = k_in > k_out ? k_in : k_out;
     const int R = kmax <= 32 ? 1 : kmax <= 64 ? 2 : kmax <= 128 ? 4 : 8;
+    // Every CTA waits on flags (its own rank's included, which the LAST local CTA publishes), so
+    // the whole grid must be co-resident: cap it with the occupancy of THIS instantiation (the
+    // register-resident lists of R = 4 / 8 allow fewer CTAs per SM than R = 1).
+    int per_sm = 0;
+    cudaError_t oe;
+    switch (R) {
+        case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_merge_kernel<1>, 128, 0); break;
+        case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_merge_kernel<2>, 128, 0); break;
+        case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_merge_kernel<4>, 128, 0); break;
+        default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_merge_kernel<8>, 128, 0); break;
+    }
+    if (oe != cudaSuccess || per_sm < 1) {
+        set_error("exchange: occupancy query: %s", cudaGetErrorString(oe));
+        return -2;
+    }
+    if (per_sm > 4) per_sm = 4;                            // headroom for whatever else shares the SMs
+    int grid = (b + 3) / 4;
+    const int max_grid = sm_count * per_sm;
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
     dim3 g(grid), blk(128);
     switch (R) {
         case 1: exchange_merge_kernel<1><<<g, blk, 0, stream>>>(scores, idx, b, k_in, k_out, rank, world, peers, cap, epoch, wait_mask, out_score, out_idx); break;

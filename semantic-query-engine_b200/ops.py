@@ -369,7 +369,9 @@ class SingleQueryGraph:
                 self._body()
             side.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
+            # thread_local: CUDA calls of OTHER host threads (an ingest thread's cudaMalloc / pageable
+            # copy / stream sync, main.py:454-455) neither fail nor invalidate this capture
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
                 self._body()
         self._np_q = self.host_q.numpy()
         self._np_out = self.host_out.numpy()

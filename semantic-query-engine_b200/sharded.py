@@ -48,6 +48,7 @@ class ShardedCorpusIndex:
         self._exchange_req = exchange
         self.exchange = "nccl"          # decided collectively on first use
         self._xchg = None               # (buffer, handle, peer pointers, capacity)
+        self._p2p_failed = False        # symmetric memory could not be set up: stay on NCCL (reset_exchange())
         self._epoch = 0
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -113,6 +114,9 @@ class ShardedCorpusIndex:
         if self._exchange_req == "nccl" or dev.type != "cuda" or self._merge is not None:
             self.exchange = "nccl"
             return
+        if self._p2p_failed:                        # decided collectively once; no per-search retries
+            self.exchange = "nccl"
+            return
         if self._xchg is not None and self._xchg[3] >= need:
             return
         if self._xchg is not None:                  # grow: nobody may still be reading the old one
@@ -120,8 +124,14 @@ class ShardedCorpusIndex:
             dist.barrier(group=self.group)
         cap = max(need, 1024 * 16)
         self.exchange = "p2p" if self._setup_p2p(cap) else "nccl"
-        if self.exchange == "nccl" and self._exchange_req == "p2p":
-            raise RuntimeError("exchange='p2p' requested but symmetric memory could not be set up")
+        if self.exchange == "nccl":
+            self._p2p_failed = True                 # the same on every rank (all-reduced flag)
+            if self._exchange_req == "p2p":
+                raise RuntimeError("exchange='p2p' requested but symmetric memory could not be set up")
+
+    def reset_exchange(self) -> None:
+        """Collective: forget a failed symmetric-memory set-up so the next search tries again."""
+        self._p2p_failed = False
 
     # ------------------------------------------------------------------ search
     def search_device(self, q_dev: torch.Tensor, k: int, out=None) -> Tuple[torch.Tensor, torch.Tensor]:

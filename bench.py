@@ -33,7 +33,35 @@ if ROOT not in sys.path:
 
 DIM = 1024
 GEN_BLOCK = 250_000            # rows per synthetic block; shard bounds are multiples of it
-METRIC = "queries/sec exact cosine top-10 @10Mx1024"
+
+
+def human_rows(n: int) -> str:
+    if n % 1_000_000 == 0:
+        return f"{n // 1_000_000}M"
+    if n >= 1_000_000:
+        return f"{n / 1e6:g}M"
+    if n % 1000 == 0:
+        return f"{n // 1000}k"
+    return str(n)
+
+
+def metric_name(rows: int, k: int) -> str:
+    """The metric string from what is ACTUALLY run (the default run gives BASELINE.json's
+    "queries/sec exact cosine top-10 @10Mx1024")."""
+    return f"queries/sec exact cosine top-{k} @{human_rows(rows)}x1024"
+
+
+def baseline_tag(rows: int, dtype: str, b: int, k: int) -> str:
+    """Which BASELINE.json configuration (if any) these parameters are."""
+    if (rows, dtype, k) == (10_000_000, "bf16", 10) and b in (1, 1024):
+        return "BASELINE configs[2] / metric headline" if b == 1024 else "BASELINE metric headline, batch-1 half"
+    if (rows, dtype, b, k) == (1_000_000, "fp32", 1, 10):
+        return "BASELINE configs[1]"
+    if (dtype, b, k) == ("fp16", 256, 100) and rows == 100_000_000:
+        return "BASELINE configs[3]"
+    if (dtype, b, k) == ("fp16", 256, 100) and rows == 12_500_000:
+        return "one rank's 12.5M-row share of BASELINE configs[3] (100M rows / 8 GPUs)"
+    return "not a BASELINE configuration"
 
 
 def parse_args():
@@ -62,6 +90,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-yardstick", action="store_true",
                     help="skip the cuBLAS GEMM of the same shape reported beside the tensor roofline")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 0.6 s repeat of the step loop")
+    ap.add_argument("--no-cfg4", action="store_true",
+                    help="skip the BASELINE configs[3] block (100M x 1024 fp16, b=256, k=100 over the ranks; "
+                         "one 12.5M-row shard at N=1) that rides along with the default workload")
+    ap.add_argument("--no-traffic-probe", action="store_true",
+                    help="do not measure the dominant kernel's DRAM bytes under ncu (a second, untimed process)")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the batch-1 measurement that rides along with the b1024 workload")
     return ap.parse_args()
@@ -209,11 +244,17 @@ def run_reference_arm(args):
     sample = (f"{b} queries x {sample_rows} fp32 rows per step (numpy Q@D.T + stable top-{k}); "
               f"q/s scaled by {sample_rows}/{total_rows} rows")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s",
+        "impl": "reference", "metric": metric_name(total_rows, k) if args.workload != "cache64"
+        else "queries/sec cache top-1+threshold @1Mx1024", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),     # our arm's config at this N
+        # what THIS arm really ran per step (a bounded sample of that config, scaled linearly in rows)
+        "sample_config": {"rows": sample_rows, "batch": b, "k": k, "dtype": "fp32",
+                          "scaled_to_rows": total_rows, "scale_factor": sample_rows / float(total_rows),
+                          "arithmetic": "numpy fp32 Q@D.T (BLAS, all host threads) + stable top-k (oracle port of "
+                                        "main.py:59-64 applied to every row)"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0,
@@ -232,10 +273,202 @@ def workload_config(args, world):
     b = (args.batch or 1024) if args.workload == "b1024" else 1
     pf = ", int8 prefilter + exact rescoring (K3p)" if (getattr(args, "prefilter", False) and b == 1) else ""
     return {"workload": f"{args.rows}x1024 {args.dtype} corpus, batch-{b} cosine top-{args.k}{pf} "
-                        f"(BASELINE configs[2] / metric headline)",
+                        f"({baseline_tag(args.rows, args.dtype, b, args.k)})",
             "rows": args.rows, "batch": b, "k": args.k, "dtype": args.dtype,
             "sharding": f"rows split over {world} rank(s), all-gather + merge" if world > 1 else "single shard",
             "l2": "inputs larger than L2 (shard >= 2.5 GB per rank vs 126 MB L2)"}
+
+
+
+# ------------------------------------------------- literal reference
+def cpu_literal_reference(budget_s: float = 12.0):
+    """The reference's LITERAL CPU path, one query at a time as its handlers issue them, on one
+    core (it is plain Python): (i) `lfu_cache_get` over a full cache of 1000 entries -- every
+    entry `json.loads`-ed and turned into an ndarray, then row-by-row `cosine_similarity` with the
+    strict-'>' running maximum (main.py:67-98; oracle.LfuCacheModel.get restates it line by line);
+    (ii) the similarity top-k the way the reference would do it without its external index:
+    `cosine_similarity(q, row)` for each of the 32,717 PMC chunk vectors + stable sort
+    (main.py:59-64)."""
+    import oracle
+    rng = np.random.default_rng(5)
+    model = oracle.LfuCacheModel(max_items=1000, threshold=0.96)
+    for i in range(1000):
+        model.put(rng.standard_normal((1, DIM)).astype(np.float32), f"answer {i}")
+    qs = rng.standard_normal((64, 1, DIM)).astype(np.float32)
+    n_get, t0 = 0, time.perf_counter()
+    while n_get < 3 or (time.perf_counter() - t0 < budget_s / 2 and n_get < 64):
+        assert model.get(qs[n_get]) is None                       # random queries: misses
+        n_get += 1
+    t_get = (time.perf_counter() - t0) / n_get
+    chunks = oracle.normalize_rows(rng.standard_normal((32717, DIM)).astype(np.float32))
+    n_s, t0 = 0, time.perf_counter()
+    while n_s < 2 or (time.perf_counter() - t0 < budget_s / 2 and n_s < 64):
+        qv = qs[n_s, 0]
+        sims = np.array([oracle.cosine_similarity(qv, row) for row in chunks], dtype=np.float32)
+        np.argsort(-sims, kind="stable")[:10]
+        n_s += 1
+    t_s = (time.perf_counter() - t0) / n_s
+    return {"kind": "port", "cores": 1,
+            "lfu_cache_get_1000_entries": {"value": 1.0 / t_get, "unit": "queries/s", "ms_per_query": t_get * 1e3,
+                                           "queries": n_get,
+                                           "what": "json.loads + np.array of all 1000 entries, then row-by-row cosine "
+                                                   "(main.py:67-98), all misses"},
+            "row_by_row_cosine_top10_32717_chunks": {"value": 1.0 / t_s, "unit": "queries/s",
+                                                     "ms_per_query": t_s * 1e3, "queries": n_s,
+                                                     "what": "cosine_similarity(q, row) per chunk + stable argsort "
+                                                             "(main.py:59-64)",
+                                                     "scaled_to_10M_rows_qps": 1.0 / t_s * 32717 / 10_000_000}}
+
+
+# ------------------------------------------------------- measured DRAM traffic (ncu)
+def measure_traffic(args, kname: str, b: int, k: int, dtype: str, rows: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the
+    benchmarked shape: a second, untimed process of this file (`--traffic-probe`) under ncu with
+    those two metrics only.  Returns (bytes, source) or (None, reason)."""
+    import shutil
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.isfile("/usr/local/cuda/bin/ncu") else None)
+    if ncu is None:
+        return None, "ncu not on PATH"
+    import tempfile
+    out = tempfile.NamedTemporaryFile(suffix=".csv", delete=False)
+    out.close()
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "-k", f"regex:{kname}", "--launch-skip", "1", "--launch-count", "1", "--csv", "--log-file", out.name,
+           sys.executable, os.path.abspath(__file__), "--traffic-probe", "--rows", str(rows), "--k", str(k),
+           "--dtype", dtype, "--batch", str(b), "--workload", args.workload]
+    if getattr(args, "prefilter", False):
+        cmd.append("--prefilter")
+    env = dict(os.environ)
+    for v in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(v, None)
+    try:
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240, env=env)
+        total, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        import csv
+        with open(out.name) as f:
+            rows_csv = [r for r in csv.reader(f) if len(r) > 3]
+        hdr = next(r for r in rows_csv if "Metric Name" in r)
+        i_name, i_unit, i_val = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+        seen = 0
+        for r in rows_csv:
+            if len(r) > i_val and r[i_name] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(r[i_val].replace(",", "")) * unit_scale.get(r[i_unit], 1.0)
+                seen += 1
+        if seen < 2:
+            return None, f"ncu gave no dram counters (exit {proc.returncode}): {proc.stdout[-200:]}"
+        return total, "measured in this run: ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, same shape"
+    except Exception as e:
+        return None, f"ncu probe failed: {str(e)[:200]}"
+    finally:
+        try:
+            os.unlink(out.name)
+        except OSError:
+            pass
+
+
+def run_traffic_probe(args, torch, sqe_b200, ops, dev):
+    """Child of `measure_traffic`: build the shard, launch the dominant kernel three times, exit."""
+    is_cache = args.workload == "cache64"
+    b = args.batch or 1024
+    rows, dtype, k = args.rows, args.dtype, args.k
+    D = torch.empty((rows, ops.ROW_ELEMS[dtype]), dtype=ops.TORCH_DTYPES[dtype], device=dev)
+    gen = torch.Generator(device=dev)
+    for lo in range(0, rows, GEN_BLOCK):
+        gen.manual_seed(1234 + lo // GEN_BLOCK)
+        x = torch.randn((min(GEN_BLOCK, rows - lo), DIM), generator=gen, device=dev)
+        ops.normalize_cast(x, dtype, out=D[lo: lo + x.shape[0]])
+    q = torch.randn((b, DIM), generator=torch.Generator().manual_seed(99), dtype=torch.float32).to(dev)
+    qn = ops.normalize_cast(q, dtype)
+    coarse = ops.quantize_rows(D) if (args.prefilter and b == 1) else None
+    for _ in range(3):
+        if coarse is not None:
+            ops.topk_gemv_prefiltered(D, coarse[0], coarse[1], qn, k)
+        elif b == 1 or dtype == "fp32":
+            ops.topk_gemv(D, qn, k)
+        elif is_cache:
+            ops.cache_top1(D, qn, 0.95)
+        else:
+            ops.topk_batched(D, qn, k)
+    torch.cuda.synchronize()
+
+
+# --------------------------------------------------- BASELINE configs[3] block
+def run_cfg4_block(torch, dist, sqe_b200, ops, nat, dev, world, rank, peaks):
+    """BASELINE configs[3]: 100M x 1024 fp16 rows sharded over the ranks, batch-256 cosine top-100,
+    local scan (K2, 128-key lists) + ONE exchange + merge.  100M rows (204.8 GB) do not fit one
+    B200, so the 1-GPU point is DEFINED as one rank's share at 8 GPUs -- a 12.5M-row
+    shard on one GPU -- i.e. weak scaling in rows per GPU at N=1 vs N=8; a single GPU would need 8
+    such passes per batch for the whole corpus (`one_gpu_100m_equivalent` = value / 8)."""
+    b, k, dtype = 256, 100, "fp16"
+    total_rows = 12_500_000 if world == 1 else 100_000_000
+    blocks_total = total_rows // GEN_BLOCK
+    blo, bhi = sqe_b200.shard_bounds(blocks_total, world, rank)
+    local_rows = (bhi - blo) * GEN_BLOCK
+    index = sqe_b200.GpuCorpusIndex(dtype=dtype, device=dev, keep_payload=False)
+    index.reserve(local_rows)
+    gen = torch.Generator(device=dev)
+    for blk in range(blo, bhi):
+        gen.manual_seed(777_000 + blk)
+        index.add_device_rows(torch.randn((GEN_BLOCK, DIM), generator=gen, device=dev, dtype=torch.float32))
+    sharded = sqe_b200.ShardedCorpusIndex(index)
+    sharded.finalize(local_rows)
+    q_dev = torch.randn((b, DIM), generator=torch.Generator().manual_seed(98), dtype=torch.float32).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    step = lambda: sharded.search_device(q_dev, k)
+    for _ in range(3):
+        step()
+    ms_probe = timed(step, 3)
+    steps = int(min(2000, max(20, -(-600.0 // ms_probe))))
+    l0 = nat.launch_count
+    ms = timed(step, steps)
+    launches = nat.launch_count - l0
+    qn = ops.normalize_cast(q_dev, dtype)
+    kern = lambda: ops.topk_batched(index._shard, qn, k, n=local_rows)
+    for _ in range(2):
+        kern()
+    kms = timed(kern, max(5, steps // 2))
+    flops = 2.0 * b * local_rows * DIM
+    nbytes = local_rows * DIM * 2
+    out = {"workload": f"{total_rows}x1024 fp16 corpus over {world} rank(s), batch-256 cosine top-100 "
+                       f"({baseline_tag(total_rows, dtype, b, k)})",
+           "rows_total": total_rows, "rows_per_gpu": local_rows, "batch": b, "k": k, "dtype": dtype,
+           "value": b / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+           "scaling": "weak (12.5M rows per GPU at N=1 and N=8; 25M / 50M per GPU at N=4 / N=2)",
+           "gpu_launches": launches,
+           "exchange": sharded.exchange if world > 1 else None,
+           "roofline": {"kernel": "topk_batched_kernel<R=4, cta_group::2>", "kernel_ms": kms,
+                        "tensor": {"achieved": flops / (kms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
+                                   "unit": "TFLOP/s", "frac": flops / (kms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                                   "algorithmic_flops_per_launch": flops},
+                        "hbm": {"achieved": nbytes / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": nbytes / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                "algorithmic_bytes_per_launch": nbytes},
+                        "note": "256 FLOP per corpus byte: on the ridge (251) -- both fractions reported"}}
+    if world == 1:
+        out["one_gpu_100m_equivalent"] = {"value": out["value"] / 8.0, "unit": "queries/s",
+                                          "definition": "100M rows = 8 such shards; one GPU holding them in turn "
+                                                        "needs 8 passes per batch (SURVEY.md H7)"}
+    del index, sharded
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------- our arm
@@ -269,6 +502,8 @@ def main():
         nat.tuning_set(nat.SQE_TUNE_K2_D_HINT, args.k2_d_hint)
 
     peaks = load_peaks()
+    if args.traffic_probe:
+        return run_traffic_probe(args, torch, sqe_b200, ops, dev)
     if args.workload == "ingest":
         return run_ingest(args, torch, ops, nat, dev, peaks)
     if args.workload == "config1":
@@ -370,6 +605,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / steps
     value = b / (ms_per_step * 1e-3)
+
+    # ---- sustained: the SAME step loop again for >= 0.6 s of device time (the --steps region above
+    # can be a 40 ms burst at N = 8, too short to reach the power cap a long run sits on)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = int(min(20000, max(steps, -(-600.0 // ms_per_step))))      # same count on every rank
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        barrier()
+        sampler2.mark()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(n_sus):
+            step_device()
+        u1.record()
+        barrier()
+        tu = torch.tensor([u0.elapsed_time(u1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+        ms_sus = float(tu.item()) / n_sus
+        sustained = {"value": b / (ms_sus * 1e-3), "unit": "queries/s", "steps": n_sus, "ms_per_step": ms_sus,
+                     "seconds": float(tu.item()) * 1e-3,
+                     "clocks": sampler2.stop() if rank == 0 else None,
+                     "note": "same step loop as `value`, run back to back for >= 0.6 s after it"}
 
     # ---- dominant kernel alone (roofline numerator), CUDA events on the launch stream
     qn = ops.normalize_cast(q_dev, dtype)
@@ -491,16 +751,22 @@ def main():
     roofline["kernel"] = kname
     roofline["kernel_ms"] = kms
     roofline["peak_source"] = peaks["source"] + (" (burst)" if roofline["bound"] == "tensor" else "")
+    measured, why = (None, "probe disabled")
+    if rank == 0 and world == 1 and not args.no_traffic_probe:
+        measured, why = measure_traffic(args, kname.split()[0], b, k, dtype, local_rows)
     ratio = load_traffic(kname)
-    if ratio is not None and kname == "coarse_scan_kernel":
-        roofline["traffic"] = ratio["dram_bytes_per_algorithmic_byte"] * alg     # both passes of K3p
-        roofline["traffic_source"] = ratio["source"]
+    if measured is not None:
+        roofline["traffic"] = measured
+        roofline["traffic_source"] = why
     elif ratio is not None:
-        unit_bytes = local_rows * DIM * esize            # shard bytes one launch must stream
+        unit_bytes = alg if kname == "coarse_scan_kernel" else local_rows * DIM * esize
         roofline["traffic"] = ratio["dram_bytes_per_algorithmic_byte"] * unit_bytes
-        roofline["traffic_source"] = ratio["source"]
+        roofline["traffic_source"] = ("from profile (not measured in this run: " + why + "): " + ratio["source"]
+                                      + (f"; ratio taken at N=1 and applied to this rank's {local_rows}-row shard"
+                                         if world > 1 else ""))
     else:
         roofline["traffic"] = None
+        roofline["traffic_source"] = why
 
     # ---- end to end through the public host API (pinned host queries in, host results out)
     e2e = None
@@ -674,16 +940,38 @@ def main():
                         "sample": f"{reps} x ({cb} queries x {crow} fp32 rows), numpy Q@D.T + stable top-{k}, "
                                   f"{t_cpu:.1f} s of CPU work; q/s scaled by {crow}/{total_rows} rows"}
 
+        try:
+            cpu_baseline["literal_reference"] = cpu_literal_reference()
+        except Exception as e:
+            cpu_baseline["literal_reference"] = {"error": str(e)[:200]}
+
+    # ---- BASELINE configs[3] rides along with the default workload (every N)
+    exchange_used = sharded.exchange if (sharded is not None and world > 1) else None
+    cfg4 = None
+    if args.workload == "b1024" and not args.no_cfg4 and args.rows == 10_000_000 and not args.batch:
+        try:
+            del store, sharded, shard, kern
+            store = sharded = shard = kern = None
+            torch.cuda.empty_cache()
+        except Exception:
+            pass
+        try:
+            cfg4 = run_cfg4_block(torch, dist, sqe_b200, ops, nat, dev, world, rank, peaks)
+        except Exception as e:                          # never let the extra block break the headline
+            cfg4 = {"error": str(e)[:300]}
+
     if rank == 0:
         line = {
-            "metric": METRIC if not is_cache else "queries/sec cache top-1+threshold @1Mx1024",
+            "metric": metric_name(total_rows, k) if not is_cache else "queries/sec cache top-1+threshold @1Mx1024",
             "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "exchange": (sharded.exchange if (sharded is not None and world > 1) else None),
+            "sustained": sustained,
+            "cfg4": cfg4,
+            "exchange": exchange_used,
             "secondary": secondary,
             "secondary_prefiltered": secondary_pf,
         }

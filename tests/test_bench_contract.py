@@ -47,3 +47,29 @@ def test_reference_arm_line():
         assert line["impl"] == "reference" and line["gpu_launches"] == 0
         assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert line["cpu_baseline"]["value"] == line["value"]
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sqe_bench", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_labels_come_from_what_is_run():
+    b = _bench_module()
+    assert b.metric_name(10_000_000, 10) == "queries/sec exact cosine top-10 @10Mx1024"      # BASELINE.json's metric
+    assert b.metric_name(12_500_000, 100) == "queries/sec exact cosine top-100 @12.5Mx1024"
+    assert b.metric_name(32_717, 5) == "queries/sec exact cosine top-5 @32717x1024"
+    assert "configs[2]" in b.baseline_tag(10_000_000, "bf16", 1024, 10)
+    assert b.baseline_tag(1_000_000, "fp32", 1, 10) == "BASELINE configs[1]"
+    assert b.baseline_tag(100_000_000, "fp16", 256, 100) == "BASELINE configs[3]"
+    assert b.baseline_tag(2_000_000, "bf16", 1024, 10) == "not a BASELINE configuration"
+
+
+def test_literal_reference_cpu_line_runs():
+    lit = _bench_module().cpu_literal_reference(budget_s=0.5)
+    assert lit["cores"] == 1 and lit["kind"] == "port"
+    assert lit["lfu_cache_get_1000_entries"]["value"] > 0 and lit["lfu_cache_get_1000_entries"]["queries"] >= 3
+    assert lit["row_by_row_cosine_top10_32717_chunks"]["value"] > 0

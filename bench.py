@@ -80,9 +80,6 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32", "bf16x2"])
     ap.add_argument("--k2-cta-group", type=int, default=0, choices=[0, 1, 2],
                     help="force the single-CTA (1) or CTA-pair (2) tensor-core kernel; 0 = library default")
-    ap.add_argument("--k2-d-hint", type=int, default=None, choices=[0, 1, 2, 3, 4],
-                    help="L2 policy of the shard-row TMA loads (tuning experiments)")
-    ap.add_argument("--k2-window", type=int, default=None, help="progress window in d-tiles (tuning experiments)")
     ap.add_argument("--prefilter", action="store_true",
                     help="b1 workload: keep an int8 copy of the shard and answer through the prefiltered scan "
                          "(K3p: int8 scan with a rigorous bound + exact rescoring; same results, ~half the bytes)")
@@ -496,10 +493,6 @@ def main():
     nat.load()
     if args.k2_cta_group:
         nat.tuning_set(nat.SQE_TUNE_K2_CTA_GROUP, args.k2_cta_group)
-    if args.k2_window is not None:
-        nat.tuning_set(nat.SQE_TUNE_K2_WINDOW, args.k2_window)
-    if args.k2_d_hint is not None:
-        nat.tuning_set(nat.SQE_TUNE_K2_D_HINT, args.k2_d_hint)
 
     peaks = load_peaks()
     if args.traffic_probe:

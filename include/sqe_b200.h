@@ -153,12 +153,13 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
  *                          1 = single-CTA UMMA (M = 128), 2 = CTA-pair UMMA (cta_group::2, M = 256).
  *   SQE_TUNE_K2_EPILOGUE_MODE: DIAGNOSTICS ONLY, results are invalid unless 0.  1 = the epilogue
  *                          only reads TMEM, 2 = no epilogue (isolates the TMA + MMA main loop).
- *   SQE_TUNE_K2_D_HINT:    L2 cache policy attached to the shard-row TMA loads: 0 = none (default),
- *                          1 = evict_normal, 2 = evict_first, 3 = evict_last.
- *   SQE_TUNE_K2_WINDOW:    EXPERIMENT, default 0 = off.  How many d-tiles the units (CTAs / CTA pairs)
- *                          that share d-tiles may drift apart before the one ahead waits.  Measured:
- *                          it does bound the DRAM re-reads of pair mode (1.2-2x -> 1.05x the shard)
- *                          but costs 8-12 % throughput at any window size (profiles/README.md).
+ *   SQE_TUNE_K2_D_HINT, SQE_TUNE_K2_WINDOW: RETIRED round-1 experiments (L2 policy of the shard-row
+ *                          TMA loads; progress window between the units that share d-tiles).  Both
+ *                          were negative results (profiles/README.md) and their code has been removed
+ *                          from the kernel; the knobs are still accepted and ignored.
+ *   The role timers and the epilogue mode exist only in the diagnostics instantiations of the two
+ *   benchmarked kernel forms (k <= 32 CTA-pair form with shared d-tiles; k > 64 CTA-pair form with
+ *   one q-tile); every other form ignores them.
  */
 #define SQE_TUNE_K2_CTA_GROUP 0
 #define SQE_TUNE_K2_EPILOGUE_MODE 1

@@ -51,8 +51,8 @@ void set_error(const char* fmt, ...);
 // tuning knobs (api.cu)
 extern int g_k2_cta_group;      // 0 auto, 1, 2
 extern int g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
-extern int g_k2_d_hint;         // L2 policy of the shard-row TMA loads: 0 none, 1 evict_normal, 2 evict_first, 3 evict_last
-extern int g_k2_window;         // progress window in d-tiles between the units of a group (0 = off)
+extern int g_k2_d_hint;         // retired experiment (accepted, ignored)
+extern int g_k2_window;         // retired experiment (accepted, ignored)
 extern void* g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
 
 }  // namespace sqe

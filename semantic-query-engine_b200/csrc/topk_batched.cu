@@ -33,10 +33,18 @@
 //            to 32 keys live in shared memory and are written through to the workspace.
 //            First tile: a register-only bootstrap pass derives a lower bound per query so the
 //            empty lists are not rebuilt 256 times.
+//            k > 32 ("log mode"): no sorted lists at all in the main loop.  A passing score is
+//            APPENDED (one 8-byte store, no load, no merge) to the (query, group) candidate log in
+//            the L2-resident workspace; the threshold warps consume the logs incrementally and
+//            publish the exact k-th best of everything logged so far, so only ~k ln(n/k) scores
+//            per query are ever logged.  First tile: the groups exchange the j-th best of their
+//            first 256 rows and every query starts from the m-th largest of those (j m >= k).
 //   warp 6   threshold warp: keeps merging the partial lists of ALL groups for its share of the
 //            q-tile's queries and publishes the k-th best key's score (atomicMax) -- the exact
 //            k-th best over everything merged so far on the whole GPU.  Every epilogue thread
-//            filters with max(own list's k-th best, that shared bound).
+//            filters with max(own list's k-th best, that shared bound).  In log mode it keeps
+//            the merged top list of each of its queries in shared memory and only reads log
+//            entries it has not seen yet.
 //   A second small kernel merges the G partial lists of every query and writes (score, row).
 //
 // Exactness: a score below a valid lower bound of the final k-th best can never be in the
@@ -95,24 +103,40 @@ constexpr int kQueriesPerLaunch = 1024;
 // NARROW (single-CTA form, k <= 16): the smem-resident lists keep only their best 16 keys, which
 // frees a fourth operand stage -- this form serves small batches and is HBM-bound, so bytes in
 // flight are what counts (3 stages: 5.7 TB/s, 4 stages: 6.5 TB/s).
+//
+// LOG (R > 1, i.e. k > 32) = candidate logs instead of sorted lists (see the file header): per
+// (query, group) an append-only array of kLogCap = 64 R keys in the workspace plus one count word
+// (epoch << 16 | entries).  When a log is full its owner's warp sorts it, keeps the best k and
+// bumps the epoch (rare: the published bounds keep the logs short).  No candidate buffers and no
+// lists in shared memory; the space goes to the threshold warp's per-query state instead.
+constexpr int kMaxGroups = 160;                // >= #SMs: groups per q-tile (seen[] words per query)
 template <int CG, int R = 1, bool TOP1 = false, bool DEEP = false, bool NARROW = false>
 struct Cfg {
     static constexpr int kQTile = kRowsPerCta * CG;          // queries per q-tile
     static constexpr int kBRows = kTileN / CG;               // D rows this CTA loads per chunk
     static constexpr int kBBytes = kBRows * kChunkK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB / 32 KB
+    static constexpr bool kLog = (R > 1) && !TOP1;
+    static constexpr int kLogCap = 64 * R;                   // entries per (query, group) log
     static constexpr bool kSmemLists = (R == 1) && !TOP1;
     static constexpr int kListWidth = kSmemLists ? (NARROW ? 16 : 32) : 0;     // keys per list in smem
     static constexpr int kListBytes = kRowsPerCta * kListWidth * 8;
-    static constexpr int kBufBytes = TOP1 ? 0 : kRowsPerCta * kBufStride * 8;
+    static constexpr int kBufBytes = (TOP1 || kLog) ? 0 : kRowsPerCta * kBufStride * 8;
     static constexpr int kStages = (CG == 1) ? ((kSmemLists && !NARROW) ? 3 : 4)
                                    : !DEEP    ? 4
                                               : (kSmemLists ? 5 : (TOP1 ? 7 : 6));
+    // threshold warp state (log mode): per tracked query a merged list of 32 R keys + one
+    // `seen` word per group
+    static constexpr int kThrSlotBytes = 32 * R * 8 + kMaxGroups * 4;
+    static constexpr int kThrSlots = !kLog ? 0 : ((CG == 1 || DEEP) ? 16 : 48);
+    static constexpr int kThrBytes = kThrSlots * kThrSlotBytes;
     static constexpr int kOffLists = kStages * kStageBytes;
     static constexpr int kOffBuf = kOffLists + kListBytes;
-    static constexpr int kOffBar = kOffBuf + kBufBytes;
+    static constexpr int kOffThr = kOffBuf + kBufBytes;
+    static constexpr int kOffBar = kOffThr + kThrBytes;
     static constexpr int kOffTmemPtr = kOffBar + 24 * 8;       // u32 tmem base, u32 epilogue-done counter
     static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 }  // namespace k2
 
@@ -152,14 +176,17 @@ __device__ __forceinline__ float thr_of(float tau_l, uint32_t tau_g) {
 // SL = the master copy of the list is in shared memory (`slists`, this warp's 32 x 32 keys)
 // and the global copy is write-only here; otherwise the list of the next pending query is
 // fetched from L2 while the current one is sorted/merged.
-template <int R, int LW>
+template <int R, int LW, bool DBG>
 __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const uint64_t* wbuf,
                                             uint64_t* slists, uint64_t* wlists, uint32_t* wtau,
                                             int k, int lane) {
     constexpr int L = 32 * R;
     constexpr bool SL = LW > 0;          // LW = keys per list kept in smem (0: lists only in the workspace)
-    const long long t_in = clock64();
-    st.n_flush += __popc(mask);
+    long long t_in = 0;
+    if constexpr (DBG) {
+        t_in = clock64();
+        st.n_flush += __popc(mask);
+    }
     __syncwarp();                                               // owners' buffer stores are visible
     int r = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -228,13 +255,13 @@ __device__ __forceinline__ void flush_lanes(unsigned mask, EpiState& st, const u
         r = r_next;
     }
     __syncwarp();
-    st.t_flush += clock64() - t_in;
+    if constexpr (DBG) st.t_flush += clock64() - t_in;
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // One 32-column strip of the accumulator: v[j] = score of (this thread's query, row col0+j).
-template <int R, int LW>
+template <int R, int LW, bool DBG>
 __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, uint32_t n,
                                               bool row_valid, EpiState& st, uint64_t* wbuf,
                                               uint64_t* slists, uint64_t* wlists, uint32_t* wtau,
@@ -261,7 +288,7 @@ __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, 
     // slow path, one half-strip (16 columns = one candidate buffer) at a time: make room where
     // needed (merge the pending candidates of the lanes that would overflow), then branch-free
     // predicated appends.  Works at any pass rate; normally neither half needs a merge.
-    ++st.n_slow;
+    if constexpr (DBG) ++st.n_slow;
     uint64_t* mybuf = wbuf + lane * k2::kBufStride;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -271,7 +298,7 @@ __device__ __forceinline__ void process_strip(uint32_t (&v)[32], uint32_t col0, 
         for (int j = 16 * h; j < 16 * h + 16; ++j) pc += (want && f[j] > thr0) ? 1 : 0;
         if (!__any_sync(kFull, pc > 0)) continue;
         const unsigned over = __ballot_sync(kFull, st.cnt + pc > k2::kCap);
-        if (over) flush_lanes<R, LW>(over, st, wbuf, slists, wlists, wtau, k, lane);   // their cnt > 0
+        if (over) flush_lanes<R, LW, DBG>(over, st, wbuf, slists, wlists, wtau, k, lane);   // their cnt > 0
 #pragma unroll
         for (int j = 16 * h; j < 16 * h + 16; ++j) {
             if (want && f[j] > thr0) {
@@ -307,66 +334,27 @@ __device__ __forceinline__ void bootstrap_strip(const uint32_t (&v)[32], uint32_
     }
 }
 
-// Bootstrap for k > 16 (first d-tile of a CTA): the first 32*R columns become the query's
-// list as they are (unsorted), then the warp sorts each of its 32 lists once.  Without this
-// every one of those columns goes through the candidate buffers and k/16 full merges.
-template <int R, bool SL>
+// Bootstrap for 16 < k <= 32 (first d-tile of a CTA, lists in shared memory): the first 32
+// columns become the query's list as they are (unsorted), then the warp sorts each of its 32
+// lists once.  Without this every one of those columns goes through the candidate buffers.
 __device__ __forceinline__ void direct_fill_strip(const uint32_t (&v)[32], uint32_t col0, uint32_t n,
-                                                  bool row_valid, int c, uint64_t* slists,
-                                                  uint64_t* dst, int lane) {
-    constexpr int L = 32 * R;
+                                                  bool row_valid, uint64_t* slists, int lane) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const uint64_t key = (row_valid && col0 + j < n) ? make_key(__uint_as_float(v[j]), col0 + j) : 0ull;
-        if constexpr (SL) slists[lane * 32 + j] = key;
-        else __stcg(dst + static_cast<size_t>(lane) * L + (c % R) * 32 + j, key);
-    }
+    for (int j = 0; j < 32; ++j)
+        slists[lane * 32 + j] = (row_valid && col0 + j < n) ? make_key(__uint_as_float(v[j]), col0 + j) : 0ull;
 }
 
-// `src` = where the unsorted batch was written (the list itself for the first batch, the
-// scratch list afterwards); `merge` = fold the sorted batch into the existing list.
-template <int R, bool SL>
 __device__ __forceinline__ void sort_filled_lists(EpiState& st, uint64_t* slists, uint64_t* wlists,
-                                                  const uint64_t* src, bool merge, uint32_t* wtau,
-                                                  int k, int lane) {
-    constexpr int L = 32 * R;
+                                                  uint32_t* wtau, int k, int lane) {
     __syncwarp();                                               // the owners' stores are visible
-    uint64_t nxt[R];
-    if constexpr (!SL) {
-#pragma unroll
-        for (int i = 0; i < R; ++i) nxt[i] = __ldcg(src + i * 32 + lane);
-    }
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) {
-        WarpList<R> cur;
-        if constexpr (SL) {
-            cur.key[0] = slists[r * 32 + lane];
-        } else {
-#pragma unroll
-            for (int i = 0; i < R; ++i) cur.key[i] = nxt[i];
-            if (r + 1 < 32) {
-#pragma unroll
-                for (int i = 0; i < R; ++i)
-                    nxt[i] = __ldcg(src + static_cast<size_t>(r + 1) * L + i * 32 + lane);
-            }
-        }
+        WarpList<1> cur;
+        cur.key[0] = slists[r * 32 + lane];
         cur.sort(lane);
-        if constexpr (!SL) {
-            if (merge) {
-                uint64_t old[R];
-#pragma unroll
-                for (int i = 0; i < R; ++i) old[i] = __ldcg(wlists + static_cast<size_t>(r) * L + i * 32 + lane);
-                cur.merge_sorted(old, lane);
-            }
-        }
-        if constexpr (SL) slists[r * 32 + lane] = cur.key[0];
-#pragma unroll
-        for (int i = 0; i < R; ++i) __stcg(wlists + static_cast<size_t>(r) * L + i * 32 + lane, cur.key[i]);
-        uint64_t kth_src = 0ull;
-#pragma unroll
-        for (int i = 0; i < R; ++i)
-            if (i == ((k - 1) >> 5)) kth_src = cur.key[i];
-        const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
+        slists[r * 32 + lane] = cur.key[0];
+        __stcg(wlists + static_cast<size_t>(r) * 32 + lane, cur.key[0]);
+        const uint64_t kth = shfl_u64(cur.key[0], (k - 1) & 31);
         if (lane == r && kth != 0ull) {
             st.tau_l = key_score(kth);
             const uint32_t o = static_cast<uint32_t>(kth >> 32);
@@ -406,6 +394,273 @@ __device__ __forceinline__ void top1_strip(uint32_t (&v)[32], uint32_t col0, uin
             if (f[jj] == m) j = jj;
         best = m;
         best_col = col0 + j;
+    }
+}
+
+// =============================================================================== log mode
+// k > 32.  Per (query, group): log[kLogCap] keys + one count word (epoch << 16 | entries;
+// entries == 0xffff while the owner compacts).  Writers never fence on the append path: an
+// entry is one 8-byte store into a slot that is ZERO until then (memset at launch, re-zeroed by
+// a compaction before its count is published), so a reader that sees the count before the entry
+// sees a zero and stops there.  Everything a reader can ever see in a slot is the key of a real
+// row, so whatever it merges is a set of real, distinct rows and its k-th best is a valid lower
+// bound of the final k-th best.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct LogState {
+    float thr;        // pass iff score > thr
+    float tau_l;      // k-th best of this thread's own log at its last compaction (-inf before)
+    uint32_t tau_g;   // best published bound (orderable u32), 0 = none
+    uint32_t cnt;     // entries in this thread's log
+    uint32_t epoch;   // compactions so far (16 bits are published)
+    unsigned n_slow, n_compact;      // diagnostics
+};
+
+// The logs of the lanes in `mask` are full: sort, keep the best k, zero the rest, bump the epoch.
+// The k-th best becomes the lane's LOCAL bound (strict: a CTA visits rows in increasing order).
+template <int R>
+__device__ __forceinline__ void log_compact_lanes(unsigned mask, LogState& st, uint64_t* wlog,
+                                                  uint32_t* wcount, int gpad, uint32_t* wtau, int k,
+                                                  int lane) {
+    constexpr int CAP = 64 * R;
+    constexpr int R2 = 2 * R;
+    __syncwarp();                                               // the owners' appends are visible
+    while (mask) {
+        const int r = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t c = __shfl_sync(kFull, st.cnt, r);
+        const uint32_t ep = (__shfl_sync(kFull, st.epoch, r) + 1u) & 0xffffu;
+        uint64_t* lp = wlog + static_cast<size_t>(r) * CAP;
+        uint32_t* cp = wcount + static_cast<size_t>(r) * gpad;
+        if (lane == 0) st_relaxed_gpu(cp, (ep << 16) | 0xffffu);          // "compacting": readers skip it
+        __threadfence();
+        WarpList<R2> w;
+#pragma unroll
+        for (int i = 0; i < R2; ++i) {
+            const uint32_t idx = i * 32 + lane;
+            w.key[i] = idx < c ? __ldcg(lp + idx) : 0ull;
+        }
+        w.sort(lane);
+        uint64_t kth_src = 0ull;
+#pragma unroll
+        for (int i = 0; i < R2; ++i) {
+            const int idx = i * 32 + lane;
+            __stcg(lp + idx, idx < k ? w.key[i] : 0ull);
+            if (i == ((k - 1) >> 5)) kth_src = w.key[i];
+        }
+        const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
+        const uint32_t nc = c < static_cast<uint32_t>(k) ? c : static_cast<uint32_t>(k);
+        __threadfence();                                        // the rewritten log before its count
+        __syncwarp();
+        if (lane == 0) st_relaxed_gpu(cp, (ep << 16) | nc);
+        if (lane == r) {
+            st.cnt = nc;
+            st.epoch = ep;
+            ++st.n_compact;
+            if (kth != 0ull) {
+                st.tau_l = key_score(kth);
+                const uint32_t o = static_cast<uint32_t>(kth >> 32);
+                atomicMax(wtau + r, o);
+                st.tau_g = max(st.tau_g, o);
+            }
+            st.thr = thr_of(st.tau_l, st.tau_g);
+        }
+    }
+    __syncwarp();
+}
+
+// One 32-column strip in log mode: same fast path; a passing score is appended to the log.
+template <int R>
+__device__ __forceinline__ void process_strip_log(uint32_t (&v)[32], uint32_t col0, uint32_t n,
+                                                  bool row_valid, LogState& st, uint64_t* wlog,
+                                                  uint32_t* wcount, int gpad, uint32_t* wtau, int k,
+                                                  int lane) {
+    constexpr int CAP = 64 * R;
+    if (col0 + 32u > n) {                                       // ragged last d-tile (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j >= n) v[j] = 0xff800000u;              // -inf never passes
+    }
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = fmax3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+    t[10] = fmaxf(f[30], f[31]);
+    const float u0 = fmax3(t[0], t[1], t[2]), u1 = fmax3(t[3], t[4], t[5]);
+    const float u2 = fmax3(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
+    const float m = fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
+    const bool want = row_valid && (m > st.thr);
+    if (!__any_sync(kFull, want)) return;
+
+    ++st.n_slow;
+    int pc = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) pc += (want && f[j] > st.thr) ? 1 : 0;
+    const unsigned over = __ballot_sync(kFull, st.cnt + pc > static_cast<uint32_t>(CAP));
+    if (over) log_compact_lanes<R>(over, st, wlog, wcount, gpad, wtau, k, lane);   // <= k entries left, thr raised
+    if (want) {
+        uint64_t* mylog = wlog + static_cast<size_t>(lane) * CAP;
+        const float thr0 = st.thr;
+        uint32_t c = st.cnt;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (f[j] > thr0) {
+                __stcg(mylog + c, make_key(f[j], col0 + j));
+                ++c;
+            }
+        }
+        if (c != st.cnt) {
+            st.cnt = c;
+            st_relaxed_gpu(wcount + static_cast<size_t>(lane) * gpad, (st.epoch << 16) | c);
+        }
+    }
+}
+
+// First d-tile in log mode: the groups exchange the j-th best of their first 256 rows (`top`, from
+// bootstrap_strip: the j-th largest of the maxima of 4 columns = j distinct scores) and every
+// query takes the m-th largest of the published values as its first bound: at least m groups hold
+// j rows each at or above it, j m >= k.  The wait is bounded and nothing depends on it: a group
+// that has not published counts as -inf, fewer than m published values give no bound.
+__device__ __forceinline__ void log_boot_exchange(const float (&top)[16], int boot_j, int boot_m,
+                                                  bool row_valid, uint32_t* boot_row, int group,
+                                                  int n_groups, uint32_t* arrive, LogState& st, int lane) {
+    float jth = top[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i)
+        if (i == boot_j - 1) jth = top[i];
+    if (row_valid && jth > __int_as_float(0xff800000)) st_relaxed_gpu(boot_row + group, orderable_u32(jth));
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        atomicAdd(arrive, 1u);
+        const long long t0 = clock64();
+        while (ld_relaxed_gpu(arrive) < static_cast<uint32_t>(n_groups) && clock64() - t0 < 200000LL) {}
+    }
+    __syncwarp();
+    __threadfence();
+    uint32_t best[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) best[i] = 0u;
+    for (int g = 0; g < n_groups; g += 4) {                     // rows are padded to a multiple of 32 words
+        const uint4 x4 = __ldcg(reinterpret_cast<const uint4*>(boot_row + g));
+        const uint32_t xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uint32_t x = xs[e];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {                      // insertion network, descending
+                const uint32_t hi = max(best[i], x);
+                x = min(best[i], x);
+                best[i] = hi;
+            }
+        }
+    }
+    uint32_t mth = best[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i)
+        if (i == boot_m - 1) mth = best[i];
+    if (row_valid && mth != 0u) {
+        st.tau_g = max(st.tau_g, mth);                          // applied non-strictly (thr_of)
+        st.thr = thr_of(st.tau_l, st.tau_g);
+    }
+}
+
+// Threshold warp, log mode.  For each query it tracks (state in shared memory: the merged best
+// 32 R keys + per group how far into that group's log it has read) it polls the count words,
+// reads ONLY entries it has not seen, inserts those that beat the list's worst and publishes the
+// k-th best.  After a compaction (epoch change) a log is re-read from its start; keys are unique
+// per row, so a key already in the list is skipped.
+template <int R>
+__device__ __forceinline__ void threshold_warp_log(const uint64_t* ws_logs, const uint32_t* ws_counts,
+                                                   uint32_t* ws_tau, uint8_t* state, int n_slots, int b,
+                                                   int b_pad, int gpad, int k, int n_groups, int q_row0,
+                                                   int rows_in_qtile, int my_id, int n_ids,
+                                                   volatile uint32_t* done, int lane) {
+    constexpr int L = 32 * R;
+    constexpr int CAP = 64 * R;
+    constexpr int kSlotBytes = L * 8 + k2::kMaxGroups * 4;
+    if (n_groups < 2) return;                                   // one group: its own compactions bound it
+    int n_own = 0;
+    for (int rl = my_id; rl < rows_in_qtile && q_row0 + rl < b && n_own < n_slots; rl += n_ids) ++n_own;
+    if (n_own == 0) return;
+    for (int i = lane; i < n_own * (kSlotBytes / 4); i += 32) reinterpret_cast<uint32_t*>(state)[i] = 0u;
+    __syncwarp();
+    unsigned sleep_ns = 500;
+    while (true) {
+        bool any_new = false;
+        for (int t = 0; t < n_own; ++t) {
+            const int row = q_row0 + my_id + t * n_ids;
+            uint64_t* sl = reinterpret_cast<uint64_t*>(state + static_cast<size_t>(t) * kSlotBytes);
+            uint32_t* seen = reinterpret_cast<uint32_t*>(sl + L);
+            WarpList<R> acc;
+            acc.load(sl, lane);
+            uint64_t worst = acc.worst();
+            bool changed = false;
+            for (int g0 = 0; g0 < n_groups; g0 += 32) {
+                const int g = g0 + lane;
+                const uint32_t w = g < n_groups ? ld_relaxed_gpu(ws_counts + static_cast<size_t>(row) * gpad + g) : 0u;
+                const uint32_t sv = g < n_groups ? seen[g] : 0u;
+                unsigned todo = __ballot_sync(kFull, g < n_groups && w != sv && (w & 0xffffu) != 0xffffu);
+                while (todo) {
+                    const int gl = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t wv = __shfl_sync(kFull, w, gl);
+                    const uint32_t svv = __shfl_sync(kFull, sv, gl);
+                    uint32_t pos = ((wv >> 16) == (svv >> 16)) ? (svv & 0xffffu) : 0u;
+                    const uint32_t end = min(wv & 0xffffu, static_cast<uint32_t>(CAP));
+                    const uint64_t* lp = ws_logs + (static_cast<size_t>(g0 + gl) * b_pad + row) * CAP;
+                    while (pos < end) {
+                        const uint32_t idx = pos + lane;
+                        const uint64_t key = idx < end ? __ldcg(lp + idx) : 0ull;
+                        const unsigned zeros = __ballot_sync(kFull, idx < end && key == 0ull);   // not visible yet
+                        const uint32_t n_ok = zeros ? static_cast<uint32_t>(__ffs(zeros) - 1) : min(32u, end - pos);
+                        unsigned pass = __ballot_sync(kFull, static_cast<uint32_t>(lane) < n_ok && key > worst);
+                        while (pass) {
+                            const int l = __ffs(pass) - 1;
+                            pass &= pass - 1;
+                            const uint64_t cand = shfl_u64(key, l);
+                            if (cand > worst) {
+                                bool dup = false;
+#pragma unroll
+                                for (int i = 0; i < R; ++i) dup |= (acc.key[i] == cand);
+                                if (!__any_sync(kFull, dup)) {
+                                    acc.insert(cand, lane);
+                                    worst = acc.worst();
+                                    changed = true;
+                                }
+                            }
+                        }
+                        pos += n_ok;
+                        if (zeros) break;
+                    }
+                    if (lane == gl) seen[g] = (wv & 0xffff0000u) | pos;
+                }
+            }
+            if (changed) {
+                any_new = true;
+                acc.store(sl, lane);
+                uint64_t kth_src = 0ull;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (i == ((k - 1) >> 5)) kth_src = acc.key[i];
+                const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
+                if (lane == 0 && kth != 0ull) atomicMax(ws_tau + row, static_cast<uint32_t>(kth >> 32));
+            }
+            __syncwarp();
+        }
+        if (*done >= 4u) break;
+        if (any_new) sleep_ns = 500;
+        __nanosleep(sleep_ns);
+        if (sleep_ns < 8000u) sleep_ns *= 2;
     }
 }
 
@@ -454,22 +709,43 @@ __device__ __forceinline__ void threshold_warp(const uint64_t* ws_lists, uint32_
     }
 }
 
-template <int R, int CG, bool TOP1, bool DEEP, bool NARROW>
+// Launch geometry and workspace pointers of one launch (host -> kernel, by value).
+struct K2Args {
+    uint32_t n;               // shard rows
+    int b, k;
+    int n_qt, n_groups, n_dtiles;
+    uint32_t idesc;
+    int passes;               // 1, or 4 for split-bf16 shards
+    uint64_t* ws_lists;       // lists [group][b_pad][32 R]  |  logs [group][b_pad][64 R] (log mode)
+    uint32_t* ws_tau;         // published bounds, one per query (first 4 KB of the workspace)
+    uint32_t* ws_arrive;      // log mode: bootstrap arrivals per 32-query slice
+    uint32_t* ws_counts;      // log mode: [b_pad][gpad] count words
+    uint32_t* ws_boot;        // log mode: [b_pad][gpad] j-th best of each group's first d-tile
+    int gpad;                 // n_groups rounded up to 32
+    int boot_j, boot_m;       // log mode bootstrap (0 = none): m-th largest of the groups' j-th best
+    unsigned long long* dbg;  // role timers (DBG instantiations only)
+    int epi_mode;             // DBG only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
+};
+
+template <int R, int CG, bool TOP1, bool DEEP, bool NARROW, bool DBG>
 __global__ void __launch_bounds__(k2::kThreads, 1)
 topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
-                    const __grid_constant__ CUtensorMap tmap_d, uint32_t n, int b, int k,
-                    int n_qt, int n_groups, int n_dtiles, uint32_t idesc,
-                    uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau,
-                    uint32_t* __restrict__ ws_prog, unsigned long long* __restrict__ dbg, int epi_mode,
-                    int d_hint, int window, int passes) {
+                    const __grid_constant__ CUtensorMap tmap_d, const K2Args a) {
     using namespace k2;
     using C = Cfg<CG, R, TOP1, DEEP, NARROW>;
     constexpr int L = 32 * R;
     constexpr int kStages = C::kStages;
+    constexpr bool LOG = C::kLog;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;         // SWIZZLE_128B atoms are 1024-B aligned
     uint8_t* sm = smem_raw + (base - raw_addr);
+
+    const uint32_t n = a.n;
+    const int b = a.b, k = a.k, n_qt = a.n_qt, n_groups = a.n_groups, n_dtiles = a.n_dtiles;
+    const int passes = a.passes;
+    [[maybe_unused]] unsigned long long* dbg = DBG ? a.dbg : nullptr;
+    [[maybe_unused]] const int epi_mode = DBG ? a.epi_mode : 0;
 
     const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -493,9 +769,9 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             ptx::mbar_init(bar_full + 8 * s, 1);               // the leader's expect_tx arrival
             ptx::mbar_init(bar_empty + 8 * s, 1);              // one tcgen05.commit
         }
-        for (int a = 0; a < 2; ++a) {
-            ptx::mbar_init(bar_tfull + 8 * a, 1);              // one tcgen05.commit
-            ptx::mbar_init(bar_tempty + 8 * a, 4 * CG);        // one arrival per epilogue warp (of both CTAs)
+        for (int acc = 0; acc < 2; ++acc) {
+            ptx::mbar_init(bar_tfull + 8 * acc, 1);            // one tcgen05.commit
+            ptx::mbar_init(bar_tempty + 8 * acc, 4 * CG);      // one arrival per epilogue warp (of both CTAs)
         }
         *epi_done = 0u;
         ptx::fence_barrier_init();
@@ -510,38 +786,16 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             const uint64_t pol_q = ptx::policy_evict_last();   // 2 MB of queries: keep in L2
-            // shard rows: no hint by default (an explicit evict_normal policy is classed
-            // "evict_normal_demote" by the L2 and doubled the DRAM reads, ncu r1i_k2)
-            const uint64_t pol_d = d_hint == 2 ? ptx::policy_evict_first()
-                                 : d_hint == 3 ? ptx::policy_evict_last() : ptx::policy_evict_normal();
+            // shard rows: NO cache hint (an explicit evict_normal policy is classed
+            // "evict_normal_demote" by the L2 and doubled the DRAM reads; evict_first / evict_last
+            // were no better -- profiles/README.md)
             const int q_row = q_tile * C::kQTile + static_cast<int>(rank) * kRowsPerCta;
             int stage = 0;
             uint32_t phase = 0;
-            long long t_wait = 0;
-            const long long t_begin = clock64();
-            // Progress window (EXPERIMENT, off unless sqe_tuning_set(SQE_TUNE_K2_WINDOW, w > 0)).
-            // In pair mode the units of a group drift apart (start times ~15 us apart after 200
-            // tiles); a tile may then have left L2 when the laggards ask for it and is read from
-            // HBM again (ncu: 1.2-2x the shard).  With the window every unit publishes the tile
-            // it is loading and waits when it is more than `window` tiles ahead of a sibling.
-            // Measured: DRAM reads drop to 1.05x, but throughput drops 8-12 % at any window size
-            // and the units drift TO the limit instead of staying in their natural ~2-tile
-            // equilibrium (followers hit L2 and catch up with the DRAM-fetching leader).
-            const uint32_t kWindow = static_cast<uint32_t>(window);
-            uint32_t* my_prog = ws_prog + group * n_qt;
-            const bool sync_group = (rank == 0) && (n_qt > 1) && (window > 0);
-            uint32_t sib[8];
-            long long t_window = 0;
-            unsigned n_blocked = 0;
+            [[maybe_unused]] long long t_wait = 0;
+            [[maybe_unused]] const long long t_begin = DBG ? clock64() : 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int d_row = (group + i * n_groups) * kTileN + static_cast<int>(rank) * C::kBRows;
-                if (sync_group) {
-                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_prog + q_tile), "r"(static_cast<uint32_t>(i + 1)) : "memory");
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (u < n_qt)
-                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sib[u]) : "l"(my_prog + u) : "memory");
-                }
                 // split-bf16 shards: four passes over K into the same accumulator, smallest
                 // terms first -- (Q plane, D plane) = (lo, lo), (hi, lo), (lo, hi), (hi, hi).  The
                 // tensor core truncates when it aligns a product group to the accumulator, so the
@@ -552,55 +806,30 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const int pass = ch / kNumChunks + (4 - passes);     // plain shards: only (hi, hi)
                     const int q_plane = (pass == 0 || pass == 2) ? 1 : 0;
                     const int d_plane = (pass == 0 || pass == 1) ? 1 : 0;
-                    const long long w0 = dbg ? clock64() : 0;
+                    [[maybe_unused]] const long long w0 = DBG ? clock64() : 0;
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                    if (dbg) t_wait += clock64() - w0;
+                    if constexpr (DBG) t_wait += clock64() - w0;
                     const uint32_t sa = base + stage * C::kStageBytes;
                     if constexpr (CG == 1) {
                         const uint32_t fb = bar_full + 8 * stage;
                         ptx::mbar_expect_tx(fb, C::kStageBytes);
-                        if (d_hint == 4) ptx::tma_load_3d(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb);
-                        else ptx::tma_load_3d_hint(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb, pol_q);
-                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_3d(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb);
-                        else ptx::tma_load_3d_hint(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb, pol_d);
+                        ptx::tma_load_3d_hint(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb, pol_q);
+                        ptx::tma_load_3d(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb);
                     } else {
                         // both CTAs' bytes are counted on the LEADER's barrier
                         if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
                         const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
-                        if (d_hint == 4) ptx::tma_load_3d_cg2_nohint(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb);
-                        else ptx::tma_load_3d_cg2(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb, pol_q);
-                        if (d_hint == 0 || d_hint == 4) ptx::tma_load_3d_cg2_nohint(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb);
-                        else ptx::tma_load_3d_cg2(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb, pol_d);
+                        ptx::tma_load_3d_cg2(sa, &tmap_q, kc * kChunkK, q_plane, q_row, fb, pol_q);
+                        ptx::tma_load_3d_cg2_nohint(sa + kABytes, &tmap_d, kc * kChunkK, d_plane, d_row, fb);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                if (sync_group && i + 1 < my_tiles) {
-                    // may tile i+1 start?  every sibling must have reached tile i+1-kWindow
-                    // (published value = tile index + 1; a finished unit publishes 0xffffffff)
-                    const long long t0 = clock64();
-                    while (true) {
-                        uint32_t lo = 0xffffffffu;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (u < n_qt) lo = min(lo, sib[u]);
-                        if (lo + kWindow >= static_cast<uint32_t>(i + 2) || lo == 0xffffffffu) break;
-                        ++n_blocked;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (u < n_qt)
-                                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sib[u]) : "l"(my_prog + u) : "memory");
-                        if (clock64() - t0 > 4000000000LL) __trap();
-                    }
-                    t_window += clock64() - t0;
-                }
             }
-            if (sync_group)       // done: never hold the others back
-                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_prog + q_tile), "r"(0xffffffffu) : "memory");
-            if (dbg) {
-                dbg[blockIdx.x * 40 + 0] = clock64() - t_begin;
-                dbg[blockIdx.x * 40 + 1] = t_wait;
-                dbg[blockIdx.x * 40 + 32] = t_window;
-                dbg[blockIdx.x * 40 + 33] = n_blocked;
+            if constexpr (DBG) {
+                if (dbg) {
+                    dbg[blockIdx.x * 40 + 0] = clock64() - t_begin;
+                    dbg[blockIdx.x * 40 + 1] = t_wait;
+                }
             }
         }
     } else if (warp == 1) {
@@ -608,25 +837,27 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (lane == 0 && rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            long long t_wfull = 0, t_wtempty = 0;
-            const long long t_begin = clock64();
+            [[maybe_unused]] long long t_wfull = 0, t_wtempty = 0;
+            [[maybe_unused]] const long long t_begin = DBG ? clock64() : 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
                 const uint32_t acc_phase = (i >> 1) & 1;
-                const long long w0 = dbg ? clock64() : 0;
-                if (dbg && (i == 8 || i == 64 || i == 200)) {            // skew between the units of a group
-                    unsigned long long gt;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                    dbg[blockIdx.x * 40 + (i == 8 ? 5 : i == 64 ? 6 : 7)] = gt;
+                [[maybe_unused]] const long long w0 = DBG ? clock64() : 0;
+                if constexpr (DBG) {
+                    if (dbg && (i == 8 || i == 64 || i == 200)) {            // skew between the units of a group
+                        unsigned long long gt;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        dbg[blockIdx.x * 40 + (i == 8 ? 5 : i == 64 ? 6 : 7)] = gt;
+                    }
                 }
                 ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);   // epilogue(s) drained it
-                if (dbg) t_wtempty += clock64() - w0;
+                if constexpr (DBG) t_wtempty += clock64() - w0;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kTileN;
                 for (int kc = 0; kc < kNumChunks * passes; ++kc) {
-                    const long long w1 = dbg ? clock64() : 0;
+                    [[maybe_unused]] const long long w1 = DBG ? clock64() : 0;
                     ptx::mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
-                    if (dbg) t_wfull += clock64() - w1;
+                    if constexpr (DBG) t_wfull += clock64() - w1;
                     ptx::tc_fence_after();
                     const uint32_t sa = base + stage * C::kStageBytes;
                     const uint64_t da = make_sw128_desc(sa);
@@ -634,7 +865,7 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
                     for (int k4 = 0; k4 < kChunkK / kUmmaK; ++k4) {
                         // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-B units
-                        ptx::umma_f16<CG>(tmem_d, da + 2 * k4, db + 2 * k4, idesc,
+                        ptx::umma_f16<CG>(tmem_d, da + 2 * k4, db + 2 * k4, a.idesc,
                                           (kc | k4) != 0 ? 1u : 0u);
                     }
                     // frees the smem stage (in both CTAs) once these MMAs have read it
@@ -646,47 +877,37 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 if constexpr (CG == 1) ptx::umma_commit(bar_tfull + 8 * acc);
                 else ptx::umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
             }
-            if (dbg) {
-                dbg[blockIdx.x * 40 + 2] = clock64() - t_begin;
-                dbg[blockIdx.x * 40 + 3] = t_wfull;
-                dbg[blockIdx.x * 40 + 4] = t_wtempty;
+            if constexpr (DBG) {
+                if (dbg) {
+                    dbg[blockIdx.x * 40 + 2] = clock64() - t_begin;
+                    dbg[blockIdx.x * 40 + 3] = t_wfull;
+                    dbg[blockIdx.x * 40 + 4] = t_wtempty;
+                }
             }
         }
     } else if (warp == 6) {
         // ---------------------------------------------------------- threshold warp
-        if constexpr (!TOP1)                                 // k = 1 keeps no lists
-        threshold_warp<R>(ws_lists, ws_tau, b, n_qt * C::kQTile, k, n_groups, q_tile * C::kQTile,
-                          C::kQTile, group * CG + static_cast<int>(rank), n_groups * CG, epi_done, lane);
+        if constexpr (LOG)
+            threshold_warp_log<R>(a.ws_lists, a.ws_counts, a.ws_tau, sm + C::kOffThr, C::kThrSlots, b,
+                                  n_qt * C::kQTile, a.gpad, k, n_groups, q_tile * C::kQTile, C::kQTile,
+                                  group * CG + static_cast<int>(rank), n_groups * CG, epi_done, lane);
+        else if constexpr (!TOP1)                            // k = 1 keeps no lists
+            threshold_warp<R>(a.ws_lists, a.ws_tau, b, n_qt * C::kQTile, k, n_groups, q_tile * C::kQTile,
+                              C::kQTile, group * CG + static_cast<int>(rank), n_groups * CG, epi_done, lane);
     } else {
         // ---------------------------------------------------------------- epilogue
         const int quarter = warp & 3;                                    // TMEM lanes 32q..32q+31
         const int row0 = q_tile * C::kQTile + static_cast<int>(rank) * kRowsPerCta + quarter * 32;
         const bool row_valid = row0 + lane < b;
         const int b_pad = n_qt * C::kQTile;
-        constexpr bool SL = C::kSmemLists;
-        constexpr int LW = C::kListWidth;
-        uint64_t* wbuf = reinterpret_cast<uint64_t*>(sm + C::kOffBuf) + quarter * 32 * kBufStride;
-        uint64_t* slists = reinterpret_cast<uint64_t*>(sm + C::kOffLists) + quarter * 32 * LW;
-        if constexpr (SL) {
-            for (int i = lane; i < 32 * LW; i += 32) slists[i] = 0ull;
-            __syncwarp();
-        }
-        uint64_t* wlists = ws_lists + (static_cast<size_t>(group) * b_pad + row0) * L;
-        // scratch lists of the bootstrap (R > 1 only), behind the n_groups * b_pad real lists
-        uint64_t* wscratch = wlists + static_cast<size_t>(n_groups) * b_pad * L;
-        uint32_t* wtau = ws_tau + row0;
-
-        EpiState st;
-        st.tau_l = __int_as_float(0xff800000);
-        st.tau_g = 0u;
-        st.thr = st.tau_l;
-        st.cnt = 0;
-        st.n_slow = st.n_flush = st.n_cols = 0u;
-        st.t_flush = 0;
-        long long t_wtfull = 0, t_ld = 0;
-        const long long t_begin = clock64();
+        uint32_t* wtau = a.ws_tau + row0;
+        [[maybe_unused]] long long t_wtfull = 0, t_ld = 0;
+        [[maybe_unused]] const long long t_begin = DBG ? clock64() : 0;
+        [[maybe_unused]] unsigned d_slow = 0, d_flush = 0;
+        [[maybe_unused]] long long d_tflush = 0;
 
         if constexpr (TOP1) {
+            uint64_t* wlists = a.ws_lists + (static_cast<size_t>(group) * b_pad + row0) * L;
             float best = __int_as_float(0xff800000);
             uint32_t best_col = 0u;
             for (int i = 0; i < my_tiles; ++i) {
@@ -712,17 +933,102 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             // slot 0 of this query's (otherwise empty) list; the merge kernel does the rest
             if (best > __int_as_float(0xff800000))
                 __stcg(wlists + static_cast<size_t>(lane) * L, make_key(best, best_col));
+        } else if constexpr (LOG) {
+            // ------------------------------------------------------ k > 32: candidate logs
+            constexpr int CAP = C::kLogCap;
+            uint64_t* wlog = a.ws_lists + (static_cast<size_t>(group) * b_pad + row0) * CAP;
+            uint32_t* wcount = a.ws_counts + static_cast<size_t>(row0) * a.gpad + group;
+            LogState st;
+            st.tau_l = __int_as_float(0xff800000);
+            st.tau_g = 0u;
+            st.thr = st.tau_l;
+            st.cnt = 0u;
+            st.epoch = 0u;
+            st.n_slow = st.n_compact = 0u;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int t = group + i * n_groups;
+                const int acc = i & 1;
+                const uint32_t acc_phase = (i >> 1) & 1;
+                const uint32_t g = __ldcg(wtau + lane);                    // refresh the shared bound while waiting
+                [[maybe_unused]] const long long w0 = DBG ? clock64() : 0;
+                ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                if constexpr (DBG) t_wtfull += clock64() - w0;
+                ptx::tc_fence_after();
+                if (g > st.tau_g) {
+                    st.tau_g = g;
+                    st.thr = thr_of(st.tau_l, st.tau_g);
+                }
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kTileN;
+                if (i == 0 && a.boot_j > 0 && epi_mode == 0) {
+                    float top[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) top[j] = __int_as_float(0xff800000);
+#pragma unroll 1
+                    for (int c = 0; c < kTileN / 32; ++c) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(taddr + c * 32, v);
+                        ptx::tmem_wait_ld();
+                        bootstrap_strip(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, top);
+                    }
+                    log_boot_exchange(top, a.boot_j, a.boot_m, row_valid,
+                                      a.ws_boot + static_cast<size_t>(row0 + lane) * a.gpad, group, n_groups,
+                                      a.ws_arrive + (row0 >> 5), st, lane);
+                }
+                uint32_t g_next = __ldcg(wtau + lane);
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; ++c) {
+                    if (epi_mode == 2) break;                                 // diagnostics: MMA + TMA only
+                    if ((c & 3) == 0) {                                       // pick the bound up twice per tile
+                        if (g_next > st.tau_g) {
+                            st.tau_g = g_next;
+                            st.thr = thr_of(st.tau_l, st.tau_g);
+                        }
+                        g_next = __ldcg(wtau + lane);
+                    }
+                    uint32_t v[32];
+                    [[maybe_unused]] const long long l0 = DBG ? clock64() : 0;
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_wait_ld();
+                    if constexpr (DBG) t_ld += clock64() - l0;
+                    if (epi_mode == 1) {                                      // diagnostics: TMEM reads only
+                        asm volatile("" ::"r"(v[0]), "r"(v[31]));
+                        continue;
+                    }
+                    process_strip_log<R>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st, wlog,
+                                         wcount, a.gpad, wtau, k, lane);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
+                    else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);   // the leader's barrier
+                }
+            }
+            if constexpr (DBG) { d_slow = st.n_slow; d_flush = st.n_compact; }
         } else {
+        uint64_t* wlists = a.ws_lists + (static_cast<size_t>(group) * b_pad + row0) * L;
+        constexpr int LW = C::kListWidth;
+        uint64_t* wbuf = reinterpret_cast<uint64_t*>(sm + C::kOffBuf) + quarter * 32 * kBufStride;
+        uint64_t* slists = reinterpret_cast<uint64_t*>(sm + C::kOffLists) + quarter * 32 * LW;
+        for (int i = lane; i < 32 * LW; i += 32) slists[i] = 0ull;
+        __syncwarp();
+        EpiState st;
+        st.tau_l = __int_as_float(0xff800000);
+        st.tau_g = 0u;
+        st.thr = st.tau_l;
+        st.cnt = 0;
+        st.n_slow = st.n_flush = st.n_cols = 0u;
+        st.t_flush = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const int t = group + i * n_groups;
             const int acc = i & 1;
             const uint32_t acc_phase = (i >> 1) & 1;
             // refresh the shared bound while waiting for the accumulator
             const uint32_t g = __ldcg(wtau + lane);
-            const long long w0 = dbg ? clock64() : 0;
+            [[maybe_unused]] const long long w0 = DBG ? clock64() : 0;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            const long long w1 = dbg ? clock64() : 0;
-            if (dbg) t_wtfull += w1 - w0;
+            [[maybe_unused]] const long long w1 = DBG ? clock64() : 0;
+            if constexpr (DBG) t_wtfull += w1 - w0;
             ptx::tc_fence_after();
             if (g > st.tau_g) {
                 st.tau_g = g;
@@ -763,26 +1069,21 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     g_next = __ldcg(wtau + lane);
                 }
                 uint32_t v[32];
-                const long long l0 = dbg ? clock64() : 0;
+                [[maybe_unused]] const long long l0 = DBG ? clock64() : 0;
                 ptx::tmem_ld_32x32(taddr + c * 32, v);
                 ptx::tmem_wait_ld();
-                if (dbg) t_ld += clock64() - l0;
+                if constexpr (DBG) t_ld += clock64() - l0;
                 if (epi_mode == 1) {                                      // diagnostics: TMEM reads only
                     asm volatile("" ::"r"(v[0]), "r"(v[31]));
                     continue;
                 }
-                if (!NARROW && i == 0 && k > 16 && (c < R || !SL)) {      // bootstrap for k > 16
-                    // lists in smem (k <= 32): the first strip only; lists in the workspace:
-                    // the whole tile, in batches of 32*R columns through the scratch list
-                    uint64_t* dst = (c < R) ? wlists : wscratch;
-                    direct_fill_strip<R, SL>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid,
-                                             c, slists, dst, lane);
-                    if ((c % R) == R - 1)
-                        sort_filled_lists<R, SL>(st, slists, wlists, dst, c >= R, wtau, k, lane);
+                if (!NARROW && i == 0 && k > 16 && c == 0) {              // bootstrap for 16 < k <= 32
+                    direct_fill_strip(v, static_cast<uint32_t>(t) * kTileN, n, row_valid, slists, lane);
+                    sort_filled_lists(st, slists, wlists, wtau, k, lane);
                     continue;
                 }
-                process_strip<R, LW>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
-                                     wbuf, slists, wlists, wtau, k, lane);
+                process_strip<R, LW, DBG>(v, static_cast<uint32_t>(t) * kTileN + c * 32, n, row_valid, st,
+                                          wbuf, slists, wlists, wtau, k, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -792,28 +1093,33 @@ topk_batched_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
             // the accumulator is released; now fold this tile's candidates into the lists so
             // the threshold warps see them
-            const long long w2 = dbg ? clock64() : 0;
+            [[maybe_unused]] const long long w2 = DBG ? clock64() : 0;
             const unsigned pending = __ballot_sync(kFull, st.cnt > 0);
-            if (pending) flush_lanes<R, LW>(pending, st, wbuf, slists, wlists, wtau, k, lane);
-            if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 64) {
-                unsigned long long* tr = dbg + gridDim.x * 40 + i * 4;
-                tr[0] = w1 - w0;                 // waited for the accumulator
-                tr[1] = w2 - w1;                 // strips (until the accumulator was released)
-                tr[2] = clock64() - w2;          // tile-end list merges
-                tr[3] = __popc(pending);
+            if (pending) flush_lanes<R, LW, DBG>(pending, st, wbuf, slists, wlists, wtau, k, lane);
+            if constexpr (DBG) {
+                if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 64) {
+                    unsigned long long* tr = dbg + gridDim.x * 40 + i * 4;
+                    tr[0] = w1 - w0;                 // waited for the accumulator
+                    tr[1] = w2 - w1;                 // strips (until the accumulator was released)
+                    tr[2] = clock64() - w2;          // tile-end list merges
+                    tr[3] = __popc(pending);
+                }
             }
         }
-        }   // k > 1
+        if constexpr (DBG) { d_slow = st.n_slow; d_flush = st.n_flush; d_tflush = st.t_flush; }
+        }   // k > 1, lists
         __syncwarp();
         if (lane == 0) atomicAdd(epi_done, 1u);
-        if (dbg && lane == 0) {
-            unsigned long long* d = dbg + blockIdx.x * 40 + 8 + (warp - 2) * 6;
-            d[0] = clock64() - t_begin;
-            d[1] = t_wtfull;
-            d[2] = st.t_flush;
-            d[3] = st.n_slow;
-            d[4] = st.n_flush;
-            d[5] = t_ld;
+        if constexpr (DBG) {
+            if (dbg && lane == 0) {
+                unsigned long long* d = dbg + blockIdx.x * 40 + 8 + (warp - 2) * 6;
+                d[0] = clock64() - t_begin;
+                d[1] = t_wtfull;
+                d[2] = d_tflush;
+                d[3] = d_slow;
+                d[4] = d_flush;
+                d[5] = t_ld;
+            }
         }
     }
 
@@ -895,6 +1201,80 @@ batched_merge_kernel(const uint64_t* __restrict__ ws_lists, uint32_t* __restrict
                  out_idx + static_cast<int64_t>(query) * k, idx_offset);
 }
 
+// Log mode: fold the candidate logs of every group into the query's top list.  Same geometry as
+// above (one warp per query, or eight warps per query when there are many groups); the count
+// words of a warp's groups are fetched with one load, the first chunk of the next log while the
+// current one is folded.
+template <int R>
+__global__ void __launch_bounds__(256)
+batched_merge_log_kernel(const uint64_t* __restrict__ ws_logs, const uint32_t* __restrict__ ws_counts,
+                         uint32_t* __restrict__ ws_tau, int n_groups, int b, int b_pad, int gpad, int k,
+                         int warps_per_query, float* __restrict__ out_score, int64_t* __restrict__ out_idx,
+                         int64_t idx_offset) {
+    constexpr int L = 32 * R;
+    constexpr uint32_t CAP = 64 * R;
+    __shared__ uint64_t s_part[8][L];
+    clear_header(ws_tau);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps = blockDim.x >> 5;
+    const int query = (warps_per_query == 1) ? blockIdx.x * warps + warp : blockIdx.x;
+    const int sub = (warps_per_query == 1) ? 0 : warp;          // which share of the groups
+    const bool active = query < b;
+    WarpList<R> list;
+    list.clear();
+    if (active) {
+        uint64_t worst = 0ull;
+        for (int gb = sub; gb < n_groups; gb += 32 * warps_per_query) {       // 32 of my groups at a time
+            const int gm = gb + lane * warps_per_query;
+            uint32_t myc = gm < n_groups ? (__ldcg(ws_counts + static_cast<size_t>(query) * gpad + gm) & 0xffffu) : 0u;
+            myc = myc > CAP ? CAP : myc;
+            const int n_mine = min(32, (n_groups - gb + warps_per_query - 1) / warps_per_query);
+            uint32_t cnt = __shfl_sync(kFull, myc, 0);
+            const uint64_t* lp = ws_logs + (static_cast<size_t>(gb) * b_pad + query) * CAP;
+            uint64_t nxt = static_cast<uint32_t>(lane) < cnt ? __ldcg(lp + lane) : 0ull;
+            for (int j = 0; j < n_mine; ++j) {
+                uint64_t key = nxt;
+                const uint32_t cnt_cur = cnt;
+                const uint64_t* lp_cur = lp;
+                if (j + 1 < n_mine) {
+                    cnt = __shfl_sync(kFull, myc, j + 1);
+                    lp = ws_logs + (static_cast<size_t>(gb + (j + 1) * warps_per_query) * b_pad + query) * CAP;
+                    nxt = static_cast<uint32_t>(lane) < cnt ? __ldcg(lp + lane) : 0ull;
+                }
+                for (uint32_t pos = 0; pos < cnt_cur; pos += 32) {
+                    if (pos > 0) key = pos + lane < cnt_cur ? __ldcg(lp_cur + pos + lane) : 0ull;
+                    unsigned pass = __ballot_sync(kFull, key > worst);
+                    while (pass) {
+                        const int l = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        const uint64_t cand = shfl_u64(key, l);
+                        if (cand > worst) {
+                            list.insert(cand, lane);
+                            worst = list.worst();
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (warps_per_query > 1) {
+        list.store(s_part[warp], lane);
+        __syncthreads();
+        if (warp != 0 || !active) return;
+#pragma unroll 1
+        for (int w = 1; w < warps_per_query; ++w) {
+            WarpList<R> other;
+            other.load(s_part[w], lane);
+            list.merge_sorted(other.key, lane);
+        }
+    } else if (!active) {
+        return;
+    }
+    emit_topk<R>(list, k, lane, out_score + static_cast<int64_t>(query) * k,
+                 out_idx + static_cast<int64_t>(query) * k, idx_offset);
+}
+
 // k = 1: every group wrote at most one key (slot 0 of its list); the result is their maximum.
 __global__ void __launch_bounds__(128)
 top1_merge_kernel(const uint64_t* __restrict__ ws_lists, uint32_t* __restrict__ ws_tau, int n_groups,
@@ -956,56 +1336,82 @@ static int make_tile_map(CUtensorMap* map, const void* ptr, int dtype, uint64_t 
 static inline int r_for_k_batched(int k) { return k <= 32 ? 1 : k <= 64 ? 2 : 4; }
 
 static constexpr int64_t kTauBytes = 4096;        // kQueriesPerLaunch * 4
-static constexpr int64_t kProgBytes = 4096;       // one u32 of tile progress per unit (<= #SMs)
-static constexpr int64_t kHdrBytes = kTauBytes + kProgBytes;
+static constexpr int64_t kArriveBytes = 4096;     // log mode: one arrival counter per 32-query slice
+static constexpr int64_t kHdrBytes = kTauBytes + kArriveBytes;
 
+// Workspace: [published bounds 4 KB][arrival counters 4 KB][lists: groups x b_pad x 32 R keys]
+// or, in log mode (R > 1): [...][logs: groups x b_pad x 64 R keys][counts b_pad x gpad][boot b_pad x gpad]
 int64_t batched_workspace_bytes(int64_t /*n*/, int /*b*/, int k, int sm_count) {
     const int R = r_for_k_batched(k);
-    const int64_t L = 32 * R;
-    // R > 1: as many scratch lists again for the bootstrap of the first d-tile
-    return kHdrBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * L * 8 * (R > 1 ? 2 : 1);
+    const int64_t per_list = (R > 1 ? 64 : 32) * R * 8;
+    const int64_t gpad = (sm_count + 31) & ~31;
+    const int64_t words = R > 1 ? 2 * k2::kQueriesPerLaunch * gpad * 4 : 0;
+    return kHdrBytes + static_cast<int64_t>(sm_count) * k2::kRowsPerCta * per_list + words;
 }
 
-template <int R, int CG, bool TOP1, bool DEEP, bool NARROW = false>
-static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, int64_t n, int b, int k,
-                            int n_qt, int n_groups, int n_dtiles, uint32_t idesc, uint64_t* ws_lists,
-                            uint32_t* ws_tau, uint32_t* ws_prog, int passes, float* out_score, int64_t* out_idx,
-                            int64_t idx_offset, cudaStream_t stream) {
+template <int R, int CG, bool TOP1, bool DEEP, bool NARROW, bool DBG>
+static int launch_batched_k(const CUtensorMap& tq, const CUtensorMap& td, const K2Args& a, cudaStream_t stream) {
     using C = k2::Cfg<CG, R, TOP1, DEEP, NARROW>;
     // per device and cheap: set on every launch (one process may drive several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1, DEEP, NARROW>,
+    cudaError_t e = cudaFuncSetAttribute(topk_batched_kernel<R, CG, TOP1, DEEP, NARROW, DBG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("topk_batched: smem attribute: %s", cudaGetErrorString(e)); return -2; }
-    if (n_dtiles > 0) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(static_cast<unsigned>(n_groups * n_qt * CG));
-        cfg.blockDim = dim3(k2::kThreads);
-        cfg.dynamicSmemBytes = C::kSmemBytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CG;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1, DEEP, NARROW>, tq, td, static_cast<uint32_t>(n), b, k,
-                               n_qt, n_groups, n_dtiles, idesc, ws_lists, ws_tau, ws_prog,
-                               reinterpret_cast<unsigned long long*>(g_k2_debug), g_k2_epilogue_mode, g_k2_d_hint, g_k2_window, passes);
-        if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.n_groups * a.n_qt * CG));
+    cfg.blockDim = dim3(k2::kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, topk_batched_kernel<R, CG, TOP1, DEEP, NARROW, DBG>, tq, td, a);
+    if (e != cudaSuccess) { set_error("topk_batched: launch: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+// DBG_OK: this instantiation also exists with the role timers compiled in (sqe_debug_k2_timers);
+// the production instantiation carries no diagnostics at all.
+template <int R, int CG, bool TOP1, bool DEEP, bool NARROW = false, bool DBG_OK = false>
+static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, K2Args a, float* out_score,
+                            int64_t* out_idx, int64_t idx_offset, cudaStream_t stream) {
+    using C = k2::Cfg<CG, R, TOP1, DEEP, NARROW>;
+    a.dbg = reinterpret_cast<unsigned long long*>(g_k2_debug);
+    a.epi_mode = g_k2_epilogue_mode;
+    if (a.n_dtiles > 0) {
+        int rc;
+        if constexpr (DBG_OK) {
+            rc = (a.dbg != nullptr || a.epi_mode != 0)
+                     ? launch_batched_k<R, CG, TOP1, DEEP, NARROW, true>(tq, td, a, stream)
+                     : launch_batched_k<R, CG, TOP1, DEEP, NARROW, false>(tq, td, a, stream);
+        } else {
+            rc = launch_batched_k<R, CG, TOP1, DEEP, NARROW, false>(tq, td, a, stream);
+        }
+        if (rc != 0) return rc;
     }
-    const int mg = n_dtiles > 0 ? n_groups : 0;
+    const int mg = a.n_dtiles > 0 ? a.n_groups : 0;
+    const int b = a.b, k = a.k, b_pad = a.n_qt * C::kQTile;
     if constexpr (TOP1) {
-        top1_merge_kernel<<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, ws_tau, mg, b, n_qt * C::kQTile, out_score,
-                                                           out_idx, idx_offset);
+        top1_merge_kernel<<<(b + 3) / 4, 128, 0, stream>>>(a.ws_lists, a.ws_tau, mg, b, b_pad, out_score, out_idx,
+                                                           idx_offset);
+    } else if constexpr (C::kLog) {
+        if (mg > 32)
+            batched_merge_log_kernel<R><<<b, 256, 0, stream>>>(a.ws_lists, a.ws_counts, a.ws_tau, mg, b, b_pad, a.gpad,
+                                                               k, 8, out_score, out_idx, idx_offset);
+        else
+            batched_merge_log_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(a.ws_lists, a.ws_counts, a.ws_tau, mg, b, b_pad,
+                                                                         a.gpad, k, 1, out_score, out_idx, idx_offset);
     } else if (mg > 32) {
-        batched_merge_kernel<R><<<b, 256, 0, stream>>>(ws_lists, ws_tau, mg, b, n_qt * C::kQTile, k, 8, out_score,
-                                                       out_idx, idx_offset);
+        batched_merge_kernel<R><<<b, 256, 0, stream>>>(a.ws_lists, a.ws_tau, mg, b, b_pad, k, 8, out_score, out_idx,
+                                                       idx_offset);
     } else {
-        batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(ws_lists, ws_tau, mg, b, n_qt * C::kQTile, k, 1,
-                                                                 out_score, out_idx, idx_offset);
+        batched_merge_kernel<R><<<(b + 3) / 4, 128, 0, stream>>>(a.ws_lists, a.ws_tau, mg, b, b_pad, k, 1, out_score,
+                                                                 out_idx, idx_offset);
     }
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("topk_batched: merge launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
 }
@@ -1016,19 +1422,23 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
                              int sm_count, cudaStream_t stream) {
     using C = k2::Cfg<CG>;
     const int R = r_for_k_batched(k);
-    const int64_t L = 32 * R;
-    uint32_t* ws_tau = static_cast<uint32_t*>(ws);
-    uint32_t* ws_prog = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + kTauBytes);
-    uint64_t* ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kHdrBytes);
+    const bool log_mode = R > 1;
+    const int64_t per_list = (log_mode ? 64 : 32) * R * 8;     // bytes per (query, group) list / log
     const int n_dtiles = static_cast<int>((n + k2::kTileN - 1) / k2::kTileN);
     const uint32_t fmt = (dtype == 2) ? 0u : 1u;               // F16 = 0; BF16 = 1 (also split bf16)
-    const int passes = (dtype == 3) ? 4 : 1;                   // split bf16: Ql.Dl + Qh.Dl + Ql.Dh + Qh.Dh
     const int64_t q_row_bytes = (dtype == 3) ? 2 * kDim * 2 : kDim * 2;
+    K2Args a = {};
+    a.n = static_cast<uint32_t>(n);
+    a.k = k;
+    a.n_dtiles = n_dtiles;
+    a.passes = (dtype == 3) ? 4 : 1;                           // split bf16: Ql.Dl + Qh.Dl + Ql.Dh + Qh.Dh
     // instruction descriptor: D fp32 [4,6)=1, A fmt [7,10), B fmt [10,13), K-major both,
     // N>>3 [17,23), M>>4 [24,29)  (M = 128 per CTA, 256 for the pair)
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) |
-                           (static_cast<uint32_t>(k2::kTileN >> 3) << 17) |
-                           (static_cast<uint32_t>(C::kQTile >> 4) << 24);
+    a.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(k2::kTileN >> 3) << 17) |
+              (static_cast<uint32_t>(C::kQTile >> 4) << 24);
+    a.ws_tau = static_cast<uint32_t*>(ws);
+    a.ws_arrive = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + kTauBytes);
+    a.ws_lists = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + kHdrBytes);
     CUtensorMap td;
     if (n > 0) {
         int rc = make_tile_map(&td, D, dtype, static_cast<uint64_t>(n), C::kBRows);
@@ -1043,7 +1453,28 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         int n_groups = units / n_qt;
         if (n_groups < 1) n_groups = 1;
         if (n_dtiles > 0 && n_groups > n_dtiles) n_groups = n_dtiles;
-        const int64_t used = kHdrBytes + static_cast<int64_t>(n_groups) * n_qt * C::kQTile * L * 8;
+        if (n_groups > k2::kMaxGroups) n_groups = k2::kMaxGroups;
+        const int64_t b_pad = static_cast<int64_t>(n_qt) * C::kQTile;
+        const int64_t lists_bytes = static_cast<int64_t>(n_groups) * b_pad * per_list;
+        a.b = bc;
+        a.n_qt = n_qt;
+        a.n_groups = n_groups;
+        a.gpad = (n_groups + 31) & ~31;
+        int64_t used = kHdrBytes + lists_bytes;
+        a.boot_j = a.boot_m = 0;
+        if (log_mode) {
+            a.ws_counts = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + used);
+            a.ws_boot = a.ws_counts + b_pad * a.gpad;
+            used += 2 * b_pad * a.gpad * 4;
+            // first-tile bootstrap: the m-th largest over the groups of the j-th best of a group's
+            // first d-tile bounds the k-th best when j m >= k; j, m <= 16 (register networks)
+            int j = (k + 15) / 16;
+            while (j <= 16 && (k + j - 1) / j > n_groups) ++j;
+            if (j <= 16 && n_groups >= 2) {
+                a.boot_j = j;
+                a.boot_m = (k + j - 1) / j;
+            }
+        }
         cudaError_t e = cudaMemsetAsync(ws, 0, static_cast<size_t>(used), stream);
         if (e != cudaSuccess) { set_error("topk_batched: memset: %s", cudaGetErrorString(e)); return -2; }
         const char* qp = static_cast<const char*>(Q) + static_cast<int64_t>(q0) * q_row_bytes;
@@ -1054,18 +1485,15 @@ static int launch_batched_cg(const void* D, int dtype, int64_t n, const void* Q,
         int64_t* oi = out_idx + static_cast<int64_t>(q0) * k;
         // deep ring only when a pair has its d-tiles to itself (see Cfg)
         const bool deep = (CG == 2) && (n_qt == 1);
-#define SQE_K2_LAUNCH(R_, TOP1_)                                                                        \
-    (deep ? launch_batched_r<R_, CG, TOP1_, (CG == 2)>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc, \
-                                                       ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream) \
-          : launch_batched_r<R_, CG, TOP1_, false>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc,     \
-                                                   ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream))
-        if (k == 1) rc = SQE_K2_LAUNCH(1, true);
+#define SQE_K2_LAUNCH(R_, TOP1_, DBG_DEEP_, DBG_FLAT_)                                                              \
+    (deep ? launch_batched_r<R_, CG, TOP1_, (CG == 2), false, DBG_DEEP_>(tq, td, a, os, oi, idx_offset, stream)     \
+          : launch_batched_r<R_, CG, TOP1_, false, false, DBG_FLAT_>(tq, td, a, os, oi, idx_offset, stream))
+        if (k == 1) rc = SQE_K2_LAUNCH(1, true, false, false);
         else if (CG == 1 && k <= 16)         // narrow smem lists + a fourth stage (see Cfg)
-            rc = launch_batched_r<1, CG, false, false, (CG == 1)>(tq, td, n, bc, k, n_qt, n_groups, n_dtiles, idesc,
-                                                                  ws_lists, ws_tau, ws_prog, passes, os, oi, idx_offset, stream);
-        else if (R == 1) rc = SQE_K2_LAUNCH(1, false);
-        else if (R == 2) rc = SQE_K2_LAUNCH(2, false);
-        else rc = SQE_K2_LAUNCH(4, false);
+            rc = launch_batched_r<1, CG, false, false, (CG == 1)>(tq, td, a, os, oi, idx_offset, stream);
+        else if (R == 1) rc = SQE_K2_LAUNCH(1, false, false, (CG == 2));       // role timers: the b = 1024 headline form
+        else if (R == 2) rc = SQE_K2_LAUNCH(2, false, false, false);
+        else rc = SQE_K2_LAUNCH(4, false, (CG == 2), false);                   // role timers: the configs[3] form
 #undef SQE_K2_LAUNCH
         if (rc != 0) return rc;
     }

@@ -226,6 +226,43 @@ SQE_API int sqe_exchange_merge(const float *scores, const int64_t *idx, int b, i
                        int64_t capacity_entries, uint32_t epoch, uint32_t wait_mask,
                        float *out_score, int64_t *out_idx, void *stream);
 
+/*
+ * Sharded ONE- or TWO-query search in a single launch per rank (north_star subsystem 4 for the
+ * batch-1 path): the fused normalise + scan of sqe_search_gemv, and in the query's last CTA --
+ * the one that has just merged the rank-local top-k -- the K4x exchange: push the list into every
+ * rank's gather buffer, flag, wait for all ranks, merge, write the GLOBAL top-k.  No exchange
+ * kernel, no second launch.  Buffers, capacity and epochs exactly as for sqe_exchange_merge (the
+ * two may be mixed on the same buffers: one epoch per call, the same sequence on every rank);
+ * 1 <= nq <= SQE_MAX_NQ_FUSED_EXCHANGE; world <= 1 or peer_buffers_host == NULL: plain
+ * sqe_search_gemv.  out_idx are global rows (idx_offset + local row), < 2^32 - 1.
+ *
+ * sqe_search_gemv_prefiltered: the same for the prefiltered scan (K3p) -- RAW fp32 queries, the
+ * query normalisation fused into both passes (no K1 launch), the exchange fused into the
+ * rescoring pass.  Results are bit-identical to sqe_normalize_cast + sqe_topk_gemv_prefiltered
+ * (+ sqe_exchange_merge).  With world <= 1: 1 <= nq <= SQE_MAX_NQ_PREFILTER.
+ *
+ * flags: SQE_FLAG_QUERIES_READY -- the caller states that Q_raw was complete BEFORE the previous
+ * kernel of this stream was launched (a resident query, or one that arrived through a copy the
+ * stream waited for).  The scan is then launched with programmatic stream serialization: it
+ * starts while the previous scan of the stream is still in its tail (last-CTA merge, exchange
+ * with the other ranks) and waits for it only before touching shared state.  Without the flag the
+ * launch is an ordinary one.  Results never depend on it.
+ */
+#define SQE_MAX_NQ_FUSED_EXCHANGE 2
+#define SQE_FLAG_QUERIES_READY 1
+SQE_API int sqe_search_gemv_sharded(const void *D, int dtype, int64_t n, int dim, const float *Q_raw,
+                            int nq, int k, float *out_score, int64_t *out_idx, int64_t idx_offset,
+                            int rank, int world, void *const *peer_buffers_host,
+                            int64_t capacity_entries, uint32_t epoch, int flags, void *workspace,
+                            int64_t workspace_bytes, void *stream);
+SQE_API int sqe_search_gemv_prefiltered(const void *D, int dtype, int64_t n, int dim, const void *D8,
+                                const void *meta, const float *Q_raw, int nq, int k,
+                                float *out_score, int64_t *out_idx, int64_t idx_offset,
+                                uint32_t *out_rescored, int rank, int world,
+                                void *const *peer_buffers_host, int64_t capacity_entries,
+                                uint32_t epoch, int flags, void *workspace, int64_t workspace_bytes,
+                                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

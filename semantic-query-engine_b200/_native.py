@@ -19,6 +19,8 @@ SQE_DIM = 1024
 SQE_MAX_K_GEMV = 256
 SQE_MAX_K_BATCHED = 128
 SQE_MAX_NQ_PREFILTER = 64
+SQE_MAX_NQ_FUSED_EXCHANGE = 2
+SQE_FLAG_QUERIES_READY = 1
 DTYPE_CODES = {"fp32": SQE_F32, "bf16": SQE_BF16, "fp16": SQE_F16, "bf16x2": SQE_BF16X2}
 
 # every symbol include/sqe_b200.h declares: (name, restype, argtypes)
@@ -51,6 +53,13 @@ PROTOTYPES = [
     ("sqe_exchange_merge", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    POINTER(c_void_p), c_int64, c_uint32, c_uint32,
                                    c_void_p, c_void_p, c_void_p]),
+    ("sqe_search_gemv_sharded", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
+                                        c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_void_p),
+                                        c_int64, c_uint32, c_int, c_void_p, c_int64, c_void_p]),
+    ("sqe_search_gemv_prefiltered", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                            c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                            c_int, c_int, POINTER(c_void_p), c_int64, c_uint32, c_int,
+                                            c_void_p, c_int64, c_void_p]),
 ]
 
 
@@ -79,6 +88,8 @@ LAUNCHES_PER_CALL = {
     "sqe_cache_top1": 2,      # +1 when it takes the tensor path (counted by the caller)
     "sqe_merge_topk": 1,
     "sqe_exchange_merge": 1,
+    "sqe_search_gemv_sharded": 1,
+    "sqe_search_gemv_prefiltered": 2,
 }
 
 

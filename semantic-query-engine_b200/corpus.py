@@ -355,21 +355,39 @@ class GpuCorpusIndex:
         return ops.stream_pipeline(self.device, batches, self._as_rows, lambda b: b * k * 12,
                                    launch, unpack, depth)
 
-    def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0, out=None
-                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    def can_fuse_exchange(self, b: int) -> bool:
+        """Whether `search_device` answers a batch of `b` queries with a scan whose last CTA can
+        carry the sharded mode's exchange (`xchg=`): the one-query fused scan, or the prefiltered
+        scan for one or two queries."""
+        if self._shard is None or self._rows <= 0:
+            return False
+        if self.prefilter and self._coarse8 is not None and 1 <= b <= 2 and self._rows <= self._coarse8.shape[0]:
+            return True
+        return b == 1
+
+    def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0, out=None, xchg=None,
+                      queries_ready: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Device-resident form: fp32 CUDA queries [B,1024] (un-normalised) -> CUDA
-        (scores, rows).  No synchronisation."""
+        (scores, rows).  No synchronisation.  `xchg` (ShardedCorpusIndex): fuse the exchange with
+        the other ranks into the scan -- only when `can_fuse_exchange(B)`.  `queries_ready=True`:
+        `q_dev` was complete before the previous kernel on this stream was launched (a resident
+        query batch); one- and two-query scans may then overlap the previous scan's tail."""
         rows = self._rows
         shard = self._shard if self._shard is not None else self.shard
         q_dev = q_dev.contiguous()
         c8, cm = self._coarse8, self._coarse_meta
-        if self.prefilter and c8 is not None and 1 <= q_dev.shape[0] <= 2 and 0 < rows <= c8.shape[0]:
-            # K3p: int8 prefilter + exact rescoring -- the exact scan's results at half its bytes
-            qn = ops.normalize_cast(q_dev, self.dtype)
-            return ops.topk_gemv_prefiltered(shard, c8, cm, qn, k, idx_offset=idx_offset, n=rows, out=out)
+        if self.prefilter and c8 is not None and 1 <= q_dev.shape[0] <= 2 and 0 < rows <= c8.shape[0] \
+                and q_dev.dtype == torch.float32:
+            # K3p: int8 prefilter + exact rescoring -- the exact scan's results at half its bytes;
+            # both passes normalise the raw query themselves (no K1 launch)
+            return ops.search_gemv_prefiltered(shard, c8, cm, q_dev, k, idx_offset=idx_offset, n=rows, out=out,
+                                               xchg=xchg, queries_ready=queries_ready)
         if q_dev.shape[0] == 1 and q_dev.dtype == torch.float32:
             # the reference's own case (one query, main.py:355): normalise + scan in ONE launch
-            return ops.search_gemv(shard, q_dev, k, idx_offset=idx_offset, n=rows, out=out)
+            return ops.search_gemv(shard, q_dev, k, idx_offset=idx_offset, n=rows, out=out, xchg=xchg,
+                                   queries_ready=queries_ready)
+        if xchg is not None:
+            raise ValueError("this batch cannot carry a fused exchange (see can_fuse_exchange)")
         qn = ops.normalize_cast(q_dev, self.dtype)                       # main.py:353-354
         return ops.topk(shard, qn, k, idx_offset=idx_offset, n=rows, out=out)
 

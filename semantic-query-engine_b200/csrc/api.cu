@@ -6,6 +6,7 @@
 
 #include "../../include/sqe_b200.h"
 #include "sqe_internal.h"
+#include "sqe_select.cuh"
 
 namespace sqe {
 
@@ -216,9 +217,55 @@ int sqe_topk_gemv_prefiltered(const void* D, int dtype, int64_t n, int dim, cons
     DevInfo d;
     rc = device_info(&d);
     if (rc != SQE_OK) return rc;
-    rc = launch_topk_prefiltered(D, dtype, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset,
+    rc = launch_topk_prefiltered(D, dtype, n, D8, meta, Q, false, nq, k, out_score, out_idx, idx_offset,
                                  out_rescored, workspace, workspace_bytes, d.sm_count,
                                  static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : rc == -3 ? SQE_E_WORKSPACE : SQE_E_CUDA);
+}
+
+int sqe_search_gemv_sharded(const void* D, int dtype, int64_t n, int dim, const float* Q_raw, int nq, int k,
+                            float* out_score, int64_t* out_idx, int64_t idx_offset, int rank, int world,
+                            void* const* peer_buffers_host, int64_t capacity_entries, uint32_t epoch,
+                            int flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_common("search_gemv_sharded", D, dtype, n, dim, Q_raw, nq);
+    if (rc != SQE_OK) return rc;
+    if (k < 1 || k > SQE_MAX_K_GEMV) { set_error("search_gemv_sharded: k=%d not in [1,%d]", k, SQE_MAX_K_GEMV); return SQE_E_ARG; }
+    if (nq == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("search_gemv_sharded: null output/workspace"); return SQE_E_ARG; }
+    XchgArgs x;
+    if (make_xchg_args(&x, rank, world, peer_buffers_host, capacity_entries, epoch, nq, k) != 0) return SQE_E_ARG;
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_topk_gemv(D, dtype, n, Q_raw, true, nq, k, out_score, out_idx, idx_offset, workspace,
+                          workspace_bytes, d.sm_count, static_cast<cudaStream_t>(stream), &x,
+                          (flags & SQE_FLAG_QUERIES_READY) != 0);
+    return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : rc == -3 ? SQE_E_WORKSPACE : SQE_E_CUDA);
+}
+
+int sqe_search_gemv_prefiltered(const void* D, int dtype, int64_t n, int dim, const void* D8, const void* meta,
+                                const float* Q_raw, int nq, int k, float* out_score, int64_t* out_idx,
+                                int64_t idx_offset, uint32_t* out_rescored, int rank, int world,
+                                void* const* peer_buffers_host, int64_t capacity_entries, uint32_t epoch,
+                                int flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_common("search_gemv_prefiltered", D, dtype, n, dim, Q_raw, nq);
+    if (rc != SQE_OK) return rc;
+    if (k < 1 || k > SQE_MAX_K_GEMV) { set_error("search_gemv_prefiltered: k=%d not in [1,%d]", k, SQE_MAX_K_GEMV); return SQE_E_ARG; }
+    if (nq > SQE_MAX_NQ_PREFILTER) { set_error("search_gemv_prefiltered: nq=%d > %d", nq, SQE_MAX_NQ_PREFILTER); return SQE_E_ARG; }
+    if (nq == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("search_gemv_prefiltered: null output/workspace"); return SQE_E_ARG; }
+    if (n > 0 && (!D8 || !meta || !aligned16(D8) || !aligned16(meta))) {
+        set_error("search_gemv_prefiltered: null or unaligned coarse rows");
+        return SQE_E_ARG;
+    }
+    XchgArgs x;
+    if (make_xchg_args(&x, rank, world, peer_buffers_host, capacity_entries, epoch, nq, k) != 0) return SQE_E_ARG;
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_topk_prefiltered(D, dtype, n, D8, meta, Q_raw, true, nq, k, out_score, out_idx, idx_offset,
+                                 out_rescored, workspace, workspace_bytes, d.sm_count,
+                                 static_cast<cudaStream_t>(stream), &x, (flags & SQE_FLAG_QUERIES_READY) != 0);
     return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : rc == -3 ? SQE_E_WORKSPACE : SQE_E_CUDA);
 }
 

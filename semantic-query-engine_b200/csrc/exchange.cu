@@ -25,37 +25,11 @@
 // cross-GPU step of the path.
 #include "sqe_common.cuh"
 #include "sqe_internal.h"
+#include "sqe_select.cuh"
 
 namespace sqe {
 
-constexpr int kMaxWorld = 16;
-constexpr int kXchgHeader = 256;
-constexpr int kXchgTicketWord = 32;          // u32 index of the local CTA ticket in the header
-
-struct PeerBufs {
-    char* p[kMaxWorld];
-};
-
-struct __align__(16) XRecord {
-    long long row;
-    float score;
-    unsigned pad;
-};
-
-// One system-scope fence orders ALL the pushes before ALL the flag stores, and one after the
-// poll loop orders the flag reads before the data reads; the flag accesses themselves are
-// relaxed.  (st.release.sys per peer = one full fence per peer: measured ~3 us each.)
-__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_acq_rel_sys() {
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-}
+// kMaxWorld, the header layout, PeerBufs, XRecord and the system-scope accessors: sqe_select.cuh
 
 template <int R>
 __global__ void __launch_bounds__(128)

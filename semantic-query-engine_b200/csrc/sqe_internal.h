@@ -9,20 +9,25 @@ namespace sqe {
 int launch_normalize_cast(const float* in, void* out, int64_t n, int out_dtype, int sm_count,
                           cudaStream_t stream);
 
+struct XchgArgs;             // sqe_select.cuh: fused exchange of the sharded mode (null = none)
+
 // K3
 int64_t gemv_workspace_bytes(int nq, int k, int sm_count);
+int make_xchg_args(XchgArgs* x, int rank, int world, void* const* peer_buffers, int64_t cap, unsigned epoch,
+                   int nq, int k);
 int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, bool raw_q, int nq, int k,
                      float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
-                     int64_t ws_bytes, int sm_count, cudaStream_t stream);
+                     int64_t ws_bytes, int sm_count, cudaStream_t stream, const XchgArgs* xchg = nullptr,
+                     bool pdl = false);
 
 // K3p  int8 prefilter + exact rescoring (topk_prefilter.cu)
 int launch_quantize_rows(const void* D, int dtype, int64_t n, void* D8, void* meta, int sm_count,
                          cudaStream_t stream);
 int64_t prefilter_workspace_bytes(int64_t n, int nq, int k, int sm_count);
 int launch_topk_prefiltered(const void* D, int dtype, int64_t n, const void* D8, const void* meta,
-                            const void* Q, int nq, int k, float* out_score, int64_t* out_idx,
+                            const void* Q, bool raw_q, int nq, int k, float* out_score, int64_t* out_idx,
                             int64_t idx_offset, unsigned* out_stats, void* ws, int64_t ws_bytes,
-                            int sm_count, cudaStream_t stream);
+                            int sm_count, cudaStream_t stream, const XchgArgs* xchg = nullptr, bool pdl = false);
 
 // K2
 int64_t batched_workspace_bytes(int64_t n, int b, int k, int sm_count);

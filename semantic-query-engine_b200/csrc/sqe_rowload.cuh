@@ -77,4 +77,41 @@ __device__ __forceinline__ void elem_group<Bf16x2>(const uint4* raw, int g, floa
     for (int e = 0; e < 8; ++e) f[e] = __fadd_rn(f[e], lo[e]);
 }
 
+// x rounded to the storage class and back to fp32: the value K1 would have stored
+template <typename T> __device__ __forceinline__ float round_through(float x);
+template <> __device__ __forceinline__ float round_through<Bf16x2>(float x) {
+    __nv_bfloat16 hi, lo;
+    split_bf16x2(x, hi, lo);
+    return __fadd_rn(__bfloat162float(hi), __bfloat162float(lo));
+}
+template <> __device__ __forceinline__ float round_through<float>(float x) { return x; }
+template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float x) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+}
+template <> __device__ __forceinline__ float round_through<__half>(float x) {
+    return __half2float(__float2half_rn(x));
+}
+
+// The scans' fused query normalisation (called by ONE warp): s_q[0..1023] = the RAW fp32 query
+// `src` normalised with the K1 arithmetic bit for bit (x / (|x| + 1e-9), app/main.py:353-354) and
+// rounded to the shard's storage class -- what K1 followed by a load of the stored query gives.
+// `s_tile` = 8 * kNormBlockStride floats of scratch.
+template <typename T>
+__device__ __forceinline__ void normalize_query_to_smem(const float* src, float* s_q, float* s_tile, int lane) {
+    float4 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = *reinterpret_cast<const float4*>(src + 128 * m + 4 * lane);
+    const float ss = warp_row_sumsq_numpy(v, s_tile, lane);
+    const float den = __fadd_rn(__fsqrt_rn(ss), 1e-9f);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float4 o;
+        o.x = round_through<T>(__fdiv_rn(v[m].x, den));
+        o.y = round_through<T>(__fdiv_rn(v[m].y, den));
+        o.z = round_through<T>(__fdiv_rn(v[m].z, den));
+        o.w = round_through<T>(__fdiv_rn(v[m].w, den));
+        *reinterpret_cast<float4*>(s_q + 128 * m + 4 * lane) = o;
+    }
+}
+
 }  // namespace sqe

@@ -25,25 +25,14 @@
 #include "sqe_common.cuh"
 #include "sqe_internal.h"
 #include "sqe_rowload.cuh"
+#include "sqe_select.cuh"
+
+#include <cstring>
 
 namespace sqe {
 
 constexpr int kGemvWarps = 8;
 constexpr int kGemvCtasPerSm = 2;
-
-template <typename T> __device__ __forceinline__ float round_through(float x);
-template <> __device__ __forceinline__ float round_through<Bf16x2>(float x) {
-    __nv_bfloat16 hi, lo;
-    split_bf16x2(x, hi, lo);
-    return __fadd_rn(__bfloat162float(hi), __bfloat162float(lo));
-}
-template <> __device__ __forceinline__ float round_through<float>(float x) { return x; }
-template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float x) {
-    return __bfloat162float(__float2bfloat16_rn(x));
-}
-template <> __device__ __forceinline__ float round_through<__half>(float x) {
-    return __half2float(__float2half_rn(x));
-}
 
 // RAWQ: `Qv` holds the RAW fp32 query embeddings; every CTA normalises its query itself
 // (x / (|x| + 1e-9), the K1 arithmetic bit for bit, app/main.py:353-354) and rounds it to the
@@ -53,7 +42,7 @@ __global__ void __launch_bounds__(kGemvWarps * 32, kGemvCtasPerSm)
 topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv, int k,
                  uint64_t* __restrict__ ws_lists, unsigned* __restrict__ ws_counter,
                  float* __restrict__ out_score, int64_t* __restrict__ out_idx,
-                 int64_t idx_offset) {
+                 int64_t idx_offset, const XchgArgs xchg) {
     using E = Elem<T>;
     constexpr int LOADS = E::kLoads;
     constexpr int PER = E::kPer;
@@ -77,23 +66,9 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
     if constexpr (RAWQ) {
         __shared__ __align__(16) float s_tile[8 * kNormBlockStride];
         __shared__ __align__(16) float s_q[kDim];
-        if (warp == 0) {
-            const float* src = static_cast<const float*>(Qv) + static_cast<int64_t>(query) * kDim;
-            float4 v[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = *reinterpret_cast<const float4*>(src + 128 * m + 4 * lane);
-            const float ss = warp_row_sumsq_numpy(v, s_tile, lane);
-            const float den = __fadd_rn(__fsqrt_rn(ss), 1e-9f);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                float4 o;
-                o.x = round_through<T>(__fdiv_rn(v[m].x, den));
-                o.y = round_through<T>(__fdiv_rn(v[m].y, den));
-                o.z = round_through<T>(__fdiv_rn(v[m].z, den));
-                o.w = round_through<T>(__fdiv_rn(v[m].w, den));
-                *reinterpret_cast<float4*>(s_q + 128 * m + 4 * lane) = o;
-            }
-        }
+        if (warp == 0)
+            normalize_query_to_smem<T>(static_cast<const float*>(Qv) + static_cast<int64_t>(query) * kDim, s_q,
+                                       s_tile, lane);
         __syncthreads();
 #pragma unroll
         for (int g = 0; g < QG; ++g)
@@ -167,67 +142,18 @@ topk_gemv_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv
         }
     }
 
-    // ---- CTA merge: 8 warp lists -> 1 ----
-    list.store(s_lists[warp], lane);
-    __syncthreads();
-    uint64_t* my_slot = ws_lists + (static_cast<int64_t>(query) * nctas + cta) * L;
-    if (warp == 0) {
-#pragma unroll 1
-        for (int w = 1; w < kGemvWarps; ++w) {
-            WarpList<R> other;
-            other.load(s_lists[w], lane);
-            list.merge_sorted(other.key, lane);
-        }
-        list.store(my_slot, lane);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned ticket = atomicAdd(ws_counter + query, 1u);
-            s_is_last = (ticket == static_cast<unsigned>(nctas) - 1) ? 1 : 0;
-        }
-    }
-    __syncthreads();
-    if (!s_is_last) return;
+    // the scan is over: the next scan of the stream may start, and everything below touches
+    // memory shared with earlier kernels (sqe_select.cuh)
+    pdl_launch_dependents();
+    pdl_wait();
 
-    // ---- grid merge by the last CTA of this query ----
-    __threadfence();
-    const uint64_t* all = ws_lists + static_cast<int64_t>(query) * nctas * L;
-    list.clear();
-    {
-        // each warp folds every 8th CTA list; the next list is fetched while the current merges
-        uint64_t nxt[R];
-        int c = warp;
-        if (c < nctas) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(c) * L + r * 32 + lane);
-        }
-        while (c < nctas) {
-            WarpList<R> other;
-#pragma unroll
-            for (int r = 0; r < R; ++r) other.key[r] = nxt[r];
-            const int cn = c + kGemvWarps;
-            if (cn < nctas) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(cn) * L + r * 32 + lane);
-            }
-            list.merge_sorted(other.key, lane);
-            c = cn;
-        }
-    }
-    __syncthreads();                                   // s_lists reuse
-    list.store(s_lists[warp], lane);
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll 1
-        for (int w = 1; w < kGemvWarps; ++w) {
-            WarpList<R> other;
-            other.load(s_lists[w], lane);
-            list.merge_sorted(other.key, lane);
-        }
-        emit_topk<R>(list, k, lane, out_score + static_cast<int64_t>(query) * k,
-                     out_idx + static_cast<int64_t>(query) * k, idx_offset);
-        if (lane == 0) ws_counter[query] = 0u;
-    }
+    // ---- 8 warp lists -> CTA list -> the query's last CTA merges all CTA lists (sqe_select.cuh);
+    // in the sharded mode that same warp also exchanges the result with the other ranks ----
+    if (!merge_cta_and_grid<R, kGemvWarps>(list, s_lists, &s_is_last, ws_lists, ws_counter + query, query, cta,
+                                           nctas, warp, lane))
+        return;
+    finish_query<R>(list, k, query, lane, out_score, out_idx, idx_offset, xchg);
+    if (lane == 0) ws_counter[query] = 0u;
 }
 
 static inline int r_for_k(int k) { return k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 8; }
@@ -253,7 +179,7 @@ int64_t gemv_workspace_bytes(int nq, int k, int sm_count) {
 template <typename T, int R>
 static int launch_gemv_t(const void* D, int64_t n, const void* Q, bool raw_q, int nq, int k,
                          float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws, int sm_count,
-                         cudaStream_t stream) {
+                         const XchgArgs& xchg, bool pdl, cudaStream_t stream) {
     constexpr int RPW = 16 / Elem<T>::kLoads;
     const int gx = gemv_grid_x(n, sm_count, RPW);
     unsigned* ws_counter = static_cast<unsigned*>(ws);
@@ -263,14 +189,22 @@ static int launch_gemv_t(const void* D, int64_t n, const void* Q, bool raw_q, in
         e = cudaMemsetAsync(ws_counter, 0, static_cast<size_t>(nq) * 4, stream);
         if (e != cudaSuccess) { set_error("gemv: memset: %s", cudaGetErrorString(e)); return -2; }
     }
-    dim3 grid(nq, gx), block(kGemvWarps * 32);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nq, gx);
+    cfg.blockDim = dim3(kGemvWarps * 32);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && raw_q) ? 1 : 0;          // only the raw-query form may start early
+    const T* Dp = static_cast<const T*>(D);
     if (raw_q)
-        topk_gemv_kernel<T, R, true><<<grid, block, 0, stream>>>(
-            static_cast<const T*>(D), n, Q, k, ws_lists, ws_counter, out_score, out_idx, idx_offset);
+        e = cudaLaunchKernelEx(&cfg, topk_gemv_kernel<T, R, true>, Dp, n, Q, k, ws_lists, ws_counter, out_score,
+                               out_idx, idx_offset, xchg);
     else
-        topk_gemv_kernel<T, R, false><<<grid, block, 0, stream>>>(
-            static_cast<const T*>(D), n, Q, k, ws_lists, ws_counter, out_score, out_idx, idx_offset);
-    e = cudaGetLastError();
+        e = cudaLaunchKernelEx(&cfg, topk_gemv_kernel<T, R, false>, Dp, n, Q, k, ws_lists, ws_counter, out_score,
+                               out_idx, idx_offset, xchg);
     if (e != cudaSuccess) { set_error("gemv: launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
 }
@@ -278,28 +212,49 @@ static int launch_gemv_t(const void* D, int64_t n, const void* Q, bool raw_q, in
 template <typename T>
 static int launch_gemv_r(const void* D, int64_t n, const void* Q, bool raw_q, int nq, int k, float* out_score,
                          int64_t* out_idx, int64_t idx_offset, void* ws, int sm_count,
-                         cudaStream_t stream) {
+                         const XchgArgs& xchg, bool pdl, cudaStream_t stream) {
     switch (r_for_k(k)) {
-        case 1: return launch_gemv_t<T, 1>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 2: return launch_gemv_t<T, 2>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 4: return launch_gemv_t<T, 4>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        default: return launch_gemv_t<T, 8>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 1: return launch_gemv_t<T, 1>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, xchg, pdl, stream);
+        case 2: return launch_gemv_t<T, 2>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, xchg, pdl, stream);
+        case 4: return launch_gemv_t<T, 4>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, xchg, pdl, stream);
+        default: return launch_gemv_t<T, 8>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, xchg, pdl, stream);
     }
+}
+
+int make_xchg_args(XchgArgs* x, int rank, int world, void* const* peer_buffers, int64_t cap, unsigned epoch,
+                   int nq, int k) {
+    memset(x, 0, sizeof(*x));
+    if (world <= 1 || peer_buffers == nullptr) return 0;
+    if (world > kMaxWorld || rank < 0 || rank >= world) { set_error("exchange: bad rank %d / world %d", rank, world); return -1; }
+    if (nq > kXchgFusedQueries) { set_error("fused exchange: at most %d queries per call (got %d)", kXchgFusedQueries, nq); return -1; }
+    if (cap < static_cast<int64_t>(nq) * k) { set_error("exchange: capacity %lld < %d entries", (long long)cap, nq * k); return -1; }
+    for (int g = 0; g < world; ++g) {
+        if (!peer_buffers[g]) { set_error("exchange: peer buffer %d is null", g); return -1; }
+        x->peers.p[g] = static_cast<char*>(peer_buffers[g]);
+    }
+    x->cap = cap;
+    x->rank = rank;
+    x->world = world;
+    x->epoch = epoch;
+    return 0;
 }
 
 int launch_topk_gemv(const void* D, int dtype, int64_t n, const void* Q, bool raw_q, int nq, int k,
                      float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
-                     int64_t ws_bytes, int sm_count, cudaStream_t stream) {
+                     int64_t ws_bytes, int sm_count, cudaStream_t stream, const XchgArgs* xchg, bool pdl) {
     if (ws_bytes < gemv_workspace_bytes(nq, k, sm_count)) {
         set_error("gemv: workspace %lld < %lld bytes", (long long)ws_bytes,
                   (long long)gemv_workspace_bytes(nq, k, sm_count));
         return -3;
     }
+    XchgArgs none;
+    memset(&none, 0, sizeof(none));
+    const XchgArgs& x = xchg ? *xchg : none;
     switch (dtype) {
-        case 0: return launch_gemv_r<float>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 1: return launch_gemv_r<__nv_bfloat16>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 2: return launch_gemv_r<__half>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
-        case 3: return launch_gemv_r<Bf16x2>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, stream);
+        case 0: return launch_gemv_r<float>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, x, pdl, stream);
+        case 1: return launch_gemv_r<__nv_bfloat16>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, x, pdl, stream);
+        case 2: return launch_gemv_r<__half>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, x, pdl, stream);
+        case 3: return launch_gemv_r<Bf16x2>(D, n, Q, raw_q, nq, k, out_score, out_idx, idx_offset, ws, sm_count, x, pdl, stream);
         default: set_error("gemv: bad dtype %d", dtype); return -1;
     }
 }

@@ -33,6 +33,9 @@
 #include "sqe_common.cuh"
 #include "sqe_internal.h"
 #include "sqe_rowload.cuh"
+#include "sqe_select.cuh"
+
+#include <cstring>
 
 namespace sqe {
 
@@ -134,72 +137,6 @@ quantize_rows_kernel(const T* __restrict__ D, int64_t n, int8_t* __restrict__ D8
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// shared tail of both passes: 8 warp lists -> CTA list -> (last CTA of the query) all CTA lists
-// Returns true in warp 0 of the last CTA, with `list` = the merged result.
-// ------------------------------------------------------------------------------------------
-template <int R>
-__device__ __forceinline__ bool merge_cta_and_grid(WarpList<R>& list, uint64_t (*s_lists)[32 * R],
-                                                   int* s_is_last, uint64_t* ws_lists,
-                                                   unsigned* counter, int query, int cta, int nctas,
-                                                   int warp, int lane) {
-    constexpr int L = 32 * R;
-    list.store(s_lists[warp], lane);
-    __syncthreads();
-    uint64_t* my_slot = ws_lists + (static_cast<int64_t>(query) * nctas + cta) * L;
-    if (warp == 0) {
-#pragma unroll 1
-        for (int w = 1; w < pf::kWarps; ++w) {
-            WarpList<R> other;
-            other.load(s_lists[w], lane);
-            list.merge_sorted(other.key, lane);
-        }
-        list.store(my_slot, lane);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned ticket = atomicAdd(counter, 1u);
-            *s_is_last = (ticket == static_cast<unsigned>(nctas) - 1) ? 1 : 0;
-        }
-    }
-    __syncthreads();
-    if (!*s_is_last) return false;
-    __threadfence();
-    const uint64_t* all = ws_lists + static_cast<int64_t>(query) * nctas * L;
-    list.clear();
-    {
-        uint64_t nxt[R];
-        int c = warp;
-        if (c < nctas) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(c) * L + r * 32 + lane);
-        }
-        while (c < nctas) {
-            WarpList<R> other;
-#pragma unroll
-            for (int r = 0; r < R; ++r) other.key[r] = nxt[r];
-            const int cn = c + pf::kWarps;
-            if (cn < nctas) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) nxt[r] = __ldcg(all + static_cast<int64_t>(cn) * L + r * 32 + lane);
-            }
-            list.merge_sorted(other.key, lane);
-            c = cn;
-        }
-    }
-    __syncthreads();
-    list.store(s_lists[warp], lane);
-    __syncthreads();
-    if (warp != 0) return false;
-#pragma unroll 1
-    for (int w = 1; w < pf::kWarps; ++w) {
-        WarpList<R> other;
-        other.load(s_lists[w], lane);
-        list.merge_sorted(other.key, lane);
-    }
-    return true;
-}
-
 // value of element i of a stored query row as fp32 (hi + lo for split bf16)
 template <typename T> __device__ __forceinline__ float stored_elem(const T* q, int i);
 template <> __device__ __forceinline__ float stored_elem<float>(const float* q, int i) { return q[i]; }
@@ -229,10 +166,12 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
 // ------------------------------------------------------------------------------------------
 // pass A: int8 scan.  grid = (queries, CTAs per query), query fast (rows shared through L2).
 // ------------------------------------------------------------------------------------------
-template <typename T, int R>
+// RAWQ: `Qv` holds RAW fp32 queries; every CTA normalises its query itself (K1's arithmetic bit for
+// bit, sqe_rowload.cuh) -- the K1 launch in front of a one-query search disappears.
+template <typename T, int R, bool RAWQ>
 __global__ void __launch_bounds__(pf::kWarps * 32, pf::kCtasPerSm)
 coarse_scan_kernel(const int8_t* __restrict__ D8, const float4* __restrict__ meta, int64_t n,
-                   const T* __restrict__ Q, int k, uint64_t* __restrict__ ws_lists,
+                   const void* __restrict__ Qv, int k, uint64_t* __restrict__ ws_lists,
                    unsigned* __restrict__ ws_counter, float* __restrict__ ws_tau,
                    unsigned* __restrict__ ws_stats, float* __restrict__ U) {
     constexpr int L = 32 * R;
@@ -249,12 +188,21 @@ coarse_scan_kernel(const int8_t* __restrict__ D8, const float4* __restrict__ met
     const int nctas = gridDim.y;
 
     // ---- quantise the query: q = sq q8 + eq ----
-    const T* qrow = Q + static_cast<int64_t>(query) * Elem<T>::kRowElems;
+    [[maybe_unused]] __shared__ __align__(16) float s_qf[RAWQ ? kDim : 4];
+    [[maybe_unused]] __shared__ __align__(16) float s_tile[RAWQ ? 8 * kNormBlockStride : 4];
+    if constexpr (RAWQ) {
+        if (warp == 0)
+            normalize_query_to_smem<T>(static_cast<const float*>(Qv) + static_cast<int64_t>(query) * kDim, s_qf,
+                                       s_tile, lane);
+        __syncthreads();
+    }
+    const T* qrow = static_cast<const T*>(Qv) + static_cast<int64_t>(query) * Elem<T>::kRowElems;
     float qv[kDim / (pf::kWarps * 32)];
     float mx = 0.f, ss = 0.f;
 #pragma unroll
     for (int j = 0; j < kDim / (pf::kWarps * 32); ++j) {
-        qv[j] = stored_elem<T>(qrow, j * (pf::kWarps * 32) + threadIdx.x);
+        if constexpr (RAWQ) qv[j] = s_qf[j * (pf::kWarps * 32) + threadIdx.x];
+        else qv[j] = stored_elem<T>(qrow, j * (pf::kWarps * 32) + threadIdx.x);
         mx = fmaxf(mx, fabsf(qv[j]));
         ss = fmaf(qv[j], qv[j], ss);
     }
@@ -355,7 +303,9 @@ coarse_scan_kernel(const int8_t* __restrict__ D8, const float4* __restrict__ met
         }
     }
 
-    if (!merge_cta_and_grid<R>(list, s_lists, &s_is_last, ws_lists, ws_counter + query, query, cta, nctas, warp, lane))
+    pdl_launch_dependents();                       // the rescoring pass may be scheduled (it waits at its top)
+    pdl_wait();                                    // lists / tickets / tau are shared with earlier kernels
+    if (!merge_cta_and_grid<R, pf::kWarps>(list, s_lists, &s_is_last, ws_lists, ws_counter + query, query, cta, nctas, warp, lane))
         return;
     // last CTA, warp 0: tau = the k-th best lower bound (-inf while fewer than k rows exist)
     uint64_t kth_src = 0ull;
@@ -373,13 +323,14 @@ coarse_scan_kernel(const int8_t* __restrict__ D8, const float4* __restrict__ met
 // ------------------------------------------------------------------------------------------
 // pass B: rescore every row the bound cannot rule out with K3's arithmetic, select the top-k
 // ------------------------------------------------------------------------------------------
-template <typename T, int R>
+template <typename T, int R, bool RAWQ>
 __global__ void __launch_bounds__(pf::kWarps * 32, pf::kCtasPerSm)
-rescore_kernel(const T* __restrict__ D, int64_t n, const T* __restrict__ Q, int k,
+rescore_kernel(const T* __restrict__ D, int64_t n, const void* __restrict__ Qv, int k,
                const float* __restrict__ U, const float* __restrict__ ws_tau,
                unsigned* __restrict__ ws_stats, uint64_t* __restrict__ ws_lists,
                unsigned* __restrict__ ws_counter, float* __restrict__ out_score,
-               int64_t* __restrict__ out_idx, int64_t idx_offset, unsigned* __restrict__ out_stats) {
+               int64_t* __restrict__ out_idx, int64_t idx_offset, unsigned* __restrict__ out_stats,
+               const XchgArgs xchg) {
     using E = Elem<T>;
     constexpr int LOADS = E::kLoads;
     constexpr int PER = E::kPer;
@@ -397,8 +348,19 @@ rescore_kernel(const T* __restrict__ D, int64_t n, const T* __restrict__ Q, int 
 
     // the query in registers, the element layout of a row's loads (= K3, stored-query form)
     float q[32];
-    {
-        const T* qp = Q + static_cast<int64_t>(query) * E::kRowElems + lane * PER;
+    if constexpr (RAWQ) {
+        __shared__ __align__(16) float s_tile[8 * kNormBlockStride];
+        __shared__ __align__(16) float s_q[kDim];
+        if (warp == 0)
+            normalize_query_to_smem<T>(static_cast<const float*>(Qv) + static_cast<int64_t>(query) * kDim, s_q,
+                                       s_tile, lane);
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < QG; ++g)
+#pragma unroll
+            for (int e = 0; e < PER; ++e) q[g * PER + e] = s_q[g * (32 * PER) + lane * PER + e];
+    } else {
+        const T* qp = static_cast<const T*>(Qv) + static_cast<int64_t>(query) * E::kRowElems + lane * PER;
         uint4 qraw[LOADS];
 #pragma unroll
         for (int c = 0; c < LOADS; ++c) qraw[c] = *reinterpret_cast<const uint4*>(qp + E::load_off(c));
@@ -410,6 +372,7 @@ rescore_kernel(const T* __restrict__ D, int64_t n, const T* __restrict__ Q, int 
             for (int e = 0; e < PER; ++e) q[g * PER + e] = f[e];
         }
     }
+    pdl_wait();                                    // tau and U come from the scan pass in front of this one
     const float tau = ws_tau[query];
     const float* Uq = U + static_cast<int64_t>(query) * n;
 
@@ -481,11 +444,11 @@ rescore_kernel(const T* __restrict__ D, int64_t n, const T* __restrict__ Q, int 
         }
     }
     if (lane == 0 && rescored) atomicAdd(ws_stats + query, rescored);
+    pdl_launch_dependents();                       // U has been read: the next query's scan pass may overwrite it
 
-    if (!merge_cta_and_grid<R>(list, s_lists, &s_is_last, ws_lists, ws_counter + query, query, cta, nctas, warp, lane))
+    if (!merge_cta_and_grid<R, pf::kWarps>(list, s_lists, &s_is_last, ws_lists, ws_counter + query, query, cta, nctas, warp, lane))
         return;
-    emit_topk<R>(list, k, lane, out_score + static_cast<int64_t>(query) * k,
-                 out_idx + static_cast<int64_t>(query) * k, idx_offset);
+    finish_query<R>(list, k, query, lane, out_score, out_idx, idx_offset, xchg);
     if (lane == 0) {
         ws_counter[query] = 0u;
         if (out_stats) out_stats[query] = atomicAdd(ws_stats + query, 0u);
@@ -535,46 +498,70 @@ int launch_quantize_rows(const void* D, int dtype, int64_t n, void* D8, void* me
 
 template <typename T, int R>
 static int launch_prefiltered_t(const void* D, int64_t n, const void* D8, const void* meta, const void* Q,
-                                int nq, int k, float* out_score, int64_t* out_idx, int64_t idx_offset,
-                                unsigned* out_stats, void* ws, int sm_count, cudaStream_t stream) {
+                                bool raw_q, int nq, int k, float* out_score, int64_t* out_idx, int64_t idx_offset,
+                                unsigned* out_stats, void* ws, int sm_count, const XchgArgs& xchg, bool pdl,
+                                cudaStream_t stream) {
     char* w = static_cast<char*>(ws);
     unsigned* counters = reinterpret_cast<unsigned*>(w + pf::kOffCounters);
     float* tau = reinterpret_cast<float*>(w + pf::kOffTau);
     unsigned* stats = reinterpret_cast<unsigned*>(w + pf::kOffStats);
     uint64_t* lists = reinterpret_cast<uint64_t*>(w + pf::kOffLists);
     float* U = reinterpret_cast<float*>(w + pf_u_offset(nq, k, sm_count));
-    dim3 block(pf::kWarps * 32);
-    dim3 ga(nq, pf_grid_y(pf::kWarps * pf::kRowsPerIter, n, sm_count));
-    coarse_scan_kernel<T, R><<<ga, block, 0, stream>>>(
-        static_cast<const int8_t*>(D8), static_cast<const float4*>(meta), n, static_cast<const T*>(Q), k,
-        lists, counters, tau, stats, U);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(pf::kWarps * 32);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    const int8_t* d8 = static_cast<const int8_t*>(D8);
+    const float4* mt = static_cast<const float4*>(meta);
+    const T* Dp = static_cast<const T*>(D);
+    const float* Uc = U;
+    const float* tauc = tau;
+    cudaError_t e;
+    // pass A may start while the previous kernel of the stream is in its tail only when the caller
+    // vouches for the queries (raw-query form); pass B may always be SCHEDULED early: it waits for
+    // pass A at its top, which hides its launch latency
+    cfg.gridDim = dim3(nq, pf_grid_y(pf::kWarps * pf::kRowsPerIter, n, sm_count));
+    cfg.numAttrs = (pdl && raw_q) ? 1 : 0;
+    if (raw_q)
+        e = cudaLaunchKernelEx(&cfg, coarse_scan_kernel<T, R, true>, d8, mt, n, Q, k, lists, counters, tau, stats, U);
+    else
+        e = cudaLaunchKernelEx(&cfg, coarse_scan_kernel<T, R, false>, d8, mt, n, Q, k, lists, counters, tau, stats, U);
     if (e != cudaSuccess) { set_error("prefiltered: scan launch: %s", cudaGetErrorString(e)); return -2; }
-    dim3 gb(nq, pf_grid_y(pf::kWarps * 32 * 8, n, sm_count));
-    rescore_kernel<T, R><<<gb, block, 0, stream>>>(
-        static_cast<const T*>(D), n, static_cast<const T*>(Q), k, U, tau, stats, lists, counters,
-        out_score, out_idx, idx_offset, out_stats);
-    e = cudaGetLastError();
+    cfg.gridDim = dim3(nq, pf_grid_y(pf::kWarps * 32 * 8, n, sm_count));
+    cfg.numAttrs = 1;
+    if (raw_q)
+        e = cudaLaunchKernelEx(&cfg, rescore_kernel<T, R, true>, Dp, n, Q, k, Uc, tauc, stats, lists, counters,
+                               out_score, out_idx, idx_offset, out_stats, xchg);
+    else
+        e = cudaLaunchKernelEx(&cfg, rescore_kernel<T, R, false>, Dp, n, Q, k, Uc, tauc, stats, lists, counters,
+                               out_score, out_idx, idx_offset, out_stats, xchg);
     if (e != cudaSuccess) { set_error("prefiltered: rescore launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
 }
 
 template <typename T>
 static int launch_prefiltered_r(const void* D, int64_t n, const void* D8, const void* meta, const void* Q,
-                                int nq, int k, float* out_score, int64_t* out_idx, int64_t idx_offset,
-                                unsigned* out_stats, void* ws, int sm_count, cudaStream_t stream) {
+                                bool raw_q, int nq, int k, float* out_score, int64_t* out_idx, int64_t idx_offset,
+                                unsigned* out_stats, void* ws, int sm_count, const XchgArgs& xchg, bool pdl,
+                                cudaStream_t stream) {
     switch (pf_r_for_k(k)) {
-        case 1: return launch_prefiltered_t<T, 1>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
-        case 2: return launch_prefiltered_t<T, 2>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
-        case 4: return launch_prefiltered_t<T, 4>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
-        default: return launch_prefiltered_t<T, 8>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
+        case 1: return launch_prefiltered_t<T, 1>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
+        case 2: return launch_prefiltered_t<T, 2>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
+        case 4: return launch_prefiltered_t<T, 4>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
+        default: return launch_prefiltered_t<T, 8>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
     }
 }
 
 int launch_topk_prefiltered(const void* D, int dtype, int64_t n, const void* D8, const void* meta,
-                            const void* Q, int nq, int k, float* out_score, int64_t* out_idx,
+                            const void* Q, bool raw_q, int nq, int k, float* out_score, int64_t* out_idx,
                             int64_t idx_offset, unsigned* out_stats, void* ws, int64_t ws_bytes,
-                            int sm_count, cudaStream_t stream) {
+                            int sm_count, cudaStream_t stream, const XchgArgs* xchg_in, bool pdl) {
+    XchgArgs none;
+    memset(&none, 0, sizeof(none));
+    const XchgArgs& xchg = xchg_in ? *xchg_in : none;
     if (nq > pf::kMaxQueries) { set_error("prefiltered: at most %d queries per call", pf::kMaxQueries); return -1; }
     if (ws_bytes < prefilter_workspace_bytes(n, nq, k, sm_count)) {
         set_error("prefiltered: workspace %lld < %lld bytes", (long long)ws_bytes,
@@ -582,10 +569,10 @@ int launch_topk_prefiltered(const void* D, int dtype, int64_t n, const void* D8,
         return -3;
     }
     switch (dtype) {
-        case 0: return launch_prefiltered_r<float>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
-        case 1: return launch_prefiltered_r<__nv_bfloat16>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
-        case 2: return launch_prefiltered_r<__half>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
-        case 3: return launch_prefiltered_r<Bf16x2>(D, n, D8, meta, Q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, stream);
+        case 0: return launch_prefiltered_r<float>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
+        case 1: return launch_prefiltered_r<__nv_bfloat16>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
+        case 2: return launch_prefiltered_r<__half>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
+        case 3: return launch_prefiltered_r<Bf16x2>(D, n, D8, meta, Q, raw_q, nq, k, out_score, out_idx, idx_offset, out_stats, ws, sm_count, xchg, pdl, stream);
         default: set_error("prefiltered: bad dtype %d", dtype); return -1;
     }
 }

@@ -134,12 +134,30 @@ def topk_gemv(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
     return scores, idx
 
 
+def _xchg_args(xchg, nq: int, k: int):
+    """`xchg = (rank, peer pointers, capacity_entries, epoch)` -> the trailing C arguments of the
+    sharded entry points (rank, world, peer_buffers_host, capacity_entries, epoch)."""
+    if xchg is None:
+        return 0, 1, None, 0, 0
+    rank, peer_ptrs, cap, epoch = xchg
+    world = len(peer_ptrs)
+    if nq > nat.SQE_MAX_NQ_FUSED_EXCHANGE:
+        raise ValueError(f"the fused exchange takes at most {nat.SQE_MAX_NQ_FUSED_EXCHANGE} queries per call")
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    return int(rank), world, arr, int(cap), int(epoch) & 0xFFFFFFFF
+
+
 def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 0,
-                n: Optional[int] = None, out=None, ws: Optional[torch.Tensor] = None
-                ) -> Tuple[torch.Tensor, torch.Tensor]:
+                n: Optional[int] = None, out=None, ws: Optional[torch.Tensor] = None, xchg=None,
+                queries_ready: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """K1 (query side) + K3 in one launch: `q_raw` fp32 [nq,1024] un-normalised.  `ws`: a private
     workspace (zero-initialised uint8 tensor) instead of the per-stream one -- a captured CUDA
-    graph must own the memory its kernel uses."""
+    graph must own the memory its kernel uses.  `xchg = (rank, peer pointers, capacity, epoch)`:
+    the sharded form -- the query's last CTA also exchanges the rank-local list with the other
+    ranks and the outputs are the GLOBAL top-k (`sqe_search_gemv_sharded`, nq <= 2).
+    `queries_ready=True`: the caller states that `q_raw` was complete before the previous kernel
+    on this stream was launched (a resident tensor, not the output of the kernel just before
+    this call); the scan may then overlap the tail of the previous scan (SQE_FLAG_QUERIES_READY)."""
     dev = _require_cuda(D, q_raw)
     if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
         raise ValueError("q_raw must be fp32 [nq,1024]")
@@ -158,8 +176,55 @@ def search_gemv(D: torch.Tensor, q_raw: torch.Tensor, k: int, idx_offset: int = 
             ws = _workspace(dev, "gemv", need)
         elif ws.numel() < need or ws.device != dev or ws.dtype != torch.uint8:
             raise ValueError("bad private workspace")
-        nat.call("sqe_search_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
-                 q_raw.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+        if xchg is None and not queries_ready:
+            nat.call("sqe_search_gemv", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
+                     q_raw.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+                     ws.data_ptr(), ws.numel(), _stream(dev))
+        else:
+            nat.call("sqe_search_gemv_sharded", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows, nat.SQE_DIM,
+                     q_raw.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+                     *_xchg_args(xchg, b, k), nat.SQE_FLAG_QUERIES_READY if queries_ready else 0,
+                     ws.data_ptr(), ws.numel(), _stream(dev))
+    return scores, idx
+
+
+def search_gemv_prefiltered(D: torch.Tensor, D8: torch.Tensor, meta: torch.Tensor, q_raw: torch.Tensor,
+                            k: int, idx_offset: int = 0, n: Optional[int] = None, out=None,
+                            rescored: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
+                            xchg=None, queries_ready: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1 (query side) + K3p in two launches (no separate normalise launch): `q_raw` fp32 [nq,1024]
+    un-normalised; both passes normalise the query themselves.  Bit-identical to `normalize_cast`
+    + `topk_gemv_prefiltered`.  `xchg`: as in `search_gemv` (the exchange rides in the rescoring
+    pass's last CTA)."""
+    dev = _require_cuda(D, D8, meta, q_raw)
+    if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
+        raise ValueError("q_raw must be fp32 [nq,1024]")
+    if D.dim() != 2 or D.shape[1] != ROW_ELEMS[dtype_name(D)]:
+        raise ValueError("D must be [rows,1024] (or [rows,2048] bf16 for split bf16)")
+    rows = D.shape[0] if n is None else int(n)
+    if rows > D.shape[0]:
+        raise ValueError("n exceeds shard rows")
+    if D8.dtype != torch.int8 or meta.dtype != torch.float32 or D8.dim() != 2 or meta.dim() != 2 or \
+            D8.shape[1] != nat.SQE_DIM or meta.shape[1] != 4 or D8.shape[0] < rows or meta.shape[0] < rows:
+        raise ValueError("coarse rows must be int8 [rows,1024] + fp32 [rows,4] (ops.quantize_rows)")
+    b = q_raw.shape[0]
+    if b > nat.SQE_MAX_NQ_PREFILTER:
+        raise ValueError(f"at most {nat.SQE_MAX_NQ_PREFILTER} queries per call")
+    scores, idx = _outputs(out, dev, b, k)
+    if b == 0:
+        return scores, idx
+    if rescored is not None and (rescored.dtype != torch.int32 or rescored.numel() < b or not rescored.is_cuda):
+        raise ValueError("`rescored` must be an int32 CUDA tensor [nq]")
+    with _launch_lock, torch.cuda.device(dev):
+        need = nat.load().sqe_topk_gemv_prefiltered_workspace_bytes(rows, b, k)
+        if ws is None:
+            ws = _workspace(dev, "prefilter", need)
+        elif ws.numel() < need or ws.device != dev or ws.dtype != torch.uint8:
+            raise ValueError("bad private workspace")
+        nat.call("sqe_search_gemv_prefiltered", D.data_ptr(), nat.DTYPE_CODES[dtype_name(D)], rows,
+                 nat.SQE_DIM, D8.data_ptr(), meta.data_ptr(), q_raw.data_ptr(), b, k, scores.data_ptr(),
+                 idx.data_ptr(), idx_offset, rescored.data_ptr() if rescored is not None else None,
+                 *_xchg_args(xchg, b, k), nat.SQE_FLAG_QUERIES_READY if queries_ready else 0,
                  ws.data_ptr(), ws.numel(), _stream(dev))
     return scores, idx
 
@@ -339,7 +404,7 @@ class SingleQueryGraph:
     The shard pointer, row count, k and row offset are baked in: build a new one when they change."""
 
     def __init__(self, shard: torch.Tensor, rows: int, k: int, idx_offset: int = 0, coarse=None):
-        """`coarse = (D8, meta, dtype name)`: capture the prefiltered scan (K1 + K3p) instead of the
+        """`coarse = (D8, meta, dtype name)`: capture the prefiltered scan (K3p, raw-query form) instead of the
         fused exact scan; same results, about half the bytes per replay."""
         dev = shard.device
         self.coarse = coarse
@@ -359,7 +424,6 @@ class SingleQueryGraph:
             need = nat.load().sqe_topk_gemv_workspace_bytes(1, self.k)
         else:
             need = nat.load().sqe_topk_gemv_prefiltered_workspace_bytes(self.rows, 1, self.k)
-            self.dev_qn = torch.empty((1, ROW_ELEMS[coarse[2]]), dtype=TORCH_DTYPES[coarse[2]], device=dev)
         self._ws = torch.zeros((int(need),), dtype=torch.uint8, device=dev)
         self.host_q.zero_()
         with torch.cuda.device(dev):
@@ -379,9 +443,8 @@ class SingleQueryGraph:
     def _body(self) -> None:
         self.dev_q.copy_(self.host_q, non_blocking=True)
         if self.coarse is not None:
-            normalize_cast(self.dev_q, self.coarse[2], out=self.dev_qn)
-            topk_gemv_prefiltered(self._shard, self.coarse[0], self.coarse[1], self.dev_qn, self.k,
-                                  idx_offset=self.idx_offset, n=self.rows, out=(self.scores, self.idx), ws=self._ws)
+            search_gemv_prefiltered(self._shard, self.coarse[0], self.coarse[1], self.dev_q, self.k,
+                                    idx_offset=self.idx_offset, n=self.rows, out=(self.scores, self.idx), ws=self._ws)
         else:
             search_gemv(self._shard, self.dev_q, self.k, idx_offset=self.idx_offset, n=self.rows,
                         out=(self.scores, self.idx), ws=self._ws)
@@ -391,7 +454,7 @@ class SingleQueryGraph:
         """q_row: fp32 [1024] (raw).  Returns (scores [k] fp32, rows [k] int64) as fresh arrays."""
         self._np_q[0, :] = q_row
         self.graph.replay()
-        nat.launch_count += 1 if self.coarse is None else 3    # the replayed sqe_search_gemv | K1 + K3p
+        nat.launch_count += 1 if self.coarse is None else 2    # the replayed sqe_search_gemv | K3p (two passes)
         torch.cuda.current_stream(self.device).synchronize()
         k = self.k
         return self._np_out[k * 8:].view(np.float32).copy(), self._np_out[: k * 8].view(np.int64).copy()

@@ -58,6 +58,8 @@ class ShardedCorpusIndex:
         self.total_rows = 0
         self._gather_s = None
         self._gather_i = None
+        self.fuse_small_batches = True  # b <= 2: exchange fused into the scan kernel (p2p mode only)
+        self._fuse_ok = {}              # batch size -> every rank's local index can carry the exchange
 
     # ------------------------------------------------------------------ layout
     def finalize(self, local_rows: Optional[int] = None) -> None:
@@ -74,6 +76,9 @@ class ShardedCorpusIndex:
         counts = [int(c.item()) for c in counts]
         self.row_offset = sum(counts[: self.rank])
         self.total_rows = sum(counts)
+        self._fuse_ok.clear()
+        if self.total_rows >= 0xFFFFFFFF:
+            raise ValueError("the merge kernels carry global rows as 32-bit keys: at most 2^32 - 2 rows in total")
 
     def _comm_device(self) -> torch.device:
         if self.local is not None and hasattr(self.local, "device"):
@@ -133,15 +138,40 @@ class ShardedCorpusIndex:
         """Collective: forget a failed symmetric-memory set-up so the next search tries again."""
         self._p2p_failed = False
 
+    def _all_ranks_can_fuse(self, b: int) -> bool:
+        """Every rank must take the same path (the fused form and the exchange kernel share
+        buffers and epochs but not flags).  Decided collectively once per batch size; call
+        `finalize()` again after changing an index (e.g. enabling its prefilter) on some ranks."""
+        if b not in self._fuse_ok:
+            mine = 1 if (b <= 2 and self.local is not None and hasattr(self.local, "can_fuse_exchange")
+                         and self.local.can_fuse_exchange(b)) else 0
+            flag = torch.tensor([mine], dtype=torch.int32, device=self._comm_device())
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            self._fuse_ok[b] = bool(int(flag.item()))
+        return self._fuse_ok[b]
+
     # ------------------------------------------------------------------ search
-    def search_device(self, q_dev: torch.Tensor, k: int, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search_device(self, q_dev: torch.Tensor, k: int, out=None, queries_ready: bool = False
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
         """q_dev [B,1024] fp32 (replicated on every rank) -> merged (scores, global rows) on
         every rank: local scan, then ONE exchange + merge."""
         if self._local_topk is not None:
             s, i = self._local_topk(q_dev, k, self.row_offset)
+        elif self.world > 1 and q_dev.is_cuda and q_dev.dtype == torch.float32 and \
+                self.fuse_small_batches and self._all_ranks_can_fuse(q_dev.shape[0]):
+            # one or two queries: the exchange rides in the scan's last CTA -- ONE launch per rank
+            # (sqe_search_gemv_sharded / sqe_search_gemv_prefiltered), no exchange kernel
+            self._choose_exchange(q_dev.device, q_dev.shape[0] * k)
+            if self.exchange == "p2p":
+                self._epoch += 1
+                return self.local.search_device(q_dev, k, idx_offset=self.row_offset, out=out,
+                                                xchg=(self.rank, self._xchg[2], self._xchg[3], self._epoch),
+                                                queries_ready=queries_ready)
+            s, i = self.local.search_device(q_dev, k, idx_offset=self.row_offset)
         else:
             s, i = self.local.search_device(q_dev, k, idx_offset=self.row_offset,
-                                            out=out if self.world == 1 else None)
+                                            out=out if self.world == 1 else None,
+                                            **({"queries_ready": True} if queries_ready else {}))
         if self.world == 1:
             return s, i
         return self.exchange_lists(s, i, k, out=out)

@@ -80,8 +80,12 @@ def main():
         report.append(f"{label}: b={b} k={k} worst={worst:.1e} excused={exc}")
         return s, i
 
-    s1, i1 = check(1, 10, 2e-6, "K3 + exchange")
+    s1, i1 = check(1, 10, 2e-6, "K3 with the exchange fused into the scan")
     assert i1[0, :3].tolist() == sorted(ties[0]), i1[0].tolist()
+    sharded.fuse_small_batches = False
+    s1b, i1b = check(1, 10, 2e-6, "K3 + exchange kernel")
+    sharded.fuse_small_batches = True
+    assert torch.equal(i1, i1b) and torch.equal(s1.view(torch.int32), s1b.view(torch.int32))
     sb, ib = check(200, 100, 1e-5, "K2 (R=4) + exchange")
     assert ib[0, :3].tolist() == sorted(ties[0]) and ib[150, :2].tolist() == sorted(ties[150])
     check(130, 10, 1e-5, "K2 + exchange")
@@ -90,10 +94,25 @@ def main():
     s2, i2 = check(2, 10, 2e-6, "K3p + exchange")
     assert torch.equal(i2[:1], i1) and torch.equal(s2[:1].view(torch.int32), s1.view(torch.int32))
     # many epochs back to back (buffer parity, flags, no host sync in between): identical every time
-    outs = [sharded.search_device(q_raw[e % 4: e % 4 + 1].contiguous(), 10) for e in range(args.epochs)]
+    # -- with ordinary launches, then overlapped ones (the queries are resident: SQE_FLAG_QUERIES_READY),
+    # with and without the int8 prefilter
+    q4 = [q_raw[e: e + 1].contiguous() for e in range(4)]
     torch.cuda.synchronize()
-    for e in range(4, args.epochs):
-        assert torch.equal(outs[e][1], outs[e % 4][1]) and torch.equal(outs[e][0], outs[e % 4][0]), e
+    for pre in (True, False):
+        index.prefilter = pre
+        ref = None
+        for ready in (False, True):
+            outs = [sharded.search_device(q4[e % 4], 10, queries_ready=ready) for e in range(args.epochs)]
+            torch.cuda.synchronize()
+            for e in range(4, args.epochs):
+                assert torch.equal(outs[e][1], outs[e % 4][1]) and torch.equal(outs[e][0], outs[e % 4][0]), (pre, ready, e)
+            if ref is not None:
+                for e in range(4):
+                    assert torch.equal(outs[e][1], ref[e][1]) and torch.equal(outs[e][0], ref[e][0]), (pre, e)
+            ref = outs
+        assert torch.equal(ref[0][1], i1) and torch.equal(ref[0][0].view(torch.int32), s1.view(torch.int32))
+    index.prefilter = True
+    report.append(f"{4 * args.epochs} back-to-back one-query steps (ordinary + overlapped launches, exact + prefiltered): identical")
     assert sharded.exchange == ("nccl" if args.exchange == "nccl" else sharded.exchange)
     dist.barrier()
     print(f"[rank {rank}] exchange={sharded.exchange} " + "; ".join(report) + " -- rank ok", flush=True)

@@ -435,6 +435,94 @@ def test_exchange_merge_replayed_ranks_on_one_gpu(sqe):
             np.testing.assert_array_equal(out[0].cpu().numpy(), ws)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_fused_scan_exchange_ranks_on_two_streams_of_one_gpu(sqe, dtype):
+    """The ONE-launch sharded search (`sqe_search_gemv_sharded`, `sqe_search_gemv_prefiltered`): the
+    exchange runs in the last CTA of the scan.  Three "ranks" own consecutive row blocks of one
+    corpus and run on three streams of this GPU (each rank's gather buffer is a plain device
+    buffer, every rank sees all of them); every rank's merged result must be the oracle's top-k
+    over the WHOLE corpus, for several epochs (both buffer parities), k <= 32 and k > 32, one
+    and two queries, exact and prefiltered scan -- and equal to scan + `sqe_exchange_merge`."""
+    rng = np.random.default_rng(77)
+    n, world = 30_011, 3
+    x = make_corpus(rng, n)
+    x[20_500] = x[7]                                           # ties across ranks (7, 33, 20500, n-1)
+    q = rng.standard_normal((2, DIM)).astype(np.float32)
+    q[0] = x[7] * 0.5
+    bounds = [sqe.shard_bounds(n, world, r) for r in range(world)]
+    shards = [sqe.ops.normalize_cast(torch.from_numpy(x[lo:hi]).to(dev()), dtype) for lo, hi in bounds]
+    coarse = [sqe.ops.quantize_rows(S) for S in shards]
+    full = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    Q = sqe.ops.normalize_cast(torch.from_numpy(q).to(dev()), dtype)
+    d_st = oracle.from_storage(stored_bits(full, dtype), dtype)
+    q_st = oracle.from_storage(stored_bits(Q, dtype), dtype)
+    q_dev = torch.from_numpy(q).to(dev())
+    cap = 2 * 100
+    bufs = [torch.zeros(sqe.ops.exchange_buffer_bytes(world, cap), dtype=torch.uint8, device=dev()) for _ in range(world)]
+    ptrs = [b_.data_ptr() for b_ in bufs]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    epoch = 0
+    for nq, k, pre in [(1, 10, False), (1, 10, False), (2, 10, True), (1, 100, False), (2, 40, True), (1, 3, True),
+                       (1, 10, False)]:
+        epoch += 1
+        outs = []
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                if pre:
+                    outs.append(sqe.ops.search_gemv_prefiltered(shards[r], coarse[r][0], coarse[r][1], q_dev[:nq], k,
+                                                                idx_offset=bounds[r][0], xchg=(r, ptrs, cap, epoch)))
+                else:
+                    outs.append(sqe.ops.search_gemv(shards[r], q_dev[:nq], k, idx_offset=bounds[r][0],
+                                                    xchg=(r, ptrs, cap, epoch)))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert_topk_matches(outs[r][0].cpu().numpy(), outs[r][1].cpu().numpy(), d_st, q_st[:nq], k)
+            assert torch.equal(outs[r][1], outs[0][1]) and torch.equal(outs[r][0], outs[0][0])
+        if k >= 10:
+            got = outs[0][1][0].tolist()
+            assert got.index(7) < got.index(33) < got.index(20_500) < got.index(n - 1), got
+        # the two-kernel form on the same buffers (next epoch): identical results
+        epoch += 1
+        local = [sqe.ops.search_gemv(shards[r], q_dev[:nq], k, idx_offset=bounds[r][0]) for r in range(world)]
+        torch.cuda.synchronize()
+        res = None
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                res = sqe.ops.exchange_merge(local[r][0], local[r][1], k, r, ptrs, cap, epoch)
+        torch.cuda.synchronize()
+        assert torch.equal(res[1], outs[0][1]) and torch.equal(res[0].view(torch.int32), outs[0][0].view(torch.int32))
+
+
+def test_overlapped_scan_launches_equal_ordinary_launches(sqe):
+    """SQE_FLAG_QUERIES_READY: scans launched with programmatic stream serialization start while the
+    previous scan is still in its tail (last-CTA merge) and share its workspace, tickets and
+    outputs.  A long back-to-back sequence that alternates queries, k and exact / prefiltered
+    scans must give, call for call, what ordinary launches give."""
+    rng = np.random.default_rng(91)
+    n = 300_000
+    D = sqe.ops.normalize_cast(torch.from_numpy(rng.standard_normal((n, DIM)).astype(np.float32)).to(dev()), "bf16")
+    d8, meta = sqe.ops.quantize_rows(D)
+    qs = [torch.from_numpy(rng.standard_normal((nq, DIM)).astype(np.float32)).to(dev()) for nq in (1, 2, 1, 1, 2, 1)]
+    plan = [(i % len(qs), (10, 3, 40, 10, 100)[i % 5], i % 3 == 1) for i in range(120)]
+
+    def run(ready):
+        outs = []
+        for qi, k, pre in plan:
+            if pre:
+                s, i = sqe.ops.search_gemv_prefiltered(D, d8, meta, qs[qi], k, queries_ready=ready)
+            else:
+                s, i = sqe.ops.search_gemv(D, qs[qi], k, queries_ready=ready)
+            outs.append((s, i))
+        torch.cuda.synchronize()
+        return outs
+    want = run(False)
+    for _ in range(3):
+        got = run(True)
+        for (ws_, wi), (gs, gi) in zip(want, got):
+            assert torch.equal(wi, gi) and torch.equal(ws_.view(torch.int32), gs.view(torch.int32))
+
+
 # ------------------------------------------------------- drop-in classes, golden
 def test_corpus_index_reproduces_reference_search(sqe, golden_dir):
     g = np.load(os.path.join(golden_dir, "index_search.npz"))

@@ -263,6 +263,29 @@ SQE_API int sqe_search_gemv_prefiltered(const void *D, int dtype, int64_t n, int
                                 uint32_t epoch, int flags, void *workspace, int64_t workspace_bytes,
                                 void *stream);
 
+/*
+ * K2p  the batched counterpart of K3p: exact cosine top-k for a BATCH of queries from the int8
+ * copy of the shard on the tensor cores (tcgen05.mma kind::i8: half the bytes of a 16-bit shard,
+ * twice its tensor rate) + exact rescoring of the (query, row) pairs the rigorous bound cannot
+ * rule out.  Results are BIT-IDENTICAL to sqe_normalize_cast + sqe_topk_gemv (K3) for every
+ * input and every storage class of D -- fp32 shards included, which have no other tensor-core
+ * path.  Replaces the same reference lines as K2 (app/main.py:356-367; with k = 1 the scan of
+ * lfu_cache_get, app/main.py:73-90).
+ *   D, dtype, n      the exact stored rows (any storage class), as for sqe_topk_gemv;
+ *   D8, meta         their coarse copy as written by sqe_quantize_rows;
+ *   Q_raw            RAW fp32 queries [b, dim] (normalised and quantised by the call);
+ *   1 <= k <= SQE_MAX_K_BATCHED, any b >= 1; out_score / out_idx [b, k] as for sqe_topk_gemv;
+ *   out_rescored     (may be NULL) uint32 [b]: rows that went through the exact pass per query.
+ * Workspace: sqe_search_batched_prefiltered_workspace_bytes(n, b, k, dtype); no initialisation
+ * needed, first 4096 bytes zero again afterwards (shared-workspace contract).
+ */
+SQE_API int64_t sqe_search_batched_prefiltered_workspace_bytes(int64_t n, int b, int k, int dtype);
+SQE_API int sqe_search_batched_prefiltered(const void *D, int dtype, int64_t n, int dim, const void *D8,
+                                   const void *meta, const float *Q_raw, int b, int k,
+                                   float *out_score, int64_t *out_idx, int64_t idx_offset,
+                                   uint32_t *out_rescored, void *workspace, int64_t workspace_bytes,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

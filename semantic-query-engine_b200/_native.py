@@ -53,6 +53,10 @@ PROTOTYPES = [
     ("sqe_exchange_merge", c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    POINTER(c_void_p), c_int64, c_uint32, c_uint32,
                                    c_void_p, c_void_p, c_void_p]),
+    ("sqe_search_batched_prefiltered_workspace_bytes", c_int64, [c_int64, c_int, c_int, c_int]),
+    ("sqe_search_batched_prefiltered", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                               c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                               c_void_p, c_int64, c_void_p]),
     ("sqe_search_gemv_sharded", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_void_p),
                                         c_int64, c_uint32, c_int, c_void_p, c_int64, c_void_p]),
@@ -90,6 +94,7 @@ LAUNCHES_PER_CALL = {
     "sqe_exchange_merge": 1,
     "sqe_search_gemv_sharded": 1,
     "sqe_search_gemv_prefiltered": 2,
+    "sqe_search_batched_prefiltered": 3,      # prepare queries, int8 tensor-core scan, exact rescoring
 }
 
 

@@ -269,6 +269,37 @@ int sqe_search_gemv_prefiltered(const void* D, int dtype, int64_t n, int dim, co
     return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : rc == -3 ? SQE_E_WORKSPACE : SQE_E_CUDA);
 }
 
+int64_t sqe_search_batched_prefiltered_workspace_bytes(int64_t n, int b, int k, int dtype) {
+    DevInfo d;
+    if (device_info(&d) != SQE_OK) d.sm_count = 160;
+    if (b < 1) b = 1;
+    if (k < 1) k = 1;
+    return batched_i8_workspace_bytes(n, b, k, dtype, d.sm_count);
+}
+
+int sqe_search_batched_prefiltered(const void* D, int dtype, int64_t n, int dim, const void* D8, const void* meta,
+                                   const float* Q_raw, int b, int k, float* out_score, int64_t* out_idx,
+                                   int64_t idx_offset, uint32_t* out_rescored, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+    int rc = check_common("search_batched_prefiltered", D, dtype, n, dim, Q_raw, b);
+    if (rc != SQE_OK) return rc;
+    if (k < 1 || k > SQE_MAX_K_BATCHED) { set_error("search_batched_prefiltered: k=%d not in [1,%d]", k, SQE_MAX_K_BATCHED); return SQE_E_ARG; }
+    if (b == 0) return SQE_OK;
+    if (!out_score || !out_idx || !workspace) { set_error("search_batched_prefiltered: null output/workspace"); return SQE_E_ARG; }
+    if (n > 0 && (!D8 || !meta || !aligned16(D8) || !aligned16(meta))) {
+        set_error("search_batched_prefiltered: null or unaligned coarse rows");
+        return SQE_E_ARG;
+    }
+    if (!aligned16(workspace)) { set_error("search_batched_prefiltered: workspace must be 16-byte aligned"); return SQE_E_ARG; }
+    DevInfo d;
+    rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_search_batched_prefiltered(D, dtype, n, D8, meta, Q_raw, b, k, out_score, out_idx, idx_offset,
+                                           out_rescored, workspace, workspace_bytes, d.sm_count,
+                                           static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : rc == -3 ? SQE_E_WORKSPACE : SQE_E_CUDA);
+}
+
 int64_t sqe_topk_batched_workspace_bytes(int64_t n, int b, int k) {
     DevInfo d;
     if (device_info(&d) != SQE_OK) d.sm_count = 160;

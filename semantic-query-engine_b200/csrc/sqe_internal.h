@@ -35,6 +35,13 @@ int launch_topk_batched(const void* D, int dtype, int64_t n, const void* Q, int 
                         float* out_score, int64_t* out_idx, int64_t idx_offset, void* ws,
                         int64_t ws_bytes, int sm_count, cudaStream_t stream);
 
+// K2p  int8 tensor-core prefilter + exact rescoring (topk_batched_i8.cu)
+int64_t batched_i8_workspace_bytes(int64_t n, int b, int k, int dtype, int sm_count);
+int launch_search_batched_prefiltered(const void* D, int dtype, int64_t n, const void* D8, const void* meta,
+                                      const float* Q_raw, int b, int k, float* out_score, int64_t* out_idx,
+                                      int64_t idx_offset, uint32_t* out_rescored, void* ws, int64_t ws_bytes,
+                                      int sm_count, cudaStream_t stream);
+
 // K4
 int launch_merge_topk(const float* scores, const int64_t* idx, int lists, int b, int k_in,
                       int k_out, float* out_score, int64_t* out_idx, cudaStream_t stream);

@@ -291,6 +291,40 @@ def topk_gemv_prefiltered(D: torch.Tensor, D8: torch.Tensor, meta: torch.Tensor,
     return scores, idx
 
 
+def search_batched_prefiltered(D: torch.Tensor, D8: torch.Tensor, meta: torch.Tensor, q_raw: torch.Tensor,
+                               k: int, idx_offset: int = 0, n: Optional[int] = None, out=None,
+                               rescored: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K2p: exact cosine top-k for a batch of RAW fp32 queries from the int8 copy on the tensor cores
+    (`quantize_rows`) + exact rescoring: the results of `normalize_cast` + `topk_gemv`, bit for
+    bit, for any storage class of `D` (fp32 shards included).  `rescored`: optional int32 CUDA
+    tensor [b] that receives the number of rows scored exactly per query."""
+    dev = _require_cuda(D, D8, meta, q_raw)
+    if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
+        raise ValueError("q_raw must be fp32 [b,1024]")
+    if D.dim() != 2 or D.shape[1] != ROW_ELEMS[dtype_name(D)]:
+        raise ValueError("D must be [rows,1024] (or [rows,2048] bf16 for split bf16)")
+    rows = D.shape[0] if n is None else int(n)
+    if rows > D.shape[0]:
+        raise ValueError("n exceeds shard rows")
+    if D8.dtype != torch.int8 or meta.dtype != torch.float32 or D8.dim() != 2 or meta.dim() != 2 or \
+            D8.shape[1] != nat.SQE_DIM or meta.shape[1] != 4 or D8.shape[0] < rows or meta.shape[0] < rows:
+        raise ValueError("coarse rows must be int8 [rows,1024] + fp32 [rows,4] (ops.quantize_rows)")
+    b = q_raw.shape[0]
+    scores, idx = _outputs(out, dev, b, k)
+    if b == 0:
+        return scores, idx
+    if rescored is not None and (rescored.dtype != torch.int32 or rescored.numel() < b or not rescored.is_cuda):
+        raise ValueError("`rescored` must be an int32 CUDA tensor [b]")
+    code = nat.DTYPE_CODES[dtype_name(D)]
+    with _launch_lock, torch.cuda.device(dev):
+        need = nat.load().sqe_search_batched_prefiltered_workspace_bytes(rows, b, k, code)
+        ws = _workspace(dev, "batched_i8", need)
+        nat.call("sqe_search_batched_prefiltered", D.data_ptr(), code, rows, nat.SQE_DIM, D8.data_ptr(),
+                 meta.data_ptr(), q_raw.data_ptr(), b, k, scores.data_ptr(), idx.data_ptr(), idx_offset,
+                 rescored.data_ptr() if rescored is not None else None, ws.data_ptr(), ws.numel(), _stream(dev))
+    return scores, idx
+
+
 def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
                  n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K2: exact cosine top-k on the tensor cores (bf16/fp16 shards)."""

@@ -523,6 +523,102 @@ def test_overlapped_scan_launches_equal_ordinary_launches(sqe):
             assert torch.equal(wi, gi) and torch.equal(ws_.view(torch.int32), gs.view(torch.int32))
 
 
+# ------------------------------------------------------------------------ K2p
+def _k2p_case(sqe, dtype, x, q, ks):
+    """K2p == K1 + K3 bit for bit (scores, rows, tie order), and both against the oracle."""
+    D = sqe.ops.normalize_cast(torch.from_numpy(x).to(dev()), dtype)
+    d8, meta = sqe.ops.quantize_rows(D)
+    q_dev = torch.from_numpy(q).to(dev())
+    Qn = sqe.ops.normalize_cast(q_dev, dtype)
+    resc = torch.zeros((q.shape[0],), dtype=torch.int32, device=dev())
+    out = {}
+    for k in ks:
+        ws_, wi = sqe.ops.topk_gemv(D, Qn, k)
+        gs, gi = sqe.ops.search_batched_prefiltered(D, d8, meta, q_dev, k, rescored=resc)
+        torch.cuda.synchronize()
+        assert torch.equal(wi, gi), (dtype, x.shape, q.shape, k, (wi != gi).nonzero()[:5].tolist())
+        assert torch.equal(ws_.view(torch.int32), gs.view(torch.int32)), (dtype, k)
+        out[k] = resc.cpu().numpy().copy()
+    return D, Qn, out
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 1000, 40037])
+def test_batched_prefiltered_is_bit_identical_to_the_exact_scan(sqe, dtype, n):
+    rng = np.random.default_rng(3000 + n)
+    x = make_corpus(rng, n)
+    for b in (3, 130, 300):
+        q = rng.standard_normal((b, DIM)).astype(np.float32)
+        if n >= 64:
+            q[1] = x[7] * 0.25                                # planted duplicates 7 / 33 / n-1
+            q[2] = 0.0                                        # zero query: every score is 0
+        D, Qn, _ = _k2p_case(sqe, dtype, x, q, (1, 3, 10, 33, 100, 128))
+    d_st = oracle.from_storage(stored_bits(D, dtype), dtype)
+    q_st = oracle.from_storage(stored_bits(Qn, dtype), dtype)
+    s, i = sqe.ops.search_batched_prefiltered(D, *sqe.ops.quantize_rows(D), torch.from_numpy(q).to(dev()), 10)
+    assert_topk_matches(s.cpu().numpy(), i.cpu().numpy(), d_st, q_st, 10)
+
+
+def test_batched_prefiltered_many_tiles_and_launches(sqe):
+    rng = np.random.default_rng(3100)
+    x = rng.standard_normal((300_000, DIM)).astype(np.float32)
+    q = rng.standard_normal((1100, DIM)).astype(np.float32)       # more than one launch of 1024 queries
+    _, _, resc = _k2p_case(sqe, "bf16", x, q, (10, 100))
+    # the bound does its job: ~1e-3 of the rows go through the exact pass, and no query falls back to the full scan
+    print("rows scored exactly per query (k=10): median", np.median(resc[10]), "max", resc[10].max(),
+          "| k=100: median", np.median(resc[100]), "max", resc[100].max())
+    assert 10 <= np.median(resc[10]) < 3000 and resc[100].max() < 30_000, (np.median(resc[10]), resc[100].max())
+    _k2p_case(sqe, "fp32", x[:120_000], q[:64], (1, 10))
+
+
+def test_batched_prefiltered_on_hostile_data(sqe):
+    """Whatever the data does to the bound, the answer stays K3's: clustered rows (a loose bound),
+    ascending scores (every row beats the ones before it: logs overflow -> exact scan), non-finite
+    rows and queries, zero rows, fewer rows than k."""
+    rng = np.random.default_rng(3200)
+    n = 20_000
+    base = rng.standard_normal(DIM).astype(np.float32)
+    clustered = (base[None, :] + 0.05 * rng.standard_normal((n, DIM))).astype(np.float32)
+    q = np.stack([base, base + 0.01 * rng.standard_normal(DIM).astype(np.float32), rng.standard_normal(DIM).astype(np.float32),
+                  np.zeros(DIM, np.float32)]).astype(np.float32)
+    _k2p_case(sqe, "bf16", clustered, q, (1, 10, 100))
+    u = rng.standard_normal(DIM).astype(np.float32); u /= np.linalg.norm(u)
+    v = rng.standard_normal(DIM).astype(np.float32); v -= (v @ u) * u; v /= np.linalg.norm(v)
+    ang = np.linspace(1.2, 0.0, n).astype(np.float32)               # cos rises with the row number
+    asc = (np.cos(ang)[:, None] * u[None, :] + np.sin(ang)[:, None] * v[None, :]).astype(np.float32)
+    _, _, resc = _k2p_case(sqe, "fp16", asc, np.stack([u, u + 0.3 * v, v, -u]).astype(np.float32), (10, 128))
+    bad = rng.standard_normal((5000, DIM)).astype(np.float32)
+    bad[17, 5] = np.inf
+    bad[18, 7] = np.nan
+    bad[19] = 0.0
+    qb = rng.standard_normal((5, DIM)).astype(np.float32)
+    qb[3, 100] = np.nan
+    qb[4, 3] = np.inf
+    _k2p_case(sqe, "fp32", bad, qb, (1, 10))
+    _k2p_case(sqe, "bf16x2", rng.standard_normal((7, DIM)).astype(np.float32), qb[:3], (10, 33))
+
+
+def test_index_with_prefilter_answers_batches_like_the_plain_index(sqe):
+    rng = np.random.default_rng(3300)
+    emb = make_corpus(rng, 50_000)
+    q = rng.standard_normal((40, DIM)).astype(np.float32)
+    for dtype in ("bf16", "fp32"):
+        a = sqe.GpuCorpusIndex(dtype=dtype, keep_payload=False, prefilter=True)
+        e = sqe.GpuCorpusIndex(dtype=dtype, keep_payload=False, prefilter=False)
+        for lo in (0, 20_000):
+            a.add_device_rows(emb[lo: lo + 30_000 if lo else 20_000])
+            e.add_device_rows(emb[lo: lo + 30_000 if lo else 20_000])
+        sa, ia = a.search_batch(q, 10)
+        if dtype == "fp32":
+            se, ie = e.search_batch(q, 10)                        # fp32 shards: K3 -> identical bits
+            np.testing.assert_array_equal(ia, ie)
+            np.testing.assert_array_equal(sa.view(np.int32), se.view(np.int32))
+        else:                                                     # bf16 batches go through K2: tolerance class
+            se, ie = e.search_batch(q, 10)
+            np.testing.assert_allclose(sa, se, atol=K2_TOL)
+            assert (ia == ie).mean() > 0.98
+
+
 # ------------------------------------------------------- drop-in classes, golden
 def test_corpus_index_reproduces_reference_search(sqe, golden_dir):
     g = np.load(os.path.join(golden_dir, "index_search.npz"))

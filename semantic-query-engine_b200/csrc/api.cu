@@ -90,7 +90,7 @@ int sqe_tuning_set(int knob, int value) {
         g_k2_cta_group = value;
         return old;
     }
-    if (knob == SQE_TUNE_K2_EPILOGUE_MODE && value >= 0 && value <= 2) {
+    if (knob == SQE_TUNE_K2_EPILOGUE_MODE && value >= 0 && value <= 3) {
         const int old = g_k2_epilogue_mode;
         g_k2_epilogue_mode = value;
         return old;

@@ -225,6 +225,7 @@ __device__ __forceinline__ void threshold_warp_log(const int CAP, const uint64_t
     __syncwarp();
     unsigned sleep_ns = 500;
     while (true) {
+        const bool last = *done >= 4u;                          // one more round once this CTA's epilogue is through
         bool any_new = false;
         for (int t = 0; t < n_own; ++t) {
             const int row = q_row0 + my_id + t * n_ids;
@@ -232,61 +233,66 @@ __device__ __forceinline__ void threshold_warp_log(const int CAP, const uint64_t
             uint32_t* seen = reinterpret_cast<uint32_t*>(sl + L);
             WarpList<R> acc;
             acc.load(sl, lane);
-            uint64_t worst = acc.worst();
+            // only a key above the current k-th best can move the bound: that is the insertion
+            // threshold (`worst`), not the list's last element
+            auto kth_of = [&]() {
+                uint64_t src = 0ull;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (i == ((k - 1) >> 5)) src = acc.key[i];
+                return shfl_u64(src, (k - 1) & 31);
+            };
+            uint64_t worst = kth_of();
             bool changed = false;
             for (int g0 = 0; g0 < n_groups; g0 += 32) {
+                // lane l reads the log of group g0 + l: 32 logs are walked in lockstep, four entries
+                // per lane in flight, so a round costs a few L2 round trips, not one per group
                 const int g = g0 + lane;
-                const uint32_t w = g < n_groups ? ld_relaxed_gpu(ws_counts + static_cast<size_t>(row) * gpad + g) : 0u;
-                const uint32_t sv = g < n_groups ? seen[g] : 0u;
-                unsigned todo = __ballot_sync(kFull, g < n_groups && w != sv && (w & 0xffffu) != 0xffffu);
-                while (todo) {
-                    const int gl = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const uint32_t wv = __shfl_sync(kFull, w, gl);
-                    const uint32_t svv = __shfl_sync(kFull, sv, gl);
-                    uint32_t pos = ((wv >> 16) == (svv >> 16)) ? (svv & 0xffffu) : 0u;
-                    const uint32_t end = min(wv & 0xffffu, static_cast<uint32_t>(CAP));
-                    const uint64_t* lp = ws_logs + (static_cast<size_t>(g0 + gl) * b_pad + row) * CAP;
-                    while (pos < end) {
-                        const uint32_t idx = pos + lane;
-                        const uint64_t key = idx < end ? __ldcg(lp + idx) : 0ull;
-                        const unsigned zeros = __ballot_sync(kFull, idx < end && key == 0ull);   // not visible yet
-                        const uint32_t n_ok = zeros ? static_cast<uint32_t>(__ffs(zeros) - 1) : min(32u, end - pos);
-                        unsigned pass = __ballot_sync(kFull, static_cast<uint32_t>(lane) < n_ok && key > worst);
+                const bool valid = g < n_groups;
+                const uint32_t w = valid ? ld_relaxed_gpu(ws_counts + static_cast<size_t>(row) * gpad + g) : 0u;
+                const uint32_t sv = valid ? seen[g] : 0u;
+                const bool act = valid && w != sv && (w & 0xffffu) != 0xffffu;
+                uint32_t pos = (act && (w >> 16) == (sv >> 16)) ? (sv & 0xffffu) : 0u;
+                uint32_t end = act ? min(w & 0xffffu, static_cast<uint32_t>(CAP)) : 0u;
+                const uint64_t* lp = ws_logs + (static_cast<size_t>(valid ? g : 0) * b_pad + row) * CAP;
+                while (__any_sync(kFull, pos < end)) {
+                    uint64_t key[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) key[u] = (pos + u < end) ? __ldcg(lp + pos + u) : 0ull;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool have = pos + u < end;
+                        if (have && key[u] == 0ull) end = pos + u;      // not visible yet: stop here this round
+                        unsigned pass = __ballot_sync(kFull, pos + u < end && key[u] > worst);
                         while (pass) {
                             const int l = __ffs(pass) - 1;
                             pass &= pass - 1;
-                            const uint64_t cand = shfl_u64(key, l);
+                            const uint64_t cand = shfl_u64(key[u], l);
                             if (cand > worst) {
                                 bool dup = false;
 #pragma unroll
                                 for (int i = 0; i < R; ++i) dup |= (acc.key[i] == cand);
                                 if (!__any_sync(kFull, dup)) {
                                     acc.insert(cand, lane);
-                                    worst = acc.worst();
+                                    worst = kth_of();
                                     changed = true;
                                 }
                             }
                         }
-                        pos += n_ok;
-                        if (zeros) break;
                     }
-                    if (lane == gl) seen[g] = (wv & 0xffff0000u) | pos;
+                    pos = min(pos + 4u, end);
                 }
+                if (act) seen[g] = (w & 0xffff0000u) | pos;
             }
             if (changed) {
                 any_new = true;
                 acc.store(sl, lane);
-                uint64_t kth_src = 0ull;
-#pragma unroll
-                for (int i = 0; i < R; ++i)
-                    if (i == ((k - 1) >> 5)) kth_src = acc.key[i];
-                const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
+                const uint64_t kth = worst;
                 if (lane == 0 && kth != 0ull) atomicMax(ws_tau + row, static_cast<uint32_t>(kth >> 32));
             }
             __syncwarp();
         }
-        if (*done >= 4u) break;
+        if (last) break;
         if (any_new) sleep_ns = 500;
         __nanosleep(sleep_ns);
         if (sleep_ns < 8000u) sleep_ns *= 2;

@@ -19,9 +19,10 @@
 //                            so only pairs with U >= tau can be in the result.  tau is not known
 //                            until the end; the kernel uses the running, GPU-wide k-th best L (the
 //                            candidate-log machinery of K2's k > 32 mode: every pair with U above the
-//                            running bound is appended to its (query, group) log keyed by L, the
-//                            threshold warps merge the logs incrementally and publish the k-th best
-//                            L) -- a bound that only grows, so the logged set is a superset.
+//                            running bound is appended to the (query, group) CANDIDATE log -- write-only
+//                            during the scan --, the few pairs whose L itself beats the bound also to
+//                            the small BOUND log the threshold warps merge incrementally to publish
+//                            the k-th best L) -- a bound that only grows, so the logged set is a superset.
 //   batched_rescore_kernel   one CTA per query: every logged row is scored exactly (K3's loads, FMA
 //                            chains and butterfly -> K3's bits) and goes through the warp-list /
 //                            CTA-merge selection.  A query whose log overflowed (adversarial data:
@@ -39,7 +40,7 @@ using namespace k2;
 constexpr int kChunkI8 = 128;                      // int8 elements per K chunk = one 128-byte swizzle row
 constexpr int kNumChunksI8 = kDim / kChunkI8;      // 8
 constexpr int kUmmaKI8 = 32;                       // elements per tcgen05.mma kind::i8
-constexpr int kLogCapMax = 1024;                   // entries per (query, group) log (the launch picks 256 or 1024)
+constexpr int kLogCapMax = 1024;                   // entries per (query, group) candidate log
 constexpr int kSpillCap = 8192;                    // entries per query of the shared spill area (full logs)
 constexpr int kMetaBufs = 4;                       // row-constant tiles in flight (see the producer)
 constexpr int kMetaBytes = kTileN * 16;            // {sd, eps, nd, 0} per shard row of a d-tile
@@ -54,7 +55,8 @@ struct CfgI8 {
     static constexpr int kStageBytes = kABytes + kBBytes;          // 48 KB / 32 KB, as for 16-bit operands
     static constexpr int kStages = (CG == 1) ? 4 : (DEEP ? 6 : 4);
     static constexpr int kOffMeta = kStages * kStageBytes;
-    static constexpr int kOffThr = kOffMeta + kMetaBufs * kMetaBytes;
+    static constexpr int kOffXbuf = kOffMeta + kMetaBufs * kMetaBytes;     // 4 epilogue warps x 32 words
+    static constexpr int kOffThr = kOffXbuf + 4 * 32 * 4;
     static constexpr int kThrSlotBytes = 32 * R * 8 + kMaxGroups * 4;
     static constexpr int kBarBytes = 32 * 8 + 16;
     static constexpr int kFree = 227 * 1024 - 1024 - kBarBytes - kOffThr;
@@ -71,7 +73,9 @@ struct K2I8Args {
     int b, k;
     int n_qt, n_groups, n_dtiles;
     uint32_t idesc;
-    uint64_t* ws_logs;        // [group][b_pad][log_cap] keys (L, row)
+    uint64_t* ws_logs;        // bound logs [group][b_pad][64 R] keys (L, row) with L above the bound when logged
+    uint64_t* ws_clogs;       // candidate logs [group][b_pad][log_cap] keys (L, row) with U above the bound
+    uint32_t* ws_ccounts;     // [b_pad][gpad] entries per candidate log (written when the scan ends)
     uint32_t* ws_tau;         // published bounds (k-th best L), first 4 KB of the workspace
     uint32_t* ws_arrive;      // bootstrap arrivals per 32-query slice
     uint32_t* ws_counts;      // [b_pad][gpad]
@@ -80,7 +84,8 @@ struct K2I8Args {
     uint32_t* ws_spill_cnt;   // [b_pad] entries in the query's spill area
     uint64_t* ws_spill;       // [b_pad][kSpillCap] keys that did not fit their (query, group) log (never zeroed:
                               // read by the exact pass only, after the kernel, up to the count)
-    int log_cap;              // entries per (query, group) log
+    int log_cap;              // entries per candidate log
+    int blog_cap;             // entries per bound log (64 R)
     int epi_mode;             // diagnostics (SQE_TUNE_K2_EPILOGUE_MODE): 2 = no epilogue work (results invalid)
     int gpad;
     int boot_j, boot_m;
@@ -114,18 +119,36 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
 struct I8State {
     float thr;        // a pair is logged iff !(U <= thr)
     uint32_t tau_g;   // best published bound on the k-th best L (orderable u32), 0 = none
-    uint32_t cnt;     // entries in this thread's log
+    uint32_t cnt;     // entries in this thread's candidate log
+    uint32_t bcnt;    // entries in this thread's bound log
     bool dead;        // log and spill area overflowed: the query is flagged for the exact scan, nothing more is logged
     float sq, qe, qn; // query constants
+};
+
+// Per-warp pointers of the epilogue's logs: lane w's log / counter is base + w * stride.
+struct I8Logs {
+    uint64_t* clog;       // candidate logs of this warp's 32 queries (stride log_cap)
+    uint64_t* blog;       // bound logs (stride blog_cap)
+    uint32_t* bcount;     // bound-log count words (stride gpad)
+    uint64_t* spill;      // spill areas (stride kSpillCap)
+    uint32_t* spill_cnt;  // (stride 1)
+    uint32_t* over;       // (stride 1)
+    uint32_t log_cap, blog_cap, gpad;
+    uint32_t* xbuf;       // 32 words of shared memory per warp: one lane's accumulators, transposed
 };
 
 // One 32-column strip: v[j] = the s32 accumulator of (this thread's query, row col0 + j).
 // mt = the row constants of this d-tile in shared memory; m_max = the margin with the tile's
 // largest nd and eps (>= every column's margin: the expression is monotone in both).
+//
+// Fast path (per thread = per query): can any column's upper bound U reach thr?  With a margin of
+// ~half a score sigma that is true for some lane of the warp in about every second strip, so the
+// slow path is TRANSPOSED: a lane that wants hands its 32 accumulators over through shared
+// memory and the 32 lanes evaluate one column each (exact bounds, one conflict-free LDS.128 of
+// the row constants), then append the passing columns to that query's logs in parallel.
 __device__ __forceinline__ void process_strip_i8(const uint32_t (&v)[32], uint32_t col0, int c_in_tile, uint32_t n,
                                                  bool row_valid, I8State& st, const float4* mt, float m_max,
-                                                 uint64_t* mylog, uint32_t* mycount, uint32_t* myover,
-                                                 uint32_t log_cap, uint64_t* myspill, uint32_t* myspill_cnt) {
+                                                 const I8Logs& lg, int lane) {
     const float4* mc = mt + c_in_tile * 32;
     float r[32];
 #pragma unroll
@@ -143,42 +166,74 @@ __device__ __forceinline__ void process_strip_i8(const uint32_t (&v)[32], uint32
     const float u2 = fmax3(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
     const float rmax = fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
     // no column of the strip can reach thr if even the largest s8 plus the largest margin stays below
-    // it; (sq rmax) differs from the slow path's (sd sq) acc by roundings only: 2e-6 relative covers
-    // them.  Negated comparison: a NaN (non-finite query or row constants) goes to the slow path.
+    // it; (sq rmax) differs from the slow path's (sd sq) acc by roundings only: the relative and
+    // absolute slack covers them.  Negated comparison: a NaN (non-finite query or row constants)
+    // goes to the slow path.
     float hi = st.sq * rmax;
-    hi = hi + fabsf(hi) * 2e-6f;
-    const bool want = row_valid && !st.dead && !(hi + m_max <= st.thr);
-    if (!__any_sync(kFull, want)) return;
-    if (!want) return;
-    uint32_t c = st.cnt;
-    bool over = false;
+    hi = hi + fabsf(hi) * 2e-6f + 2e-7f;
+    const bool want = row_valid && !st.dead && !(hi <= st.thr - m_max);
+    unsigned todo = __ballot_sync(kFull, want);
+    while (todo) {
+        const int w = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (lane == w) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float4 m4 = mc[j];
-        const float s8 = (m4.x * st.sq) * static_cast<float>(static_cast<int>(v[j]));
-        const float m = fmaf(st.qe, m4.z, st.qn * m4.y) + 1e-30f;
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(lg.xbuf + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncwarp();
+        const int acc = static_cast<int>(lg.xbuf[lane]);        // column `lane` of query w
+        const float sq = __shfl_sync(kFull, st.sq, w);
+        const float qe = __shfl_sync(kFull, st.qe, w);
+        const float qn = __shfl_sync(kFull, st.qn, w);
+        const float thr = __shfl_sync(kFull, st.thr, w);
+        const uint32_t cnt = __shfl_sync(kFull, st.cnt, w);
+        const uint32_t bcnt = __shfl_sync(kFull, st.bcnt, w);
+        const float4 m4 = mc[lane];
+        const float s8 = (m4.x * sq) * static_cast<float>(acc);
+        const float m = fmaf(qe, m4.z, qn * m4.y) + 1e-30f;
         const float U = s8 + m;
-        if (col0 + j < n && !(U <= st.thr)) {
-            const uint64_t key = make_key(s8 - m, col0 + j);            // keyed by L (NaN -> -inf)
-            if (c < log_cap) {
-                __stcg(mylog + c, key);
-                ++c;
+        const float Lb = s8 - m;
+        const uint32_t col = col0 + lane;
+        const bool pass = col < n && !(U <= thr);
+        const unsigned pm = __ballot_sync(kFull, pass);
+        const unsigned bm = __ballot_sync(kFull, pass && Lb > thr);
+        const unsigned below = (1u << lane) - 1u;
+        bool over = false;
+        if (pass) {
+            const uint64_t key = make_key(Lb, col);              // keyed by L (NaN -> -inf)
+            const uint32_t slot = cnt + __popc(pm & below);
+            if (slot < lg.log_cap) {
+                __stcg(lg.clog + static_cast<size_t>(w) * lg.log_cap + slot, key);
             } else {
-                // this (query, group) log is full (a loose bound: clustered or sorted data): the
-                // pair goes to the query's spill area, shared by all groups
-                const uint32_t s = atomicAdd(myspill_cnt, 1u);
-                if (s < static_cast<uint32_t>(k2i::kSpillCap)) __stcg(myspill + s, key);
+                // this candidate log is full (a loose bound: clustered or sorted data): the pair
+                // goes to the query's spill area, shared by all groups
+                const uint32_t sp = atomicAdd(lg.spill_cnt + w, 1u);
+                if (sp < static_cast<uint32_t>(k2i::kSpillCap))
+                    __stcg(lg.spill + static_cast<size_t>(w) * k2i::kSpillCap + sp, key);
                 else over = true;
             }
+            // a lower bound that itself beats the running bound can raise it: bound log (a full one
+            // just stops feeding the threshold warps; the bound stays valid)
+            if ((bm >> lane) & 1u) {
+                const uint32_t bslot = bcnt + __popc(bm & below);
+                if (bslot < lg.blog_cap) __stcg(lg.blog + static_cast<size_t>(w) * lg.blog_cap + bslot, key);
+            }
         }
-    }
-    if (c != st.cnt) {
-        st.cnt = c;
-        st_relaxed_gpu(mycount, c);                             // epoch 0: these logs are never compacted
-    }
-    if (over) {
-        st.dead = true;
-        st_relaxed_gpu(myover, 1u);
+        over = __any_sync(kFull, over);
+        if (lane == w) {
+            st.cnt = min(cnt + __popc(pm), lg.log_cap);
+            const uint32_t nb = min(bcnt + __popc(bm), lg.blog_cap);
+            if (nb != st.bcnt) {
+                st.bcnt = nb;
+                st_relaxed_gpu(lg.bcount + static_cast<size_t>(w) * lg.gpad, nb);   // epoch 0: never compacted
+            }
+            if (over) {
+                st.dead = true;
+                st_relaxed_gpu(lg.over + w, 1u);
+            }
+        }
+        __syncwarp();                                           // xbuf is reused by the next lane
     }
 }
 
@@ -327,7 +382,7 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         }
     } else if (warp == 6) {
         // ---------------------------------------------------------- threshold warp
-        threshold_warp_log<R>(a.log_cap, a.ws_logs, a.ws_counts, a.ws_tau, sm + C::kOffThr, C::kThrSlots, b,
+        threshold_warp_log<R>(a.blog_cap, a.ws_logs, a.ws_counts, a.ws_tau, sm + C::kOffThr, C::kThrSlots, b,
                               n_qt * C::kQTile, a.gpad, k, n_groups, q_tile * C::kQTile, C::kQTile,
                               group * CG + static_cast<int>(rank), n_groups * CG, epi_done, lane, 1);
     } else {
@@ -338,16 +393,22 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const bool row_valid = row < b;
         const int b_pad = n_qt * C::kQTile;
         uint32_t* wtau = a.ws_tau + row0;
-        const uint32_t log_cap = static_cast<uint32_t>(a.log_cap);
-        uint64_t* mylog = a.ws_logs + (static_cast<size_t>(group) * b_pad + row) * log_cap;
-        uint32_t* mycount = a.ws_counts + static_cast<size_t>(row) * a.gpad + group;
-        uint32_t* myover = a.ws_over + row;
-        uint64_t* myspill = a.ws_spill + static_cast<size_t>(row) * kSpillCap;
-        uint32_t* myspill_cnt = a.ws_spill_cnt + row;
+        I8Logs lg;
+        lg.log_cap = static_cast<uint32_t>(a.log_cap);
+        lg.blog_cap = static_cast<uint32_t>(a.blog_cap);
+        lg.gpad = static_cast<uint32_t>(a.gpad);
+        lg.clog = a.ws_clogs + (static_cast<size_t>(group) * b_pad + row0) * lg.log_cap;
+        lg.blog = a.ws_logs + (static_cast<size_t>(group) * b_pad + row0) * lg.blog_cap;
+        lg.bcount = a.ws_counts + static_cast<size_t>(row0) * a.gpad + group;
+        lg.over = a.ws_over + row0;
+        lg.spill = a.ws_spill + static_cast<size_t>(row0) * kSpillCap;
+        lg.spill_cnt = a.ws_spill_cnt + row0;
+        lg.xbuf = reinterpret_cast<uint32_t*>(sm + C::kOffXbuf) + quarter * 32;
         I8State st;
         st.tau_g = 0u;
         st.thr = __int_as_float(0xff800000);
         st.cnt = 0u;
+        st.bcnt = 0u;
         st.dead = false;
         const float4 qm = row_valid ? a.qmeta[row] : make_float4(0.f, 0.f, 0.f, 0.f);
         st.sq = qm.x;
@@ -428,8 +489,7 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     asm volatile("" ::"r"(v[0]), "r"(v[31]));
                     continue;
                 }
-                process_strip_i8(v, static_cast<uint32_t>(t) * kTileN + c * 32, c, n, row_valid, st, mt, m_max,
-                                 mylog, mycount, myover, log_cap, myspill, myspill_cnt);
+                process_strip_i8(v, static_cast<uint32_t>(t) * kTileN + c * 32, c, n, row_valid, st, mt, m_max, lg, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -438,6 +498,7 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
             }
         }
+        if (row_valid) a.ws_ccounts[static_cast<size_t>(row) * a.gpad + group] = st.cnt;   // read by the exact pass
         __syncwarp();
         if (lane == 0) atomicAdd(epi_done, 1u);
     }
@@ -528,10 +589,13 @@ prepare_queries_kernel(const float* __restrict__ Q_raw, int b, T* __restrict__ Q
 }
 
 // ------------------------------------------------------------------------------------------
-// exact pass: one CTA per query.  Pass 1 over the query's logged keys: tau = the k-th best L (the
-// FINAL lower bound of the k-th best score).  Pass 2: a logged row whose upper bound U = L + 2 m
-// (m recomputed from its row constants) stays below tau cannot be in the result; every other
-// row is scored with K3's arithmetic.
+// exact pass: one CTA per query.  tau' = the bound the threshold warps published last (a lower
+// bound of the k-th best L, hence of the k-th best score).  All logged keys of the query (its
+// group logs + its spill area) form one flat index space that the 256 threads walk together
+// (every load of a step is independent: a few L2 round trips per 4096 keys, not one per group):
+// a key whose upper bound U = L + 2 m (m recomputed from the row constants) stays below tau'
+// cannot be in the result; the surviving rows are staged in shared memory and scored with K3's
+// arithmetic, RIF rows in flight per warp.
 // ------------------------------------------------------------------------------------------
 template <typename T, int R>
 __global__ void __launch_bounds__(256)
@@ -541,7 +605,7 @@ batched_rescore_kernel(const T* __restrict__ D, uint32_t n, const T* __restrict_
                        const uint64_t* __restrict__ ws_spill, uint32_t* __restrict__ ws_tau, int n_groups, int gpad,
                        int log_cap, const float4* __restrict__ meta, const float4* __restrict__ qmeta,
                        float* __restrict__ out_score, int64_t* __restrict__ out_idx, int64_t idx_offset,
-                       uint32_t* __restrict__ out_rescored) {
+                       uint32_t* __restrict__ out_rescored, int report_logged) {
     using E = Elem<T>;
     constexpr int LOADS = E::kLoads;
     constexpr int PER = E::kPer;
@@ -549,15 +613,22 @@ batched_rescore_kernel(const T* __restrict__ D, uint32_t n, const T* __restrict_
     constexpr int L = 32 * R;
     constexpr int kWarps = 8;
     constexpr int RIF = (LOADS >= 8) ? 2 : 4;                    // rows in flight per warp
-    constexpr int kStage = 64;                                  // surviving rows staged per warp
+    constexpr int kChunk = 4096;                                // keys examined per round = staged rows at most
     __shared__ uint64_t s_lists[kWarps][L];
-    __shared__ uint32_t s_rows[kWarps][kStage];
-    __shared__ float s_tau;
-    clear_header(ws_tau);
+    __shared__ uint32_t s_rows[kChunk];
+    __shared__ uint32_t s_pref[k2::kMaxGroups + 2];             // exclusive prefix of the segment lengths
+    __shared__ uint32_t s_n;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int query = blockIdx.x;
+    // header contract: the published bounds are zero again after the call (each CTA its own entry,
+    // after reading it; CTA 0 the entries of the queries this launch does not have)
+    if (blockIdx.x == 0)
+        for (int i = b + threadIdx.x; i < k2::kQueriesPerLaunch; i += blockDim.x) ws_tau[i] = 0u;
     if (query >= b) return;
+    const uint32_t tau_o = ws_tau[query];
+    __syncthreads();
+    if (threadIdx.x == 0) ws_tau[query] = 0u;
 
     float q[32];
     {
@@ -617,7 +688,7 @@ batched_rescore_kernel(const T* __restrict__ D, uint32_t n, const T* __restrict_
         }
     };
 
-    unsigned rescored = 0u;
+    unsigned rescored = 0u;                                      // meaningful in warp 0
     if (ws_over[query] != 0u) {
         // log and spill area of this query overflowed: exact scan of every row (K3's loop)
         for (uint32_t base_row = warp * RIF; base_row < n; base_row += kWarps * RIF) {
@@ -630,112 +701,75 @@ batched_rescore_kernel(const T* __restrict__ D, uint32_t n, const T* __restrict_
             }
             score_rows(rows, valid);
         }
-        rescored = (warp == 0) ? n : 0u;
+        rescored = n;
     } else {
-        // the query's key segments: one per group log, plus the spill area as segment n_groups
-        uint32_t spill = __ldcg(ws_spill_cnt + query);
-        spill = spill > static_cast<uint32_t>(k2i::kSpillCap) ? static_cast<uint32_t>(k2i::kSpillCap) : spill;
-        auto seg = [&](int g, const uint64_t*& lp, uint32_t& c) {
-            if (g < n_groups) {
-                c = __ldcg(ws_counts + static_cast<size_t>(query) * gpad + g) & 0xffffu;
-                c = c > static_cast<uint32_t>(log_cap) ? static_cast<uint32_t>(log_cap) : c;
-                lp = ws_logs + (static_cast<size_t>(g) * b_pad + query) * log_cap;
-            } else {
-                c = spill;
-                lp = ws_spill + static_cast<size_t>(query) * k2i::kSpillCap;
-            }
-        };
-        // ---- pass 1: tau = k-th best L over everything logged
-        WarpList<R> lb;
-        lb.clear();
-        uint64_t lb_worst = 0ull;
-        for (int g = warp; g <= n_groups; g += kWarps) {
-            const uint64_t* lp;
+        // segment g < n_groups: the log of group g; segment n_groups: the spill area
+        const int n_seg = n_groups + 1;
+        for (int g = threadIdx.x; g < n_seg; g += blockDim.x) {
             uint32_t c;
-            seg(g, lp, c);
-            for (uint32_t e0 = 0; e0 < c; e0 += 32) {
-                const uint64_t key = e0 + lane < c ? __ldcg(lp + e0 + lane) : 0ull;
-                unsigned pass = __ballot_sync(kFull, key > lb_worst);
-                while (pass) {
-                    const int l = __ffs(pass) - 1;
-                    pass &= pass - 1;
-                    const uint64_t cand = shfl_u64(key, l);
-                    if (cand > lb_worst) {
-                        lb.insert(cand, lane);
-                        lb_worst = lb.worst();
-                    }
+            if (g < n_groups) {
+                c = __ldcg(ws_counts + static_cast<size_t>(query) * gpad + g);
+                c = c > static_cast<uint32_t>(log_cap) ? static_cast<uint32_t>(log_cap) : c;
+            } else {
+                c = __ldcg(ws_spill_cnt + query);
+                c = c > static_cast<uint32_t>(k2i::kSpillCap) ? static_cast<uint32_t>(k2i::kSpillCap) : c;
+            }
+            s_pref[g + 1] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_pref[0] = 0u;
+            for (int g = 0; g < n_seg; ++g) s_pref[g + 1] += s_pref[g];
+        }
+        __syncthreads();
+        const uint32_t total = s_pref[n_seg];
+        if (report_logged) rescored = total;                     // diagnostics: pairs logged instead of rows scored
+        const float tau = tau_o ? from_orderable_u32(tau_o) : __int_as_float(0xff800000);
+        const float4 qm = qmeta[query];
+        for (uint32_t c0 = 0; c0 < total; c0 += kChunk) {
+            if (threadIdx.x == 0) s_n = 0u;
+            __syncthreads();
+            const uint32_t c1 = min(total, c0 + static_cast<uint32_t>(kChunk));
+            for (uint32_t idx = c0 + threadIdx.x; idx < c1; idx += blockDim.x) {
+                int lo = 0, hi = n_seg;                           // the segment holding flat index idx
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_pref[mid] <= idx) lo = mid; else hi = mid;
+                }
+                const uint32_t off = idx - s_pref[lo];
+                const uint64_t* lp = lo < n_groups ? ws_logs + (static_cast<size_t>(lo) * b_pad + query) * log_cap
+                                                   : ws_spill + static_cast<size_t>(query) * k2i::kSpillCap;
+                const uint64_t key = __ldcg(lp + off);
+                const uint32_t row = key_row(key);
+                if (row < n) {
+                    const float4 m4 = __ldg(meta + row);
+                    const float m = fmaf(qm.y, m4.z, qm.z * m4.y) + 1e-30f;
+                    // U = s8 + m with s8 = L + m up to the rounding of the subtraction that made L:
+                    // 1e-6 of slack covers it.  Negated comparison: NaN bounds are kept.
+                    const float U = key_score(key) + 2.f * m + 1e-6f;
+                    if (!(U < tau)) s_rows[atomicAdd(&s_n, 1u)] = row;
                 }
             }
-        }
-        lb.store(s_lists[warp], lane);
-        __syncthreads();
-        if (warp == 0) {
-#pragma unroll 1
-            for (int w = 1; w < kWarps; ++w) {
-                WarpList<R> other;
-                other.load(s_lists[w], lane);
-                lb.merge_sorted(other.key, lane);
-            }
-            uint64_t kth_src = 0ull;
-#pragma unroll
-            for (int i = 0; i < R; ++i)
-                if (i == ((k - 1) >> 5)) kth_src = lb.key[i];
-            const uint64_t kth = shfl_u64(kth_src, (k - 1) & 31);
-            if (lane == 0) s_tau = kth ? key_score(kth) : __int_as_float(0xff800000);
-        }
-        __syncthreads();
-        const float tau = s_tau;
-        const float4 qm = qmeta[query];
-        // ---- pass 2: rows whose upper bound reaches tau -> staged per warp -> scored exactly
-        uint32_t staged = 0;                                      // warp-uniform
-        auto drain = [&]() {
-            __syncwarp();
-            for (uint32_t e0 = 0; e0 < staged; e0 += RIF) {
+            __syncthreads();
+            const uint32_t cand = s_n;
+            for (uint32_t e0 = warp * RIF; e0 < cand; e0 += kWarps * RIF) {
                 uint32_t rows[RIF];
                 int valid = 0;
 #pragma unroll
                 for (int j = 0; j < RIF; ++j) {
-                    rows[j] = (e0 + j < staged) ? s_rows[warp][e0 + j] : 0u;
-                    valid += (e0 + j < staged) ? 1 : 0;
+                    rows[j] = (e0 + j < cand) ? s_rows[e0 + j] : 0u;
+                    valid += (e0 + j < cand) ? 1 : 0;
                 }
                 score_rows(rows, valid);
             }
-            rescored += staged;
-            staged = 0;
-            __syncwarp();
-        };
-        for (int g = warp; g <= n_groups; g += kWarps) {
-            const uint64_t* lp;
-            uint32_t c;
-            seg(g, lp, c);
-            for (uint32_t e0 = 0; e0 < c; e0 += 32) {
-                bool keep = false;
-                uint32_t row = 0;
-                if (e0 + lane < c) {
-                    const uint64_t key = __ldcg(lp + e0 + lane);
-                    row = key_row(key);
-                    const float4 m4 = __ldg(meta + row);
-                    const float m = fmaf(qm.y, m4.z, qm.z * m4.y) + 1e-30f;
-                    // U = s8 + m with s8 = L + m up to one rounding of the subtraction that made L:
-                    // 1e-6 of slack covers it.  Negated comparison: NaN bounds are kept.
-                    const float U = key_score(key) + 2.f * m + 1e-6f;
-                    keep = !(U < tau);
-                }
-                const unsigned mask = __ballot_sync(kFull, keep);
-                const uint32_t cnt = __popc(mask);
-                if (staged + cnt > kStage) drain();
-                if (keep) s_rows[warp][staged + __popc(mask & ((1u << lane) - 1u))] = row;
-                staged += cnt;
-            }
+            if (!report_logged) rescored += cand;
+            __syncthreads();
         }
-        drain();
     }
-    __syncthreads();                                             // s_lists reuse (pass 1)
 
     // ---- 8 warp lists -> the query's result ----
     list.store(s_lists[warp], lane);
     __syncthreads();
-    if (lane == 0 && out_rescored && rescored) atomicAdd(out_rescored + query, rescored);
     if (warp != 0) return;
 #pragma unroll 1
     for (int w = 1; w < kWarps; ++w) {
@@ -745,6 +779,7 @@ batched_rescore_kernel(const T* __restrict__ D, uint32_t n, const T* __restrict_
     }
     emit_topk<R>(list, k, lane, out_score + static_cast<int64_t>(query) * k,
                  out_idx + static_cast<int64_t>(query) * k, idx_offset);
+    if (lane == 0 && out_rescored) out_rescored[query] = rescored;
 }
 
 // ------------------------------------------------------------------------------ host
@@ -756,19 +791,21 @@ static int64_t i8_stage_bytes(int dtype) {
     return static_cast<int64_t>(k2::kQueriesPerLaunch) * (row + kDim + 16);
 }
 
-// [bounds | arrivals][logs: groups x b_pad x cap keys][counts, boot: b_pad x gpad each][over, spill
-// counts: b_pad each] -- all of that is zeroed per launch -- then [spill: b_pad x kSpillCap keys]
-// and the query staging area (stored queries, int8 queries, query constants), which are not.
-static int64_t i8_words_bytes(int64_t gpad) { return (2 * gpad + 2) * k2::kQueriesPerLaunch * 4; }
-static int64_t i8_spill_offset(int sm_count) {
+// [bounds | arrivals][bound logs: groups x b_pad x 64 R keys][counts, boot, candidate counts: b_pad x
+// gpad each][over, spill counts: b_pad each] -- all of that is zeroed per launch -- then, never
+// zeroed: [candidate logs: groups x b_pad x 1024 keys][spill: b_pad x kSpillCap keys] and the query
+// staging area (stored queries, int8 queries, query constants).
+static int64_t i8_words_bytes(int64_t gpad) { return (3 * gpad + 2) * k2::kQueriesPerLaunch * 4; }
+static int64_t i8_clog_offset(int sm_count) {
     const int64_t gpad = (sm_count + 31) & ~31;
-    const int64_t logs = static_cast<int64_t>(sm_count) * k2::kRowsPerCta * k2i::kLogCapMax * 8;
-    return (kI8HdrBytes + logs + i8_words_bytes(gpad) + 255) & ~static_cast<int64_t>(255);
+    const int64_t blogs = static_cast<int64_t>(sm_count) * k2::kRowsPerCta * 256 * 8;      // 64 R <= 256
+    return (kI8HdrBytes + blogs + i8_words_bytes(gpad) + 255) & ~static_cast<int64_t>(255);
 }
+static int64_t i8_clog_bytes(int sm_count) { return static_cast<int64_t>(sm_count) * k2::kRowsPerCta * k2i::kLogCapMax * 8; }
 static int64_t i8_spill_bytes() { return static_cast<int64_t>(k2::kQueriesPerLaunch) * k2i::kSpillCap * 8; }
 
 int64_t batched_i8_workspace_bytes(int64_t /*n*/, int /*b*/, int /*k*/, int dtype, int sm_count) {
-    return i8_spill_offset(sm_count) + i8_spill_bytes() + i8_stage_bytes(dtype);
+    return i8_clog_offset(sm_count) + i8_clog_bytes(sm_count) + i8_spill_bytes() + i8_stage_bytes(dtype);
 }
 
 template <int R, int CG, bool DEEP>
@@ -799,7 +836,8 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
                        int b, int k, float* out_score, int64_t* out_idx, int64_t idx_offset,
                        uint32_t* out_rescored, void* ws, int sm_count, cudaStream_t stream) {
     char* w = static_cast<char*>(ws);
-    char* spill = w + i8_spill_offset(sm_count);
+    char* clogs = w + i8_clog_offset(sm_count);
+    char* spill = clogs + i8_clog_bytes(sm_count);
     char* stage = spill + i8_spill_bytes();
     const int64_t row_bytes = static_cast<int64_t>(Elem<T>::kRowElems) * sizeof(T);
     T* Qst = reinterpret_cast<T*>(stage);
@@ -818,6 +856,9 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
     a.qmeta = qmeta;
     a.epi_mode = g_k2_epilogue_mode;
     a.ws_spill = reinterpret_cast<uint64_t*>(spill);
+    a.ws_clogs = reinterpret_cast<uint64_t*>(clogs);
+    a.log_cap = k2i::kLogCapMax;
+    a.blog_cap = 64 * R;
     for (int q0 = 0; q0 < b; q0 += k2::kQueriesPerLaunch) {
         const int bc = (b - q0 < k2::kQueriesPerLaunch) ? (b - q0) : k2::kQueriesPerLaunch;
         const int cg = (bc > k2::kRowsPerCta) ? 2 : 1;
@@ -828,20 +869,17 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
         if (n_dtiles > 0 && n_groups > n_dtiles) n_groups = n_dtiles;
         if (n_groups > k2::kMaxGroups) n_groups = k2::kMaxGroups;
         const int64_t b_pad = static_cast<int64_t>(n_qt) * q_tile_rows;
-        // log capacity: a short scan (few d-tiles per group) cannot log much and is latency
-        // sensitive (the logs are zeroed per launch); a long one sees the bound's start-up phase
-        const int tiles_per_group = n_dtiles > 0 ? (n_dtiles + n_groups - 1) / n_groups : 0;
-        a.log_cap = tiles_per_group > 64 ? k2i::kLogCapMax : 256;
-        const int64_t logs = static_cast<int64_t>(n_groups) * b_pad * a.log_cap * 8;
+        const int64_t logs = static_cast<int64_t>(n_groups) * b_pad * a.blog_cap * 8;        // bound logs (zeroed)
         a.b = bc;
         a.n_qt = n_qt;
         a.n_groups = n_groups;
         a.gpad = (n_groups + 31) & ~31;
         a.ws_counts = reinterpret_cast<uint32_t*>(w + kI8HdrBytes + logs);
         a.ws_boot = a.ws_counts + b_pad * a.gpad;
-        a.ws_over = a.ws_boot + b_pad * a.gpad;
+        a.ws_ccounts = a.ws_boot + b_pad * a.gpad;
+        a.ws_over = a.ws_ccounts + b_pad * a.gpad;
         a.ws_spill_cnt = a.ws_over + b_pad;
-        const int64_t used = kI8HdrBytes + logs + (2 * a.gpad + 2) * b_pad * 4;
+        const int64_t used = kI8HdrBytes + logs + (3 * a.gpad + 2) * b_pad * 4;
         // instruction descriptor (kind::i8): D s32 [4,6) = 2, A / B signed 8-bit [7,10) = [10,13) = 1,
         // K-major both, N >> 3 [17,23), M >> 4 [24,29)
         a.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(k2::kTileN >> 3) << 17) |
@@ -857,10 +895,6 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
         }
         cudaError_t e = cudaMemsetAsync(ws, 0, static_cast<size_t>(used), stream);
         if (e != cudaSuccess) { set_error("search_batched_prefiltered: memset: %s", cudaGetErrorString(e)); return -2; }
-        if (out_rescored) {
-            e = cudaMemsetAsync(out_rescored + q0, 0, static_cast<size_t>(bc) * 4, stream);
-            if (e != cudaSuccess) { set_error("search_batched_prefiltered: memset: %s", cudaGetErrorString(e)); return -2; }
-        }
         prepare_queries_kernel<T><<<(bc + 3) / 4, 128, 0, stream>>>(Q_raw + static_cast<int64_t>(q0) * kDim, bc, Qst, Q8,
                                                                     qmeta);
         e = cudaGetLastError();
@@ -878,10 +912,10 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
             if (rc != 0) return rc;
         }
         batched_rescore_kernel<T, R><<<bc, 256, 0, stream>>>(
-            static_cast<const T*>(D), static_cast<uint32_t>(n), Qst, bc, static_cast<int>(b_pad), k, a.ws_logs, a.ws_counts,
+            static_cast<const T*>(D), static_cast<uint32_t>(n), Qst, bc, static_cast<int>(b_pad), k, a.ws_clogs, a.ws_ccounts,
             a.ws_over, a.ws_spill_cnt, a.ws_spill, a.ws_tau, n_dtiles > 0 ? n_groups : 0, a.gpad, a.log_cap, a.meta,
             qmeta, out_score + static_cast<int64_t>(q0) * k, out_idx + static_cast<int64_t>(q0) * k, idx_offset,
-            out_rescored ? out_rescored + q0 : nullptr);
+            out_rescored ? out_rescored + q0 : nullptr, g_k2_epilogue_mode == 3 ? 1 : 0);
         e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("search_batched_prefiltered: rescore launch: %s", cudaGetErrorString(e)); return -2; }
     }

@@ -152,6 +152,14 @@ def test_config5_cache_1m_entries_b64_vs_oracle(sqe, dtype):
                 if abs(cos - thr) > margin:
                     assert gh[qi] == (1 if cos > thr else 0), (dtype, thr, qi, cos, gs[qi])
             assert gh[10:].sum() == 0                                  # random queries: cos ~ 0.15 at best
+    # K2p, k = 1 (what a prefiltered cache lookup runs): bit-identical to K3 on this storage class
+    c8, cmeta = sqe.ops.quantize_rows(C)
+    sp, ip = sqe.ops.search_batched_prefiltered(C, c8, cmeta, q_raw, 1)
+    s3, i3 = sqe.ops.topk_gemv(C, Q[:16].contiguous(), 1)
+    torch.cuda.synchronize()
+    assert torch.equal(ip[:16], i3) and torch.equal(sp[:16].view(torch.int32), s3.view(torch.int32))
+    for r in range(b):
+        assert ip[r, 0].item() == wi[r] or abs(float(sp[r, 0]) - ws[r]) <= 1e-6, (r, ip[r, 0].item(), wi[r])
 
 
 # ------------------------------------------------------------------ configs[3]
@@ -172,6 +180,14 @@ def test_config4_shape_fp16_b256_k100_vs_oracle(sqe):
     assert (i[200, :2] - 5_000_000_000).tolist() == [77, 1_000_001]
     print(f"configs[3] shape: worst |score - fp64| = {worst:.2e}, excused near-ties = {exc}")
     assert exc <= 2, exc
+    d8, meta = sqe.ops.quantize_rows(D)
+    sp, ip = sqe.ops.search_batched_prefiltered(D, d8, meta, _q, k, idx_offset=5_000_000_000)
+    torch.cuda.synchronize()
+    excp, worstp = assert_topk_matches_at_size(sp.cpu().numpy(), ip.cpu().numpy(), D, "fp16", n, q_st, k,
+                                               score_tol=2e-6, tie_eps=1e-6, idx_offset=5_000_000_000)
+    assert (ip[3, :3] - 5_000_000_000).tolist() == [11, 640_000, 1_249_999]
+    print(f"configs[3] shape, K2p: worst |score - fp64| = {worstp:.2e}, excused near-ties = {excp}")
+    assert excp == 0, excp
 
 
 # ------------------------------------------------------------------ configs[2]
@@ -203,6 +219,21 @@ def test_config3_10m_rows_b1024_vs_oracle_on_64_queries(sqe):
                                                score_tol=2e-6, tie_eps=1e-6, cands=cands[:8])
     print(f"configs[2] K3: worst |score - fp64| = {worst3:.2e}, excused near-ties = {exc3}")
     assert exc3 == 0, exc3
+    # K2p (int8 tensor-core prefilter + exact rescoring) on the same shard and the same 1024 raw queries:
+    # the same 64 queries against the oracle lists, and bit-identical to K3 where K3 was run
+    d8, meta = sqe.ops.quantize_rows(D)
+    resc = torch.zeros((b,), dtype=torch.int32, device=dev())
+    sp, ip = sqe.ops.search_batched_prefiltered(D, d8, meta, _q, k, rescored=resc)
+    torch.cuda.synchronize()
+    excp, worstp = assert_topk_matches_at_size(sp.cpu().numpy()[sample], ip.cpu().numpy()[sample], D, "bf16", n,
+                                               q_st, k, score_tol=2e-6, tie_eps=1e-6, cands=cands)
+    assert torch.equal(ip[torch.from_numpy(sample[:8]).to(dev())], ig)
+    assert torch.equal(sp[torch.from_numpy(sample[:8]).to(dev())].view(torch.int32), sg.view(torch.int32))
+    assert ip[0, :3].tolist() == [3, 5_000_000, 9_999_999] and ip[512, :2].tolist() == [2_500_000, 2_500_001]
+    r = resc.cpu().numpy()
+    print(f"configs[2] K2p: worst |score - fp64| = {worstp:.2e}, excused near-ties = {excp}, rows scored exactly "
+          f"per query median {int(np.median(r))} max {r.max()} of {n}")
+    assert excp == 0 and r.max() < n // 100, (excp, r.max())
 
 
 # ------------------------------------------------------------------- multi-GPU

@@ -34,6 +34,7 @@ EMBED_DIM = nat.SQE_DIM          # main.py:38
 
 class GpuCorpusIndex:
     _GRAPH_RETRY_S = 5.0
+    K2P_MAX_K = 32          # largest k a batch on a 16-bit shard is answered through the int8 prefilter
 
     def __init__(self, client=None, index_name: str = "", *, dtype: str = "bf16",
                  device: Optional[torch.device] = None, initial_capacity: int = 65536,
@@ -384,8 +385,11 @@ class GpuCorpusIndex:
             return ops.search_gemv_prefiltered(shard, c8, cm, q_dev, k, idx_offset=idx_offset, n=rows, out=out,
                                                xchg=xchg, queries_ready=queries_ready)
         if self.prefilter and c8 is not None and q_dev.shape[0] > 2 and 0 < rows <= c8.shape[0] \
-                and q_dev.dtype == torch.float32 and k <= nat.SQE_MAX_K_BATCHED and xchg is None:
-            # K2p: the batch form of the same idea on the int8 tensor cores (any storage class)
+                and q_dev.dtype == torch.float32 and xchg is None \
+                and k <= (nat.SQE_MAX_K_BATCHED if self.dtype == "fp32" else self.K2P_MAX_K):
+            # K2p: the batch form of the same idea on the int8 tensor cores.  16-bit shards: up to
+            # K2P_MAX_K (beyond that the exact pass outweighs the cheaper scan and K2 is as fast);
+            # fp32 shards: always (their only other batch path is one streaming pass per query)
             return ops.search_batched_prefiltered(shard, c8, cm, q_dev, k, idx_offset=idx_offset, n=rows, out=out)
         if q_dev.shape[0] == 1 and q_dev.dtype == torch.float32:
             # the reference's own case (one query, main.py:355): normalise + scan in ONE launch

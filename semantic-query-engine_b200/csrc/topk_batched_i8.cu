@@ -55,8 +55,9 @@ struct CfgI8 {
     static constexpr int kStageBytes = kABytes + kBBytes;          // 48 KB / 32 KB, as for 16-bit operands
     static constexpr int kStages = (CG == 1) ? 4 : (DEEP ? 6 : 4);
     static constexpr int kOffMeta = kStages * kStageBytes;
-    static constexpr int kOffXbuf = kOffMeta + kMetaBufs * kMetaBytes;     // 4 epilogue warps x 32 words
-    static constexpr int kOffThr = kOffXbuf + 4 * 32 * 4;
+    static constexpr int kOffXbuf = kOffMeta + kMetaBufs * kMetaBytes;     // per epilogue warp: 32 words of transpose
+    static constexpr int kXbufWords = 32 + kTileN;                         // buffer + the tile's 256 row scales, packed
+    static constexpr int kOffThr = kOffXbuf + 4 * kXbufWords * 4;
     static constexpr int kThrSlotBytes = 32 * R * 8 + kMaxGroups * 4;
     static constexpr int kBarBytes = 32 * 8 + 16;
     static constexpr int kFree = 227 * 1024 - 1024 - kBarBytes - kOffThr;
@@ -135,6 +136,7 @@ struct I8Logs {
     uint32_t* over;       // (stride 1)
     uint32_t log_cap, blog_cap, gpad;
     uint32_t* xbuf;       // 32 words of shared memory per warp: one lane's accumulators, transposed
+    const float* sds;     // the d-tile's 256 row scales sd, packed (per warp; written in the tile prologue)
 };
 
 // One 32-column strip: v[j] = the s32 accumulator of (this thread's query, row col0 + j).
@@ -152,7 +154,13 @@ __device__ __forceinline__ void process_strip_i8(const uint32_t (&v)[32], uint32
     const float4* mc = mt + c_in_tile * 32;
     float r[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = static_cast<float>(static_cast<int>(v[j])) * mc[j].x;     // acc * sd
+    for (int j = 0; j < 32; j += 4) {                            // acc * sd, four row scales per (broadcast) LDS.128
+        const float4 a4 = *reinterpret_cast<const float4*>(lg.sds + c_in_tile * 32 + j);
+        r[j] = static_cast<float>(static_cast<int>(v[j])) * a4.x;
+        r[j + 1] = static_cast<float>(static_cast<int>(v[j + 1])) * a4.y;
+        r[j + 2] = static_cast<float>(static_cast<int>(v[j + 2])) * a4.z;
+        r[j + 3] = static_cast<float>(static_cast<int>(v[j + 3])) * a4.w;
+    }
     if (col0 + 32u > n) {                                       // ragged last d-tile (warp-uniform)
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -403,7 +411,9 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         lg.over = a.ws_over + row0;
         lg.spill = a.ws_spill + static_cast<size_t>(row0) * kSpillCap;
         lg.spill_cnt = a.ws_spill_cnt + row0;
-        lg.xbuf = reinterpret_cast<uint32_t*>(sm + C::kOffXbuf) + quarter * 32;
+        lg.xbuf = reinterpret_cast<uint32_t*>(sm + C::kOffXbuf) + quarter * C::kXbufWords;
+        float* sds = reinterpret_cast<float*>(lg.xbuf + 32);
+        lg.sds = sds;
         I8State st;
         st.tau_g = 0u;
         st.thr = __int_as_float(0xff800000);
@@ -429,8 +439,10 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 #pragma unroll
             for (int j = 0; j < kTileN / 32; ++j) {
                 const uint32_t col = static_cast<uint32_t>(t) * kTileN + j * 32 + lane;
+                const float4 m4r = mt[j * 32 + lane];
+                sds[j * 32 + lane] = col < n ? m4r.x : 0.f;
                 if (col < n) {
-                    const float4 m4 = mt[j * 32 + lane];
+                    const float4 m4 = m4r;
                     bmax = fmaxf(bmax, m4.z);
                     cmax = fmaxf(cmax, m4.y);
                     odd |= !(m4.z == m4.z) || !(m4.y == m4.y) || !(m4.x == m4.x);
@@ -442,6 +454,7 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, d));
             }
             odd = __any_sync(kFull, odd);
+            __syncwarp();                                        // the packed row scales are visible to the whole warp
             const float m_max = odd ? __int_as_float(0x7fc00000) : fmaf(st.qe, bmax, st.qn * cmax) + 1e-30f;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
             ptx::tc_fence_after();
@@ -472,24 +485,35 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 st.thr = ls.thr;
             }
             uint32_t g_next = __ldcg(wtau + lane);
+            if (a.epi_mode == 0 || a.epi_mode == 3) {
+                // two strips in registers: the TMEM load of strip c + 1 is in flight while strip c is
+                // processed (the epilogue, not the tensor pipe, bounds this kernel)
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32; ++c) {
-                if ((c & 3) == 0) {
-                    if (g_next > st.tau_g) {
-                        st.tau_g = g_next;
-                        st.thr = thr_of(ninf, st.tau_g);
+                for (int c = 0; c < kTileN / 32; c += 2) {
+                    if ((c & 3) == 0) {
+                        if (g_next > st.tau_g) {
+                            st.tau_g = g_next;
+                            st.thr = thr_of(ninf, st.tau_g);
+                        }
+                        g_next = __ldcg(wtau + lane);
                     }
-                    g_next = __ldcg(wtau + lane);
+                    ptx::tmem_wait_ld();
+                    ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                    process_strip_i8(va, static_cast<uint32_t>(t) * kTileN + c * 32, c, n, row_valid, st, mt, m_max, lg, lane);
+                    ptx::tmem_wait_ld();
+                    if (c + 2 < kTileN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                    process_strip_i8(vb, static_cast<uint32_t>(t) * kTileN + (c + 1) * 32, c + 1, n, row_valid, st, mt, m_max, lg, lane);
                 }
-                if (a.epi_mode == 2) break;
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(taddr + c * 32, v);
-                ptx::tmem_wait_ld();
-                if (a.epi_mode == 1) {
+            } else if (a.epi_mode == 1) {                            // diagnostics: TMEM reads only
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, v);
+                    ptx::tmem_wait_ld();
                     asm volatile("" ::"r"(v[0]), "r"(v[31]));
-                    continue;
                 }
-                process_strip_i8(v, static_cast<uint32_t>(t) * kTileN + c * 32, c, n, row_valid, st, mt, m_max, lg, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();

@@ -639,7 +639,7 @@ def main():
 
     # ---- dominant kernel alone (roofline numerator), CUDA events on the launch stream
     qn = ops.normalize_cast(q_dev, dtype)
-    shard = store._buf[store._head:] if is_cache else store._shard
+    shard = store.scan_view()[0] if is_cache else store._shard
     rescored = None
     if b == 1 and args.prefilter and not is_cache:
         resc = torch.zeros((1,), dtype=torch.int32, device=dev)

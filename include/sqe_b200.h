@@ -286,6 +286,18 @@ SQE_API int sqe_search_batched_prefiltered(const void *D, int dtype, int64_t n, 
                                    uint32_t *out_rescored, void *workspace, int64_t workspace_bytes,
                                    void *stream);
 
+/*
+ * K5 through K2p: the query-cache lookup (top-1 + threshold, app/main.py:73-90) for a batch of RAW
+ * fp32 queries from the int8 copy of the cache rows + exact rescoring.  Outputs and threshold rule
+ * as for sqe_cache_top1; the best entry and its score are K3's bit for bit ("first maximum wins" =
+ * the lowest row), for any storage class of C.  C8 / meta: sqe_quantize_rows of the same rows.
+ */
+SQE_API int64_t sqe_cache_top1_prefiltered_workspace_bytes(int64_t n, int b, int dtype);
+SQE_API int sqe_cache_top1_prefiltered(const void *C, int dtype, int64_t n, int dim, const void *C8,
+                               const void *meta, const float *Q_raw, int b, double threshold,
+                               float *out_score, int32_t *out_idx, uint8_t *out_hit, void *workspace,
+                               int64_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

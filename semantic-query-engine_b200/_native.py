@@ -57,6 +57,9 @@ PROTOTYPES = [
     ("sqe_search_batched_prefiltered", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                                c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
                                                c_void_p, c_int64, c_void_p]),
+    ("sqe_cache_top1_prefiltered_workspace_bytes", c_int64, [c_int64, c_int, c_int]),
+    ("sqe_cache_top1_prefiltered", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                           c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     ("sqe_search_gemv_sharded", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_void_p),
                                         c_int64, c_uint32, c_int, c_void_p, c_int64, c_void_p]),
@@ -95,6 +98,7 @@ LAUNCHES_PER_CALL = {
     "sqe_search_gemv_sharded": 1,
     "sqe_search_gemv_prefiltered": 2,
     "sqe_search_batched_prefiltered": 3,      # prepare queries, int8 tensor-core scan, exact rescoring
+    "sqe_cache_top1_prefiltered": 4,          # the same + the threshold epilogue
 }
 
 

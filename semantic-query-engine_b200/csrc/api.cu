@@ -364,6 +364,33 @@ int sqe_cache_top1(const void* C, int dtype, int64_t n, int dim, const void* Q, 
     return rc == 0 ? SQE_OK : SQE_E_CUDA;
 }
 
+int64_t sqe_cache_top1_prefiltered_workspace_bytes(int64_t n, int b, int dtype) {
+    if (b < 1) b = 1;
+    return cache_stage_bytes(b) + 256 + sqe_search_batched_prefiltered_workspace_bytes(n, b, 1, dtype);
+}
+
+int sqe_cache_top1_prefiltered(const void* C, int dtype, int64_t n, int dim, const void* C8, const void* meta,
+                               const float* Q_raw, int b, double threshold, float* out_score, int32_t* out_idx,
+                               uint8_t* out_hit, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_common("cache_top1_prefiltered", C, dtype, n, dim, Q_raw, b);
+    if (rc != SQE_OK) return rc;
+    if (b == 0) return SQE_OK;
+    if (!out_score || !out_idx || !out_hit || !workspace) { set_error("cache_top1_prefiltered: null output/workspace"); return SQE_E_ARG; }
+    const int64_t stage = cache_stage_bytes(b);
+    if (workspace_bytes < stage) { set_error("cache_top1_prefiltered: workspace too small"); return SQE_E_WORKSPACE; }
+    // same layout as sqe_cache_top1: [kernel workspace ... | staging (idx, score) at the END]
+    char* ws = static_cast<char*>(workspace);
+    char* st = ws + ((workspace_bytes - stage) & ~static_cast<int64_t>(255));
+    int64_t* st_idx = reinterpret_cast<int64_t*>(st);
+    float* st_score = reinterpret_cast<float*>(st + static_cast<int64_t>(b) * 8);
+    rc = sqe_search_batched_prefiltered(C, dtype, n, dim, C8, meta, Q_raw, b, 1, st_score, st_idx, 0, nullptr, ws,
+                                        st - ws, stream);
+    if (rc != SQE_OK) return rc;
+    rc = launch_cache_finalize(st_score, st_idx, b, threshold, out_score, out_idx, out_hit,
+                               static_cast<cudaStream_t>(stream));
+    return rc == 0 ? SQE_OK : SQE_E_CUDA;
+}
+
 int sqe_merge_topk(const float* scores, const int64_t* idx, int lists, int b, int k_in, int k_out,
                    float* out_score, int64_t* out_idx, void* stream) {
     if (lists < 1 || b < 0 || k_in < 1 || k_out < 1 || k_in > SQE_MAX_K_GEMV || k_out > SQE_MAX_K_GEMV) {

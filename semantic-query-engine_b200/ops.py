@@ -381,6 +381,36 @@ def cache_top1(C: torch.Tensor, Q: torch.Tensor, threshold: float, path: int = 0
     return idx, score, hit
 
 
+def cache_top1_prefiltered(C: torch.Tensor, C8: torch.Tensor, meta: torch.Tensor, q_raw: torch.Tensor,
+                           threshold: float, n: Optional[int] = None, out=None
+                           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """K5 through K2p: (idx int32 [b], score fp32 [b], hit uint8 [b]) for RAW fp32 queries, from the
+    int8 copy of the cache rows + exact rescoring (any storage class of `C`)."""
+    dev = _require_cuda(C, C8, meta, q_raw)
+    if q_raw.dtype != torch.float32 or q_raw.dim() != 2 or q_raw.shape[1] != nat.SQE_DIM:
+        raise ValueError("q_raw must be fp32 [b,1024]")
+    rows = C.shape[0] if n is None else int(n)
+    if rows > C.shape[0] or C8.shape[0] < rows or meta.shape[0] < rows:
+        raise ValueError("n exceeds the cache rows / their coarse copy")
+    b = q_raw.shape[0]
+    if out is None:
+        score = torch.empty((b,), dtype=torch.float32, device=dev)
+        idx = torch.empty((b,), dtype=torch.int32, device=dev)
+        hit = torch.empty((b,), dtype=torch.uint8, device=dev)
+    else:
+        idx, score, hit = out
+    if b == 0:
+        return idx, score, hit
+    code = nat.DTYPE_CODES[dtype_name(C)]
+    with _launch_lock, torch.cuda.device(dev):
+        need = nat.load().sqe_cache_top1_prefiltered_workspace_bytes(rows, b, code)
+        ws = _workspace(dev, "cache_i8", need)
+        nat.call("sqe_cache_top1_prefiltered", C.data_ptr(), code, rows, nat.SQE_DIM, C8.data_ptr(), meta.data_ptr(),
+                 q_raw.data_ptr(), b, float(threshold), score.data_ptr(), idx.data_ptr(), hit.data_ptr(),
+                 ws.data_ptr(), ws.numel(), _stream(dev))
+    return idx, score, hit
+
+
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k_out: int, out=None
                ) -> Tuple[torch.Tensor, torch.Tensor]:
     """K4: scores/idx [lists,b,k_in] -> best-first [b,k_out]."""

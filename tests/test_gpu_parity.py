@@ -754,6 +754,87 @@ def test_query_cache_warm_start_from_the_reference_redis_list(sqe, golden_dir):
     assert empty.load_from_redis() == 0 and len(empty) == 0
 
 
+class _ListLfu:
+    """The reference's list semantics without the JSON (main.py:67-128): newest first, first maximum
+    wins, LFU eviction of the FIRST entry with the minimal freq.  Fast enough for thousands of
+    entries; pinned against oracle.LfuCacheModel (the JSON restatement) below."""
+
+    def __init__(self, max_items, threshold):
+        self.max_items, self.threshold = max_items, threshold
+        self.emb, self.resp, self.freq = [], [], []
+
+    def get(self, q):
+        if not self.emb:
+            return None
+        E = np.stack(self.emb).astype(np.float64)
+        qq = q[0].astype(np.float64)
+        sims = (E @ qq) / (np.linalg.norm(E, axis=1) * np.linalg.norm(qq))
+        i = int(np.argmax(sims))                            # first maximum
+        if sims[i] < self.threshold:
+            return None
+        self.freq[i] += 1
+        return self.resp[i]
+
+    def put(self, q, response):
+        if len(self.emb) >= self.max_items:
+            i = int(np.argmin(self.freq))                   # first minimum
+            del self.emb[i], self.resp[i], self.freq[i]
+        self.emb.insert(0, q[0].copy()); self.resp.insert(0, response); self.freq.insert(0, 1)
+
+
+@pytest.mark.parametrize("prefilter", [False, True])
+def test_query_cache_long_random_replay_with_tombstones_and_packing(sqe, prefilter):
+    """O(1) mutation (round 2): thousands of puts / hits / LFU evictions on a cache far beyond the
+    reference's 1000 entries.  Victims deep in the list leave tombstones, the buffer is packed
+    several times; responses, freq counters and every get() must follow the reference's list
+    semantics, and batch lookups (K5, or K2p when the cache keeps its int8 copy) must agree."""
+    rng = np.random.default_rng(404 + int(prefilter))
+    small = _ListLfu(6, 0.96)                                # the fast model == the JSON restatement
+    model = no.LfuCacheModel(6, 0.96)
+    for step in range(60):
+        v = rng.standard_normal((1, DIM)).astype(np.float32) if step % 3 else np.asarray([small.emb[0]]) if small.emb else rng.standard_normal((1, DIM)).astype(np.float32)
+        assert small.get(v) == model.get(v)
+        if step % 2 == 0:
+            small.put(v, f"s{step}"); model.put(v, f"s{step}")
+    assert small.resp == model.responses() and small.freq == model.freqs()
+
+    cap = 700
+    cache = sqe.GpuQueryCache(max_items=cap, threshold=0.96, dtype="fp32", prefilter=prefilter, use_graphs=False)
+    cache._SLIDE_MAX = 3                                     # force tombstones
+    ref = _ListLfu(cap, 0.96)
+    pool = []
+    packs0 = 0
+    for step in range(3000):
+        r = rng.random()
+        if pool and r < 0.35:                                # exact repeat of a cached query: a hit, freq += 1
+            v = pool[int(rng.integers(len(pool)))]
+        else:
+            v = rng.standard_normal((1, DIM)).astype(np.float32) * np.float32(rng.uniform(0.2, 5.0))
+        want = ref.get(v)
+        assert cache.get(v) == want, step
+        if want is None:
+            resp = f"r{step}"
+            ref.put(v, resp); cache.put(v, resp)
+            pool.append(v)
+            if len(pool) > 400:
+                pool.pop(0)
+        if step % 500 == 499:
+            assert cache.responses() == ref.resp and cache.freqs() == ref.freq, step
+    assert cache.responses() == ref.resp and cache.freqs() == ref.freq
+    assert len(cache) == cap and cache.tombstones() >= 0
+    # batch lookups over the mutated cache (tombstones included in the scan): best entry + hit flag
+    qb = np.concatenate([pool[i] for i in (0, 57, 200)] + [rng.standard_normal((5, DIM)).astype(np.float32)])
+    idx, score, hit = cache.lookup_batch(qb)
+    E = np.stack(ref.emb).astype(np.float64)
+    for j in range(len(qb)):
+        sims = (E @ qb[j].astype(np.float64)) / (np.linalg.norm(E, axis=1) * np.linalg.norm(qb[j]))
+        i = int(np.argmax(sims))
+        if sims[i] >= 0:                                     # else a tombstone (0.0) may be the scan's best row
+            assert cache.index_of_scanned_row(idx[j]) == i, (j, idx[j], i)
+            assert abs(score[j] - sims[i]) < 2e-6
+        assert bool(hit[j]) == bool(sims[i] >= 0.96)
+
+
 def test_corpus_index_speaks_the_reference_opensearch_bulk_format(sqe):
     """export_bulk_actions yields the reference's own bulk actions (main.py:318-331); feeding them
     (or search hits of the same shape) to import_bulk_actions rebuilds an equivalent index."""

@@ -1,0 +1,194 @@
+"""SURVEY.md 8f(3), literally: the REFERENCE'S OWN handlers on the GPU path.
+
+When a copy of the reference's `app/` is reachable -- `SQE_REFERENCE_ROOT`, `/root/reference`, or a
+copy staged under the git-ignored `oracle/_ref/reference/` by `scripts/stage_reference.sh` for a
+GPU run -- this loads the reference's unmodified `app/main.py` (absent services stubbed,
+oracle/ref_loader.py), calls `sqe_b200.plugin.install(main)` and then runs the reference's code:
+
+  * `RAGModel()` + `OpenSearchIndexer.add_embeddings` + `ask_websocket_endpoint` (main.py:650-735)
+    on the recorded request sequence of tests/golden/ws_session.* -- every client message and
+    every prompt must equal what the reference recorded with its own retrieval path;
+  * the lifespan ingest (main.py:568-580 -> `build_embeddings_from_scratch`, main.py:413-456) over
+    a synthetic PMC directory of 3,027 files = 32,717 chunks (the size of the reference's own sample
+    corpus), through `run_in_executor(add_embeddings)`, followed by websocket
+    requests whose expected messages come from the oracle over all 32,717 chunk vectors.
+
+Skipped when no reference copy is present (the driver's GPU box has none)."""
+import asyncio
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIM = 1024
+
+
+def _reference_root():
+    for cand in (os.environ.get("SQE_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(ROOT, "oracle", "_ref", "reference")):
+        if cand and os.path.isfile(os.path.join(cand, "app", "main.py")):
+            return cand
+    return None
+
+
+@pytest.fixture()
+def ref_main():
+    root = _reference_root()
+    if root is None:
+        pytest.skip("no copy of the reference's app/ here (scripts/stage_reference.sh stages one for a GPU run)")
+    import sqe_b200
+    sqe_b200._native.load()
+    from oracle import ref_loader
+    ref_loader.REFERENCE_ROOT = root
+    m = ref_loader.load_reference_main()
+    return sqe_b200, m
+
+
+class FakeWebSocket:
+    def __init__(self, payload):
+        self.payload, self.sent, self.closed = payload, [], False
+
+    async def accept(self):
+        pass
+
+    async def receive_text(self):
+        return self.payload
+
+    async def send_text(self, text):
+        self.sent.append(text)
+
+    async def close(self):
+        self.closed = True
+
+
+def _drive(m, requests, prompts):
+    results = []
+    for req in requests:
+        ws = FakeWebSocket(json.dumps(req))
+        before = len(prompts)
+        asyncio.run(m.ask_websocket_endpoint(ws))
+        assert ws.closed
+        results.append({"sent": ws.sent, "prompt": prompts[before] if len(prompts) > before else None})
+    return results
+
+
+def _stub_generation(m, prompts):
+    async def fake_stream(prompt, system_msg=""):                       # main.py:615-647's interface
+        prompts.append(prompt)
+        yield "Answer "
+        yield f"#{len(prompts)}"
+    m.openai_generate_text_stream = fake_stream
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_reference_websocket_handler_on_the_gpu_path_reproduces_its_recorded_session(ref_main, golden_dir, dtype):
+    sqe, m = ref_main
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ws_replay import load_session
+    meta, emb, qvec = load_session(golden_dir)
+    cache = sqe.plugin.install(m, dtype=dtype, strict=True)
+    assert m.OpenSearchIndexer.__mro__[1] is sqe.GpuCorpusIndex
+    m.rag_model = m.RAGModel()                                          # main.py:408-411 -> GpuCorpusIndex
+    assert isinstance(m.rag_model.os_indexer, sqe.GpuCorpusIndex)
+    m.rag_model.os_indexer.add_embeddings(emb, meta["docs"])            # main.py:309-338
+
+    async def fake_ollama(text, model=None):                            # main.py:134-153's result
+        return qvec[text].tolist()
+    m.ollama_embed_text = fake_ollama
+    prompts = []
+    _stub_generation(m, prompts)
+    results = _drive(m, meta["requests"], prompts)
+    assert results == meta["results"]
+    assert cache.responses() == meta["final_cache_responses"] and cache.freqs() == meta["final_cache_freqs"]
+
+
+def test_reference_lifespan_ingest_of_32717_chunks_then_websocket_requests(ref_main, tmp_path):
+    sqe, m = ref_main
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ws_replay
+    rng = np.random.default_rng(2026)
+    n_docs, n_chunks = 3027, 32717                                      # the reference's PMC sample
+    per = np.full(n_docs, n_chunks // n_docs)
+    per[: n_chunks - per.sum()] += 1
+    rng.shuffle(per)
+    chunk_of_text, expect_docs = {}, []
+    pmc = tmp_path / "PMC"
+    pmc.mkdir()
+    for d in range(n_docs):
+        name = f"PMC{100000 + d}.txt"
+        words = []
+        for c in range(int(per[d])):
+            n_words = m.CHUNK_SIZE if c + 1 < per[d] else int(rng.integers(1, m.CHUNK_SIZE))
+            words.append(" ".join([f"{name[:-4]}c{c}"] + ["lorem"] * (n_words - 1)))
+        (pmc / name).write_text("\n".join(words))
+    (pmc / "README.md").write_text("not a PMC file")                    # ignored by main.py:431
+    emb = (rng.standard_normal((n_chunks, DIM)) * rng.uniform(0.3, 3.0, size=(n_chunks, 1))).astype(np.float32)
+
+    # the order the reference will see the chunks in: os.listdir order, then chunk order
+    row = 0
+    for fname in os.listdir(str(pmc)):
+        if fname.startswith("PMC") and fname.endswith(".txt"):
+            text = m.basic_cleaning((pmc / fname).read_text())
+            for chunk in m.chunk_text(text, m.CHUNK_SIZE):
+                chunk_of_text[chunk] = row
+                expect_docs.append({"doc_id": fname, "text": chunk})
+                row += 1
+    assert row == n_chunks
+
+    unit = emb / np.linalg.norm(emb, axis=1, keepdims=True)
+
+    def mix(rows):
+        w = np.array([1.0, 0.85, 0.7, 0.58, 0.48, 0.4, 0.33, 0.27][: len(rows)], dtype=np.float32)
+        return ((w[:, None] * unit[rows]).sum(axis=0) * np.float32(2.5)).astype(np.float32)
+
+    qvec = {"first question": mix([13, 14, 15, 9000, 9001, 20000, 17, 33]),
+            "second question": mix([32716, 32715, 5, 6, 7, 15000, 15001, 15002]),
+            "third question": mix([100, 200, 300, 400, 500, 600, 700, 800])}
+    qvec["first question again"] = qvec["first question"] * np.float32(1.7)     # cos 1 -> cache hit
+
+    async def fake_ollama(text, model=None):                            # main.py:134-153, stubbed
+        if text in qvec:
+            return qvec[text]
+        return emb[chunk_of_text[text]]
+    m.ollama_embed_text = fake_ollama
+    cache = sqe.plugin.install(m, dtype="bf16", strict=True)
+    m.EMB_DIR = str(pmc)
+    prompts = []
+    _stub_generation(m, prompts)
+
+    async def lifespan():                                               # main.py:568-580
+        async with m.lifespan(m.app):
+            pass
+    asyncio.run(lifespan())
+    index = m.rag_model.os_indexer
+    assert isinstance(index, sqe.GpuCorpusIndex) and index.num_rows == n_chunks and index.has_any_data()
+    assert index._docs == expect_docs
+
+    requests = [{"query": "first question", "top_k": 8}, {"query": "second question"},
+                {"query": "first question again", "top_k": 8}, {"query": ""},
+                {"query": "third question", "top_k": 5}, {"query": "second question", "top_k": 6}]
+    results = _drive(m, requests, prompts)
+
+    # expected: the same handler flow with the oracle as the retrieval path (stored bf16 rows)
+    d_st = oracle.from_storage(oracle.to_storage(oracle.normalize_rows(emb), "bf16"), "bf16")
+    model = oracle.LfuCacheModel(m.REDIS_MAX_ITEMS, m.CACHE_SIM_THRESHOLD)
+
+    def os_search(q, k):
+        q_st = oracle.from_storage(oracle.to_storage(oracle.normalize_rows(q), "bf16"), "bf16")
+        s, i = oracle.topk_cosine(d_st, q_st, k)
+        return [(expect_docs[int(r)], float(sc)) for sc, r in zip(s[0], i[0]) if r >= 0]
+    want = ws_replay.replay({"requests": requests}, qvec, model.get, model.put, os_search, sqe.build_context_text)
+    assert [r["sent"] for r in results] == [w["sent"] for w in want]
+    assert [r["prompt"] for r in results] == [w["prompt"] for w in want]
+    assert cache.responses() == model.responses() and cache.freqs() == model.freqs()
+    print(f"reference lifespan ingest: {n_chunks} chunks of {n_docs} files through run_in_executor(add_embeddings); "
+          f"{len(requests)} websocket requests through main.ask_websocket_endpoint, {len(prompts)} prompts, "
+          f"cache {cache.freqs()}")

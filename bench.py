@@ -71,7 +71,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SQE_BENCH_WORKLOAD", "b1024"),
-                    choices=["b1024", "b1", "cache64", "ingest", "config1", "serve"])
+                    choices=["b1024", "b1", "cache64", "ingest", "config1", "serve", "cachemut"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=None,
@@ -268,15 +268,25 @@ def run_reference_arm(args):
 def workload_config(args, world):
     if args.workload == "cache64":
         cdt = args.dtype if args.dtype in ("bf16x2", "fp16") else "bf16"
+        pfc = not getattr(args, "no_prefilter", False)
+        if pfc and args.dtype == "fp32":
+            cdt = "fp32"
         return {"workload": f"query cache 1Mx1024 {cdt}, streaming batch-64 top-1 + 0.95 threshold "
                             "(BASELINE configs[4])", "rows": 1_000_000, "batch": 64, "k": 1,
-                "dtype": cdt, "l2": "inputs larger than L2"}
+                "dtype": cdt, "l2": "inputs larger than L2",
+                "path": ("K2p: int8 tensor-core prefilter + exact rescoring + threshold" if pfc
+                         else "K5: 16-bit tensor-core scan (k = 1) + threshold")}
     b = (args.batch or 1024) if args.workload == "b1024" else 1
     pf = ", int8 prefilter + exact rescoring (K3p)" if (getattr(args, "prefilter", False) and b == 1) else ""
     return {"workload": f"{args.rows}x1024 {args.dtype} corpus, batch-{b} cosine top-{args.k}{pf} "
                         f"({baseline_tag(args.rows, args.dtype, b, args.k)})",
             "rows": args.rows, "batch": b, "k": args.k, "dtype": args.dtype,
             "sharding": f"rows split over {world} rank(s), all-gather + merge" if world > 1 else "single shard",
+            "path": ("K2p: int8 tensor-core prefilter (tcgen05 kind::i8) + exact rescoring, results bit-identical to "
+                     "the exact scan; the bf16 tensor-core kernel (K2) is timed beside it in roofline.bf16_path"
+                     if (b > 2 and args.k <= 32 and not getattr(args, "no_prefilter", False))
+                     else "K2: bf16/fp16 tensor-core scan with fused top-k" if b > 2
+                     else "K3p: int8 prefilter + exact rescoring" if pf else "K3: exact streaming scan"),
             "l2": "inputs larger than L2 (shard >= 2.5 GB per rank vs 126 MB L2)"}
 
 
@@ -382,7 +392,7 @@ def run_traffic_probe(args, torch, sqe_b200, ops, dev):
         ops.normalize_cast(x, dtype, out=D[lo: lo + x.shape[0]])
     q = torch.randn((b, DIM), generator=torch.Generator().manual_seed(99), dtype=torch.float32).to(dev)
     qn = ops.normalize_cast(q, dtype)
-    k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter and not is_cache
+    k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter
     coarse = ops.quantize_rows(D) if ((args.prefilter and b == 1) or k2p) else None
     for _ in range(3):
         if k2p:
@@ -512,12 +522,16 @@ def main():
         return run_config1(args, torch, sqe_b200, nat, dev, peaks)
     if args.workload == "serve":
         return run_serve(args, torch, sqe_b200, nat, dev, peaks)
+    if args.workload == "cachemut":
+        return run_cachemut(args, torch, sqe_b200, nat, dev, peaks)
     is_cache = args.workload == "cache64"
     b = {"b1024": 1024, "b1": 1, "cache64": 64}[args.workload]
     if args.batch and args.workload == "b1024":
         b = args.batch
     k = 1 if is_cache else args.k
-    dtype = args.dtype if (not is_cache or args.dtype in ("bf16x2", "fp16")) else "bf16"
+    cache_pf = is_cache and not args.no_prefilter
+    dtype = args.dtype if (not is_cache or args.dtype in ("bf16x2", "fp16") or
+                           (cache_pf and args.dtype == "fp32")) else "bf16"
     total_rows = 1_000_000 if is_cache else args.rows
     steps = args.steps or (20 if b > 1 else 50)
     warmup = args.warmup if args.warmup is not None else 3
@@ -530,7 +544,8 @@ def main():
     local_rows = row_hi - row_lo
     use_k2p = False
     if is_cache:
-        store = sqe_b200.GpuQueryCache(max_items=local_rows, threshold=0.95, dtype=dtype, device=dev)
+        store = sqe_b200.GpuQueryCache(max_items=local_rows, threshold=0.95, dtype=dtype, device=dev,
+                                       prefilter=cache_pf)
     else:
         use_k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter
         store = sqe_b200.GpuCorpusIndex(dtype=dtype, device=dev, keep_payload=False,
@@ -649,6 +664,10 @@ def main():
     elif b == 1:
         kern = lambda: ops.topk_gemv(shard, qn, k, n=local_rows)
         kname = "topk_gemv_kernel"
+    elif cache_pf:
+        c8v, cmv = store._c8[store._head:], store._cm[store._head:]
+        kern = lambda: ops.cache_top1_prefiltered(shard, c8v, cmv, q_dev, 0.95, n=local_rows)
+        kname = "topk_batched_i8_kernel"
     else:
         kern = lambda: ops.topk_batched(shard, qn, k, n=local_rows)
         kname = "topk_batched_kernel"
@@ -678,6 +697,33 @@ def main():
                     "note": "results are bit-identical to the exact scan (topk_gemv_kernel); the roofline "
                             "fraction is taken on the bytes THIS path moves, the speed-up over the exact "
                             "scan's roofline comes from moving about half as many"}
+    elif cache_pf:
+        alg = local_rows * (DIM + 16)                    # the int8 rows + their 16 B of constants
+        roofline = {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
+                    "kernel_ms_covers": "the whole prefiltered lookup: workspace memset + prepare_queries_kernel + "
+                                        "topk_batched_i8_kernel (int8 scan) + batched_rescore_kernel (exact pass) + "
+                                        "cache_finalize_kernel (threshold)",
+                    "exact_scan_bytes": local_rows * DIM * esize,
+                    "note": "best entry and score are those of the exact scan bit for bit (K3 arithmetic in the "
+                            "exact pass); the fraction is taken on the bytes THIS path must move"}
+        if dtype != "fp32":
+            k5 = lambda: ops.cache_top1(shard, qn, 0.95, path=2, n=local_rows)
+            for _ in range(3):
+                k5()
+            torch.cuda.synchronize()
+            k0.record()
+            for _ in range(kiters):
+                k5()
+            k1.record()
+            torch.cuda.synchronize()
+            kms5 = k0.elapsed_time(k1) / kiters
+            a5 = local_rows * DIM * esize
+            roofline["bf16_path"] = {"kernel": "topk_batched_kernel<TOP1>", "kernel_ms": kms5, "bound": "hbm",
+                                     "achieved": a5 / (kms5 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": a5 / (kms5 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                     "algorithmic_bytes_per_launch": a5}
+            roofline["speedup_over_bf16_path"] = kms5 / kms
     elif b == 1 or is_cache:
         alg = local_rows * DIM * esize
         roofline = {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
@@ -1038,7 +1084,8 @@ def run_serve(args, torch, sqe_b200, nat, dev, peaks):
     from concurrent.futures import ThreadPoolExecutor
     rows, k, clients = args.rows, args.k, 256
     per_client = args.steps or 24
-    index = sqe_b200.GpuCorpusIndex(dtype=args.dtype, device=dev, keep_payload=False)
+    index = sqe_b200.GpuCorpusIndex(dtype=args.dtype, device=dev, keep_payload=False,
+                                    prefilter=not args.no_prefilter)       # micro-batches go through K2p
     index.reserve(rows)
     gen = torch.Generator(device=dev)
     for blk in range((rows + GEN_BLOCK - 1) // GEN_BLOCK):
@@ -1132,12 +1179,69 @@ def run_serve(args, torch, sqe_b200, nat, dev, peaks):
                                "MicroBatcher.search (GIL-bound client side)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
-                         "kernel": "topk_batched_kernel", "traffic": None,
+                         "kernel": "topk_batched_kernel" if args.no_prefilter else "topk_batched_i8_kernel", "traffic": None,
                          "note": f"{served} requests in {batches} batched launches (mean batch {served / max(batches, 1):.0f})"},
             "cpu_baseline": None,
             "asyncio_clients": aio,
             "direct_b1": {"value": qps_direct, "unit": "queries/s", "clients": 16, "latency_ms_p50": p50_d,
                           "latency_ms_p99": p99_d, "note": "same clients calling GpuCorpusIndex.search directly"}}
+    print(json.dumps(line), flush=True)
+
+
+def run_cachemut(args, torch, sqe_b200, nat, dev, peaks):
+    """Cache mutation at BASELINE configs[4] size: a FULL cache of 1M entries, then
+    `lfu_cache_put` calls (main.py:121-128) that each evict the least-frequently-used entry first
+    (main.py:101-118) -- host bookkeeping + the row write on the device.  The reference does two
+    LRANGE + JSON passes over the whole list per such call.  Also: `lfu_cache_get` of a cached query."""
+    n = 1_000_000 if args.rows == 10_000_000 else args.rows
+    dtype = args.dtype if args.dtype != "bf16" else "fp32"           # the reference's cache holds fp32 vectors
+    cycles = args.steps or 4000
+    cache = sqe_b200.GpuQueryCache(max_items=n, threshold=0.96, dtype=dtype, device=dev, use_graphs=False)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    blocks = [torch.randn((min(GEN_BLOCK, n - lo), DIM), generator=gen, device=dev) for lo in range(0, n, GEN_BLOCK)]
+    cache.bulk_load(torch.cat(blocks))
+    keep = blocks[0][:64].cpu().numpy()
+    del blocks
+    rng = np.random.default_rng(6)
+    newq = rng.standard_normal((cycles + 64, 1, DIM)).astype(np.float32)
+    # some entries are popular: hits raise their freq, so later victims are not always the newest entry
+    for i in range(32):
+        assert cache.get(keep[i: i + 1]) == str(i)
+    for i in range(64):
+        cache.put(newq[cycles + i], f"warm {i}")
+    torch.cuda.synchronize()
+    l0 = nat.launch_count
+    t0 = time.perf_counter()
+    for i in range(cycles):
+        cache.put(newq[i], f"answer {i}")                           # full cache: evict + insert
+    torch.cuda.synchronize()
+    dt_put = (time.perf_counter() - t0) / cycles
+    launches = nat.launch_count - l0
+    assert len(cache) == n
+    t0 = time.perf_counter()
+    g = 20
+    for i in range(g):
+        assert cache.get(keep[i: i + 1]) == str(i)                  # a hit: scan + freq bump
+    dt_get = (time.perf_counter() - t0) / g
+    esize = {"bf16": 2, "fp16": 2, "fp32": 4, "bf16x2": 4}[dtype]
+    rows_scanned = cache.scan_view()[1]
+    line = {"metric": f"cache mutations/sec (lfu_cache_put with LFU eviction) on a full {human_rows(n)}-entry cache",
+            "value": 1.0 / dt_put, "unit": "puts/s", "n_gpus": 1, "steps": cycles, "warmup": 64,
+            "ms_per_step": dt_put * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"workload": f"GpuQueryCache(max_items={n}, {dtype}), full; {cycles} x put() each evicting first "
+                                   "(main.py:101-128); then get() of cached queries",
+                       "rows": n, "l2": "host bookkeeping + one 4 KB row write per put"},
+            "clocks": None,
+            "e2e": {"value": 1.0 / dt_put, "unit": "puts/s", "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": 0,
+                    "us_per_put_with_eviction": dt_put * 1e6},
+            "gpu_launches": launches,
+            "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None,
+                         "kernel": "normalize_cast_kernel (one row)", "traffic": None},
+            "cpu_baseline": None,
+            "get_hit": {"ms_per_get": dt_get * 1e3, "rows_scanned": rows_scanned, "tombstones": cache.tombstones(),
+                        "scan_gbs": rows_scanned * DIM * esize / dt_get / 1e9}}
     print(json.dumps(line), flush=True)
 
 

@@ -153,10 +153,12 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
  *                          1 = single-CTA UMMA (M = 128), 2 = CTA-pair UMMA (cta_group::2, M = 256).
  *   SQE_TUNE_K2_EPILOGUE_MODE: DIAGNOSTICS ONLY, results are invalid unless 0.  1 = the epilogue
  *                          only reads TMEM, 2 = no epilogue (isolates the TMA + MMA main loop).
- *   SQE_TUNE_K2_D_HINT, SQE_TUNE_K2_WINDOW: RETIRED round-1 experiments (L2 policy of the shard-row
- *                          TMA loads; progress window between the units that share d-tiles).  Both
- *                          were negative results (profiles/README.md) and their code has been removed
- *                          from the kernel; the knobs are still accepted and ignored.
+ *   SQE_TUNE_K2_D_HINT:    RETIRED round-1 experiment (L2 policy of the shard-row TMA loads): a negative
+ *                          result (profiles/README.md), removed from the kernel; accepted and ignored.
+ *   SQE_TUNE_K2_WINDOW:    the int8 kernel (K2p) only: how many d-tiles a unit may run ahead of the
+ *                          slowest unit that shares its d-tiles.  0 = default (8), -1 = unbounded,
+ *                          n > 0 = n tiles.  (For the bf16 kernel the window was a negative result in
+ *                          round 1 and is not compiled in.)
  *   The role timers and the epilogue mode exist only in the diagnostics instantiations of the two
  *   benchmarked kernel forms (k <= 32 CTA-pair form with shared d-tiles; k > 64 CTA-pair form with
  *   one q-tile); every other form ignores them.

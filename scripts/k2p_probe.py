@@ -36,13 +36,15 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 nat = sqe_b200._native
+if os.environ.get("K2P_WINDOW"):
+    nat.tuning_set(nat.SQE_TUNE_K2_WINDOW, int(os.environ["K2P_WINDOW"]))
 nat.tuning_set(nat.SQE_TUNE_K2_EPILOGUE_MODE, 3)          # report pairs logged
 ops.search_batched_prefiltered(D, d8, meta, q, K, rescored=resc)
 logged = resc.cpu().numpy().copy()
 nat.tuning_set(nat.SQE_TUNE_K2_EPILOGUE_MODE, 0)
 t_p = timeit(lambda: ops.search_batched_prefiltered(D, d8, meta, q, K, rescored=resc))
 r = resc.cpu().numpy()
-line = f"rows={rows} b={b} k={K} {DT}: K2p {t_p:.3f} ms ({b / t_p * 1e3:.0f} q/s), exact rows/query median {int(__import__('numpy').median(r))} max {r.max()} full-scans {(r >= rows).sum()}, logged/query median {int(__import__('numpy').median(logged))} max {logged.max()}"
+line = f"window={os.environ.get('K2P_WINDOW', 'default')} rows={rows} b={b} k={K} {DT}: K2p {t_p:.3f} ms ({b / t_p * 1e3:.0f} q/s), exact rows/query median {int(__import__('numpy').median(r))} max {r.max()} full-scans {(r >= rows).sum()}, logged/query median {int(__import__('numpy').median(logged))} max {logged.max()}"
 if DT != "fp32":
     t_2 = timeit(lambda: ops.topk_batched(D, qn, K))
     line += f" | K2 {t_2:.3f} ms ({b / t_2 * 1e3:.0f} q/s) -> x{t_2 / t_p:.2f}"

@@ -95,7 +95,7 @@ int sqe_tuning_set(int knob, int value) {
         g_k2_epilogue_mode = value;
         return old;
     }
-    if (knob == SQE_TUNE_K2_WINDOW && value >= 0 && value <= 1024) {
+    if (knob == SQE_TUNE_K2_WINDOW && value >= -1 && value <= 1024) {
         const int old = g_k2_window;
         g_k2_window = value;
         return old;

@@ -88,6 +88,8 @@ struct K2I8Args {
     int log_cap;              // entries per candidate log
     int blog_cap;             // entries per bound log (64 R)
     int epi_mode;             // diagnostics (SQE_TUNE_K2_EPILOGUE_MODE): 2 = no epilogue work (results invalid)
+    uint32_t* ws_prog;        // [group][n_qt] d-tile progress of the units that share d-tiles (in the arrivals page)
+    int window;               // how many d-tiles a unit may run ahead of the slowest sibling (0 = unbounded)
     int gpad;
     int boot_j, boot_m;
     const float4* meta;       // row constants {sd, eps, nd, 0} (sqe_quantize_rows)
@@ -328,9 +330,29 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const int q_row = q_tile * C::kQTile + static_cast<int>(rank) * kRowsPerCta;
             int stage = 0;
             uint32_t phase = 0;
+            // The units of a group (one per q-tile) read the SAME d-tiles and should read them from L2
+            // once one of them has fetched them from HBM.  This kernel is bound by its epilogue, whose
+            // pace differs from unit to unit (slow-path frequency), so without a bound the units drift
+            // apart by hundreds of tiles and every d-tile is fetched from HBM up to n_qt times (ncu:
+            // 2.3 x the int8 shard).  A unit therefore publishes the tile it is about to load and does
+            // not run more than `window` tiles ahead of its slowest sibling; the group finishes when
+            // its slowest unit does, so waiting costs nothing.
+            uint32_t* my_prog = a.ws_prog + group * n_qt;
+            const bool gate = (rank == 0) && (n_qt > 1) && (a.window > 0);
             for (int i = 0; i < my_tiles; ++i) {
                 const int t = group + i * n_groups;
                 const int d_row = t * kTileN + static_cast<int>(rank) * C::kBRows;
+                if (gate) {
+                    st_relaxed_gpu(my_prog + q_tile, static_cast<uint32_t>(i + 1));
+                    const long long t0 = clock64();
+                    while (true) {
+                        uint32_t lo = 0xffffffffu;
+                        for (int u = 0; u < n_qt; ++u) lo = min(lo, ld_relaxed_gpu(my_prog + u));
+                        if (lo + static_cast<uint32_t>(a.window) >= static_cast<uint32_t>(i + 1)) break;
+                        if (clock64() - t0 > 2000000000LL) break;      // never hang on a sibling: just stop waiting
+                        __nanosleep(200);
+                    }
+                }
                 for (int kc = 0; kc < kNumChunksI8; ++kc) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                     if (kc == 0) {
@@ -359,6 +381,7 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (gate) st_relaxed_gpu(my_prog + q_tile, 0xffffffffu);    // done: never hold the others back
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
@@ -879,6 +902,8 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
     a.meta = static_cast<const float4*>(meta);
     a.qmeta = qmeta;
     a.epi_mode = g_k2_epilogue_mode;
+    a.ws_prog = reinterpret_cast<uint32_t*>(w + 4096 + 2048);     // second half of the arrivals page (zeroed per launch)
+    a.window = g_k2_window > 0 ? g_k2_window : (g_k2_window < 0 ? 0 : 8);
     a.ws_spill = reinterpret_cast<uint64_t*>(spill);
     a.ws_clogs = reinterpret_cast<uint64_t*>(clogs);
     a.log_cap = k2i::kLogCapMax;

@@ -33,6 +33,10 @@ def main():
     ap.add_argument("--rows", type=int, default=600_037)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--epochs", type=int, default=200)
+    ap.add_argument("--stress", type=int, default=0,
+                    help="protocol stress run: this many exchange epochs with skewed ranks (random host-side delays), "
+                         "alternating the fused and the kernel exchange, batch shapes and scans; every result is "
+                         "compared with the first result of the same request")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -112,6 +116,33 @@ def main():
             ref = outs
         assert torch.equal(ref[0][1], i1) and torch.equal(ref[0][0].view(torch.int32), s1.view(torch.int32))
     index.prefilter = True
+    if args.stress:
+        # skewed ranks: every rank sleeps for its own random times between launches, so the ranks enter
+        # the exchanges out of step (a rank may be a full call ahead of a peer: buffer parity, epoch flags)
+        import time as _time
+        rng = np.random.default_rng(1000 + rank)
+        shapes = [(1, 10, True), (1, 10, False), (4, 10, True), (2, 10, True), (1, 100, True), (130, 10, True), (2, 33, False)]
+        first = {}
+        t0 = _time.time()
+        for e in range(args.stress):
+            b_, k_, fused = shapes[e % len(shapes)]
+            sharded.fuse_small_batches = fused
+            index.prefilter = (e // len(shapes)) % 2 == 0
+            if rng.random() < 0.3:
+                _time.sleep(float(rng.uniform(0, 3e-4)) * (1 + 3 * (rank == (e // 97) % world)))
+            out = sharded.search_device(q_raw[:b_].contiguous(), k_, queries_ready=bool(e % 2))
+            key = (b_, k_)
+            if key not in first:
+                torch.cuda.synchronize()
+                first[key] = (out[0].clone(), out[1].clone())
+            elif e % 7 == 0 or e > args.stress - 50:
+                torch.cuda.synchronize()
+                assert torch.equal(out[1], first[key][1]) and torch.equal(out[0], first[key][0]), (e, key)
+        torch.cuda.synchronize()
+        sharded.fuse_small_batches = True
+        index.prefilter = True
+        report.append(f"stress: {args.stress} exchange epochs with skewed ranks in {_time.time() - t0:.1f} s, "
+                      f"{len(shapes)} request shapes, fused / kernel exchange, exact / prefiltered: all identical")
     report.append(f"{4 * args.epochs} back-to-back one-query steps (ordinary + overlapped launches, exact + prefiltered): identical")
     assert sharded.exchange == ("nccl" if args.exchange == "nccl" else sharded.exchange)
     dist.barrier()

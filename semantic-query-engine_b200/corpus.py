@@ -357,15 +357,13 @@ class GpuCorpusIndex:
         return ops.stream_pipeline(self.device, batches, self._as_rows, lambda b: b * k * 12,
                                    launch, unpack, depth)
 
-    def can_fuse_exchange(self, b: int) -> bool:
+    @staticmethod
+    def can_fuse_exchange(b: int) -> bool:
         """Whether `search_device` answers a batch of `b` queries with a scan whose last CTA can
-        carry the sharded mode's exchange (`xchg=`): the one-query fused scan, or the prefiltered
-        scan for one or two queries."""
-        if self._shard is None or self._rows <= 0:
-            return False
-        if self.prefilter and self._coarse8 is not None and 1 <= b <= 2 and self._rows <= self._coarse8.shape[0]:
-            return True
-        return b == 1
+        carry the sharded mode's exchange (`xchg=`): one or two queries (the fused exact scan, or
+        the prefiltered scan when the index keeps its int8 copy).  Depends on nothing but `b`, so
+        every rank of a sharded index takes the same path."""
+        return 1 <= b <= 2
 
     def search_device(self, q_dev: torch.Tensor, k: int, idx_offset: int = 0, out=None, xchg=None,
                       queries_ready: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -391,7 +389,7 @@ class GpuCorpusIndex:
             # K2P_MAX_K (beyond that the exact pass outweighs the cheaper scan and K2 is as fast);
             # fp32 shards: always (their only other batch path is one streaming pass per query)
             return ops.search_batched_prefiltered(shard, c8, cm, q_dev, k, idx_offset=idx_offset, n=rows, out=out)
-        if q_dev.shape[0] == 1 and q_dev.dtype == torch.float32:
+        if q_dev.dtype == torch.float32 and (q_dev.shape[0] == 1 or (xchg is not None and q_dev.shape[0] == 2)):
             # the reference's own case (one query, main.py:355): normalise + scan in ONE launch
             return ops.search_gemv(shard, q_dev, k, idx_offset=idx_offset, n=rows, out=out, xchg=xchg,
                                    queries_ready=queries_ready)

@@ -59,7 +59,6 @@ class ShardedCorpusIndex:
         self._gather_s = None
         self._gather_i = None
         self.fuse_small_batches = True  # b <= 2: exchange fused into the scan kernel (p2p mode only)
-        self._fuse_ok = {}              # batch size -> every rank's local index can carry the exchange
 
     # ------------------------------------------------------------------ layout
     def finalize(self, local_rows: Optional[int] = None) -> None:
@@ -76,7 +75,6 @@ class ShardedCorpusIndex:
         counts = [int(c.item()) for c in counts]
         self.row_offset = sum(counts[: self.rank])
         self.total_rows = sum(counts)
-        self._fuse_ok.clear()
         if self.total_rows >= 0xFFFFFFFF:
             raise ValueError("the merge kernels carry global rows as 32-bit keys: at most 2^32 - 2 rows in total")
 
@@ -139,16 +137,10 @@ class ShardedCorpusIndex:
         self._p2p_failed = False
 
     def _all_ranks_can_fuse(self, b: int) -> bool:
-        """Every rank must take the same path (the fused form and the exchange kernel share
-        buffers and epochs but not flags).  Decided collectively once per batch size; call
-        `finalize()` again after changing an index (e.g. enabling its prefilter) on some ranks."""
-        if b not in self._fuse_ok:
-            mine = 1 if (b <= 2 and self.local is not None and hasattr(self.local, "can_fuse_exchange")
-                         and self.local.can_fuse_exchange(b)) else 0
-            flag = torch.tensor([mine], dtype=torch.int32, device=self._comm_device())
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            self._fuse_ok[b] = bool(int(flag.item()))
-        return self._fuse_ok[b]
+        """Every rank must take the same path (the fused form and the exchange kernel share buffers
+        and epochs but not flags): the decision depends on the batch size only."""
+        return self.local is not None and hasattr(self.local, "can_fuse_exchange") and \
+            self.local.can_fuse_exchange(b)
 
     # ------------------------------------------------------------------ search
     def search_device(self, q_dev: torch.Tensor, k: int, out=None, queries_ready: bool = False

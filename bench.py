@@ -265,6 +265,11 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def k2p_pays_rows(rows, b, dtype):
+    import sqe_b200
+    return sqe_b200.ops.k2p_pays(rows, b, dtype)
+
+
 def workload_config(args, world):
     if args.workload == "cache64":
         cdt = args.dtype if args.dtype in ("bf16x2", "fp16") else "bf16"
@@ -284,7 +289,8 @@ def workload_config(args, world):
             "sharding": f"rows split over {world} rank(s), all-gather + merge" if world > 1 else "single shard",
             "path": ("K2p: int8 tensor-core prefilter (tcgen05 kind::i8) + exact rescoring, results bit-identical to "
                      "the exact scan; the bf16 tensor-core kernel (K2) is timed beside it in roofline.bf16_path"
-                     if (b > 2 and args.k <= 32 and not getattr(args, "no_prefilter", False))
+                     if (b > 2 and args.k <= 32 and not getattr(args, "no_prefilter", False)
+                         and k2p_pays_rows(args.rows // max(world, 1), b, args.dtype))
                      else "K2: bf16/fp16 tensor-core scan with fused top-k" if b > 2
                      else "K3p: int8 prefilter + exact rescoring" if pf else "K3: exact streaming scan"),
             "l2": "inputs larger than L2 (shard >= 2.5 GB per rank vs 126 MB L2)"}
@@ -392,7 +398,7 @@ def run_traffic_probe(args, torch, sqe_b200, ops, dev):
         ops.normalize_cast(x, dtype, out=D[lo: lo + x.shape[0]])
     q = torch.randn((b, DIM), generator=torch.Generator().manual_seed(99), dtype=torch.float32).to(dev)
     qn = ops.normalize_cast(q, dtype)
-    k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter
+    k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter and ops.k2p_pays(rows, b, dtype)
     coarse = ops.quantize_rows(D) if ((args.prefilter and b == 1) or k2p) else None
     for _ in range(3):
         if k2p:
@@ -547,7 +553,8 @@ def main():
         store = sqe_b200.GpuQueryCache(max_items=local_rows, threshold=0.95, dtype=dtype, device=dev,
                                        prefilter=cache_pf)
     else:
-        use_k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter
+        use_k2p = b > 2 and k <= sqe_b200.GpuCorpusIndex.K2P_MAX_K and not args.no_prefilter and \
+            ops.k2p_pays(local_rows, b, dtype)       # small shards (N = 8: 1.25M rows per rank) stay on K2
         store = sqe_b200.GpuCorpusIndex(dtype=dtype, device=dev, keep_payload=False,
                                         prefilter=bool((args.prefilter and b == 1) or use_k2p))
         store.reserve(local_rows)

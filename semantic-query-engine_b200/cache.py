@@ -344,7 +344,8 @@ class GpuQueryCache:
         3 = force K2p."""
         live, rows = self._scan()
         q_dev = q_dev.contiguous()
-        if (path == 3 or (path == 0 and self.prefilter and q_dev.shape[0] > 2)) and rows > 0:
+        if (path == 3 or (path == 0 and self.prefilter and q_dev.shape[0] > 2 and
+                          ops.k2p_pays(rows, q_dev.shape[0], self.dtype))) and rows > 0:
             if self._c8 is None:
                 raise ValueError("this cache was built without prefilter=True")
             return ops.cache_top1_prefiltered(live, self._c8[self._head:], self._cm[self._head:], q_dev,

@@ -384,10 +384,12 @@ class GpuCorpusIndex:
                                                xchg=xchg, queries_ready=queries_ready)
         if self.prefilter and c8 is not None and q_dev.shape[0] > 2 and 0 < rows <= c8.shape[0] \
                 and q_dev.dtype == torch.float32 and xchg is None \
-                and k <= (nat.SQE_MAX_K_BATCHED if self.dtype == "fp32" else self.K2P_MAX_K):
+                and k <= (nat.SQE_MAX_K_BATCHED if self.dtype == "fp32" else self.K2P_MAX_K) \
+                and ops.k2p_pays(rows, q_dev.shape[0], self.dtype):
             # K2p: the batch form of the same idea on the int8 tensor cores.  16-bit shards: up to
-            # K2P_MAX_K (beyond that the exact pass outweighs the cheaper scan and K2 is as fast);
-            # fp32 shards: always (their only other batch path is one streaming pass per query)
+            # K2P_MAX_K (beyond that the exact pass outweighs the cheaper scan and K2 is as fast) and
+            # from the shard size where it pays (ops.k2p_pays); fp32 shards: always (their only
+            # other batch path is one streaming pass per query)
             return ops.search_batched_prefiltered(shard, c8, cm, q_dev, k, idx_offset=idx_offset, n=rows, out=out)
         if q_dev.dtype == torch.float32 and (q_dev.shape[0] == 1 or (xchg is not None and q_dev.shape[0] == 2)):
             # the reference's own case (one query, main.py:355): normalise + scan in ONE launch

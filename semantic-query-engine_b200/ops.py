@@ -325,6 +325,19 @@ def search_batched_prefiltered(D: torch.Tensor, D8: torch.Tensor, meta: torch.Te
     return scores, idx
 
 
+def k2p_pays(rows: int, b: int, dtype: str) -> bool:
+    """Routing rule between the two tensor-core batch paths, from the measured grid
+    (profiles/r2_k2p_grid.txt, 0.5M-10M rows x b = 32..1024): K2p's scan moves half the bytes at
+    twice the tensor rate but pays ~0.1-0.3 ms of fixed work (query preparation, the bound's
+    start-up phase, the exact pass), so it wins from ~1M rows for small batches and from ~2.5M
+    rows for b = 1024 (1.3-1.7 x at 4M rows, 1.5-1.6 x at 10M).  fp32 shards: always (their only
+    other batch path is one streaming pass per query)."""
+    if dtype == "fp32":
+        return True
+    need = 1_000_000 if b <= 64 else 1_500_000 if b <= 128 else 2_000_000 if b <= 512 else 2_500_000
+    return rows >= need
+
+
 def topk_batched(D: torch.Tensor, Q: torch.Tensor, k: int, idx_offset: int = 0,
                  n: Optional[int] = None, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """K2: exact cosine top-k on the tensor cores (bf16/fp16 shards)."""

@@ -41,7 +41,7 @@ extern "C" {
 #define SQE_API
 #endif
 
-#define SQE_ABI_VERSION 1
+#define SQE_ABI_VERSION 2
 #define SQE_DIM 1024            /* app/main.py:38 EMBED_DIM */
 #define SQE_MAX_K_GEMV 256      /* largest k of sqe_topk_gemv / sqe_merge_topk */
 #define SQE_MAX_K_BATCHED 128   /* largest k of sqe_topk_batched */
@@ -159,6 +159,8 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
  *                          slowest unit that shares its d-tiles.  0 = default (8), -1 = unbounded,
  *                          n > 0 = n tiles.  (For the bf16 kernel the window was a negative result in
  *                          round 1 and is not compiled in.)
+ *   SQE_TUNE_ENC_GEMM_FORM: tile geometry of sqe_encoder_gemm: 0 = choose by the number of tiles,
+ *                          1 = 128 x 64 tiles (single CTA), 2 = 256 x 256 tiles (CTA pairs).
  *   The role timers and the epilogue mode exist only in the diagnostics instantiations of the two
  *   benchmarked kernel forms (k <= 32 CTA-pair form with shared d-tiles; k > 64 CTA-pair form with
  *   one q-tile); every other form ignores them.
@@ -167,6 +169,7 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
 #define SQE_TUNE_K2_EPILOGUE_MODE 1
 #define SQE_TUNE_K2_D_HINT 2
 #define SQE_TUNE_K2_WINDOW 3
+#define SQE_TUNE_ENC_GEMM_FORM 4
 SQE_API int sqe_tuning_set(int knob, int value);
 
 /*
@@ -299,6 +302,59 @@ SQE_API int sqe_cache_top1_prefiltered(const void *C, int dtype, int64_t n, int 
                                const void *meta, const float *Q_raw, int b, double threshold,
                                float *out_score, int32_t *out_idx, uint8_t *out_hit, void *workspace,
                                int64_t workspace_bytes, void *stream);
+
+/*
+ * ENC  the embedding encoder in front of the path.
+ * Replaces the HTTP round trip to the Ollama server that produces every embedding the path
+ * consumes:  ollama_embed_text / embed_texts_in_batches / embed_query, app/main.py:134-180 and
+ * app/embedding_gen.py:143-190 (model "mxbai-embed-large": a BERT-large encoder -- 24 post-LN
+ * layers, hidden 1024, 16 heads of 64, FFN 4096 with erf-GELU, learned absolute positions <= 512,
+ * CLS pooling; the arithmetic lives in the external server, so it is restated from the published
+ * architecture, oracle/bert_oracle.py).  The host side (tokeniser, layer loop) is
+ * semantic-query-engine_b200/encoder.py; these are its five kernels.  Tokens of all sequences of
+ * a batch are PACKED into one [T, 1024] activation matrix (each sequence starts at the next multiple
+ * of 8 rows, nothing else separates them); buffers
+ * that feed a tensor-core operand are fp16, the residual stream and LayerNorm are fp32.
+ *
+ *   sqe_encoder_embed_ln   rows of word_emb[ids] + pos_emb[pos] + type_emb[0] -> LayerNorm ->
+ *                          out_f32 [rows, 1024] and its fp16 copy out_f16; ids < 0 = padding row
+ *                          (written as zeros).
+ *   sqe_encoder_layernorm  in [rows, 1024] fp32 -> LayerNorm -> out_f32 + out_f16.
+ *   sqe_encoder_gemm       Y = X W^T + bias on tcgen05 (X [m, k] fp16 with ldx elements per row,
+ *                          W [n, k] fp16 = a torch Linear weight), n % 256 == 0, k % 64 == 0, fused
+ *                          epilogue:
+ *       SQE_ENC_EPI_SPLIT   columns < n_split -> fp16 out0 [m, ld0] (columns < q_cols scaled by
+ *                           q_scale first), columns >= n_split -> fp16 TRANSPOSED
+ *                           out1[(col - n_split), row] with ld1 elements per row (V^T of the attention);
+ *                           n_split = n: a plain fp16 linear layer;
+ *       SQE_ENC_EPI_RES_F32 + residual [m, ldr] fp32 -> fp32 out0 [m, ld0] (pre-LayerNorm sum);
+ *       SQE_ENC_EPI_GELU    gelu(.) (erf form) -> fp16 out0 [m, ld0].
+ *   sqe_encoder_attention  softmax(Q K^T) V per (sequence, head); qk [t_pad, 2048] fp16 = Q (already
+ *                          scaled by 1/8) | K, vt [1024, t_pad] fp16 = V^T (t_pad % 8 == 0);
+ *                          tiles int32 [n_tiles, 4] = (first token of the sequence, its length,
+ *                          first query row of this 128-query tile, 0); the first token of a sequence
+ *                          must be a multiple of 8 (a TMA box of V^T starts on a 16-byte boundary);
+ *                          max_len = longest sequence (1..512); ctx [t_pad, 1024] fp16.
+ *   sqe_encoder_pool       out[s, :] = h[first_token[s], :] (CLS pooling), ldo elements per row.
+ */
+#define SQE_ENC_HIDDEN 1024
+#define SQE_ENC_MAX_TOKENS 512
+#define SQE_ENC_EPI_SPLIT 0
+#define SQE_ENC_EPI_RES_F32 1
+#define SQE_ENC_EPI_GELU 2
+SQE_API int sqe_encoder_embed_ln(const int32_t *ids, const int32_t *pos, const float *word_emb, int vocab,
+                         const float *pos_emb, int max_pos, const float *type_emb, const float *gamma,
+                         const float *beta, float eps, int64_t rows, float *out_f32, void *out_f16,
+                         void *stream);
+SQE_API int sqe_encoder_layernorm(const float *in, const float *gamma, const float *beta, float eps,
+                          int64_t rows, float *out_f32, void *out_f16, void *stream);
+SQE_API int sqe_encoder_gemm(const void *X, int64_t ldx, const void *W, const float *bias, int64_t m, int n,
+                     int k, int epilogue, void *out0, int64_t ld0, void *out1, int64_t ld1, int n_split,
+                     int q_cols, float q_scale, const float *residual, int64_t ldr, void *stream);
+SQE_API int sqe_encoder_attention(const void *qk, const void *vt, int64_t t_pad, const int32_t *tiles,
+                          int n_tiles, int max_len, void *ctx, void *stream);
+SQE_API int sqe_encoder_pool(const float *h, const int32_t *first_token, int n_seq, float *out, int64_t ldo,
+                     void *stream);
 
 #ifdef __cplusplus
 }

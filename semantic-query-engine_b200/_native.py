@@ -67,6 +67,13 @@ PROTOTYPES = [
                                             c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
                                             c_int, c_int, POINTER(c_void_p), c_int64, c_uint32, c_int,
                                             c_void_p, c_int64, c_void_p]),
+    ("sqe_encoder_embed_ln", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p]),
+    ("sqe_encoder_layernorm", c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p]),
+    ("sqe_encoder_gemm", c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
+                                 c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64, c_void_p]),
+    ("sqe_encoder_attention", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    ("sqe_encoder_pool", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
 ]
 
 
@@ -99,7 +106,14 @@ LAUNCHES_PER_CALL = {
     "sqe_search_gemv_prefiltered": 2,
     "sqe_search_batched_prefiltered": 3,      # prepare queries, int8 tensor-core scan, exact rescoring
     "sqe_cache_top1_prefiltered": 4,          # the same + the threshold epilogue
+    "sqe_encoder_embed_ln": 1,
+    "sqe_encoder_layernorm": 1,
+    "sqe_encoder_gemm": 1,
+    "sqe_encoder_attention": 1,
+    "sqe_encoder_pool": 1,
 }
+SQE_ENC_EPI_SPLIT, SQE_ENC_EPI_RES_F32, SQE_ENC_EPI_GELU = 0, 1, 2
+SQE_ENC_MAX_TOKENS = 512
 
 
 def load():
@@ -141,6 +155,7 @@ SQE_TUNE_K2_CTA_GROUP = 0
 SQE_TUNE_K2_EPILOGUE_MODE = 1      # diagnostics only
 SQE_TUNE_K2_D_HINT = 2
 SQE_TUNE_K2_WINDOW = 3
+SQE_TUNE_ENC_GEMM_FORM = 4     # 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs
 
 
 def tuning_set(knob: int, value: int) -> int:

@@ -20,7 +20,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsqe_b200.so")
 
-SOURCES = ["api.cu", "normalize_cast.cu", "topk_gemv.cu", "topk_prefilter.cu", "topk_batched.cu", "topk_batched_i8.cu", "exchange.cu"]
+SOURCES = ["api.cu", "normalize_cast.cu", "topk_gemv.cu", "topk_prefilter.cu", "topk_batched.cu", "topk_batched_i8.cu", "exchange.cu",
+           "encoder_gemm.cu", "encoder_attn.cu", "encoder_rows.cu"]
 COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -105,6 +105,11 @@ int sqe_tuning_set(int knob, int value) {
         g_k2_d_hint = value;
         return old;
     }
+    if (knob == SQE_TUNE_ENC_GEMM_FORM && value >= 0 && value <= 2) {
+        const int old = g_enc_gemm_form;
+        g_enc_gemm_form = value;
+        return old;
+    }
     set_error("tuning_set: unknown knob %d / value %d", knob, value);
     return SQE_E_ARG;
 }
@@ -434,6 +439,106 @@ int sqe_exchange_merge(const float* scores, const int64_t* idx, int b, int k_in,
                                capacity_entries, epoch, wait_mask, out_score, out_idx, d.sm_count,
                                static_cast<cudaStream_t>(stream));
     return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : SQE_E_CUDA);
+}
+
+// ------------------------------------------------------------------ ENC  embedding encoder
+static int rc_map(int rc) { return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : SQE_E_CUDA); }
+
+int sqe_encoder_embed_ln(const int32_t* ids, const int32_t* pos, const float* word_emb, int vocab,
+                         const float* pos_emb, int max_pos, const float* type_emb, const float* gamma,
+                         const float* beta, float eps, int64_t rows, float* out_f32, void* out_f16, void* stream) {
+    if (rows < 0 || vocab < 1 || max_pos < 1) { set_error("encoder_embed_ln: bad sizes"); return SQE_E_ARG; }
+    if (rows == 0) return SQE_OK;
+    if (!ids || !pos || !word_emb || !pos_emb || !type_emb || !gamma || !beta || !out_f32 || !out_f16 ||
+        !aligned16(word_emb) || !aligned16(pos_emb) || !aligned16(type_emb) || !aligned16(gamma) || !aligned16(beta) ||
+        !aligned16(out_f32) || !aligned16(out_f16)) {
+        set_error("encoder_embed_ln: null or unaligned pointer");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return rc_map(launch_encoder_embed_ln(ids, pos, word_emb, pos_emb, type_emb, gamma, beta, eps, rows, vocab, max_pos,
+                                          out_f32, out_f16, static_cast<cudaStream_t>(stream)));
+}
+
+int sqe_encoder_layernorm(const float* in, const float* gamma, const float* beta, float eps, int64_t rows,
+                          float* out_f32, void* out_f16, void* stream) {
+    if (rows < 0) { set_error("encoder_layernorm: negative rows"); return SQE_E_ARG; }
+    if (rows == 0) return SQE_OK;
+    if (!in || !gamma || !beta || !out_f32 || !out_f16 || !aligned16(in) || !aligned16(gamma) || !aligned16(beta) ||
+        !aligned16(out_f32) || !aligned16(out_f16)) {
+        set_error("encoder_layernorm: null or unaligned pointer");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return rc_map(launch_encoder_layernorm(in, gamma, beta, eps, rows, out_f32, out_f16, static_cast<cudaStream_t>(stream)));
+}
+
+int sqe_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
+                     int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
+                     float q_scale, const float* residual, int64_t ldr, void* stream) {
+    if (m < 0 || m >= (1LL << 31) - 256 || n < 256 || n % 256 != 0 || k < 64 || k % 64 != 0) {
+        set_error("encoder_gemm: need 0 <= m < 2^31, n %% 256 == 0, k %% 64 == 0 (m=%lld n=%d k=%d)", (long long)m, n, k);
+        return SQE_E_ARG;
+    }
+    if (epilogue < SQE_ENC_EPI_SPLIT || epilogue > SQE_ENC_EPI_GELU) { set_error("encoder_gemm: bad epilogue %d", epilogue); return SQE_E_ARG; }
+    if (m == 0) return SQE_OK;
+    if (!X || !W || !bias || !out0 || !aligned16(X) || !aligned16(W) || !aligned16(bias) || !aligned16(out0) ||
+        ldx < k || ldx % 8 != 0 || ld0 % 8 != 0) {
+        set_error("encoder_gemm: null / unaligned pointer or bad leading dimension");
+        return SQE_E_ARG;
+    }
+    if (epilogue == SQE_ENC_EPI_SPLIT) {
+        if (n_split < 0 || n_split > n || n_split % 64 != 0 || q_cols < 0 || q_cols > n_split || q_cols % 32 != 0 ||
+            ld0 < n_split || (n_split < n && (!out1 || ld1 < m))) {
+            set_error("encoder_gemm: bad split (n_split=%d q_cols=%d ld0=%lld ld1=%lld)", n_split, q_cols, (long long)ld0,
+                      (long long)ld1);
+            return SQE_E_ARG;
+        }
+    } else if (ld0 < n) {
+        set_error("encoder_gemm: ld0 < n");
+        return SQE_E_ARG;
+    }
+    if (epilogue == SQE_ENC_EPI_RES_F32 && (!residual || !aligned16(residual) || ldr < n || ldr % 4 != 0)) {
+        set_error("encoder_gemm: residual null / unaligned / too narrow");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return rc_map(launch_encoder_gemm(X, ldx, W, bias, m, n, k, epilogue, out0, ld0, out1, ld1, n_split, q_cols, q_scale,
+                                      residual, ldr, d.sm_count, static_cast<cudaStream_t>(stream)));
+}
+
+int sqe_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const int32_t* tiles, int n_tiles,
+                          int max_len, void* ctx, void* stream) {
+    if (n_tiles < 0 || n_tiles > 0x7fffffff / 16 || t_pad < 0 || t_pad % 8 != 0 || t_pad >= (1LL << 31) - 1024) {
+        set_error("encoder_attention: bad sizes (n_tiles=%d t_pad=%lld; t_pad %% 8 == 0)", n_tiles, (long long)t_pad);
+        return SQE_E_ARG;
+    }
+    if (n_tiles == 0) return SQE_OK;
+    if (max_len < 1 || max_len > SQE_ENC_MAX_TOKENS) { set_error("encoder_attention: max_len=%d not in [1,%d]", max_len, SQE_ENC_MAX_TOKENS); return SQE_E_ARG; }
+    if (!qk || !vt || !tiles || !ctx || !aligned16(qk) || !aligned16(vt) || !aligned16(tiles) || !aligned16(ctx)) {
+        set_error("encoder_attention: null or unaligned pointer");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return rc_map(launch_encoder_attention(qk, vt, t_pad, tiles, n_tiles, max_len, ctx, static_cast<cudaStream_t>(stream)));
+}
+
+int sqe_encoder_pool(const float* h, const int32_t* first_token, int n_seq, float* out, int64_t ldo, void* stream) {
+    if (n_seq < 0 || ldo < SQE_ENC_HIDDEN || ldo % 4 != 0) { set_error("encoder_pool: bad sizes"); return SQE_E_ARG; }
+    if (n_seq == 0) return SQE_OK;
+    if (!h || !first_token || !out || !aligned16(h) || !aligned16(out)) { set_error("encoder_pool: null or unaligned pointer"); return SQE_E_ARG; }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    return rc_map(launch_encoder_pool(h, first_token, n_seq, out, ldo, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -1,0 +1,258 @@
+// Encoder self-attention, one shot per (sequence, head, 128-query tile) on tcgen05.
+//
+// BERT sequences are at most 512 tokens, so a whole row of scores fits the tensor memory:
+// 128 queries (TMEM lanes) x up to 512 keys (fp32 columns) = all 512 columns of one SM.  No
+// online softmax, no rescaling of partial outputs:
+//
+//   1. TMA:  Q tile [128 x 64], K [S x 64] and V^T [64 x S] of this (sequence, head) into shared
+//            memory (128-byte swizzle, K-major: exactly the operand layout of the scoring kernels);
+//   2. MMA:  S = Q K^T into TMEM (Q was scaled by 1/8 in the QKV epilogue);
+//   3. eight warps (two per lane quarter, each half of the keys): row maximum, then
+//            p = exp2((s - max) log2 e), masked beyond the sequence end, rounded to fp16 and written
+//            to shared memory IN the swizzled K-major operand layout, over the dead Q / K tiles;
+//            the row sum is taken over the rounded values so that the weights sum to one;
+//   4. MMA:  O = P V  (A = P from step 3, B = V^T), accumulator over the dead score columns;
+//   5. the same warps scale O by 1 / sum and store fp16 rows of the context matrix.
+//
+// Sequences are PACKED (no padding between them): the tile list gives (first token, length,
+// first query of the tile); keys beyond the end of a sequence are whatever follows in the packed
+// buffer (the next sequence, or zero rows) and are masked by index.
+//
+// Roofline: tensor pipe nominally (4 * 128 * S * 64 FLOP per tile) but at head_dim 64 the MUFU
+// (one ex2 per score) is the binding unit: 128 S / 16 per clock per SM.
+#include "sqe_enc.cuh"
+
+namespace sqe {
+namespace enc {
+
+constexpr int kAttnThreads = 288;              // warp 0: TMA + MMA; warps 1..8: softmax / output
+constexpr int kQBytes = kBM * 128;             // 16 KB
+constexpr int kKVBlockBytes = 64 * 128;        // 8 KB: 64 keys x 64 dims (K) or 64 dims x 64 keys (V^T)
+constexpr int kPBlockBytes = kBM * 128;        // 16 KB: 128 queries x 64 keys
+
+struct AttnArgs {
+    const int4* tiles;        // (first token of the sequence, its length, first query of the tile, 0)
+    __half* ctx;              // [T, 1024]
+    int s_max;                // keys staged per tile: max sequence length rounded up to 64
+    uint32_t tmem_cols;       // power of two >= max(s_max, 64)
+};
+
+__host__ __device__ inline int attn_region_a_bytes(int s_max) {
+    const int qk = kQBytes + s_max * 128;       // Q + K
+    const int p = s_max * 256;                   // P: (s_max / 64) blocks of 16 KB
+    return qk > p ? qk : p;
+}
+__host__ __device__ inline int attn_smem_bytes(int s_max) {
+    return attn_region_a_bytes(s_max) + s_max * 128 /* V^T */ + 2 * 2 * kBM * 4 /* max, sum */ + 64 + 1024;
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
+                         const AttnArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_addr);
+
+    const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+    const int4 tile = __ldg(a.tiles + blockIdx.x);
+    const int seq_start = tile.x, seq_len = tile.y, q0 = tile.z;
+    const int s_pad = (seq_len + 63) & ~63;                    // keys this tile scores
+    const int n_kc = s_pad >> 6;
+
+    const int region_a = attn_region_a_bytes(a.s_max);
+    const uint32_t sm_q = base;
+    const uint32_t sm_k = base + kQBytes;
+    const uint32_t sm_p = base;                                 // over Q and K once S is in TMEM
+    const uint32_t sm_vt = base + region_a;
+    float* red_max = reinterpret_cast<float*>(sm + region_a + a.s_max * 128);      // [2][128]
+    float* red_sum = red_max + 2 * kBM;                                            // [2][128]
+    const uint32_t bar_base = base + region_a + a.s_max * 128 + 2 * 2 * kBM * 4;
+    const uint32_t bar_load = bar_base;         // Q, K, V^T have landed
+    const uint32_t bar_s = bar_base + 8;        // scores complete
+    const uint32_t bar_p = bar_base + 16;       // P written (8 warp arrivals)
+    const uint32_t bar_o = bar_base + 24;       // output complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + region_a + a.s_max * 128 + 2 * 2 * kBM * 4 + 32);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tmap_qk);
+            ptx::prefetch_tensormap(&tmap_vt);
+            ptx::mbar_init(bar_load, 1);
+            ptx::mbar_init(bar_s, 1);
+            ptx::mbar_init(bar_p, 8);
+            ptx::mbar_init(bar_o, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_smem), a.tmem_cols);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------- loads
+            ptx::mbar_expect_tx(bar_load, kQBytes + 2 * n_kc * kKVBlockBytes);
+            ptx::tma_load_2d(sm_q, &tmap_qk, head * kHeadDim, seq_start + q0, bar_load);          // rows 0..63
+            ptx::tma_load_2d(sm_q + kKVBlockBytes, &tmap_qk, head * kHeadDim, seq_start + q0 + 64, bar_load);
+            for (int kc = 0; kc < n_kc; ++kc)
+                ptx::tma_load_2d(sm_k + kc * kKVBlockBytes, &tmap_qk, kHidden + head * kHeadDim,
+                                 seq_start + 64 * kc, bar_load);
+            for (int kc = 0; kc < n_kc; ++kc)
+                ptx::tma_load_2d(sm_vt + kc * kKVBlockBytes, &tmap_vt, seq_start + 64 * kc, head * kHeadDim,
+                                 bar_load);
+            ptx::mbar_wait(bar_load, 0);
+            ptx::tc_fence_after();
+            // ------------------------------------------------------- S = Q K^T
+            const uint64_t dq = make_sw128_desc(sm_q);
+            for (int n0 = 0; n0 < s_pad; n0 += 256) {
+                const int nn = (s_pad - n0 < 256) ? (s_pad - n0) : 256;
+                const uint32_t idesc = idesc_f16(kBM, nn);
+                const uint64_t dk = make_sw128_desc(sm_k + n0 * 128);
+#pragma unroll
+                for (int k4 = 0; k4 < kHeadDim / kUmmaK; ++k4)
+                    ptx::umma_f16<1>(tmem_base + n0, dq + 2 * k4, dk + 2 * k4, idesc, k4 != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(bar_s);
+            // ------------------------------------------------------- O = P V
+            ptx::mbar_wait(bar_p, 0);
+            ptx::tc_fence_after();
+            constexpr uint32_t idesc_o = idesc_f16(kBM, kHeadDim);
+            for (int kc = 0; kc < n_kc; ++kc) {
+                const uint64_t dp = make_sw128_desc(sm_p + kc * kPBlockBytes);
+                const uint64_t dv = make_sw128_desc(sm_vt + kc * kKVBlockBytes);
+#pragma unroll
+                for (int k4 = 0; k4 < kChunkK / kUmmaK; ++k4)
+                    ptx::umma_f16<1>(tmem_base, dp + 2 * k4, dv + 2 * k4, idesc_o, (kc | k4) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(bar_o);
+        }
+    } else {
+        // ---------------------------------------------------------------- softmax + output
+        const int quarter = warp & 3;                          // TMEM lanes 32 q .. 32 q + 31
+        const int half = (warp - 1) >> 2;                      // which half of the keys
+        const int r = quarter * 32 + lane;                     // query row of the tile
+        const int n_strips = s_pad >> 6;                       // strips of 32 keys in this half
+        const int col_base = half * (s_pad >> 1);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        constexpr float kLog2e = 1.4426950408889634f;
+        const float ninf = __int_as_float(0xff800000);
+
+        ptx::mbar_wait(bar_s, 0);
+        ptx::tc_fence_after();
+        float mx = ninf;
+#pragma unroll 1
+        for (int s = 0; s < n_strips; ++s) {
+            const int c0 = col_base + 32 * s;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + c0, v);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < seq_len) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+        red_max[half * kBM + r] = mx;
+        ptx::bar_sync_named(1, 256);
+        mx = fmaxf(red_max[r], red_max[kBM + r]);              // finite: key 0 is always inside the sequence
+        const float mb = mx * kLog2e;
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int s = 0; s < n_strips; ++s) {
+            const int c0 = col_base + 32 * s;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + c0, v);
+            ptx::tmem_wait_ld();
+            uint32_t h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float p0 = (c0 + 2 * j < seq_len) ? exp2f(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mb)) : 0.0f;
+                const float p1 = (c0 + 2 * j + 1 < seq_len) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mb)) : 0.0f;
+                const __half2 hh = __floats2half2_rn(p0, p1);
+                const float2 back = __half22float2(hh);
+                sum += back.x + back.y;
+                h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            // operand layout: block kc = 64 keys, row r at r * 128 B, 16-byte chunk c at (c ^ (r & 7))
+            const uint32_t blk = sm_p + (c0 >> 6) * kPBlockBytes + r * 128;
+            const int ch0 = (c0 & 63) >> 3;                    // 0 or 4
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t addr = blk + (static_cast<uint32_t>((ch0 + c) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[4 * c]), "r"(h[4 * c + 1]),
+                             "r"(h[4 * c + 2]), "r"(h[4 * c + 3])
+                             : "memory");
+            }
+        }
+        red_sum[half * kBM + r] = sum;
+        ptx::tc_fence_before();                // the score columns are about to be overwritten by O
+        ptx::fence_proxy_async_smem();         // P: generic-proxy stores -> tensor-core operand reads
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_p);
+        ptx::bar_sync_named(1, 256);           // both halves' sums are in shared memory
+
+        ptx::mbar_wait(bar_o, 0);
+        ptx::tc_fence_after();
+        const float inv = 1.0f / (red_sum[r] + red_sum[kBM + r]);
+        {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + half * 32, v);          // this warp's 32 of the 64 output dims
+            ptx::tmem_wait_ld();
+            if (q0 + r < seq_len) {
+                uint4* op = reinterpret_cast<uint4*>(a.ctx + static_cast<int64_t>(seq_start + q0 + r) * kHidden +
+                                                     head * kHeadDim + half * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 hh = __floats2half2_rn(__uint_as_float(v[8 * j + 2 * e]) * inv,
+                                                             __uint_as_float(v[8 * j + 2 * e + 1]) * inv);
+                        w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem_base, a.tmem_cols);
+    }
+}
+
+}  // namespace enc
+
+int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const void* tiles, int n_tiles,
+                             int max_len, void* ctx, cudaStream_t stream) {
+    using namespace enc;
+    if (n_tiles == 0) return 0;
+    AttnArgs a = {};
+    a.tiles = static_cast<const int4*>(tiles);
+    a.ctx = static_cast<__half*>(ctx);
+    a.s_max = (max_len + 63) & ~63;
+    a.tmem_cols = 64;
+    while (a.tmem_cols < static_cast<uint32_t>(a.s_max)) a.tmem_cols *= 2;
+    CUtensorMap tq, tv;
+    // Q | K: [t_pad, 2048], box = 64 elements x 64 rows (the Q tile is two boxes); V^T: [1024, t_pad]
+    int rc = make_map_2d(&tq, qk, 2 * kHidden, static_cast<uint64_t>(t_pad), 2 * kHidden, 64);
+    if (rc != 0) return rc;
+    rc = make_map_2d(&tv, vt, static_cast<uint64_t>(t_pad), kHidden, static_cast<uint64_t>(t_pad), 64);
+    if (rc != 0) return rc;
+    const int smem = attn_smem_bytes(a.s_max);
+    cudaError_t e = cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("encoder_attention: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+    encoder_attention_kernel<<<dim3(static_cast<unsigned>(n_tiles), kHeads), kAttnThreads, smem, stream>>>(tq, tv, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("encoder_attention: launch: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+}  // namespace sqe

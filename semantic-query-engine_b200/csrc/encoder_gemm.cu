@@ -1,0 +1,349 @@
+// Encoder linear layers on tcgen05:  Y[M, N] = X[M, K] . W[N, K]^T  (+ bias, + fused epilogue).
+//
+// X (activations, fp16 row-major) and W (a torch Linear weight [out, in], fp16 row-major) are both
+// K-major, so the operand staging is the scoring kernel's (topk_batched.cu): TMA boxes of
+// 64 elements x rows with the 128-byte swizzle, a ring of smem stages, tcgen05.mma issued by one
+// thread, two fp32 accumulators in TMEM so that the epilogue of tile i overlaps the main loop of
+// tile i + 1.  Persistent CTAs (or CTA pairs) walk the tile list with a fixed stride; tiles that
+// share a row block of X are adjacent so X is read from HBM once and W stays in L2.
+//
+// Two geometries:
+//   <BN = 256, CG = 2>  a CTA pair computes a 256 x 256 tile (cta_group::2, each CTA stages its 128
+//                       rows of X and half of the W rows): the throughput form (ingest batches);
+//   <BN = 64,  CG = 1>  128 x 64 tiles: the latency form (a handful of queries: M = 128, so the
+//                       number of CTAs that stream W is N / 64 instead of N / 256).
+//
+// Epilogues (8 warps: two per TMEM lane quarter, each takes half of the tile's columns):
+//   kEpiSplit   y = acc + bias;  columns < n_split -> fp16 row-major out0 (columns < q_cols are
+//               multiplied by q_scale first: the 1/sqrt(64) of the attention scores, exact in fp16),
+//               columns >= n_split -> fp16 TRANSPOSED out1[(col - n_split), row]  (V^T for the
+//               attention kernel's second MMA: lanes are consecutive rows, so each column is one
+//               coalesced 64-byte store per warp).  n_split = N gives a plain fp16 linear layer.
+//   kEpiResF32  y = acc + bias + residual (fp32) -> fp32 out0: the pre-LayerNorm sum.
+//   kEpiGelu    y = gelu(acc + bias) (erf form, as BERT) -> fp16 out0.
+//
+// Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 M N K.
+#include "sqe_enc.cuh"
+
+namespace sqe {
+namespace enc {
+
+constexpr int kGemmThreads = 320;              // TMA, MMA, 8 epilogue warps
+constexpr int kABytes = kBM * kChunkK * 2;     // 16 KB: this CTA's 128 rows of one K chunk
+
+template <int BN, int CG>
+struct GemmCfg {
+    static constexpr int kTileM = kBM * CG;
+    static constexpr int kBRows = BN / CG;               // W rows this CTA stages per chunk
+    static constexpr int kBBytes = kBRows * kChunkK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (192 * 1024) / kStageBytes;     // 6 x 32 KB or 8 x 24 KB
+    static constexpr int kTmemCols = 2 * BN;             // two accumulators
+    static constexpr int kOffBar = kStages * kStageBytes;
+    static constexpr int kOffTmemPtr = kOffBar + (2 * kStages + 4) * 8;
+    static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(kTmemCols == 128 || kTmemCols == 512, "TMEM allocation must be a power of two");
+};
+
+enum { kEpiSplit = 0, kEpiResF32 = 1, kEpiGelu = 2 };
+
+struct GemmArgs {
+    int64_t m;                // rows of X that exist (stores are guarded by it)
+    int n, k;
+    int n_mt, n_nt, n_units;  // tiles along M and N, CTAs (or pairs) in the grid
+    const float* bias;        // [n]
+    void* out0;
+    int64_t ld0;
+    __half* out1;             // kEpiSplit: transposed part, [n - n_split, ld1]
+    int64_t ld1;
+    int n_split, q_cols;
+    float q_scale;
+    const float* residual;    // kEpiResF32: [m, ldr] fp32
+    int64_t ldr;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int BN, int CG, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const GemmArgs a) {
+    using C = GemmCfg<BN, CG>;
+    constexpr int kStages = C::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;         // SWIZZLE_128B atoms are 1024-B aligned
+    uint8_t* sm = smem_raw + (base - raw_addr);
+
+    const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+    const int unit = blockIdx.x / CG;
+    const int n_tiles = a.n_mt * a.n_nt;
+    const int n_chunks = a.k / kChunkK;
+
+    const uint32_t bar_full = base + C::kOffBar;               // [kStages]
+    const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;        // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + C::kOffTmemPtr);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_x);
+        ptx::prefetch_tensormap(&tmap_w);
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(bar_full + 8 * s, 1);               // the leader's expect_tx arrival
+            ptx::mbar_init(bar_empty + 8 * s, 1);              // one tcgen05.commit
+        }
+        for (int acc = 0; acc < 2; ++acc) {
+            ptx::mbar_init(bar_tfull + 8 * acc, 1);            // one tcgen05.commit
+            ptx::mbar_init(bar_tempty + 8 * acc, 8 * CG);      // one arrival per epilogue warp (of both CTAs)
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_ptr_smem), C::kTmemCols);
+    ptx::tc_fence_before();
+    if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint64_t pol_w = ptx::policy_evict_last();   // the weights are re-read by every row block
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = unit; t < n_tiles; t += a.n_units) {
+                const int x_row = (t / a.n_nt) * C::kTileM + static_cast<int>(rank) * kBM;
+                const int w_row = (t % a.n_nt) * BN + static_cast<int>(rank) * C::kBRows;
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    if constexpr (CG == 1) {
+                        const uint32_t fb = bar_full + 8 * stage;
+                        ptx::mbar_expect_tx(fb, C::kStageBytes);
+                        ptx::tma_load_2d(sa, &tmap_x, kc * kChunkK, x_row, fb);
+                        ptx::tma_load_2d_hint(sa + kABytes, &tmap_w, kc * kChunkK, w_row, fb, pol_w);
+                    } else {
+                        // both CTAs' bytes are counted on the LEADER's barrier
+                        if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
+                        const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
+                        ptx::tma_load_2d_cg2(sa, &tmap_x, kc * kChunkK, x_row, fb);
+                        ptx::tma_load_2d_cg2(sa + kABytes, &tmap_w, kc * kChunkK, w_row, fb);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = idesc_f16(C::kTileM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int i = 0;
+            for (int t = unit; t < n_tiles; t += a.n_units, ++i) {
+                const int acc = i & 1;
+                ptx::mbar_wait(bar_tempty + 8 * acc, ((i >> 1) & 1) ^ 1u);   // the epilogue drained it
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    ptx::mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
+                    ptx::tc_fence_after();
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    const uint64_t da = make_sw128_desc(sa);
+                    const uint64_t db = make_sw128_desc(sa + kABytes);
+#pragma unroll
+                    for (int k4 = 0; k4 < kChunkK / kUmmaK; ++k4) {
+                        // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-B units
+                        ptx::umma_f16<CG>(tmem_d, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+                    }
+                    if constexpr (CG == 1) ptx::umma_commit(bar_empty + 8 * stage);
+                    else ptx::umma_commit_cg2(bar_empty + 8 * stage, 0x3);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                if constexpr (CG == 1) ptx::umma_commit(bar_tfull + 8 * acc);
+                else ptx::umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue
+        const int quarter = warp & 3;                          // TMEM lanes 32 q .. 32 q + 31
+        const int half = (warp - 2) >> 2;                      // which half of the tile's columns
+        constexpr int kStrips = BN / 64;                       // strips of 32 columns per warp
+        int i = 0;
+        for (int t = unit; t < n_tiles; t += a.n_units, ++i) {
+            const int acc = i & 1;
+            const int64_t row = static_cast<int64_t>(t / a.n_nt) * C::kTileM + rank * kBM + quarter * 32 + lane;
+            const int col_t = (t % a.n_nt) * BN + half * (BN / 2);
+            const bool row_ok = row < a.m;
+            ptx::mbar_wait(bar_tfull + 8 * acc, (i >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+            for (int s = 0; s < kStrips; ++s) {
+                const int col0 = col_t + 32 * s;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + 32 * s, v);
+                float y[32];
+                const float4* bp = reinterpret_cast<const float4*>(a.bias + col0);
+                if constexpr (EPI == kEpiResF32) {
+                    float4 r4[8];
+                    const float4* rp = reinterpret_cast<const float4*>(a.residual + row * a.ldr + col0);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) r4[j] = __ldg(rp + j);
+                    }
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(bp + j);
+                        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+                        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+                        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                    }
+                    if (row_ok) {
+                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out0) + row * a.ld0 + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            op[j] = make_float4(y[4 * j] + r4[j].x, y[4 * j + 1] + r4[j].y, y[4 * j + 2] + r4[j].z,
+                                                y[4 * j + 3] + r4[j].w);
+                    }
+                } else {
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(bp + j);
+                        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+                        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+                        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                    }
+                    if constexpr (EPI == kEpiGelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
+                    }
+                    if (EPI == kEpiSplit && col0 >= a.n_split) {
+                        // transposed: lanes are consecutive rows -> one 64-byte run per column
+                        if (row_ok) {
+                            __half* op = a.out1 + static_cast<int64_t>(col0 - a.n_split) * a.ld1 + row;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) op[static_cast<int64_t>(j) * a.ld1] = __float2half_rn(y[j]);
+                        }
+                    } else {
+                        if (EPI == kEpiSplit && col0 < a.q_cols) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) y[j] *= a.q_scale;
+                        }
+                        if (row_ok) {
+                            uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(a.out0) + row * a.ld0 + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                op[j] = make_uint4(pack_half2(y[8 * j], y[8 * j + 1]), pack_half2(y[8 * j + 2], y[8 * j + 3]),
+                                                   pack_half2(y[8 * j + 4], y[8 * j + 5]), pack_half2(y[8 * j + 6], y[8 * j + 7]));
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
+                else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);   // the leader's barrier
+            }
+        }
+    }
+
+    // Teardown.  In pair mode neither CTA may exit (or free TMEM) while the other still reads
+    // its shared memory / signals its barriers.
+    ptx::tc_fence_before();
+    if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<CG>(tmem_base, C::kTmemCols);
+    }
+}
+
+template <int BN, int CG, int EPI>
+static int launch_gemm_t(const void* X, const void* W, GemmArgs a, int64_t ldx, int sm_count, cudaStream_t stream) {
+    using C = GemmCfg<BN, CG>;
+    a.n_mt = static_cast<int>((a.m + C::kTileM - 1) / C::kTileM);
+    a.n_nt = a.n / BN;
+    const int tiles = a.n_mt * a.n_nt;
+    int units = sm_count / CG;
+    if (units > tiles) units = tiles;
+    a.n_units = units;
+    CUtensorMap tx, tw;
+    int rc = make_map_2d(&tx, X, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.m), static_cast<uint64_t>(ldx), kBM);
+    if (rc != 0) return rc;
+    rc = make_map_2d(&tw, W, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.n), static_cast<uint64_t>(a.k), C::kBRows);
+    if (rc != 0) return rc;
+    cudaError_t e = cudaFuncSetAttribute(encoder_gemm_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) { set_error("encoder_gemm: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, encoder_gemm_kernel<BN, CG, EPI>, tx, tw, a);
+    if (e != cudaSuccess) { set_error("encoder_gemm: launch: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+}  // namespace enc
+
+int g_enc_gemm_form = 0;        // 0 auto, 1 = <64, 1>, 2 = <256, 2>
+
+int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
+                        int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
+                        float q_scale, const float* residual, int64_t ldr, int sm_count, cudaStream_t stream) {
+    using namespace enc;
+    GemmArgs a = {};
+    a.m = m;
+    a.n = n;
+    a.k = k;
+    a.bias = bias;
+    a.out0 = out0;
+    a.ld0 = ld0;
+    a.out1 = static_cast<__half*>(out1);
+    a.ld1 = ld1;
+    a.n_split = (epilogue == kEpiSplit) ? n_split : n;
+    a.q_cols = q_cols;
+    a.q_scale = q_scale;
+    a.residual = residual;
+    a.ldr = ldr;
+    if (m == 0) return 0;
+    // pairs once there are enough 256 x 256 tiles to occupy most of the chip
+    int form = g_enc_gemm_form;
+    if (form == 0) form = (((m + 255) / 256) * (n / 256) >= sm_count / 4) ? 2 : 1;
+#define SQE_ENC_GEMM(EPI_)                                                                         \
+    (form == 2 ? launch_gemm_t<256, 2, EPI_>(X, W, a, ldx, sm_count, stream)                       \
+               : launch_gemm_t<64, 1, EPI_>(X, W, a, ldx, sm_count, stream))
+    switch (epilogue) {
+        case kEpiSplit: return SQE_ENC_GEMM(kEpiSplit);
+        case kEpiResF32: return SQE_ENC_GEMM(kEpiResF32);
+        case kEpiGelu: return SQE_ENC_GEMM(kEpiGelu);
+    }
+#undef SQE_ENC_GEMM
+    set_error("encoder_gemm: unknown epilogue %d", epilogue);
+    return -1;
+}
+
+}  // namespace sqe

@@ -58,6 +58,20 @@ int launch_cache_finalize(const float* score, const int64_t* idx, int b, double 
                           float* out_score, int32_t* out_idx, uint8_t* out_hit,
                           cudaStream_t stream);
 
+// ENC  embedding encoder (encoder_gemm.cu, encoder_attn.cu, encoder_rows.cu)
+int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
+                        int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
+                        float q_scale, const float* residual, int64_t ldr, int sm_count, cudaStream_t stream);
+int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const void* tiles, int n_tiles,
+                             int max_len, void* ctx, cudaStream_t stream);
+int launch_encoder_layernorm(const float* in, const float* gamma, const float* beta, float eps, int64_t rows,
+                             float* out32, void* out16, cudaStream_t stream);
+int launch_encoder_embed_ln(const int32_t* ids, const int32_t* pos, const float* word, const float* position,
+                            const float* type0, const float* gamma, const float* beta, float eps, int64_t rows,
+                            int vocab, int max_pos, float* out32, void* out16, cudaStream_t stream);
+int launch_encoder_pool(const float* h, const int32_t* first_token, int n_seq, float* out, int64_t ldo,
+                        cudaStream_t stream);
+
 void set_error(const char* fmt, ...);
 
 // tuning knobs (api.cu)
@@ -65,6 +79,7 @@ extern int g_k2_cta_group;      // 0 auto, 1, 2
 extern int g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
 extern int g_k2_d_hint;         // retired experiment (accepted, ignored)
 extern int g_k2_window;         // retired experiment (accepted, ignored)
+extern int g_enc_gemm_form;    // 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs (encoder_gemm.cu)
 extern void* g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
 
 }  // namespace sqe

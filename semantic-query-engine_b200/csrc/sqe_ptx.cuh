@@ -221,5 +221,42 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
 }
 
+
+// ---------------------------------------------------------- encoder additions
+// 2-D tiled load {element, row}; completion (bytes) signalled on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+        : "memory");
+}
+// 2-CTA form: the bytes are signalled on `bar_cluster` (a mapa'd address of the leader CTA)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, int c0, int c1,
+                                                uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster)
+        : "memory");
+}
+// generic-proxy writes to shared memory (st.shared) become visible to the async proxy
+// (tcgen05.mma operand reads, TMA) after this fence
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// named barrier over `nthreads` threads of the CTA (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 }  // namespace ptx
 }  // namespace sqe

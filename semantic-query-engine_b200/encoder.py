@@ -1,0 +1,520 @@
+"""The embedding step in front of the retrieval path, on the same B200.
+
+The reference gets every embedding from an Ollama server over HTTP, one request per text
+(`ollama_embed_text`, app/main.py:134-146; `embed_texts_in_batches`, :149-169; `embed_query`,
+:172-180; twins in app/embedding_gen.py:143-190).  `GpuEmbeddingEncoder` keeps those three call
+signatures and runs the model itself -- mxbai-embed-large is a BERT-large encoder (24 post-LN
+layers, hidden 1024, 16 heads, FFN 4096, erf-GELU, CLS pooling, 512 positions, uncased WordPiece) --
+so that a query embedding is born in HBM next to the shard it is scored against and ingest no
+longer waits on 32,717 HTTP round trips.
+
+Host side (this file, Python like the reference): WordPiece tokeniser, packing of a batch of
+sequences into ONE [tokens, 1024] activation matrix (no padding between sequences), the layer
+loop.  Device side: five hand-written sm_100a kernels behind the C ABI (`sqe_encoder_*`,
+include/sqe_b200.h): tcgen05 GEMMs with fused bias / GELU / residual / QKV-split epilogues, a
+one-shot tcgen05 attention kernel, LayerNorm / embedding / pooling row kernels.  There is no CPU
+path and no library GEMM.
+
+Weights: a `transformers`-style BertModel state dict (`from_state_dict`, `load` of a torch /
+safetensors file) -- or seeded random weights of the same architecture (`random_init`) when, as in
+this build environment, the real checkpoint cannot be fetched.  Matmul operands are stored fp16
+(the Ollama model file is F16 as well); biases, LayerNorm parameters, the embedding tables, the
+residual stream and every LayerNorm are fp32.
+"""
+from __future__ import annotations
+
+import asyncio
+import threading
+import unicodedata
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+HIDDEN = 1024
+HEADS = 16
+HEAD_DIM = 64
+MAX_TOKENS = nat.SQE_ENC_MAX_TOKENS          # BERT positions
+EMBED_DIM = HIDDEN
+
+
+# ------------------------------------------------------------------------------- tokeniser
+def _char_class(ch: str) -> int:
+    """0 keep, 1 whitespace, 2 drop (control / NUL / U+FFFD), 3 punctuation, 4 CJK."""
+    cp = ord(ch)
+    if ch in (" ", "\t", "\n", "\r"):
+        return 1
+    if cp == 0 or cp == 0xFFFD:
+        return 2
+    cat = unicodedata.category(ch)
+    if cat == "Zs":
+        return 1
+    if cat[0] == "C":
+        return 2
+    if 33 <= cp <= 47 or 58 <= cp <= 64 or 91 <= cp <= 96 or 123 <= cp <= 126 or cat[0] == "P":
+        return 3
+    if (0x4E00 <= cp <= 0x9FFF or 0x3400 <= cp <= 0x4DBF or 0xF900 <= cp <= 0xFAFF or
+            0x20000 <= cp <= 0x2A6DF or 0x2A700 <= cp <= 0x2CEAF or 0x2F800 <= cp <= 0x2FA1F):
+        return 4
+    return 0
+
+
+class WordPieceTokenizer:
+    """BERT's uncased tokeniser: clean the text, isolate CJK characters and punctuation, lower-case,
+    strip accents, then greedy longest-match-first WordPiece (`##` continuation pieces, a word that
+    cannot be covered or is longer than 100 characters is one [UNK]).  Words are memoised: natural
+    text repeats them, so a chunk costs about one dictionary lookup per word."""
+
+    def __init__(self, vocab: Dict[str, int], *, unk: str = "[UNK]", cls: str = "[CLS]", sep: str = "[SEP]",
+                 max_chars_per_word: int = 100, cache_words: int = 1 << 20):
+        for t in (unk, cls, sep):
+            if t not in vocab:
+                raise ValueError(f"vocabulary has no {t} token")
+        self.vocab = vocab
+        self.unk_id, self.cls_id, self.sep_id = vocab[unk], vocab[cls], vocab[sep]
+        self.max_chars = max_chars_per_word
+        self._cache: Dict[str, Tuple[int, ...]] = {}
+        self._cache_cap = cache_words
+        self._class_cache: Dict[str, int] = {}
+
+    @classmethod
+    def from_file(cls, path: str, **kw) -> "WordPieceTokenizer":
+        """A BERT `vocab.txt`: one token per line, the line number is the id."""
+        with open(path, encoding="utf-8") as f:
+            vocab = {line.rstrip("\n"): i for i, line in enumerate(f)}
+        return cls(vocab, **kw)
+
+    def _split(self, text: str) -> List[str]:
+        cc = self._class_cache
+        words: List[str] = []
+        cur: List[str] = []
+        for ch in text:
+            k = cc.get(ch)
+            if k is None:
+                k = cc[ch] = _char_class(ch)
+            if k == 0:
+                cur.append(ch)
+            elif k == 2:
+                continue
+            else:
+                if cur:
+                    words.append("".join(cur))
+                    cur = []
+                if k >= 3:
+                    words.append(ch)
+        if cur:
+            words.append("".join(cur))
+        return words
+
+    def _pieces(self, word: str) -> Tuple[int, ...]:
+        hit = self._cache.get(word)
+        if hit is not None:
+            return hit
+        # lower-case + strip accents; the result may contain NEW punctuation-free pieces only, but
+        # decomposition can expose punctuation (rare): split again in that case
+        norm = "".join(c for c in unicodedata.normalize("NFD", word) if unicodedata.category(c) != "Mn").lower()
+        out: List[int] = []
+        for sub in (self._split(norm) if norm != word else [norm]):
+            out.extend(self._wordpiece(sub))
+        res = tuple(out)
+        if len(self._cache) < self._cache_cap:
+            self._cache[word] = res
+        return res
+
+    def _wordpiece(self, word: str) -> List[int]:
+        if not word:
+            return []
+        if len(word) > self.max_chars:
+            return [self.unk_id]
+        vocab = self.vocab
+        pieces: List[int] = []
+        start, n = 0, len(word)
+        while start < n:
+            end = n
+            found = None
+            while start < end:
+                sub = word[start:end] if start == 0 else "##" + word[start:end]
+                found = vocab.get(sub)
+                if found is not None:
+                    break
+                end -= 1
+            if found is None:
+                return [self.unk_id]
+            pieces.append(found)
+            start = end
+        return pieces
+
+    def tokenize(self, text: str) -> List[int]:
+        """Piece ids without [CLS] / [SEP]."""
+        ids: List[int] = []
+        for w in self._split(text):
+            ids.extend(self._pieces(w))
+        return ids
+
+    def encode(self, text: str, max_tokens: int = MAX_TOKENS) -> List[int]:
+        """[CLS] pieces [SEP], truncated to the model's positions (Ollama truncates to the context too)."""
+        return [self.cls_id] + self.tokenize(text)[: max_tokens - 2] + [self.sep_id]
+
+
+# --------------------------------------------------------------------------------- weights
+class EncoderWeights:
+    """Device-resident parameters.  Per layer: Wqkv [3072,1024] fp16 (query | key | value rows of the
+    three Linear weights), Wo [1024,1024], W1 [4096,1024], W2 [1024,4096] fp16; biases and LayerNorm
+    parameters fp32."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        self.word = self.position = self.type0 = self.emb_g = self.emb_b = None
+        self.vocab_size = 0
+        self.max_pos = 0
+        self.eps = 1e-12
+
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], device=None, eps: float = 1e-12) -> "EncoderWeights":
+        """`sd`: BertModel names, with or without a `bert.` prefix."""
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.type != "cuda":
+            raise RuntimeError("sqe_b200 has no CPU path: the encoder needs a CUDA device")
+        if any(k.startswith("bert.") for k in sd):
+            sd = {k[5:]: v for k, v in sd.items() if k.startswith("bert.")}
+        w = cls(dev)
+        w.eps = float(eps)
+
+        def f32(name):
+            return sd[name].detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        def f16(t):
+            return t.detach().to(device=dev, dtype=torch.float16).contiguous()
+
+        w.word = f32("embeddings.word_embeddings.weight")
+        w.position = f32("embeddings.position_embeddings.weight")
+        w.type0 = f32("embeddings.token_type_embeddings.weight")[0].contiguous()
+        w.emb_g = f32("embeddings.LayerNorm.weight")
+        w.emb_b = f32("embeddings.LayerNorm.bias")
+        w.vocab_size, hidden = w.word.shape
+        w.max_pos = w.position.shape[0]
+        if hidden != HIDDEN:
+            raise ValueError(f"hidden size {hidden}: the kernels are built for {HIDDEN} (mxbai-embed-large)")
+        i = 0
+        while f"encoder.layer.{i}.attention.self.query.weight" in sd:
+            p = f"encoder.layer.{i}."
+            wq, wk, wv = (sd[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value"))
+            bq, bk, bv = (sd[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value"))
+            layer = {
+                "wqkv": f16(torch.cat([wq, wk, wv], dim=0)),
+                "bqkv": torch.cat([bq, bk, bv]).detach().to(device=dev, dtype=torch.float32).contiguous(),
+                "wo": f16(sd[p + "attention.output.dense.weight"]), "bo": f32(p + "attention.output.dense.bias"),
+                "g1": f32(p + "attention.output.LayerNorm.weight"), "b1": f32(p + "attention.output.LayerNorm.bias"),
+                "w1": f16(sd[p + "intermediate.dense.weight"]), "bi": f32(p + "intermediate.dense.bias"),
+                "w2": f16(sd[p + "output.dense.weight"]), "bo2": f32(p + "output.dense.bias"),
+                "g2": f32(p + "output.LayerNorm.weight"), "b2": f32(p + "output.LayerNorm.bias"),
+            }
+            if layer["wqkv"].shape != (3 * HIDDEN, HIDDEN) or layer["w1"].shape[1] != HIDDEN or \
+                    layer["w1"].shape[0] % 256 != 0 or layer["w2"].shape != (HIDDEN, layer["w1"].shape[0]):
+                raise ValueError("unsupported layer geometry")
+            w.layers.append(layer)
+            i += 1
+        if not w.layers:
+            raise ValueError("state dict has no encoder layers")
+        return w
+
+    @classmethod
+    def load(cls, path: str, device=None) -> "EncoderWeights":
+        """A `pytorch_model.bin` / `.pt` state dict or a `.safetensors` file of a BERT encoder."""
+        if path.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            sd = load_file(path)
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+        return cls.from_state_dict(sd, device=device)
+
+    @classmethod
+    def random_init(cls, seed: int = 0, layers: int = 24, device=None, vocab: int = 30522,
+                    intermediate: int = 4096) -> "EncoderWeights":
+        """Random weights of the mxbai-embed-large architecture, generated on the device (the real
+        checkpoint cannot be fetched in an offline environment; bench.py says so in `data`)."""
+        dev = torch.device(device if device is not None else "cuda")
+        g = torch.Generator(device=dev).manual_seed(seed)
+
+        def rnd(*shape, s=0.03):
+            return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32) * s
+
+        sd = {
+            "embeddings.word_embeddings.weight": rnd(vocab, HIDDEN, s=0.5),
+            "embeddings.position_embeddings.weight": rnd(MAX_TOKENS, HIDDEN, s=0.3),
+            "embeddings.token_type_embeddings.weight": rnd(2, HIDDEN, s=0.1),
+            "embeddings.LayerNorm.weight": 1.0 + rnd(HIDDEN, s=0.1),
+            "embeddings.LayerNorm.bias": rnd(HIDDEN, s=0.1),
+        }
+        for i in range(layers):
+            p = f"encoder.layer.{i}."
+            for n in ("query", "key", "value"):
+                sd[p + f"attention.self.{n}.weight"] = rnd(HIDDEN, HIDDEN, s=0.05 if n != "value" else 0.03)
+                sd[p + f"attention.self.{n}.bias"] = rnd(HIDDEN, s=0.1)
+            sd[p + "attention.output.dense.weight"] = rnd(HIDDEN, HIDDEN)
+            sd[p + "attention.output.dense.bias"] = rnd(HIDDEN, s=0.1)
+            sd[p + "attention.output.LayerNorm.weight"] = 1.0 + rnd(HIDDEN, s=0.1)
+            sd[p + "attention.output.LayerNorm.bias"] = rnd(HIDDEN, s=0.1)
+            sd[p + "intermediate.dense.weight"] = rnd(intermediate, HIDDEN)
+            sd[p + "intermediate.dense.bias"] = rnd(intermediate, s=0.1)
+            sd[p + "output.dense.weight"] = rnd(HIDDEN, intermediate)
+            sd[p + "output.dense.bias"] = rnd(HIDDEN, s=0.1)
+            sd[p + "output.LayerNorm.weight"] = 1.0 + rnd(HIDDEN, s=0.1)
+            sd[p + "output.LayerNorm.bias"] = rnd(HIDDEN, s=0.1)
+        return cls.from_state_dict(sd, device=dev)
+
+    @property
+    def intermediate(self) -> int:
+        return self.layers[0]["w1"].shape[0]
+
+    def flops_per_token(self) -> float:
+        """Linear layers only (2 FLOP per multiply-add); attention adds 4 * S * 1024 per token."""
+        return 2.0 * len(self.layers) * (4 * HIDDEN * HIDDEN + 2 * HIDDEN * self.intermediate)
+
+
+# ------------------------------------------------------------------------------ tensor ops
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def gemm(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int, out0: torch.Tensor, *,
+         m: Optional[int] = None, out1: Optional[torch.Tensor] = None, n_split: int = 0, q_cols: int = 0,
+         q_scale: float = 1.0, residual: Optional[torch.Tensor] = None) -> None:
+    """`sqe_encoder_gemm` on the current stream: out0 (+ out1) = epilogue(x[:m] @ w.T + bias)."""
+    dev = x.device
+    if not x.is_cuda:
+        raise RuntimeError("sqe_b200 has no CPU path: tensors must live on a CUDA device")
+    m = x.shape[0] if m is None else m
+    n, k = w.shape
+    with torch.cuda.device(dev):
+        nat.call("sqe_encoder_gemm", x.data_ptr(), x.stride(0), w.data_ptr(), bias.data_ptr(), m, n, k, epilogue,
+                 out0.data_ptr(), out0.stride(0), _ptr(out1), 0 if out1 is None else out1.stride(0), n_split, q_cols,
+                 q_scale, _ptr(residual), 0 if residual is None else residual.stride(0),
+                 torch.cuda.current_stream(dev).cuda_stream)
+
+
+def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps: float, out32: torch.Tensor,
+              out16: torch.Tensor, rows: Optional[int] = None) -> None:
+    dev = x.device
+    with torch.cuda.device(dev):
+        nat.call("sqe_encoder_layernorm", x.data_ptr(), g.data_ptr(), b.data_ptr(), eps,
+                 x.shape[0] if rows is None else rows, out32.data_ptr(), out16.data_ptr(),
+                 torch.cuda.current_stream(dev).cuda_stream)
+
+
+def attention(qk: torch.Tensor, vt: torch.Tensor, tiles: torch.Tensor, n_tiles: int, max_len: int,
+              ctx: torch.Tensor) -> None:
+    dev = qk.device
+    with torch.cuda.device(dev):
+        nat.call("sqe_encoder_attention", qk.data_ptr(), vt.data_ptr(), qk.shape[0], tiles.data_ptr(), n_tiles,
+                 max_len, ctx.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _Buffers:
+    """Activation buffers of one token capacity (a multiple of 128 rows; V^T's row pitch depends on it)."""
+
+    def __init__(self, t_pad: int, inter: int, dev: torch.device):
+        z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=dev)          # noqa: E731
+        self.t_pad = t_pad
+        self.h32 = z(t_pad, HIDDEN, dt=torch.float32)      # residual stream
+        self.h16 = z(t_pad, HIDDEN, dt=torch.float16)      # its tensor-core operand copy
+        self.sum32 = z(t_pad, HIDDEN, dt=torch.float32)    # pre-LayerNorm sums
+        self.qk = z(t_pad, 2 * HIDDEN, dt=torch.float16)   # Q / 8 | K
+        self.vt = z(HIDDEN, t_pad, dt=torch.float16)       # V^T
+        self.ctx = z(t_pad, HIDDEN, dt=torch.float16)
+        self.ffn = z(t_pad, inter, dt=torch.float16)
+        # per-forward metadata, one H2D copy: ids | pos | first_token | tiles
+        self.meta_cap = 2 * t_pad + t_pad + 4 * (t_pad // 128 + t_pad)
+        self.meta_dev = torch.zeros(self.meta_cap, dtype=torch.int32, device=dev)
+        # two pinned staging buffers, alternating: the copy of forward i may still be queued when
+        # the host fills the metadata of forward i + 1
+        self.meta_host = [torch.zeros(self.meta_cap, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.meta_done = [None, None]
+        self.turn = 0
+
+
+class GpuEmbeddingEncoder:
+    """`embed_texts(texts) -> np.ndarray [n, 1024]` and the reference's three coroutines.
+
+    `normalize=False` returns the raw CLS hidden state (what an embedding server returns is
+    normalised downstream anyway: app/main.py:315-316, :353-354 divide by the norm again)."""
+
+    def __init__(self, weights: EncoderWeights, tokenizer: Optional[WordPieceTokenizer] = None, *,
+                 max_batch_tokens: int = 32768, blank_policy: str = "main"):
+        self.w = weights
+        self.device = weights.device
+        self.tok = tokenizer
+        self.max_batch_tokens = max(int(max_batch_tokens), MAX_TOKENS)
+        self.blank_policy = blank_policy
+        self._bufs: Dict[int, _Buffers] = {}
+        self._lock = threading.Lock()
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.launches_last_forward = 0
+        nat.load()                                          # fail loudly when the CUDA library is missing
+
+    # ------------------------------------------------------------------ device forward
+    def _buffers(self, t_pad: int) -> _Buffers:
+        b = self._bufs.get(t_pad)
+        if b is None:
+            if len(self._bufs) >= 4:                        # keep the few capacities that recur
+                self._bufs.pop(next(iter(self._bufs)))
+            b = self._bufs[t_pad] = _Buffers(t_pad, self.w.intermediate, self.device)
+        return b
+
+    @staticmethod
+    def plan(lengths: Sequence[int]) -> Tuple[int, np.ndarray, np.ndarray, np.ndarray]:
+        """Packing of sequences of the given lengths: (t_pad, pos [t_pad], first_token [n], tiles [m,4]).
+        Every sequence starts at a multiple of 8 tokens: the attention kernel fetches V^T with TMA
+        boxes whose innermost coordinate is the token index, and a box must start on a 16-byte
+        boundary.  pos = -1 marks the (zero) filler rows."""
+        lens = np.asarray(lengths, dtype=np.int64)
+        if lens.size == 0 or lens.min() < 1 or lens.max() > MAX_TOKENS:
+            raise ValueError(f"sequence lengths must be in [1, {MAX_TOKENS}]")
+        slots = (lens + 7) // 8 * 8
+        starts = np.concatenate([[0], np.cumsum(slots)[:-1]])
+        t_pad = (int(slots.sum()) + 127) // 128 * 128
+        pos = np.full(t_pad, -1, dtype=np.int32)
+        rows = np.repeat(starts, lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
+        pos[rows] = rows - np.repeat(starts, lens)
+        n_q = (lens + 127) // 128
+        seq_of_tile = np.repeat(np.arange(lens.size), n_q)
+        first_tile = np.concatenate([[0], np.cumsum(n_q)[:-1]])
+        q0 = (np.arange(seq_of_tile.size) - first_tile[seq_of_tile]) * 128
+        tiles = np.zeros((seq_of_tile.size, 4), dtype=np.int32)
+        tiles[:, 0] = starts[seq_of_tile]
+        tiles[:, 1] = lens[seq_of_tile]
+        tiles[:, 2] = q0
+        return t_pad, pos, starts.astype(np.int32), tiles
+
+    def forward_ids(self, seqs: Sequence[Sequence[int]], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One packed forward pass on the current stream: CLS hidden states [n, 1024] fp32 on the
+        device.  The caller bounds the batch (`embed_token_ids` splits by `max_batch_tokens`)."""
+        n = len(seqs)
+        lens = [len(s) for s in seqs]
+        t_pad, pos, first, tiles = self.plan(lens)
+        total = int(sum(lens))
+        dev = self.device
+        rows = np.flatnonzero(pos >= 0)                     # token rows (the rest is filler: id -1 -> zeros)
+        with self._lock:
+            b = self._buffers(t_pad)
+            n_tiles = tiles.shape[0]
+            slot = b.turn
+            b.turn ^= 1
+            if b.meta_done[slot] is not None:
+                b.meta_done[slot].synchronize()             # its previous copy has left the buffer
+            mh = b.meta_host[slot].numpy()
+            o_pos, o_first, o_tiles = t_pad, 2 * t_pad, 2 * t_pad + ((n + 3) // 4) * 4
+            used = o_tiles + 4 * n_tiles
+            if used > b.meta_cap:
+                raise ValueError("too many sequences for this token capacity")
+            mh[:t_pad] = -1
+            mh[rows] = np.fromiter((t for s in seqs for t in s), dtype=np.int32, count=total)
+            mh[o_pos:o_pos + t_pad] = np.maximum(pos, 0)
+            mh[o_first:o_first + n] = first
+            mh[o_tiles:used] = tiles.reshape(-1)
+            b.meta_dev[:used].copy_(b.meta_host[slot][:used], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            b.meta_done[slot] = ev
+            ids_d, pos_d = b.meta_dev[:t_pad], b.meta_dev[o_pos:o_pos + t_pad]
+            first_d, tiles_d = b.meta_dev[o_first:o_first + n], b.meta_dev[o_tiles:used]
+            if out is None:
+                out = torch.empty((n, HIDDEN), dtype=torch.float32, device=dev)
+            self._layers(b, ids_d, pos_d, tiles_d, n_tiles, max(lens), t_pad)
+            with torch.cuda.device(dev):
+                nat.call("sqe_encoder_pool", b.h32.data_ptr(), first_d.data_ptr(), n, out.data_ptr(), out.stride(0),
+                         torch.cuda.current_stream(dev).cuda_stream)
+        return out
+
+    def _layers(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, m: int) -> None:
+        w = self.w
+        dev = self.device
+        before = nat.launch_count
+        with torch.cuda.device(dev):
+            nat.call("sqe_encoder_embed_ln", ids_d.data_ptr(), pos_d.data_ptr(), w.word.data_ptr(), w.vocab_size,
+                     w.position.data_ptr(), w.max_pos, w.type0.data_ptr(), w.emb_g.data_ptr(), w.emb_b.data_ptr(),
+                     w.eps, m, b.h32.data_ptr(), b.h16.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        for L in w.layers:
+            gemm(b.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, b.qk, m=m, out1=b.vt, n_split=2 * HIDDEN,
+                 q_cols=HIDDEN, q_scale=0.125)
+            attention(b.qk, b.vt, tiles_d, n_tiles, max_len, b.ctx)
+            gemm(b.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, b.sum32, m=m, residual=b.h32)
+            layernorm(b.sum32, L["g1"], L["b1"], w.eps, b.h32, b.h16, rows=m)
+            gemm(b.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, b.ffn, m=m)
+            gemm(b.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, b.sum32, m=m, residual=b.h32)
+            layernorm(b.sum32, L["g2"], L["b2"], w.eps, b.h32, b.h16, rows=m)
+        self.launches_last_forward = nat.launch_count - before + 1          # + the pooling kernel
+
+    # ----------------------------------------------------------------------- batching
+    def _batches(self, lens: Sequence[int]) -> Iterable[Tuple[int, int]]:
+        i, n = 0, len(lens)
+        while i < n:
+            j, tok = i, 0
+            while j < n and tok + lens[j] <= self.max_batch_tokens:
+                tok += lens[j]
+                j += 1
+            yield i, j
+            i = j
+
+    def embed_token_ids(self, seqs: Sequence[Sequence[int]]) -> torch.Tensor:
+        """[n, 1024] fp32 on the device (asynchronous on `self.stream`; synchronise before reading)."""
+        n = len(seqs)
+        out = torch.empty((n, HIDDEN), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        lens = [len(s) for s in seqs]
+        with torch.cuda.stream(self.stream):
+            for i, j in self._batches(lens):
+                self.forward_ids(seqs[i:j], out=out[i:j])
+        return out
+
+    def embed_texts_device(self, texts: Sequence[str]) -> torch.Tensor:
+        if self.tok is None:
+            raise RuntimeError("this encoder was built without a tokenizer (pass token ids instead)")
+        return self.embed_token_ids([self.tok.encode(t) for t in texts])
+
+    def embed_texts(self, texts: Sequence[str]) -> np.ndarray:
+        """Host array [n, 1024] fp32; blank texts give zero rows (embedding_gen.py:147-148)."""
+        texts = list(texts)
+        out = np.zeros((len(texts), HIDDEN), dtype=np.float32)
+        keep = [i for i, t in enumerate(texts) if t.strip()]
+        if keep:
+            dev = self.embed_texts_device([texts[i] for i in keep])
+            self.stream.synchronize()
+            out[keep] = dev.cpu().numpy()
+        return out
+
+    # ------------------------------------------------- the reference's call signatures
+    async def ollama_embed_text(self, text: str, model: str = "") -> List[float]:
+        """app/main.py:134-146 / app/embedding_gen.py:143-166 (`model` is accepted and ignored: this
+        object IS the model).  Blank text: a zero vector, as the upload service returns."""
+        return self.embed_texts([text])[0].tolist()
+
+    async def embed_texts_in_batches(self, texts: List[str], batch_size: int = 64) -> np.ndarray:
+        """app/main.py:149-169: `np.array([])` for no texts; app/embedding_gen.py:169-190 returns
+        `zeros((0, 1024))` -- `blank_policy` picks which module's convention applies."""
+        if not texts:
+            return np.array([]) if self.blank_policy == "main" else np.zeros((0, HIDDEN), dtype=np.float32)
+        loop = asyncio.get_running_loop()
+        return await loop.run_in_executor(None, self.embed_texts, texts)
+
+    async def embed_query(self, query: str) -> np.ndarray:
+        """app/main.py:172-180: `np.array([])` for a blank query, else shape (1, 1024) fp32."""
+        if not query.strip():
+            return np.array([])
+        return self.embed_texts([query])
+
+
+def install_encoder(module, encoder: GpuEmbeddingEncoder) -> GpuEmbeddingEncoder:
+    """Patch a loaded reference module (`main` or `embedding_gen`) so that its embedding calls run
+    on the GPU instead of going to the Ollama server."""
+    encoder.blank_policy = "embedding_gen" if hasattr(module, "bulk_index_embeddings") else "main"
+    module.ollama_embed_text = encoder.ollama_embed_text
+    module.embed_texts_in_batches = encoder.embed_texts_in_batches
+    if hasattr(module, "embed_query"):
+        module.embed_query = encoder.embed_query
+    module._sqe_b200_encoder = encoder
+    return encoder

@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol(sqe):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sqe_abi_version() == 1
+    assert lib.sqe_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", sqe._native.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (sqe_\w+)", out))
     assert declared <= exported

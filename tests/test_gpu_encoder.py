@@ -1,0 +1,274 @@
+"""The embedding encoder on the GPU, through the C ABI, against fp32 references:
+each kernel against the same op in plain fp32 torch, the whole model against the CPU oracle
+(oracle/bert_oracle.py).  Floating point: the tolerances are written next to each comparison; what
+they cover is the fp16 storage of the matmul operands (relative 2^-11 per element), nothing else --
+accumulation, softmax and LayerNorm are fp32."""
+import asyncio
+import math
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import bert_oracle as bo
+
+H = 1024
+
+
+@pytest.fixture(scope="module")
+def sqe():
+    import sqe_b200
+    sqe_b200._native.load()
+    rc, sms, major, _ = sqe_b200._native.device_info()
+    assert rc == 1 and major == 10, sqe_b200._native.last_error()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return sqe_b200
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _gen(seed):
+    return torch.Generator(device=dev()).manual_seed(seed)
+
+
+def _randn(g, *shape, s=1.0, dtype=torch.float32):
+    return (torch.randn(*shape, generator=g, device=dev(), dtype=torch.float32) * s).to(dtype)
+
+
+@pytest.fixture(params=[1, 2], ids=["tiles128x64", "pairs256x256"])
+def gemm_form(request, sqe):
+    nat = sqe._native
+    old = nat.tuning_set(nat.SQE_TUNE_ENC_GEMM_FORM, request.param)
+    yield request.param
+    nat.tuning_set(nat.SQE_TUNE_ENC_GEMM_FORM, old)
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("m,n,k", [(128, 1024, 1024), (200, 3072, 1024), (640, 4096, 1024), (1000, 1024, 4096),
+                                   (2304, 3072, 1024)])
+def test_gemm_residual_fp32_epilogue(sqe, gemm_form, m, n, k):
+    g = _gen(m + n + k)
+    x = _randn(g, m, k, dtype=torch.float16)
+    w = _randn(g, n, k, s=0.03, dtype=torch.float16)
+    bias = _randn(g, n, s=0.5)
+    res = _randn(g, m, n)
+    out = torch.full((m, n), float("nan"), device=dev())
+    sqe.encoder.gemm(x, w, bias, sqe._native.SQE_ENC_EPI_RES_F32, out, residual=res)
+    want = x.float() @ w.float().T + bias + res
+    # fp32 accumulation in a different order: a few ulps of the partial sums (|sum| <= ~6)
+    err = float((out - want).abs().max())
+    assert err < 2e-4, err
+
+
+@pytest.mark.parametrize("m", [128, 333, 1536])
+def test_gemm_gelu_epilogue(sqe, gemm_form, m):
+    g = _gen(m)
+    x = _randn(g, m, H, dtype=torch.float16)
+    w = _randn(g, 4096, H, s=0.03, dtype=torch.float16)
+    bias = _randn(g, 4096, s=0.5)
+    out = torch.zeros((m, 4096), device=dev(), dtype=torch.float16)
+    sqe.encoder.gemm(x, w, bias, sqe._native.SQE_ENC_EPI_GELU, out)
+    y = x.float() @ w.float().T + bias
+    want = 0.5 * y * (1.0 + torch.erf(y / math.sqrt(2.0)))
+    # fp16 output: half an ulp (2^-11 relative) + the fp32 round-off of y through the gelu slope
+    assert bool(((out.float() - want).abs() <= want.abs() * 6e-4 + 2e-4).all())
+
+
+@pytest.mark.parametrize("m", [128, 300, 1280])
+def test_gemm_qkv_split_epilogue(sqe, gemm_form, m):
+    """Q (scaled by 1/8) | K row-major, V transposed -- and rows >= m are left alone."""
+    g = _gen(7 * m)
+    t_pad = (m + 127) // 128 * 128
+    x = _randn(g, t_pad, H, dtype=torch.float16)
+    w = _randn(g, 3 * H, H, s=0.03, dtype=torch.float16)
+    bias = _randn(g, 3 * H, s=0.5)
+    qk = torch.full((t_pad, 2 * H), 7.0, device=dev(), dtype=torch.float16)
+    vt = torch.full((H, t_pad), 7.0, device=dev(), dtype=torch.float16)
+    sqe.encoder.gemm(x, w, bias, sqe._native.SQE_ENC_EPI_SPLIT, qk, m=m, out1=vt, n_split=2 * H, q_cols=H,
+                     q_scale=0.125)
+    y = x[:m].float() @ w.float().T + bias
+    y[:, :H] *= 0.125
+    tol = lambda want: want.abs() * 6e-4 + 2e-4                                  # noqa: E731
+    assert bool(((qk[:m].float() - y[:, :2 * H]).abs() <= tol(y[:, :2 * H])).all())
+    assert bool(((vt[:, :m].float() - y[:, 2 * H:].T).abs() <= tol(y[:, 2 * H:].T)).all())
+    assert bool((qk[m:] == 7.0).all()) and bool((vt[:, m:] == 7.0).all())
+
+
+def test_gemm_argument_errors(sqe):
+    nat = sqe._native
+    x = torch.zeros((128, H), device=dev(), dtype=torch.float16)
+    w = torch.zeros((1000, H), device=dev(), dtype=torch.float16)               # n % 256 != 0
+    with pytest.raises(nat.SqeError) as e:
+        sqe.encoder.gemm(x, w, torch.zeros(1000, device=dev()), nat.SQE_ENC_EPI_GELU,
+                         torch.zeros((128, 1000), device=dev(), dtype=torch.float16))
+    assert e.value.code == -1
+    with pytest.raises(RuntimeError):
+        sqe.encoder.gemm(x.cpu(), w.cpu(), torch.zeros(1000), nat.SQE_ENC_EPI_GELU, torch.zeros((128, 1000)))
+
+
+# ------------------------------------------------------------------------------ row kernels
+def test_layernorm_matches_torch(sqe):
+    g = _gen(3)
+    x = _randn(g, 777, H, s=3.0) + 1.5
+    x[5] = 0.25                                                                   # constant row: variance 0
+    gamma, beta = 1.0 + _randn(g, H, s=0.2), _randn(g, H, s=0.2)
+    o32, o16 = torch.empty_like(x), torch.empty((777, H), device=dev(), dtype=torch.float16)
+    sqe.encoder.layernorm(x, gamma, beta, 1e-12, o32, o16)
+    want = torch.nn.functional.layer_norm(x, (H,), gamma, beta, eps=1e-12)
+    assert float((o32 - want).abs().max()) < 2e-5
+    assert torch.equal(o16, o32.half())
+    assert bool((o32[5] - beta).abs().max() < 1e-6)
+
+
+def test_embed_ln_matches_torch(sqe):
+    nat = sqe._native
+    g = _gen(4)
+    vocab, max_pos, rows = 999, 512, 300
+    word, pos_e, type_e = _randn(g, vocab, H, s=0.5), _randn(g, max_pos, H, s=0.3), _randn(g, 2, H, s=0.1)
+    gamma, beta = 1.0 + _randn(g, H, s=0.1), _randn(g, H, s=0.1)
+    ids = torch.randint(0, vocab, (rows,), generator=g, device=dev(), dtype=torch.int32)
+    pos = torch.randint(0, max_pos, (rows,), generator=g, device=dev(), dtype=torch.int32)
+    ids[[7, 100]] = -1                                                            # padding rows
+    o32 = torch.full((rows, H), 9.0, device=dev())
+    o16 = torch.full((rows, H), 9.0, device=dev(), dtype=torch.float16)
+    nat.call("sqe_encoder_embed_ln", ids.data_ptr(), pos.data_ptr(), word.data_ptr(), vocab, pos_e.data_ptr(),
+             max_pos, type_e[0].contiguous().data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-12, rows,
+             o32.data_ptr(), o16.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    safe = ids.clamp(min=0).long()
+    want = torch.nn.functional.layer_norm((word[safe] + type_e[0]) + pos_e[pos.long()], (H,), gamma, beta, eps=1e-12)
+    want[[7, 100]] = 0.0
+    assert float((o32 - want).abs().max()) < 2e-5
+    assert torch.equal(o16, o32.half())
+
+
+# ------------------------------------------------------------------------------- attention
+def _attention_case(sqe, lens, seed, junk=0.0):
+    g = _gen(seed)
+    t_pad, pos, first, tiles = sqe.GpuEmbeddingEncoder.plan(lens)
+    total = int(first[-1]) + lens[-1]
+    qk = _randn(g, t_pad, 2 * H, s=1.6, dtype=torch.float16)
+    qk[:, :H] *= 0.125
+    v = _randn(g, t_pad, H, dtype=torch.float16)
+    if junk:
+        qk[total:] = junk                                                          # rows after the last sequence
+        v[total:] = junk
+    vt = v.T.contiguous()
+    ctx = torch.full((t_pad, H), 5.0, device=dev(), dtype=torch.float16)
+    tiles_d = torch.from_numpy(tiles).to(dev())
+    sqe.encoder.attention(qk, vt, tiles_d, tiles.shape[0], max(lens), ctx)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for s0, n in zip(first.tolist(), lens):
+        q = qk[s0:s0 + n, :H].float().view(n, 16, 64).transpose(0, 1)
+        k = qk[s0:s0 + n, H:].float().view(n, 16, 64).transpose(0, 1)
+        vv = v[s0:s0 + n].float().view(n, 16, 64).transpose(0, 1)
+        want = (torch.softmax(q @ k.transpose(1, 2), dim=-1) @ vv).transpose(0, 1).reshape(n, H)
+        worst = max(worst, float((ctx[s0:s0 + n].float() - want).abs().max()))
+    assert bool((ctx[total:] == 5.0).all())                                        # nothing stored past the end
+    return worst
+
+
+@pytest.mark.parametrize("lens", [[1], [2], [63], [64], [65], [128], [129], [255, 257], [511], [512],
+                                  [5, 130, 1, 512, 64, 300, 17], [384] * 3, [12] * 40])
+def test_attention_matches_torch(sqe, lens):
+    # P is rounded to fp16 (2^-11 relative per weight, weights sum to 1, |v| <~ 4) and so is the output
+    assert _attention_case(sqe, lens, seed=sum(lens)) < 4e-3
+
+
+def test_attention_masks_whatever_follows_a_sequence(sqe):
+    assert _attention_case(sqe, [70, 3, 200], seed=1, junk=30000.0) < 4e-3
+
+
+# -------------------------------------------------------------------------------- the model
+def _pair(sqe, seed, layers, vocab=2000):
+    w = bo.random_bert_weights(seed, layers=layers, vocab=vocab)
+    gw = sqe.EncoderWeights.from_state_dict(w, device=dev())
+    return w, sqe.GpuEmbeddingEncoder(gw)
+
+
+def _check_vs_oracle(got, want, emulated, atol, atol_emulated):
+    err = float((got - want).abs().max())
+    cos = float(torch.nn.functional.cosine_similarity(got, want).min())
+    err_e = float((got - emulated).abs().max())
+    assert err < atol and err_e < atol_emulated and cos > 0.9999, (err, err_e, cos)
+
+
+def test_two_layer_model_vs_oracle(sqe):
+    w, e = _pair(sqe, 21, layers=2)
+    g = torch.Generator().manual_seed(5)
+    seqs = [torch.randint(0, 2000, (n,), generator=g).tolist() for n in (2, 9, 64, 65, 130, 300, 512, 1, 31)]
+    got = e.embed_token_ids(seqs)
+    torch.cuda.synchronize()
+    # hidden states are O(1) (LayerNorm outputs); fp16 operands move them by <~ 1e-2 in two layers; against
+    # the oracle WITH the same operand rounding only accumulation order and the fp16 P matrix remain
+    _check_vs_oracle(got.cpu(), bo.bert_embed(w, seqs), bo.bert_embed(w, seqs, round_operands=lambda t: t.half().float()),
+                     atol=2e-2, atol_emulated=6e-3)
+    again = e.embed_token_ids(seqs)
+    torch.cuda.synchronize()
+    assert torch.equal(got, again)                                                 # deterministic
+    alone = e.embed_token_ids([seqs[4]])
+    torch.cuda.synchronize()
+    assert float((alone[0] - got[4]).abs().max()) < 1e-3                           # batch composition: same rows
+
+
+def test_full_depth_model_vs_oracle(sqe):
+    """24 layers, the mxbai-embed-large geometry (random weights: the checkpoint cannot be fetched)."""
+    w, e = _pair(sqe, 22, layers=24, vocab=1000)
+    g = torch.Generator().manual_seed(6)
+    seqs = [torch.randint(0, 1000, (n,), generator=g).tolist() for n in (7, 140, 33)]
+    got = e.embed_token_ids(seqs)
+    torch.cuda.synchronize()
+    assert e.launches_last_forward == 2 + 24 * 7
+    _check_vs_oracle(got.cpu(), bo.bert_embed(w, seqs), bo.bert_embed(w, seqs, round_operands=lambda t: t.half().float()),
+                     atol=6e-2, atol_emulated=3e-2)
+
+
+def test_many_tokens_split_into_batches(sqe):
+    w, e = _pair(sqe, 23, layers=1)
+    e.max_batch_tokens = 1024
+    g = torch.Generator().manual_seed(8)
+    seqs = [torch.randint(0, 2000, (int(n),), generator=g).tolist() for n in torch.randint(1, 400, (30,), generator=g)]
+    got = e.embed_token_ids(seqs)
+    torch.cuda.synchronize()
+    want = bo.bert_embed(w, seqs)
+    assert float((got.cpu() - want).abs().max()) < 1e-2
+
+
+# ----------------------------------------------------------- the reference's call signatures
+VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]"] + [chr(c) for c in range(97, 123)] + ["##" + chr(c) for c in range(97, 123)] + \
+        ["the", "cell", "##s", "protein", "bind", "##ing", "gene", "expression", "tumor", "patient", ".", ",", "?"]
+
+
+def test_drop_in_coroutines_and_retrieval_end_to_end(sqe):
+    """`install_encoder` patches the three embedding coroutines of a loaded reference module; their
+    outputs feed `add_embeddings` / `search` (main.py:455, :499) unchanged."""
+    w = bo.random_bert_weights(31, layers=2, vocab=len(VOCAB))
+    vocab = {t: i for i, t in enumerate(VOCAB)}
+    e = sqe.GpuEmbeddingEncoder(sqe.EncoderWeights.from_state_dict(w, device=dev()), sqe.WordPieceTokenizer(vocab))
+    main = types.SimpleNamespace(embed_query=None)
+    sqe.install_encoder(main, e)
+    chunks = ["the cells bind the protein.", "gene expression, tumor cells", "patient tumor binding?", "  ",
+              "protein " * 600]
+    emb = asyncio.run(main.embed_texts_in_batches(chunks))
+    assert emb.shape == (5, 1024) and emb.dtype == np.float32 and not emb[3].any()
+    want = bo.bert_embed(w, [bo.encode_text(t, vocab) for t in chunks if t.strip()]).numpy()
+    assert np.abs(emb[[0, 1, 2, 4]] - want).max() < 2e-2
+    q = asyncio.run(main.embed_query("gene expression, tumor cells"))
+    assert q.shape == (1, 1024) and np.abs(q[0] - emb[1]).max() < 1e-3
+    assert asyncio.run(main.embed_query(" ")).size == 0
+    one = asyncio.run(main.ollama_embed_text("patient tumor binding?"))
+    assert isinstance(one, list) and len(one) == 1024 and abs(one[0] - float(emb[2, 0])) < 1e-3
+    index = sqe.GpuCorpusIndex(dtype="fp32")
+    index.add_embeddings(emb, [{"doc_id": f"d{i}", "text": t} for i, t in enumerate(chunks)])
+    hits = index.search(q, k=2)
+    assert hits[0][0]["doc_id"] == "d1" and hits[0][1] > 0.9999
+    gen = types.SimpleNamespace(bulk_index_embeddings=None)
+    sqe.install_encoder(gen, e)
+    assert asyncio.run(gen.embed_texts_in_batches([])).shape == (0, 1024) and not hasattr(gen, "embed_query")

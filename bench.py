@@ -71,7 +71,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SQE_BENCH_WORKLOAD", "b1024"),
-                    choices=["b1024", "b1", "cache64", "ingest", "config1", "serve", "cachemut"])
+                    choices=["b1024", "b1", "cache64", "ingest", "config1", "serve", "cachemut", "encode"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=None,
@@ -530,6 +530,8 @@ def main():
         return run_serve(args, torch, sqe_b200, nat, dev, peaks)
     if args.workload == "cachemut":
         return run_cachemut(args, torch, sqe_b200, nat, dev, peaks)
+    if args.workload == "encode":
+        return run_encode(args, torch, sqe_b200, nat, dev, peaks)
     is_cache = args.workload == "cache64"
     b = {"b1024": 1024, "b1": 1, "cache64": 64}[args.workload]
     if args.batch and args.workload == "b1024":
@@ -1379,6 +1381,161 @@ def run_ingest(args, torch, ops, nat, dev, peaks):
                          "frac": ach / peaks["hbm_gbs"], "kernel": "normalize_cast_kernel", "kernel_ms": ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peaks["source"], "traffic": None},
             "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
+def run_encode(args, torch, sqe_b200, nat, dev, peaks):
+    """The embedding step in front of the path (app/main.py:134-180): the BERT-large
+    encoder (mxbai-embed-large geometry, 24 layers, random weights) on one batch of the reference's
+    ingest shape -- BATCH_SIZE = 64 chunks (main.py:36) of CHUNK_SIZE = 512 words (main.py:37), which
+    the model truncates to its 512 positions -- plus the single-query latency (main.py:172-180).
+    FLOPs per token: 2 * 24 * 12 * 1024^2 = 604 M in the linear layers + 4 * S * 1024 * 24 in attention."""
+    from sqe_b200 import encoder as enc
+    n_seq = args.batch or 64
+    seq_len = 512
+    layers = 24
+    steps = args.steps or 10
+    warmup = args.warmup if args.warmup is not None else 3
+    w = sqe_b200.EncoderWeights.random_init(seed=0, layers=layers, device=dev)
+    e = sqe_b200.GpuEmbeddingEncoder(w, max_batch_tokens=n_seq * seq_len)
+    rng = np.random.default_rng(0)
+    seqs = [rng.integers(0, 30522, size=seq_len).tolist() for _ in range(n_seq)]
+    tokens = n_seq * seq_len
+    lin_flops = w.flops_per_token() * tokens
+    att_flops = 4.0 * seq_len * 1024 * layers * tokens
+    # ---- device-timed: ids resident in the staging buffer is not separable from the call, so the
+    # device value times the layer loop on pre-planned metadata (forward_ids does plan + H2D + loop)
+    t_pad, pos, first, tiles = e.plan([seq_len] * n_seq)
+    buf = e._buffers(t_pad)
+    ids_d = torch.from_numpy(np.asarray(seqs, dtype=np.int32).reshape(-1)).to(dev)
+    pos_d = torch.from_numpy(np.maximum(pos, 0)).to(dev)
+    tiles_d = torch.from_numpy(tiles).to(dev)
+    first_d = torch.from_numpy(first).to(dev)
+    out = torch.empty((n_seq, 1024), dtype=torch.float32, device=dev)
+
+    def step_device():
+        e._layers(buf, ids_d, pos_d, tiles_d, tiles.shape[0], seq_len, t_pad)
+        nat.call("sqe_encoder_pool", buf.h32.data_ptr(), first_d.data_ptr(), n_seq, out.data_ptr(), 1024,
+                 torch.cuda.current_stream(dev).cuda_stream)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(warmup):
+        step_device()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    time.sleep(0.5)
+    sampler.mark()
+    l0 = nat.launch_count
+    ms = timed(step_device, steps)
+    launches = nat.launch_count - l0
+    clocks = sampler.stop()
+    # ---- the kernels by class, each timed alone on the same buffers (the activations of one layer,
+    # 1.7 GB, are larger than L2; weights are meant to stay in L2)
+    L = w.layers[0]
+    H = 1024
+
+    def gemms():
+        enc.gemm(buf.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, buf.qk, m=t_pad, out1=buf.vt, n_split=2 * H,
+                 q_cols=H, q_scale=0.125)
+        enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
+        enc.gemm(buf.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, buf.ffn, m=t_pad)
+        enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
+
+    def one(which):
+        return {
+            "qkv": lambda: enc.gemm(buf.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, buf.qk, m=t_pad, out1=buf.vt,
+                                    n_split=2 * H, q_cols=H, q_scale=0.125),
+            "attn_out": lambda: enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad,
+                                         residual=buf.h32),
+            "ffn1_gelu": lambda: enc.gemm(buf.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, buf.ffn, m=t_pad),
+            "ffn2": lambda: enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad,
+                                     residual=buf.h32),
+        }[which]
+
+    gemm_ms = timed(gemms, 24)
+    shapes = {"qkv": (3 * H, H), "attn_out": (H, H), "ffn1_gelu": (4 * H, H), "ffn2": (H, 4 * H)}
+    per_gemm = {}
+    for name, (n_, k_) in shapes.items():
+        t = timed(one(name), 24)
+        per_gemm[name] = {"ms": t, "tflops": 2.0 * t_pad * n_ * k_ / (t * 1e-3) / 1e12}
+    attn_ms = timed(lambda: enc.attention(buf.qk, buf.vt, tiles_d, tiles.shape[0], seq_len, buf.ctx), 24)
+    ln_ms = timed(lambda: enc.layernorm(buf.sum32, L["g1"], L["b1"], 1e-12, buf.h32, buf.h16, rows=t_pad), 24)
+    gemm_tflops = lin_flops / layers / (gemm_ms * 1e-3) / 1e12
+    breakdown = {"per_layer_ms": {"gemms": gemm_ms, "attention": attn_ms, "layernorm_x2": 2 * ln_ms},
+                 "per_layer_sum_x_layers_ms": layers * (gemm_ms + attn_ms + 2 * ln_ms), "per_gemm": per_gemm,
+                 "attention_tflops": att_flops / layers / (attn_ms * 1e-3) / 1e12,
+                 "layernorm_gbs": t_pad * 1024 * (4 + 4 + 2) / (ln_ms * 1e-3) / 1e9}
+    # ---- end to end: host token lists -> packing -> H2D -> 24 layers -> D2H of the embeddings
+    e2e = None
+    if not args.no_e2e:
+        def run_e2e():
+            o = e.embed_token_ids(seqs)
+            e.stream.synchronize()
+            return o.cpu()
+        for _ in range(2):
+            run_e2e()
+        esteps = max(3, min(steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            run_e2e()
+        dt = (time.perf_counter() - t0) / esteps
+        e2e = {"value": tokens / dt, "unit": "tokens/s", "h2d_bytes_per_step": int(buf.meta_cap * 4),
+               "d2h_bytes_per_step": n_seq * 1024 * 4, "ms_per_step": dt * 1e3, "chunks_per_s": n_seq / dt,
+               "api": "GpuEmbeddingEncoder.embed_token_ids(host token lists) -> host fp32 [64, 1024]"}
+    # ---- one query (16 tokens): the latency the /ask handler sees instead of an HTTP round trip
+    q = [rng.integers(0, 30522, size=16).tolist()]
+
+    def run_q():
+        o = e.embed_token_ids(q)
+        e.stream.synchronize()
+        return o
+    for _ in range(5):
+        run_q()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        run_q()
+    query_ms = (time.perf_counter() - t0) / 50 * 1e3
+    # ---- CPU baseline: the oracle (fp32 torch, every core) on a bounded sample of the same workload
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import bert_oracle as bo
+        cores = cpu_use_all_cores()
+        torch.set_num_threads(cores)
+        wsd = bo.random_bert_weights(0, layers=2, vocab=1000)
+        sample = [rng.integers(0, 1000, size=seq_len).tolist() for _ in range(2)]
+        bo.bert_embed(wsd, sample[:1])
+        t0 = time.perf_counter()
+        bo.bert_embed(wsd, sample)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 2 * seq_len / (dt * layers / 2), "unit": "tokens/s", "cores": cores, "kind": "port",
+               "sample": "oracle/bert_oracle.py (fp32 torch) on 2 chunks x 512 tokens x 2 layers, scaled by 2/24 "
+                         "to the 24-layer model"}
+    line = {"metric": "tokens/sec BERT-large embedding encoder (mxbai-embed-large geometry), 64 chunks x 512 tokens",
+            "value": tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic token ids, random-init weights of the mxbai-embed-large architecture (no checkpoint offline)",
+            "config": {"workload": f"{n_seq} chunks x {seq_len} tokens, 24-layer BERT-large encoder, CLS pooling "
+                                   "(app/main.py:36-37 BATCH_SIZE x CHUNK_SIZE; main.py:134-169)",
+                       "chunks_per_s": n_seq / (ms * 1e-3), "tokens": tokens,
+                       "l2": "activations of one layer (1.7 GB) are larger than L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": gemm_tflops / peaks["bf16_tflops"],
+                         "frac_sustained": (gemm_tflops / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
+                         "kernel": "encoder_gemm_kernel<256, 2, *> (the four linear layers of a block, 84 % of the step)",
+                         "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": lin_flops / layers,
+                         "peak_source": peaks["source"], "traffic": None,
+                         "whole_step_tflops": (lin_flops + att_flops) / (ms * 1e-3) / 1e12},
+            "breakdown": breakdown, "query_latency_ms": query_ms, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 

@@ -182,6 +182,10 @@ SQE_API int sqe_tuning_set(int knob, int value);
  * NULL switches it off (the default).
  */
 SQE_API void sqe_debug_k2_timers(void *device_buffer);
+/* Diagnostics: phase time stamps of sqe_encoder_attention, int64 [n_tiles * 16][8] per launch
+ * (clock64 at: start, setup done, scores ready, maxima done, P written, output ready, end; then the
+ * global timer at the end); NULL = off (the default). */
+SQE_API void sqe_debug_encoder_attention_timers(void *device_buffer);
 
 /*
  * K5  query-cache lookup: top-1 + similarity threshold.

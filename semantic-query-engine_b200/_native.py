@@ -30,6 +30,7 @@ PROTOTYPES = [
     ("sqe_device_info", c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     ("sqe_tuning_set", c_int, [c_int, c_int]),
     ("sqe_debug_k2_timers", None, [c_void_p]),
+    ("sqe_debug_encoder_attention_timers", None, [c_void_p]),
     ("sqe_normalize_cast", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     ("sqe_topk_gemv_workspace_bytes", c_int64, [c_int, c_int]),
     ("sqe_topk_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,

@@ -116,6 +116,8 @@ int sqe_tuning_set(int knob, int value) {
 
 void sqe_debug_k2_timers(void* device_buffer) { g_k2_debug = device_buffer; }
 
+void sqe_debug_encoder_attention_timers(void* device_buffer) { g_enc_attn_debug = device_buffer; }
+
 int sqe_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     DevInfo d;
     int rc = device_info(&d);

@@ -35,7 +35,14 @@ struct AttnArgs {
     __half* ctx;              // [T, 1024]
     int s_max;                // keys staged per tile: max sequence length rounded up to 64
     uint32_t tmem_cols;       // power of two >= max(s_max, 64)
+    long long* dbg;           // diagnostics: [CTA][8] phase time stamps (null in production)
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __host__ __device__ inline int attn_region_a_bytes(int s_max) {
     const int qk = kQBytes + s_max * 128;       // Q + K
@@ -57,6 +64,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
     const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int head = blockIdx.y;
+    if (a.dbg != nullptr && threadIdx.x == 32)
+        a.dbg[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8] = clock64();
     const int4 tile = __ldg(a.tiles + blockIdx.x);
     const int seq_start = tile.x, seq_len = tile.y, q0 = tile.z;
     const int s_pad = (seq_len + 63) & ~63;                    // keys this tile scores
@@ -143,39 +152,76 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
         constexpr float kLog2e = 1.4426950408889634f;
         const float ninf = __int_as_float(0xff800000);
 
+        const bool stamp = a.dbg != nullptr && threadIdx.x == 32;
+        long long* dbg = a.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+        if (stamp) dbg[1] = clock64();
         ptx::mbar_wait(bar_s, 0);
         ptx::tc_fence_after();
-        float mx = ninf;
+        if (stamp) dbg[2] = clock64();
+        // pass 1: row maximum over this warp's keys.  Strips that lie inside the sequence need no
+        // mask; strips beyond its end are skipped (their P entries are zeros, written in pass 2).
+        float m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;
 #pragma unroll 1
         for (int s = 0; s < n_strips; ++s) {
             const int c0 = col_base + 32 * s;
+            if (c0 >= seq_len) break;
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + c0, v);
             ptx::tmem_wait_ld();
+            if (c0 + 32 <= seq_len) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (c0 + j < seq_len) mx = fmaxf(mx, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(v[j]));
+                    m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+                    m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < seq_len) m0 = fmaxf(m0, __uint_as_float(v[j]));
+            }
         }
-        red_max[half * kBM + r] = mx;
+        red_max[half * kBM + r] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         ptx::bar_sync_named(1, 256);
-        mx = fmaxf(red_max[r], red_max[kBM + r]);              // finite: key 0 is always inside the sequence
+        const float mx = fmaxf(red_max[r], red_max[kBM + r]);  // finite: key 0 is always inside the sequence
         const float mb = mx * kLog2e;
-        float sum = 0.0f;
+        if (stamp) dbg[3] = clock64();
+        // pass 2: p = 2^(s log2 e - max log2 e), fp16, into the operand layout; the row sum is taken
+        // in fp32 before the rounding (the two differ by 2^-12 relative, far below the fp16 output)
+        float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll 1
         for (int s = 0; s < n_strips; ++s) {
             const int c0 = col_base + 32 * s;
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(taddr + c0, v);
-            ptx::tmem_wait_ld();
             uint32_t h[16];
+            if (c0 >= seq_len) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float p0 = (c0 + 2 * j < seq_len) ? exp2f(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mb)) : 0.0f;
-                const float p1 = (c0 + 2 * j + 1 < seq_len) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mb)) : 0.0f;
-                const __half2 hh = __floats2half2_rn(p0, p1);
-                const float2 back = __half22float2(hh);
-                sum += back.x + back.y;
-                h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                for (int j = 0; j < 16; ++j) h[j] = 0u;
+            } else {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + c0, v);
+                ptx::tmem_wait_ld();
+                if (c0 + 32 <= seq_len) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mb));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mb));
+                        s0 += p0;
+                        s1 += p1;
+                        const __half2 hh = __floats2half2_rn(p0, p1);
+                        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = (c0 + 2 * j < seq_len) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mb)) : 0.0f;
+                        const float p1 = (c0 + 2 * j + 1 < seq_len) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mb)) : 0.0f;
+                        s0 += p0;
+                        s1 += p1;
+                        const __half2 hh = __floats2half2_rn(p0, p1);
+                        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                }
             }
             // operand layout: block kc = 64 keys, row r at r * 128 B, 16-byte chunk c at (c ^ (r & 7))
             const uint32_t blk = sm_p + (c0 >> 6) * kPBlockBytes + r * 128;
@@ -188,6 +234,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
                              : "memory");
             }
         }
+        const float sum = s0 + s1;
+        if (stamp) dbg[4] = clock64();
         red_sum[half * kBM + r] = sum;
         ptx::tc_fence_before();                // the score columns are about to be overwritten by O
         ptx::fence_proxy_async_smem();         // P: generic-proxy stores -> tensor-core operand reads
@@ -197,6 +245,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
 
         ptx::mbar_wait(bar_o, 0);
         ptx::tc_fence_after();
+        if (stamp) dbg[5] = clock64();
         const float inv = 1.0f / (red_sum[r] + red_sum[kBM + r]);
         {
             uint32_t v[32];
@@ -222,6 +271,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (a.dbg != nullptr && threadIdx.x == 32) {
+        long long* dbg = a.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+        dbg[6] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[7] = static_cast<long long>(gt);
+    }
     if (warp == 0) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<1>(tmem_base, a.tmem_cols);
@@ -229,6 +285,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
 }
 
 }  // namespace enc
+
+void* g_enc_attn_debug = nullptr;      // diagnostics: device buffer [n_tiles * 16][8] i64 of phase time stamps
 
 int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const void* tiles, int n_tiles,
                              int max_len, void* ctx, cudaStream_t stream) {
@@ -238,6 +296,7 @@ int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, cons
     a.tiles = static_cast<const int4*>(tiles);
     a.ctx = static_cast<__half*>(ctx);
     a.s_max = (max_len + 63) & ~63;
+    a.dbg = static_cast<long long*>(g_enc_attn_debug);
     a.tmem_cols = 64;
     while (a.tmem_cols < static_cast<uint32_t>(a.s_max)) a.tmem_cols *= 2;
     CUtensorMap tq, tv;

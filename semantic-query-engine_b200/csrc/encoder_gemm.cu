@@ -8,6 +8,7 @@
 // share a row block of X are adjacent so X is read from HBM once and W stays in L2.
 //
 // Two geometries:
+// (5 operand stages of 32 KB for pairs, 7 of 24 KB for single CTAs, + 36 KB of epilogue staging)
 //   <BN = 256, CG = 2>  a CTA pair computes a 256 x 256 tile (cta_group::2, each CTA stages its 128
 //                       rows of X and half of the W rows): the throughput form (ingest batches);
 //   <BN = 64,  CG = 1>  128 x 64 tiles: the latency form (a handful of queries: M = 128, so the
@@ -37,9 +38,14 @@ struct GemmCfg {
     static constexpr int kBRows = BN / CG;               // W rows this CTA stages per chunk
     static constexpr int kBBytes = kBRows * kChunkK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (192 * 1024) / kStageBytes;     // 6 x 32 KB or 8 x 24 KB
+    // epilogue staging: per warp a 32 x 32 fp32 strip, rows padded to 36 floats (16-byte aligned,
+    // conflict-free for the row-per-lane 128-bit stores)
+    static constexpr int kStageRowFloats = 36;
+    static constexpr int kStagingBytes = 8 * 32 * kStageRowFloats * 4;       // 36 KB
+    static constexpr int kStages = (226 * 1024 - kStagingBytes - 1024) / kStageBytes;     // 5 x 32 KB or 7 x 24 KB
     static constexpr int kTmemCols = 2 * BN;             // two accumulators
-    static constexpr int kOffBar = kStages * kStageBytes;
+    static constexpr int kOffStaging = kStages * kStageBytes;
+    static constexpr int kOffBar = kOffStaging + kStagingBytes;
     static constexpr int kOffTmemPtr = kOffBar + (2 * kStages + 4) * 8;
     static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -63,8 +69,24 @@ struct GemmArgs {
     int64_t ldr;
 };
 
+// gelu(x) = x Phi(x) = 0.5 x (1 + erf(x / sqrt 2)), the erf form BERT uses.  erf by Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7 absolute, i.e. <= 1e-7 |x| on the result -- three orders of
+// magnitude below the fp16 rounding of the output): with z = |x| / sqrt 2, t = 1 / (1 + p z),
+// 1 - erf(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2) =: c, and
+// gelu(x) = x - x c / 2 for x >= 0, x c / 2 for x < 0.  Two MUFU (rcp, ex2) + 12 FMA-pipe
+// instructions per element; erff() costs ~35, which made the FFN epilogue longer than its main loop.
 __device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float pl = fmaf(t, 1.061405429f, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));
+    const float hc = 0.5f * x * (pl * t * ex);             // x c / 2
+    return x >= 0.0f ? x - hc : hc;
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -176,15 +198,23 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
     } else {
         // ---------------------------------------------------------------- epilogue
+        // TMEM gives every thread one ROW of the tile (32 consecutive columns per load).  Stored
+        // as such, a warp-wide 128-bit access touches 32 different lines (16 useful bytes each) and
+        // the LSU, not the tensor pipe, bounds the narrow-K layers.  So each warp transposes its
+        // 32 x 32 strip through shared memory and reads / writes global memory row-contiguously:
+        // eight lanes cover one 128-byte row segment, a warp instruction covers four rows.
         const int quarter = warp & 3;                          // TMEM lanes 32 q .. 32 q + 31
         const int half = (warp - 2) >> 2;                      // which half of the tile's columns
         constexpr int kStrips = BN / 64;                       // strips of 32 columns per warp
+        constexpr int RS = C::kStageRowFloats;
+        float* stg = reinterpret_cast<float*>(sm + C::kOffStaging) + (warp - 2) * 32 * RS;
+        const int sub_row = lane >> 3;                         // row of a 4-row group in the coalesced phase
+        const int c4 = (lane & 7) * 4;                         // first of this lane's 4 columns there
         int i = 0;
         for (int t = unit; t < n_tiles; t += a.n_units, ++i) {
             const int acc = i & 1;
-            const int64_t row = static_cast<int64_t>(t / a.n_nt) * C::kTileM + rank * kBM + quarter * 32 + lane;
+            const int64_t row0 = static_cast<int64_t>(t / a.n_nt) * C::kTileM + rank * kBM + quarter * 32;
             const int col_t = (t % a.n_nt) * BN + half * (BN / 2);
-            const bool row_ok = row < a.m;
             ptx::mbar_wait(bar_tfull + 8 * acc, (i >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
@@ -193,66 +223,64 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 const int col0 = col_t + 32 * s;
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(taddr + 32 * s, v);
-                float y[32];
-                const float4* bp = reinterpret_cast<const float4*>(a.bias + col0);
+                if (EPI == kEpiSplit && col0 >= a.n_split) {
+                    // V^T: lanes are consecutive rows -> every column is one 64-byte run already
+                    const int64_t row = row0 + lane;
+                    const float4* bp = reinterpret_cast<const float4*>(a.bias + col0);
+                    ptx::tmem_wait_ld();
+                    if (row < a.m) {
+                        __half* op = a.out1 + static_cast<int64_t>(col0 - a.n_split) * a.ld1 + row;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(bp + j);
+                            op[static_cast<int64_t>(4 * j + 0) * a.ld1] = __float2half_rn(__uint_as_float(v[4 * j + 0]) + b4.x);
+                            op[static_cast<int64_t>(4 * j + 1) * a.ld1] = __float2half_rn(__uint_as_float(v[4 * j + 1]) + b4.y);
+                            op[static_cast<int64_t>(4 * j + 2) * a.ld1] = __float2half_rn(__uint_as_float(v[4 * j + 2]) + b4.z);
+                            op[static_cast<int64_t>(4 * j + 3) * a.ld1] = __float2half_rn(__uint_as_float(v[4 * j + 3]) + b4.w);
+                        }
+                    }
+                    continue;
+                }
+                // this lane's bias (its 4 columns of every row) and, for the residual form, the
+                // residual values of its 8 rows: issued before the TMEM data is awaited
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + c4));
+                [[maybe_unused]] float4 r4[8];
                 if constexpr (EPI == kEpiResF32) {
-                    float4 r4[8];
-                    const float4* rp = reinterpret_cast<const float4*>(a.residual + row * a.ldr + col0);
-                    if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) r4[j] = __ldg(rp + j);
-                    }
-                    ptx::tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = __ldg(bp + j);
-                        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-                    }
-                    if (row_ok) {
-                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out0) + row * a.ld0 + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            op[j] = make_float4(y[4 * j] + r4[j].x, y[4 * j + 1] + r4[j].y, y[4 * j + 2] + r4[j].z,
-                                                y[4 * j + 3] + r4[j].w);
-                    }
-                } else {
-                    ptx::tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = __ldg(bp + j);
-                        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-                    }
-                    if constexpr (EPI == kEpiGelu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
-                    }
-                    if (EPI == kEpiSplit && col0 >= a.n_split) {
-                        // transposed: lanes are consecutive rows -> one 64-byte run per column
-                        if (row_ok) {
-                            __half* op = a.out1 + static_cast<int64_t>(col0 - a.n_split) * a.ld1 + row;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) op[static_cast<int64_t>(j) * a.ld1] = __float2half_rn(y[j]);
-                        }
-                    } else {
-                        if (EPI == kEpiSplit && col0 < a.q_cols) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) y[j] *= a.q_scale;
-                        }
-                        if (row_ok) {
-                            uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(a.out0) + row * a.ld0 + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                op[j] = make_uint4(pack_half2(y[8 * j], y[8 * j + 1]), pack_half2(y[8 * j + 2], y[8 * j + 3]),
-                                                   pack_half2(y[8 * j + 4], y[8 * j + 5]), pack_half2(y[8 * j + 6], y[8 * j + 7]));
-                        }
+                    for (int g = 0; g < 8; ++g) {
+                        const int64_t row = row0 + 4 * g + sub_row;
+                        r4[g] = (row < a.m) ? __ldg(reinterpret_cast<const float4*>(a.residual + row * a.ldr + col0 + c4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+                ptx::tmem_wait_ld();
+                float* srow = stg + lane * RS;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const float qs = (EPI == kEpiSplit && col0 < a.q_cols) ? a.q_scale : 1.0f;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int64_t row = row0 + 4 * g + sub_row;
+                    float4 y = *reinterpret_cast<const float4*>(stg + (4 * g + sub_row) * RS + c4);
+                    y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+                    if constexpr (EPI == kEpiResF32) {
+                        y.x += r4[g].x; y.y += r4[g].y; y.z += r4[g].z; y.w += r4[g].w;
+                        if (row < a.m)
+                            *reinterpret_cast<float4*>(static_cast<float*>(a.out0) + row * a.ld0 + col0 + c4) = y;
+                    } else {
+                        if constexpr (EPI == kEpiGelu) {
+                            y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
+                        } else {
+                            y.x *= qs; y.y *= qs; y.z *= qs; y.w *= qs;
+                        }
+                        if (row < a.m)
+                            *reinterpret_cast<uint2*>(static_cast<__half*>(a.out0) + row * a.ld0 + col0 + c4) =
+                                make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+                    }
+                }
+                __syncwarp();                                  // the strip buffer is rewritten by the next strip
             }
             ptx::tc_fence_before();
             __syncwarp();

@@ -79,6 +79,7 @@ extern int g_k2_cta_group;      // 0 auto, 1, 2
 extern int g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
 extern int g_k2_d_hint;         // retired experiment (accepted, ignored)
 extern int g_k2_window;         // retired experiment (accepted, ignored)
+extern void* g_enc_attn_debug;  // encoder_attn.cu: phase time stamps per CTA, or null
 extern int g_enc_gemm_form;    // 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs (encoder_gemm.cu)
 extern void* g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
 

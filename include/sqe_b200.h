@@ -336,7 +336,9 @@ SQE_API int sqe_cache_top1_prefiltered(const void *C, int dtype, int64_t n, int 
  *   sqe_encoder_attention  softmax(Q K^T) V per (sequence, head); qk [t_pad, 2048] fp16 = Q (already
  *                          scaled by 1/8) | K, vt [1024, t_pad] fp16 = V^T (t_pad % 8 == 0);
  *                          tiles int32 [n_tiles, 4] = (first token of the sequence, its length,
- *                          first query row of this 128-query tile, 0); the first token of a sequence
+ *                          first query row of this entry, its number of query rows): one CTA per
+ *                          (entry, head) keeps K / V of the sequence in shared memory and walks the
+ *                          entry's 128-query tiles; the first token of a sequence
  *                          must be a multiple of 8 (a TMA box of V^T starts on a 16-byte boundary);
  *                          max_len = longest sequence (1..512); ctx [t_pad, 1024] fp16.
  *   sqe_encoder_pool       out[s, :] = h[first_token[s], :] (CLS pooling), ldo elements per row.

@@ -44,13 +44,14 @@ if "--timers" in sys.argv:
     torch.cuda.synchronize()
     nat.load().sqe_debug_encoder_attention_timers(None)
     d = dbg.cpu().numpy().astype(np.float64)
-    names = ["setup (alloc, barriers)", "loads + QK^T", "row maxima", "exp + P stores", "PV MMA", "output + teardown"]
+    nq = d[:, 6]
+    names = ["CTA total", "wait for scores (loads, QK^T)", "row maxima", "exp + P stores (+ PV overlap)",
+             "wait for PV", "output"]
     for i, nm in enumerate(names):
-        dt = d[:, i + 1] - d[:, i]
-        print(f"{nm:28s} mean {dt.mean():9.0f}  p10 {np.percentile(dt, 10):9.0f}  p90 {np.percentile(dt, 90):9.0f} cycles")
-    tot = d[:, 6] - d[:, 0]
+        dt = d[:, i] / nq
+        print(f"{nm:32s} per q-tile: mean {dt.mean():9.0f}  p10 {np.percentile(dt, 10):9.0f}  p90 {np.percentile(dt, 90):9.0f} cycles")
     span_us = (d[:, 7].max() - d[:, 7].min()) / 1e3
-    print(f"CTA total mean {tot.mean():.0f} cycles; {n_cta} CTAs; ends span {span_us:.1f} us")
+    print(f"{n_cta} CTAs x {nq.mean():.1f} q-tiles; ends span {span_us:.1f} us")
 else:
     block()
     torch.cuda.synchronize()

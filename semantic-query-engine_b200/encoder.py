@@ -366,7 +366,7 @@ class GpuEmbeddingEncoder:
 
     @staticmethod
     def plan(lengths: Sequence[int]) -> Tuple[int, np.ndarray, np.ndarray, np.ndarray]:
-        """Packing of sequences of the given lengths: (t_pad, pos [t_pad], first_token [n], tiles [m,4]).
+        """Packing of sequences of the given lengths: (t_pad, pos [t_pad], first_token [n], entries [m,4]).
         Every sequence starts at a multiple of 8 tokens: the attention kernel fetches V^T with TMA
         boxes whose innermost coordinate is the token index, and a box must start on a 16-byte
         boundary.  pos = -1 marks the (zero) filler rows."""
@@ -379,14 +379,20 @@ class GpuEmbeddingEncoder:
         pos = np.full(t_pad, -1, dtype=np.int32)
         rows = np.repeat(starts, lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
         pos[rows] = rows - np.repeat(starts, lens)
+        # attention work list: (first token, length, first query row, query rows).  One CTA keeps the
+        # K / V of its (sequence, head) in shared memory and walks `group` 128-query tiles; small
+        # batches get one tile per entry (more CTAs), ingest batches whole sequences (K / V fetched once).
         n_q = (lens + 127) // 128
-        seq_of_tile = np.repeat(np.arange(lens.size), n_q)
-        first_tile = np.concatenate([[0], np.cumsum(n_q)[:-1]])
-        q0 = (np.arange(seq_of_tile.size) - first_tile[seq_of_tile]) * 128
-        tiles = np.zeros((seq_of_tile.size, 4), dtype=np.int32)
-        tiles[:, 0] = starts[seq_of_tile]
-        tiles[:, 1] = lens[seq_of_tile]
+        group = int(min(4, max(1, (int(n_q.sum()) * HEADS) // (3 * 148))))
+        n_e = (n_q + group - 1) // group
+        seq_of = np.repeat(np.arange(lens.size), n_e)
+        first_e = np.concatenate([[0], np.cumsum(n_e)[:-1]])
+        q0 = (np.arange(seq_of.size) - first_e[seq_of]) * (128 * group)
+        tiles = np.zeros((seq_of.size, 4), dtype=np.int32)
+        tiles[:, 0] = starts[seq_of]
+        tiles[:, 1] = lens[seq_of]
         tiles[:, 2] = q0
+        tiles[:, 3] = np.minimum(128 * group, lens[seq_of] - q0)
         return t_pad, pos, starts.astype(np.int32), tiles
 
     def forward_ids(self, seqs: Sequence[Sequence[int]], out: Optional[torch.Tensor] = None) -> torch.Tensor:

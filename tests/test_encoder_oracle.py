@@ -114,8 +114,13 @@ def test_packing_plan():
     assert pos[:8].tolist() == [0, 1, 2, 3, 4, -1, -1, -1] and pos[8] == 0 and pos[137] == 129
     assert pos[138:144].tolist() == [-1] * 6 and pos[144:152].tolist() == [0] + [-1] * 7
     assert pos[152:664].tolist() == list(range(512)) and (pos[664:] == -1).all()
-    assert tiles.tolist() == [[0, 5, 0, 0], [8, 130, 0, 0], [8, 130, 128, 0], [144, 1, 0, 0],
-                              [152, 512, 0, 0], [152, 512, 128, 0], [152, 512, 256, 0], [152, 512, 384, 0]]
+    assert tiles.tolist() == [[0, 5, 0, 5], [8, 130, 0, 128], [8, 130, 128, 2], [144, 1, 0, 1],
+                              [152, 512, 0, 128], [152, 512, 128, 128], [152, 512, 256, 128], [152, 512, 384, 128]]
+    # an ingest batch: one entry per sequence (its K / V are fetched once), all four query tiles
+    _, _, _, big = enc.GpuEmbeddingEncoder.plan([512] * 64)
+    assert big.shape == (64, 4) and big[3].tolist() == [3 * 512, 512, 0, 512]
+    _, _, _, mid = enc.GpuEmbeddingEncoder.plan([300] * 20)
+    assert mid.shape == (40, 4) and mid[1].tolist() == [0, 300, 256, 44]
     with pytest.raises(ValueError):
         enc.GpuEmbeddingEncoder.plan([0])
     with pytest.raises(ValueError):

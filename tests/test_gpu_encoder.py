@@ -176,7 +176,9 @@ def _attention_case(sqe, lens, seed, junk=0.0):
 
 
 @pytest.mark.parametrize("lens", [[1], [2], [63], [64], [65], [128], [129], [255, 257], [511], [512],
-                                  [5, 130, 1, 512, 64, 300, 17], [384] * 3, [12] * 40])
+                                  [5, 130, 1, 512, 64, 300, 17], [384] * 3, [12] * 40,
+                                  [512] * 28, [300] * 20, [130] * 60, [449, 77, 512, 200] * 8],
+                         ids=lambda v: f"{len(v)}x{max(v)}")
 def test_attention_matches_torch(sqe, lens):
     # P is rounded to fp16 (2^-11 relative per weight, weights sum to 1, |v| <~ 4) and so is the output
     assert _attention_case(sqe, lens, seed=sum(lens)) < 4e-3

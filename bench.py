@@ -92,6 +92,7 @@ def parse_args():
     ap.add_argument("--no-yardstick", action="store_true",
                     help="skip the cuBLAS GEMM of the same shape reported beside the tensor roofline")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 0.6 s repeat of the step loop")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the embedding-encoder block of the default line")
     ap.add_argument("--no-cfg4", action="store_true",
                     help="skip the BASELINE configs[3] block (100M x 1024 fp16, b=256, k=100 over the ranks; "
                          "one 12.5M-row shard at N=1) that rides along with the default workload")
@@ -1063,6 +1064,16 @@ def main():
         except Exception as e:                          # never let the extra block break the headline
             cfg4 = {"error": str(e)[:300]}
 
+    # ---- the embedding step in front of the path (one GPU: chunks are independent, replicas only)
+    encoder = None
+    if args.workload == "b1024" and not args.no_encoder and world == 1 and args.rows == 10_000_000 and not args.batch:
+        try:
+            store = sharded = shard = kern = None
+            torch.cuda.empty_cache()
+            encoder = run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=True)
+        except Exception as e:                          # never let the extra block break the headline
+            encoder = {"error": str(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": metric_name(total_rows, k) if not is_cache else "queries/sec cache top-1+threshold @1Mx1024",
@@ -1074,6 +1085,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "sustained": sustained,
             "cfg4": cfg4,
+            "encoder": encoder,
             "exchange": exchange_used,
             "secondary": secondary,
             "secondary_prefiltered": secondary_pf,
@@ -1384,18 +1396,18 @@ def run_ingest(args, torch, ops, nat, dev, peaks):
     print(json.dumps(line), flush=True)
 
 
-def run_encode(args, torch, sqe_b200, nat, dev, peaks):
+def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
     """The embedding step in front of the path (app/main.py:134-180): the BERT-large
     encoder (mxbai-embed-large geometry, 24 layers, random weights) on one batch of the reference's
     ingest shape -- BATCH_SIZE = 64 chunks (main.py:36) of CHUNK_SIZE = 512 words (main.py:37), which
     the model truncates to its 512 positions -- plus the single-query latency (main.py:172-180).
     FLOPs per token: 2 * 24 * 12 * 1024^2 = 604 M in the linear layers + 4 * S * 1024 * 24 in attention."""
     from sqe_b200 import encoder as enc
-    n_seq = args.batch or 64
+    n_seq = 64 if compact else (args.batch or 64)
     seq_len = 512
     layers = 24
-    steps = args.steps or 10
-    warmup = args.warmup if args.warmup is not None else 3
+    steps = 5 if compact else (args.steps or 10)
+    warmup = 3 if compact else (args.warmup if args.warmup is not None else 3)
     w = sqe_b200.EncoderWeights.random_init(seed=0, layers=layers, device=dev)
     e = sqe_b200.GpuEmbeddingEncoder(w, max_batch_tokens=n_seq * seq_len)
     rng = np.random.default_rng(0)
@@ -1414,9 +1426,7 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks):
     out = torch.empty((n_seq, 1024), dtype=torch.float32, device=dev)
 
     def step_device():
-        e._layers(buf, ids_d, pos_d, tiles_d, tiles.shape[0], seq_len, t_pad)
-        nat.call("sqe_encoder_pool", buf.h32.data_ptr(), first_d.data_ptr(), n_seq, out.data_ptr(), 1024,
-                 torch.cuda.current_stream(dev).cuda_stream)
+        e._forward(buf, ids_d, pos_d, tiles_d, tiles.shape[0], seq_len, first_d, n_seq, out)
 
     def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1438,6 +1448,24 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks):
     ms = timed(step_device, steps)
     launches = nat.launch_count - l0
     clocks = sampler.stop()
+    if compact:                                              # the block that rides along with the default line
+        qc = [rng.integers(0, 30522, size=16).tolist()]
+        for _ in range(5):
+            e.embed_token_ids(qc)
+        e.stream.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(30):
+            e.embed_token_ids(qc)
+            e.stream.synchronize()
+        return {"what": "the embedding step in front of the path on the same GPU (SURVEY 8f rank 4, app/main.py:134-180): "
+                        "24-layer BERT-large encoder, mxbai-embed-large geometry, random-init weights, fp16 operands; "
+                        "64 chunks x 512 tokens per step (main.py:36-37); `python bench.py --workload encode` gives the "
+                        "full line (roofline, per-kernel breakdown, e2e, cpu_baseline)",
+                "tokens_per_s": tokens / (ms * 1e-3), "chunks_per_s": n_seq / (ms * 1e-3), "ms_per_step": ms,
+                "steps": steps, "tflops_linear_plus_attention": (lin_flops + att_flops) / (ms * 1e-3) / 1e12,
+                "frac_of_bf16_peak": (lin_flops + att_flops) / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                "gpu_launches": launches, "query_latency_ms_16_tokens": (time.perf_counter() - t0) / 30 * 1e3,
+                "clocks": clocks}
     # ---- the kernels by class, each timed alone on the same buffers (the activations of one layer,
     # 1.7 GB, are larger than L2; weights are meant to stay in L2)
     L = w.layers[0]
@@ -1531,12 +1559,14 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks):
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / peaks["bf16_tflops"],
                          "frac_sustained": (gemm_tflops / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
-                         "kernel": "encoder_gemm_kernel<256, 2, *> (the four linear layers of a block, 84 % of the step)",
+                         "kernel": "encoder_gemm_kernel<256, 2, *> (the four linear layers of a block)",
+                         "kernel_share_of_step": layers * gemm_ms / ms,
                          "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": lin_flops / layers,
                          "peak_source": peaks["source"], "traffic": None,
                          "whole_step_tflops": (lin_flops + att_flops) / (ms * 1e-3) / 1e12},
             "breakdown": breakdown, "query_latency_ms": query_ms, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    return line
 
 
 def load_traffic(kernel_name: str):

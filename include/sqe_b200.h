@@ -362,6 +362,47 @@ SQE_API int sqe_encoder_attention(const void *qk, const void *vt, int64_t t_pad,
 SQE_API int sqe_encoder_pool(const float *h, const int32_t *first_token, int n_seq, float *out, int64_t ldo,
                      void *stream);
 
+/*
+ * The whole forward pass in ONE call (what `GpuEmbeddingEncoder` issues per packed batch): embed_ln,
+ * then per layer  QKV gemm -> attention -> output gemm (+ residual) -> LayerNorm -> FFN gemm (gelu) ->
+ * FFN gemm (+ residual) -> LayerNorm,  then CLS pooling -- 2 + 7 n_layers kernel launches on `stream`,
+ * nothing else (capturable in a CUDA graph).  The structs hold DEVICE pointers; the structs
+ * themselves (and the `layers` array) live in HOST memory and are read during the call only.
+ */
+typedef struct SqeEncoderLayer {
+    const void *wqkv;           /* [3072, 1024] fp16: query | key | value Linear weights */
+    const float *bqkv;          /* [3072] */
+    const void *wo;             /* [1024, 1024] fp16 attention.output.dense */
+    const float *bo, *ln1_gamma, *ln1_beta;
+    const void *w1;             /* [intermediate, 1024] fp16 intermediate.dense */
+    const float *b1;
+    const void *w2;             /* [1024, intermediate] fp16 output.dense */
+    const float *b2, *ln2_gamma, *ln2_beta;
+} SqeEncoderLayer;
+
+typedef struct SqeEncoderWeights {
+    int n_layers, vocab, max_pos, intermediate;
+    float eps;
+    const float *word_emb, *pos_emb, *type_emb, *emb_gamma, *emb_beta;
+    const SqeEncoderLayer *layers;      /* host array [n_layers] */
+} SqeEncoderWeights;
+
+typedef struct SqeEncoderBuffers {      /* activations of one packed batch, t_pad rows (t_pad % 128 == 0) */
+    int64_t t_pad;
+    float *h32;                 /* [t_pad, 1024] residual stream */
+    void *h16;                  /* [t_pad, 1024] fp16 copy (tensor-core operand) */
+    float *sum32;               /* [t_pad, 1024] pre-LayerNorm sums */
+    void *qk;                   /* [t_pad, 2048] fp16 */
+    void *vt;                   /* [1024, t_pad] fp16 */
+    void *ctx;                  /* [t_pad, 1024] fp16 */
+    void *ffn;                  /* [t_pad, intermediate] fp16 */
+} SqeEncoderBuffers;
+
+SQE_API int sqe_encoder_forward(const SqeEncoderWeights *weights_host, const SqeEncoderBuffers *buffers_host,
+                        const int32_t *ids, const int32_t *pos, const int32_t *tiles, int n_tiles,
+                        int max_len, const int32_t *first_token, int n_seq, float *out, int64_t ldo,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,8 @@ e = sqe_b200.GpuEmbeddingEncoder(w)
 t_pad, pos, first, tiles = e.plan([seq_len] * n_seq)
 buf = e._buffers(t_pad)
 rng = np.random.default_rng(0)
-ids_d = torch.from_numpy(rng.integers(0, 30522, size=t_pad).astype(np.int32)).to(dev)
+ids_np = np.where(pos >= 0, rng.integers(0, 30522, size=t_pad), -1).astype(np.int32)
+ids_d = torch.from_numpy(ids_np).to(dev)
 pos_d = torch.from_numpy(np.maximum(pos, 0)).to(dev)
 tiles_d = torch.from_numpy(tiles).to(dev)
 L = w.layers[0]
@@ -34,7 +35,9 @@ def block():
     enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
 
 
-e._layers(buf, ids_d, pos_d, tiles_d, tiles.shape[0], seq_len, t_pad)          # real activations in the buffers
+first_d = torch.from_numpy(first).to(dev)
+out = torch.empty((n_seq, H), dtype=torch.float32, device=dev)
+e._forward(buf, ids_d, pos_d, tiles_d, tiles.shape[0], seq_len, first_d, n_seq, out)   # real activations in the buffers
 torch.cuda.synchronize()
 if "--timers" in sys.argv:
     n_cta = tiles.shape[0] * 16

@@ -75,7 +75,25 @@ PROTOTYPES = [
                                  c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64, c_void_p]),
     ("sqe_encoder_attention", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     ("sqe_encoder_pool", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    ("sqe_encoder_forward", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_int64, c_void_p]),
 ]
+
+
+class SqeEncoderLayer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("wqkv", "bqkv", "wo", "bo", "ln1_gamma", "ln1_beta", "w1", "b1", "w2", "b2",
+                                        "ln2_gamma", "ln2_beta")]
+
+
+class SqeEncoderWeights(ctypes.Structure):
+    _fields_ = [("n_layers", c_int), ("vocab", c_int), ("max_pos", c_int), ("intermediate", c_int), ("eps", c_float),
+                ("word_emb", c_void_p), ("pos_emb", c_void_p), ("type_emb", c_void_p), ("emb_gamma", c_void_p),
+                ("emb_beta", c_void_p), ("layers", POINTER(SqeEncoderLayer))]
+
+
+class SqeEncoderBuffers(ctypes.Structure):
+    _fields_ = [("t_pad", c_int64)] + [(n, c_void_p) for n in ("h32", "h16", "sum32", "qk", "vt", "ctx", "ffn")]
+
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -112,6 +130,7 @@ LAUNCHES_PER_CALL = {
     "sqe_encoder_gemm": 1,
     "sqe_encoder_attention": 1,
     "sqe_encoder_pool": 1,
+    "sqe_encoder_forward": 0,                 # 2 + 7 n_layers, counted by the caller
 }
 SQE_ENC_EPI_SPLIT, SQE_ENC_EPI_RES_F32, SQE_ENC_EPI_GELU = 0, 1, 2
 SQE_ENC_MAX_TOKENS = 512

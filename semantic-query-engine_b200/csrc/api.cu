@@ -543,4 +543,37 @@ int sqe_encoder_pool(const float* h, const int32_t* first_token, int n_seq, floa
     return rc_map(launch_encoder_pool(h, first_token, n_seq, out, ldo, static_cast<cudaStream_t>(stream)));
 }
 
+int sqe_encoder_forward(const SqeEncoderWeights* w, const SqeEncoderBuffers* b, const int32_t* ids, const int32_t* pos,
+                        const int32_t* tiles, int n_tiles, int max_len, const int32_t* first_token, int n_seq,
+                        float* out, int64_t ldo, void* stream) {
+    if (!w || !b || !w->layers || w->n_layers < 1 || w->intermediate < 256 || w->intermediate % 256 != 0) {
+        set_error("encoder_forward: bad weights (layers / intermediate size)");
+        return SQE_E_ARG;
+    }
+    const int64_t m = b->t_pad;
+    if (m <= 0 || m % 128 != 0) { set_error("encoder_forward: t_pad must be a positive multiple of 128"); return SQE_E_ARG; }
+    const int H = SQE_ENC_HIDDEN, I = w->intermediate;
+    int rc = sqe_encoder_embed_ln(ids, pos, w->word_emb, w->vocab, w->pos_emb, w->max_pos, w->type_emb, w->emb_gamma,
+                                  w->emb_beta, w->eps, m, b->h32, b->h16, stream);
+    for (int l = 0; l < w->n_layers && rc == SQE_OK; ++l) {
+        const SqeEncoderLayer& L = w->layers[l];
+        rc = sqe_encoder_gemm(b->h16, H, L.wqkv, L.bqkv, m, 3 * H, H, SQE_ENC_EPI_SPLIT, b->qk, 2 * H, b->vt, m, 2 * H, H,
+                              0.125f, nullptr, 0, stream);
+        if (rc == SQE_OK) rc = sqe_encoder_attention(b->qk, b->vt, m, tiles, n_tiles, max_len, b->ctx, stream);
+        if (rc == SQE_OK)
+            rc = sqe_encoder_gemm(b->ctx, H, L.wo, L.bo, m, H, H, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f,
+                                  b->h32, H, stream);
+        if (rc == SQE_OK) rc = sqe_encoder_layernorm(b->sum32, L.ln1_gamma, L.ln1_beta, w->eps, m, b->h32, b->h16, stream);
+        if (rc == SQE_OK)
+            rc = sqe_encoder_gemm(b->h16, H, L.w1, L.b1, m, I, H, SQE_ENC_EPI_GELU, b->ffn, I, nullptr, 0, 0, 0, 1.0f, nullptr,
+                                  0, stream);
+        if (rc == SQE_OK)
+            rc = sqe_encoder_gemm(b->ffn, I, L.w2, L.b2, m, H, I, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f,
+                                  b->h32, H, stream);
+        if (rc == SQE_OK) rc = sqe_encoder_layernorm(b->sum32, L.ln2_gamma, L.ln2_beta, w->eps, m, b->h32, b->h16, stream);
+    }
+    if (rc == SQE_OK) rc = sqe_encoder_pool(b->h32, first_token, n_seq, out, ldo, stream);
+    return rc;
+}
+
 }  // extern "C"

@@ -24,6 +24,7 @@ residual stream and every LayerNorm are fp32.
 from __future__ import annotations
 
 import asyncio
+import ctypes
 import threading
 import unicodedata
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
@@ -270,6 +271,21 @@ class EncoderWeights:
     def intermediate(self) -> int:
         return self.layers[0]["w1"].shape[0]
 
+    def c_struct(self) -> "nat.SqeEncoderWeights":
+        """The `SqeEncoderWeights` view of these tensors for `sqe_encoder_forward` (built once)."""
+        if getattr(self, "_c", None) is None:
+            arr = (nat.SqeEncoderLayer * len(self.layers))()
+            names = (("wqkv", "wqkv"), ("bqkv", "bqkv"), ("wo", "wo"), ("bo", "bo"), ("ln1_gamma", "g1"), ("ln1_beta", "b1"),
+                     ("w1", "w1"), ("b1", "bi"), ("w2", "w2"), ("b2", "bo2"), ("ln2_gamma", "g2"), ("ln2_beta", "b2"))
+            for i, L in enumerate(self.layers):
+                for field, key in names:
+                    setattr(arr[i], field, L[key].data_ptr())
+            c = nat.SqeEncoderWeights(len(self.layers), self.vocab_size, self.max_pos, self.intermediate, self.eps,
+                                      self.word.data_ptr(), self.position.data_ptr(), self.type0.data_ptr(),
+                                      self.emb_g.data_ptr(), self.emb_b.data_ptr(), arr)
+            self._c = (c, arr)                              # keep the layer array alive
+        return self._c[0]
+
     def flops_per_token(self) -> float:
         """Linear layers only (2 FLOP per multiply-add); attention adds 4 * S * 1024 per token."""
         return 2.0 * len(self.layers) * (4 * HIDDEN * HIDDEN + 2 * HIDDEN * self.intermediate)
@@ -334,6 +350,11 @@ class _Buffers:
         self.meta_host = [torch.zeros(self.meta_cap, dtype=torch.int32).pin_memory() for _ in range(2)]
         self.meta_done = [None, None]
         self.turn = 0
+        self.c = nat.SqeEncoderBuffers(t_pad, self.h32.data_ptr(), self.h16.data_ptr(), self.sum32.data_ptr(),
+                                       self.qk.data_ptr(), self.vt.data_ptr(), self.ctx.data_ptr(), self.ffn.data_ptr())
+        self.graph_out = torch.zeros(t_pad // 8, HIDDEN, dtype=torch.float32, device=dev)     # one row per sequence
+        self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
+        self.seen: Dict[tuple, int] = {}
 
 
 class GpuEmbeddingEncoder:
@@ -343,7 +364,8 @@ class GpuEmbeddingEncoder:
     normalised downstream anyway: app/main.py:315-316, :353-354 divide by the norm again)."""
 
     def __init__(self, weights: EncoderWeights, tokenizer: Optional[WordPieceTokenizer] = None, *,
-                 max_batch_tokens: int = 32768, blank_policy: str = "main"):
+                 max_batch_tokens: int = 32768, blank_policy: str = "main", use_graphs: bool = True,
+                 graph_max_tokens: int = 256):
         self.w = weights
         self.device = weights.device
         self.tok = tokenizer
@@ -353,6 +375,11 @@ class GpuEmbeddingEncoder:
         self._lock = threading.Lock()
         self.stream = torch.cuda.Stream(device=self.device)
         self.launches_last_forward = 0
+        # a query is a handful of tokens: its 170 launches are captured in a CUDA graph the second
+        # time a batch shape (token capacity, entries, longest sequence, sequences) shows up
+        self.use_graphs = use_graphs
+        self.graph_max_tokens = graph_max_tokens
+        self.graph_replays = 0
         nat.load()                                          # fail loudly when the CUDA library is missing
 
     # ------------------------------------------------------------------ device forward
@@ -429,30 +456,56 @@ class GpuEmbeddingEncoder:
             first_d, tiles_d = b.meta_dev[o_first:o_first + n], b.meta_dev[o_tiles:used]
             if out is None:
                 out = torch.empty((n, HIDDEN), dtype=torch.float32, device=dev)
-            self._layers(b, ids_d, pos_d, tiles_d, n_tiles, max(lens), t_pad)
-            with torch.cuda.device(dev):
-                nat.call("sqe_encoder_pool", b.h32.data_ptr(), first_d.data_ptr(), n, out.data_ptr(), out.stride(0),
-                         torch.cuda.current_stream(dev).cuda_stream)
+            max_len = max(lens)
+            key = (n_tiles, (max_len + 63) // 64, n, o_first, o_tiles)
+            graph = None
+            if self.use_graphs and t_pad <= self.graph_max_tokens:
+                graph = b.graphs.get(key)
+                b.seen[key] = b.seen.get(key, 0) + 1
+                if graph is None and b.seen[key] == 2 and len(b.graphs) < 16:
+                    graph = self._capture(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, key)
+            if graph is not None:
+                graph.replay()
+                self.graph_replays += 1
+                out.copy_(b.graph_out[:n])
+                self.launches_last_forward = 2 + 7 * len(self.w.layers)
+            else:
+                self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, out)
         return out
 
-    def _layers(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, m: int) -> None:
-        w = self.w
+    def _forward(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, first_d, n: int,
+                 out: torch.Tensor) -> None:
+        """`sqe_encoder_forward` on the current stream: 2 + 7 layers kernel launches, one call."""
         dev = self.device
-        before = nat.launch_count
         with torch.cuda.device(dev):
-            nat.call("sqe_encoder_embed_ln", ids_d.data_ptr(), pos_d.data_ptr(), w.word.data_ptr(), w.vocab_size,
-                     w.position.data_ptr(), w.max_pos, w.type0.data_ptr(), w.emb_g.data_ptr(), w.emb_b.data_ptr(),
-                     w.eps, m, b.h32.data_ptr(), b.h16.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        for L in w.layers:
-            gemm(b.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, b.qk, m=m, out1=b.vt, n_split=2 * HIDDEN,
-                 q_cols=HIDDEN, q_scale=0.125)
-            attention(b.qk, b.vt, tiles_d, n_tiles, max_len, b.ctx)
-            gemm(b.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, b.sum32, m=m, residual=b.h32)
-            layernorm(b.sum32, L["g1"], L["b1"], w.eps, b.h32, b.h16, rows=m)
-            gemm(b.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, b.ffn, m=m)
-            gemm(b.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, b.sum32, m=m, residual=b.h32)
-            layernorm(b.sum32, L["g2"], L["b2"], w.eps, b.h32, b.h16, rows=m)
-        self.launches_last_forward = nat.launch_count - before + 1          # + the pooling kernel
+            nat.call("sqe_encoder_forward", ctypes.addressof(self.w.c_struct()), ctypes.addressof(b.c),
+                     ids_d.data_ptr(), pos_d.data_ptr(), tiles_d.data_ptr(), n_tiles, max_len, first_d.data_ptr(), n,
+                     out.data_ptr(), out.stride(0), torch.cuda.current_stream(dev).cuda_stream)
+        self.launches_last_forward = 2 + 7 * len(self.w.layers)
+        nat.launch_count += self.launches_last_forward
+
+    def _capture(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, first_d, n: int, key):
+        """Capture the forward pass of this batch shape (it reads the metadata from fixed device
+        addresses, so a replay serves any batch of the same shape).  None if capture fails."""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        try:
+            self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, b.graph_out)     # warm: attributes set
+            cur.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode="thread_local"):
+                self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, b.graph_out)
+        except Exception as e:                              # noqa: BLE001 -- the eager path still works
+            print(f"[sqe_b200] encoder graph capture failed ({e}); staying on direct launches")
+            self.use_graphs = False
+            return None
+        b.graphs[key] = g
+        return g
+
+    def _capture_stream(self) -> "torch.cuda.Stream":
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(device=self.device)
+        return self._cap_stream
 
     # ----------------------------------------------------------------------- batching
     def _batches(self, lens: Sequence[int]) -> Iterable[Tuple[int, int]]:

@@ -55,7 +55,7 @@ def test_header_is_plain_c_and_library_is_usable_from_c(sqe, tmp_path):
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
-    assert "abi 1 ok" in run.stdout
+    assert "abi 2 ok" in run.stdout
 
 
 def test_no_cpu_fallback(sqe):

@@ -232,6 +232,26 @@ def test_full_depth_model_vs_oracle(sqe):
                      atol=6e-2, atol_emulated=3e-2)
 
 
+def test_query_shapes_replay_a_cuda_graph_with_identical_results(sqe):
+    """The second batch of a shape is captured; replays serve other token ids of that shape."""
+    w, e = _pair(sqe, 24, layers=2)
+    plain = sqe.GpuEmbeddingEncoder(e.w, use_graphs=False)
+    g = torch.Generator().manual_seed(9)
+    for rep in range(5):
+        seqs = [torch.randint(0, 2000, (11,), generator=g).tolist()]
+        got = e.embed_token_ids(seqs)
+        want = plain.embed_token_ids(seqs)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), rep
+    assert e.graph_replays >= 3 and plain.graph_replays == 0
+    pair = [torch.randint(0, 2000, (n,), generator=g).tolist() for n in (5, 40)]
+    for rep in range(3):
+        got, want = e.embed_token_ids(pair), plain.embed_token_ids(pair)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    assert float((got.cpu() - bo.bert_embed(w, pair)).abs().max()) < 2e-2
+
+
 def test_many_tokens_split_into_batches(sqe):
     w, e = _pair(sqe, 23, layers=1)
     e.max_batch_tokens = 1024

@@ -1495,11 +1495,29 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
     for name, (n_, k_) in shapes.items():
         t = timed(one(name), 24)
         per_gemm[name] = {"ms": t, "tflops": 2.0 * t_pad * n_ * k_ / (t * 1e-3) / 1e12}
+    # library yardstick: the same four products through torch.mm (cuBLAS fp16, no bias / gelu / residual)
+    yard = None
+    if not args.no_yardstick:
+        try:
+            yard = {}
+            for name, (n_, k_) in shapes.items():
+                xa = buf.ffn if k_ == 4 * H else buf.h16
+                wt = {"qkv": L["wqkv"], "attn_out": L["wo"], "ffn1_gelu": L["w1"], "ffn2": L["w2"]}[name]
+                yo = torch.empty((t_pad, n_), dtype=torch.float16, device=dev)
+                for _ in range(3):
+                    torch.mm(xa, wt.t(), out=yo)                     # library warm-up (handle, heuristics)
+                t = timed(lambda: torch.mm(xa, wt.t(), out=yo), 24)
+                yard[name] = {"ms": t, "tflops": 2.0 * t_pad * n_ * k_ / (t * 1e-3) / 1e12}
+            ytot = sum(v["ms"] for v in yard.values())
+            yard["all_four"] = {"ms": ytot, "tflops": lin_flops / layers / (ytot * 1e-3) / 1e12}
+        except Exception as ex:                              # noqa: BLE001
+            yard = {"error": str(ex)[:200]}
     attn_ms = timed(lambda: enc.attention(buf.qk, buf.vt, tiles_d, tiles.shape[0], seq_len, buf.ctx), 24)
     ln_ms = timed(lambda: enc.layernorm(buf.sum32, L["g1"], L["b1"], 1e-12, buf.h32, buf.h16, rows=t_pad), 24)
     gemm_tflops = lin_flops / layers / (gemm_ms * 1e-3) / 1e12
     breakdown = {"per_layer_ms": {"gemms": gemm_ms, "attention": attn_ms, "layernorm_x2": 2 * ln_ms},
                  "per_layer_sum_x_layers_ms": layers * (gemm_ms + attn_ms + 2 * ln_ms), "per_gemm": per_gemm,
+                 "cublas_fp16_yardstick_no_epilogue": yard,
                  "attention_tflops": att_flops / layers / (attn_ms * 1e-3) / 1e12,
                  "layernorm_gbs": t_pad * 1024 * (4 + 4 + 2) / (ln_ms * 1e-3) / 1e9}
     # ---- end to end: host token lists -> packing -> H2D -> 24 layers -> D2H of the embeddings
@@ -1519,6 +1537,29 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
         e2e = {"value": tokens / dt, "unit": "tokens/s", "h2d_bytes_per_step": int(buf.meta_cap * 4),
                "d2h_bytes_per_step": n_seq * 1024 * 4, "ms_per_step": dt * 1e3, "chunks_per_s": n_seq / dt,
                "api": "GpuEmbeddingEncoder.embed_token_ids(host token lists) -> host fp32 [64, 1024]"}
+        # the same from TEXT: 64 chunks of 512 words through the WordPiece tokeniser (synthetic vocabulary
+        # of 30522 entries, Zipf word frequencies), i.e. embed_texts_in_batches(chunks) -> np.ndarray
+        words = ["".join(rng.choice(list("abcdefghijklmnopqrstuvwxyz"), int(rng.integers(2, 10)))) for _ in range(40000)]
+        specials = ["[PAD]", "[UNK]", "[CLS]", "[SEP]"] + list("abcdefghijklmnopqrstuvwxyz") + \
+                   ["##" + c for c in "abcdefghijklmnopqrstuvwxyz"] + [".", ","]
+        vocab = {}
+        for t_ in specials + words:
+            if len(vocab) < 30522:
+                vocab.setdefault(t_, len(vocab))
+        et = sqe_b200.GpuEmbeddingEncoder(w, sqe_b200.WordPieceTokenizer(vocab), max_batch_tokens=n_seq * seq_len)
+        zipf = rng.zipf(1.3, size=n_seq * 512) % 40000
+        chunks = [" ".join(words[j] for j in zipf[i * 512:(i + 1) * 512]) + "." for i in range(n_seq)]
+        for _ in range(2):
+            et.embed_texts(chunks)
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            emb = et.embed_texts(chunks)
+        dtt = (time.perf_counter() - t0) / esteps
+        ntok = sum(len(et.tok.encode(c)) for c in chunks)
+        e2e["from_text"] = {"value": ntok / dtt, "unit": "tokens/s", "chunks_per_s": n_seq / dtt, "ms_per_step": dtt * 1e3,
+                            "tokens": ntok, "api": "GpuEmbeddingEncoder.embed_texts(64 chunks x 512 words) -> np.ndarray "
+                                                   "[64, 1024] (tokeniser + packing + H2D + 24 layers + D2H)"}
+        del et
     # ---- one query (16 tokens): the latency the /ask handler sees instead of an HTTP round trip
     q = [rng.integers(0, 30522, size=16).tolist()]
 

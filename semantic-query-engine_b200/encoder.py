@@ -62,6 +62,18 @@ def _char_class(ch: str) -> int:
     return 0
 
 
+class _SplitTable(dict):
+    """`str.translate` table filled on demand: code point -> None (drop), ' ' (whitespace),
+    ' c ' (punctuation / CJK: a token of its own) or the character itself."""
+
+    def __missing__(self, cp: int):
+        ch = chr(cp)
+        k = _char_class(ch)
+        v = ch if k == 0 else " " if k == 1 else None if k == 2 else " " + ch + " "
+        self[cp] = v
+        return v
+
+
 class WordPieceTokenizer:
     """BERT's uncased tokeniser: clean the text, isolate CJK characters and punctuation, lower-case,
     strip accents, then greedy longest-match-first WordPiece (`##` continuation pieces, a word that
@@ -78,7 +90,7 @@ class WordPieceTokenizer:
         self.max_chars = max_chars_per_word
         self._cache: Dict[str, Tuple[int, ...]] = {}
         self._cache_cap = cache_words
-        self._class_cache: Dict[str, int] = {}
+        self._table = _SplitTable()
 
     @classmethod
     def from_file(cls, path: str, **kw) -> "WordPieceTokenizer":
@@ -88,26 +100,10 @@ class WordPieceTokenizer:
         return cls(vocab, **kw)
 
     def _split(self, text: str) -> List[str]:
-        cc = self._class_cache
-        words: List[str] = []
-        cur: List[str] = []
-        for ch in text:
-            k = cc.get(ch)
-            if k is None:
-                k = cc[ch] = _char_class(ch)
-            if k == 0:
-                cur.append(ch)
-            elif k == 2:
-                continue
-            else:
-                if cur:
-                    words.append("".join(cur))
-                    cur = []
-                if k >= 3:
-                    words.append(ch)
-        if cur:
-            words.append("".join(cur))
-        return words
+        """Words and single punctuation / CJK characters, in order.  One `str.translate` (drop
+        control characters, blank out whitespace, put spaces around punctuation and CJK) and one
+        `split`, both at C speed; the per-character classification runs once per distinct character."""
+        return text.translate(self._table).split()
 
     def _pieces(self, word: str) -> Tuple[int, ...]:
         hit = self._cache.get(word)

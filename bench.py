@@ -1178,6 +1178,46 @@ def run_serve(args, torch, sqe_b200, nat, dev, peaks):
            "wrap_future": {"value": wrapped[0], "latency_ms_p50": wrapped[1], "latency_ms_p99": wrapped[2],
                            "note": "same, awaiting asyncio.wrap_future(mb.submit(q, k)): one loop wake-up per request"}}
     mb.close()
+    # ---- the same handlers with the embedding step on the GPU too: requests carry the QUERY (token
+    # ids of 16 tokens), the batch goes through one packed encoder pass (24-layer BERT-large, random
+    # weights) and its embeddings are searched where they are (main.py:676 + :684 in one request)
+    with_encoder = None
+    if not args.no_encoder:
+        try:
+            import asyncio
+            w = sqe_b200.EncoderWeights.random_init(seed=0, layers=24, device=dev)
+            enc = sqe_b200.GpuEmbeddingEncoder(w, use_graphs=False)
+            mbe = sqe_b200.MicroBatcher(index, max_batch=args.batch or 128, max_wait_s=500e-6, depth=2, encoder=enc)
+            rng_q = np.random.default_rng(11)
+            qids = rng_q.integers(1000, 30000, size=(clients, per_client, 16)).tolist()
+
+            def drive_text(n_clients):
+                lat = []
+
+                async def aclient(c):
+                    for r in range(per_client):
+                        t0 = time.perf_counter()
+                        await mbe.asearch_text(qids[c][r], k)
+                        lat.append(time.perf_counter() - t0)
+
+                async def amain():
+                    await asyncio.gather(*[aclient(c) for c in range(n_clients)])
+                t0 = time.perf_counter()
+                asyncio.run(amain())
+                dt = time.perf_counter() - t0
+                lat.sort()
+                return n_clients * per_client / dt, lat[len(lat) // 2] * 1e3, lat[int(len(lat) * 0.99)] * 1e3
+            drive_text(64)
+            b0, r0 = mbe.batches, mbe.requests
+            tp = sorted(drive_text(clients) for _ in range(3))
+            with_encoder = {"value": tp[1][0], "unit": "queries/s", "latency_ms_p50": tp[1][1], "latency_ms_p99": tp[1][2],
+                            "passes_qps": [p[0] for p in tp], "mean_batch": (mbe.requests - r0) / max(mbe.batches - b0, 1),
+                            "note": "await MicroBatcher.asearch_text(16 token ids, k): tokens -> packed encoder pass "
+                                    "(170 launches) -> K2p search of the embeddings on the device -> hits"}
+            mbe.close()
+            del mbe, enc, w
+        except Exception as ex:                                        # noqa: BLE001
+            with_encoder = {"error": str(ex)[:300]}
     lock = __import__("threading").Lock()
 
     def direct(q, kk):
@@ -1204,6 +1244,7 @@ def run_serve(args, torch, sqe_b200, nat, dev, peaks):
                          "note": f"{served} requests in {batches} batched launches (mean batch {served / max(batches, 1):.0f})"},
             "cpu_baseline": None,
             "asyncio_clients": aio,
+            "with_encoder": with_encoder,
             "direct_b1": {"value": qps_direct, "unit": "queries/s", "clients": 16, "latency_ms_p50": p50_d,
                           "latency_ms_p99": p99_d, "note": "same clients calling GpuCorpusIndex.search directly"}}
     print(json.dumps(line), flush=True)

@@ -557,6 +557,8 @@ class _StreamSlot:
         if self.dev_out is None or self.dev_out.numel() < out_bytes:
             self.dev_out = torch.empty((out_bytes,), dtype=torch.uint8, device=dev)
             self.host_out = torch.empty((out_bytes,), dtype=torch.uint8).pin_memory()
+        if q is None:                                   # the queries are produced on the device
+            return None
         t = torch.from_numpy(q)
         if t.is_pinned():
             return t
@@ -606,6 +608,27 @@ class StreamPipeline:
                     s.ev_h2d.record(self.h2d)
                 self.compute.wait_event(s.ev_h2d)
                 self._launch(s.dev_q[:b], s.dev_out[:nbytes], ctx)
+                s.ev_done.record(self.compute)
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(s.ev_done)
+                    s.host_out[:nbytes].copy_(s.dev_out[:nbytes], non_blocking=True)
+                    s.ev_d2h.record(self.d2h)
+        except BaseException:
+            self._free.put(s)
+            raise
+        self._pending.put((s, b, nbytes, ctx))
+
+    def submit_device(self, make_q, b: int, ctx=None) -> None:
+        """Like `submit`, for queries that are PRODUCED on the device: `make_q()` enqueues its work
+        on the compute stream and returns q_dev [b,1024] fp32 (e.g. the embedding encoder's forward
+        pass for a batch of texts) -- no host rows, no H2D stage."""
+        nbytes = self._out_bytes(b, ctx)
+        s = self._free.get()
+        try:
+            with torch.cuda.device(self.dev), torch.cuda.stream(self.compute):
+                s.stage(None, b, nbytes, self.dev)
+                qd = make_q()
+                self._launch(qd, s.dev_out[:nbytes], ctx)
                 s.ev_done.record(self.compute)
                 with torch.cuda.stream(self.d2h):
                     self.d2h.wait_event(s.ev_done)

@@ -112,9 +112,14 @@ class MicroBatcher:
     concurrent future, a chained asyncio future and a self-pipe write per request)."""
 
     def __init__(self, index: GpuCorpusIndex, max_batch: int = 256, max_wait_s: float = 200e-6,
-                 depth: int = 2):
+                 depth: int = 2, encoder=None):
+        """`encoder` (a `GpuEmbeddingEncoder` on the index's device): `submit_text` / `asearch_text`
+        then take the QUERY TEXT (main.py:676 `embed_query` + :684 `os_search` in one request): the
+        batch's token lists go through one packed encoder pass on the compute stream and its CLS
+        embeddings are searched where they are -- no embedding ever visits the host."""
         import queue
         self.index = index
+        self.encoder = encoder
         self.max_batch = int(max_batch)
         self.max_wait_s = float(max_wait_s)
         self._cv = threading.Condition()
@@ -156,6 +161,48 @@ class MicroBatcher:
 
     def search(self, query_emb: np.ndarray, k: int = 3):
         return self.submit(query_emb, k).result()
+
+    # text requests: the queue entry carries the token ids instead of an embedding
+    def _ids_of(self, query):
+        if self.encoder is None:
+            raise RuntimeError("this MicroBatcher was built without an encoder")
+        if isinstance(query, str):
+            if not query.strip():                                        # main.py:176-177 -> [] downstream
+                return None
+            return self.encoder.tok.encode(query)
+        return list(query) if len(query) else None
+
+    def submit_text(self, query, k: int = 3) -> Future:
+        """`query`: the text (tokenised here, on the caller's thread) or its token ids."""
+        fut: Future = Future()
+        ids = self._ids_of(query)
+        if ids is None:
+            fut.set_result([])
+            return fut
+        with self._cv:
+            if self._stop:
+                raise RuntimeError("MicroBatcher is closed")
+            self._queue.append((ids, int(k), fut))
+            self._cv.notify()
+        return fut
+
+    def search_text(self, query, k: int = 3):
+        return self.submit_text(query, k).result()
+
+    async def asearch_text(self, query, k: int = 3):
+        import asyncio
+        loop = asyncio.get_running_loop()
+        afut = loop.create_future()
+        ids = self._ids_of(query)
+        if ids is None:
+            afut.set_result([])
+            return await afut
+        with self._cv:
+            if self._stop:
+                raise RuntimeError("MicroBatcher is closed")
+            self._queue.append((ids, int(k), _LoopFuture(loop, afut)))
+            self._cv.notify()
+        return await afut
 
     def asubmit(self, query_emb: np.ndarray, k: int = 3):
         """Called ON an event loop: returns an asyncio future of that loop (await it)."""
@@ -230,18 +277,26 @@ class MicroBatcher:
                     self._handoff.put(None)
                     return
                 continue
-            try:
-                q = np.concatenate([b[0] for b in batch], axis=0)
-                kmax = max(b[1] for b in batch)
-                self._pipe.submit(q, kmax)                           # blocks while `depth` are in flight
-                self.batches += 1
-                self.requests += len(batch)
-                if self._pipe.depth > 1:
-                    self._handoff.put(batch)
-                else:
-                    self._deliver_one(batch)                         # depth 1: one thread does it all
-            except Exception as e:
-                self._fail([b for b in batch if not b[2].done()], e)
+            # embeddings and texts are separate launches (a batch is usually all of one kind)
+            groups = [[b for b in batch if isinstance(b[0], np.ndarray)], [b for b in batch if not isinstance(b[0], np.ndarray)]]
+            for is_text, group in enumerate(groups):
+                if not group:
+                    continue
+                try:
+                    kmax = max(b[1] for b in group)
+                    if is_text:
+                        seqs = [b[0] for b in group]
+                        self._pipe.submit_device(lambda: self.encoder.forward_ids(seqs), len(seqs), kmax)
+                    else:
+                        self._pipe.submit(np.concatenate([b[0] for b in group], axis=0), kmax)   # blocks while `depth` are in flight
+                    self.batches += 1
+                    self.requests += len(group)
+                    if self._pipe.depth > 1:
+                        self._handoff.put(group)
+                    else:
+                        self._deliver_one(group)                     # depth 1: one thread does it all
+                except Exception as e:
+                    self._fail([b for b in group if not b[2].done()], e)
 
     def _deliver_one(self, batch) -> None:
         scores, rows = self._pipe.collect()

@@ -294,3 +294,36 @@ def test_drop_in_coroutines_and_retrieval_end_to_end(sqe):
     gen = types.SimpleNamespace(bulk_index_embeddings=None)
     sqe.install_encoder(gen, e)
     assert asyncio.run(gen.embed_texts_in_batches([])).shape == (0, 1024) and not hasattr(gen, "embed_query")
+
+
+def test_micro_batcher_serves_text_queries_through_the_encoder(sqe):
+    """`MicroBatcher(index, encoder=...)`: a request is the query TEXT; the batch is encoded and
+    searched on the device.  Same hits as embed_query + search one by one (main.py:676, :684)."""
+    w = bo.random_bert_weights(33, layers=2, vocab=len(VOCAB))
+    vocab = {t: i for i, t in enumerate(VOCAB)}
+    e = sqe.GpuEmbeddingEncoder(sqe.EncoderWeights.from_state_dict(w, device=dev()), sqe.WordPieceTokenizer(vocab))
+    rng = np.random.default_rng(4)
+    words = VOCAB[-13:-3]
+    chunks = [" ".join(rng.choice(words, int(rng.integers(3, 40)))) + " ." for _ in range(300)]
+    chunks = list(dict.fromkeys(chunks))                                          # distinct texts
+    index = sqe.GpuCorpusIndex(dtype="fp32")
+    index.add_embeddings(e.embed_texts(chunks), [{"doc_id": f"d{i}", "text": t} for i, t in enumerate(chunks)])
+    mb = sqe.MicroBatcher(index, max_batch=64, max_wait_s=2e-3, depth=2, encoder=e)
+    try:
+        picks = [int(i) for i in rng.choice(len(chunks), 90, replace=False)]
+        futs = [mb.submit_text(chunks[i], 3) for i in picks]
+        for i, f in zip(picks, futs):
+            hits = f.result(timeout=60)
+            assert hits[0][0]["doc_id"] == f"d{i}" and hits[0][1] > 0.9999, (i, hits[0])
+            one = index.search(asyncio.run(e.embed_query(chunks[i])), k=3)
+            assert one[0][0]["doc_id"] == f"d{i}" and abs(one[1][1] - hits[1][1]) < 2e-3     # same runner-up score
+        assert mb.submit_text("   ", 3).result(timeout=10) == []
+        assert mb.search_text(e.tok.encode(chunks[picks[0]]), 1)[0][0]["doc_id"] == f"d{picks[0]}"
+
+        async def many():
+            return await asyncio.gather(*[mb.asearch_text(chunks[i], 2) for i in picks[:40]])
+        for i, hits in zip(picks[:40], asyncio.run(many())):
+            assert hits[0][0]["doc_id"] == f"d{i}"
+        assert mb.batches < mb.requests                                           # requests were coalesced
+    finally:
+        mb.close()

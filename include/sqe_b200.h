@@ -160,7 +160,8 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
  *                          n > 0 = n tiles.  (For the bf16 kernel the window was a negative result in
  *                          round 1 and is not compiled in.)
  *   SQE_TUNE_ENC_GEMM_FORM: tile geometry of sqe_encoder_gemm: 0 = choose by the number of tiles,
- *                          1 = 128 x 64 tiles (single CTA), 2 = 256 x 256 tiles (CTA pairs).
+ *                          1 = 128 x 64 tiles (single CTA), 2 = 256 x 256 tiles (CTA pairs), 3 = the same in
+ *                          clusters of four CTAs that share the X tile by TMA multicast.
  *   The role timers and the epilogue mode exist only in the diagnostics instantiations of the two
  *   benchmarked kernel forms (k <= 32 CTA-pair form with shared d-tiles; k > 64 CTA-pair form with
  *   one q-tile); every other form ignores them.

@@ -105,7 +105,7 @@ int sqe_tuning_set(int knob, int value) {
         g_k2_d_hint = value;
         return old;
     }
-    if (knob == SQE_TUNE_ENC_GEMM_FORM && value >= 0 && value <= 2) {
+    if (knob == SQE_TUNE_ENC_GEMM_FORM && value >= 0 && value <= 4) {
         const int old = g_enc_gemm_form;
         g_enc_gemm_form = value;
         return old;

@@ -24,6 +24,9 @@
 //   kEpiGelu    y = gelu(acc + bias) (erf form, as BERT) -> fp16 out0.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 M N K.
+#include <cstdio>
+#include <cstdlib>
+
 #include "sqe_enc.cuh"
 
 namespace sqe {
@@ -94,10 +97,18 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int BN, int CG, int EPI>
+// CL = CTAs per cluster.  CL = CG: every CTA (pair) is on its own.  CL = 4 (CG = 2): two pairs work on
+// neighbouring n-tiles of the same row block and SHARE the X tile: each CTA fetches 64 of the 128 X
+// rows it needs and multicasts them to itself and to the CTA of the other pair that needs the same rows
+// (24 KB instead of 32 KB out of L2 per CTA and K chunk: the 256 x 256 pair tile is bound by the
+// L2 -> SM bandwidth, not by the tensor pipe).  A stage is then written by two CTAs, so its "empty"
+// barrier waits for the MMAs of BOTH pairs (their commits are multicast to all four CTAs).
+template <int BN, int CG, int EPI, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const GemmArgs a) {
+                    const __grid_constant__ CUtensorMap tmap_xh, const GemmArgs a) {
+    static_assert(CL == CG || ((CL == 4 || CL == 8) && CG == 2), "cluster forms");
+    constexpr int kPairs = (CL > CG) ? CL / 2 : 1;                   // pairs that share an X tile
     using C = GemmCfg<BN, CG>;
     constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -107,10 +118,17 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
     const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
-    const int unit = blockIdx.x / CG;
-    const int n_tiles = a.n_mt * a.n_nt;
+    const uint32_t crank = (CG == 2) ? ptx::cluster_ctarank() : 0u;  // rank in the cluster
+    const uint32_t rank = crank & 1u;                                // rank in the pair; 0 = leader (issues the MMAs)
+    const uint32_t pair = crank >> 1;                                // CL > 2: which of the pairs
+    const uint32_t leader = crank & ~1u;                             // cluster rank of this pair's leader
+    const int unit = blockIdx.x / CL;
+    // CL > 2: a unit's tile = (row block, kPairs neighbouring n-tiles); this pair takes n-tile kPairs j + pair
+    const int nt_per_unit = kPairs;
+    const int n_tiles = a.n_mt * (a.n_nt / nt_per_unit);
     const int n_chunks = a.k / kChunkK;
+    auto m_tile = [&](int t) { return t / (a.n_nt / nt_per_unit); };
+    auto n_tile = [&](int t) { return (t % (a.n_nt / nt_per_unit)) * nt_per_unit + ((CL > CG) ? static_cast<int>(pair) : 0); };
 
     const uint32_t bar_full = base + C::kOffBar;               // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
@@ -121,9 +139,10 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_x);
         ptx::prefetch_tensormap(&tmap_w);
+        if constexpr (CL > CG) ptx::prefetch_tensormap(&tmap_xh);
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1);               // the leader's expect_tx arrival
-            ptx::mbar_init(bar_empty + 8 * s, 1);              // one tcgen05.commit
+            ptx::mbar_init(bar_empty + 8 * s, CL / CG);        // one tcgen05.commit per pair that writes this stage
         }
         for (int acc = 0; acc < 2; ++acc) {
             ptx::mbar_init(bar_tfull + 8 * acc, 1);            // one tcgen05.commit
@@ -144,8 +163,8 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int t = unit; t < n_tiles; t += a.n_units) {
-                const int x_row = (t / a.n_nt) * C::kTileM + static_cast<int>(rank) * kBM;
-                const int w_row = (t % a.n_nt) * BN + static_cast<int>(rank) * C::kBRows;
+                const int x_row = m_tile(t) * C::kTileM + static_cast<int>(rank) * kBM;
+                const int w_row = n_tile(t) * BN + static_cast<int>(rank) * C::kBRows;
                 for (int kc = 0; kc < n_chunks; ++kc) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                     const uint32_t sa = base + stage * C::kStageBytes;
@@ -157,8 +176,16 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     } else {
                         // both CTAs' bytes are counted on the LEADER's barrier
                         if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
-                        const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
-                        ptx::tma_load_2d_cg2(sa, &tmap_x, kc * kChunkK, x_row, fb);
+                        const uint32_t fb = ptx::mapa(bar_full + 8 * stage, leader);
+                        if constexpr (CL > CG) {
+                            // my share of the 128 X rows, to me and to the same-rank CTAs of the other pairs
+                            constexpr uint16_t kEven = (CL == 8) ? 0x55 : 0x5;
+                            const uint16_t mask = static_cast<uint16_t>(kEven << rank);
+                            ptx::tma_load_2d_cg2_mc(sa + pair * (kABytes / kPairs), &tmap_xh, kc * kChunkK,
+                                                    x_row + static_cast<int>(pair) * (kBM / kPairs), fb, mask);
+                        } else {
+                            ptx::tma_load_2d_cg2(sa, &tmap_x, kc * kChunkK, x_row, fb);
+                        }
                         ptx::tma_load_2d_cg2(sa + kABytes, &tmap_w, kc * kChunkK, w_row, fb);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -189,11 +216,11 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         ptx::umma_f16<CG>(tmem_d, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
                     }
                     if constexpr (CG == 1) ptx::umma_commit(bar_empty + 8 * stage);
-                    else ptx::umma_commit_cg2(bar_empty + 8 * stage, 0x3);
+                    else ptx::umma_commit_cg2(bar_empty + 8 * stage, static_cast<uint16_t>((1u << CL) - 1u));     // every CTA that writes it
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
                 if constexpr (CG == 1) ptx::umma_commit(bar_tfull + 8 * acc);
-                else ptx::umma_commit_cg2(bar_tfull + 8 * acc, 0x3);
+                else ptx::umma_commit_cg2(bar_tfull + 8 * acc, static_cast<uint16_t>(0x3u << leader));
             }
         }
     } else {
@@ -213,8 +240,8 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         int i = 0;
         for (int t = unit; t < n_tiles; t += a.n_units, ++i) {
             const int acc = i & 1;
-            const int64_t row0 = static_cast<int64_t>(t / a.n_nt) * C::kTileM + rank * kBM + quarter * 32;
-            const int col_t = (t % a.n_nt) * BN + half * (BN / 2);
+            const int64_t row0 = static_cast<int64_t>(m_tile(t)) * C::kTileM + rank * kBM + quarter * 32;
+            const int col_t = n_tile(t) * BN + half * (BN / 2);
             ptx::mbar_wait(bar_tfull + 8 * acc, (i >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
@@ -286,7 +313,7 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             __syncwarp();
             if (lane == 0) {
                 if constexpr (CG == 1) ptx::mbar_arrive(bar_tempty + 8 * acc);
-                else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, 0);   // the leader's barrier
+                else ptx::mbar_arrive_cluster(bar_tempty + 8 * acc, leader);   // the pair leader's barrier
             }
         }
     }
@@ -301,43 +328,62 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
 }
 
-template <int BN, int CG, int EPI>
+template <int BN, int CG, int EPI, int CL>
 static int launch_gemm_t(const void* X, const void* W, GemmArgs a, int64_t ldx, int sm_count, cudaStream_t stream) {
     using C = GemmCfg<BN, CG>;
+    auto kernel = encoder_gemm_kernel<BN, CG, EPI, CL>;
     a.n_mt = static_cast<int>((a.m + C::kTileM - 1) / C::kTileM);
     a.n_nt = a.n / BN;
-    const int tiles = a.n_mt * a.n_nt;
-    int units = sm_count / CG;
-    if (units > tiles) units = tiles;
-    a.n_units = units;
-    CUtensorMap tx, tw;
-    int rc = make_map_2d(&tx, X, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.m), static_cast<uint64_t>(ldx), kBM);
-    if (rc != 0) return rc;
-    rc = make_map_2d(&tw, W, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.n), static_cast<uint64_t>(a.k), C::kBRows);
-    if (rc != 0) return rc;
-    cudaError_t e = cudaFuncSetAttribute(encoder_gemm_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
+    const int tiles = a.n_mt * a.n_nt / (CL / CG);             // a 4-CTA cluster takes two n-tiles at a time
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("encoder_gemm: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(units * CG));
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, encoder_gemm_kernel<BN, CG, EPI>, tx, tw, a);
+    int units = sm_count / CL;
+    if constexpr (CL > CG) {
+        // larger clusters do not tile every GPC: ask how many are co-resident (cached per device)
+        static int active[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64) {
+            if (active[dev] == 0) {
+                cfg.gridDim = dim3(static_cast<unsigned>(sm_count / CL * CL));
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n > 0) active[dev] = n;
+                else { active[dev] = -1; (void)cudaGetLastError(); }
+                if (getenv("SQE_DEBUG_CLUSTERS")) fprintf(stderr, "encoder_gemm: clusters of %d co-resident: %d\n", CL, active[dev]);
+            }
+            if (active[dev] > 0) units = active[dev];
+        }
+    }
+    if (units > tiles) units = tiles;
+    a.n_units = units;
+    CUtensorMap tx, tw, txh;
+    int rc = make_map_2d(&tx, X, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.m), static_cast<uint64_t>(ldx), kBM);
+    if (rc != 0) return rc;
+    rc = make_map_2d(&tw, W, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.n), static_cast<uint64_t>(a.k), C::kBRows);
+    if (rc != 0) return rc;
+    rc = make_map_2d(&txh, X, static_cast<uint64_t>(a.k), static_cast<uint64_t>(a.m), static_cast<uint64_t>(ldx),
+                     kBM / (CL > CG ? CL / 2 : 1));
+    if (rc != 0) return rc;
+    cfg.gridDim = dim3(static_cast<unsigned>(units * CL));
+    e = cudaLaunchKernelEx(&cfg, kernel, tx, tw, txh, a);
     if (e != cudaSuccess) { set_error("encoder_gemm: launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
 }
 
 }  // namespace enc
 
-int g_enc_gemm_form = 0;        // 0 auto, 1 = <64, 1>, 2 = <256, 2>
+int g_enc_gemm_form = 0;        // 0 auto, 1 = <64, 1>, 2 = <256, 2> pairs, 3 = <256, 2> in clusters of four (X multicast)
 
 int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                         int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
@@ -361,9 +407,13 @@ int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* 
     // pairs once there are enough 256 x 256 tiles to occupy most of the chip
     int form = g_enc_gemm_form;
     if (form == 0) form = (((m + 255) / 256) * (n / 256) >= sm_count / 4) ? 2 : 1;
+    if (form == 4 && (n / 256) % 4 != 0) form = 3;            // clusters of eight take n-tiles four at a time
+    if (form == 3 && (n / 256) % 2 != 0) form = 2;            // clusters of four take n-tiles two at a time
 #define SQE_ENC_GEMM(EPI_)                                                                         \
-    (form == 2 ? launch_gemm_t<256, 2, EPI_>(X, W, a, ldx, sm_count, stream)                       \
-               : launch_gemm_t<64, 1, EPI_>(X, W, a, ldx, sm_count, stream))
+    (form == 4 ? launch_gemm_t<256, 2, EPI_, 8>(X, W, a, ldx, sm_count, stream)                    \
+     : form == 3 ? launch_gemm_t<256, 2, EPI_, 4>(X, W, a, ldx, sm_count, stream)                  \
+     : form == 2 ? launch_gemm_t<256, 2, EPI_, 2>(X, W, a, ldx, sm_count, stream)                  \
+                 : launch_gemm_t<64, 1, EPI_, 1>(X, W, a, ldx, sm_count, stream))
     switch (epilogue) {
         case kEpiSplit: return SQE_ENC_GEMM(kEpiSplit);
         case kEpiResF32: return SQE_ENC_GEMM(kEpiResF32);

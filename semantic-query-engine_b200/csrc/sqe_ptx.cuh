@@ -248,6 +248,17 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, 
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster)
         : "memory");
 }
+// 2-CTA form with multicast: the box lands at the same CTA-relative offset `dst` in every CTA of
+// `cta_mask`; in each of them the bytes are signalled on the barrier at the CTA-relative offset of
+// `bar_cluster` in that CTA's pair leader (the peer bit of the address is clear)
+__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const void* tmap, int c0, int c1,
+                                                   uint32_t bar_cluster, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar_cluster), "h"(cta_mask)
+        : "memory");
+}
 // generic-proxy writes to shared memory (st.shared) become visible to the async proxy
 // (tcgen05.mma operand reads, TMA) after this fence
 __device__ __forceinline__ void fence_proxy_async_smem() {

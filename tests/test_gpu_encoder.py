@@ -42,7 +42,7 @@ def _randn(g, *shape, s=1.0, dtype=torch.float32):
     return (torch.randn(*shape, generator=g, device=dev(), dtype=torch.float32) * s).to(dtype)
 
 
-@pytest.fixture(params=[1, 2], ids=["tiles128x64", "pairs256x256"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["tiles128x64", "pairs256x256", "clusters4_multicast", "clusters8_multicast"])
 def gemm_form(request, sqe):
     nat = sqe._native
     old = nat.tuning_set(nat.SQE_TUNE_ENC_GEMM_FORM, request.param)

@@ -171,6 +171,7 @@ SQE_API int sqe_topk_batched(const void *D, int dtype, int64_t n, int dim, const
 #define SQE_TUNE_K2_D_HINT 2
 #define SQE_TUNE_K2_WINDOW 3
 #define SQE_TUNE_ENC_GEMM_FORM 4
+#define SQE_TUNE_ENC_SMALL 5          /* 0 = few-token passes take sqe_encoder_gemm_small (default), 1 = never */
 SQE_API int sqe_tuning_set(int knob, int value);
 
 /*
@@ -187,6 +188,9 @@ SQE_API void sqe_debug_k2_timers(void *device_buffer);
  * (clock64 at: start, setup done, scores ready, maxima done, P written, output ready, end; then the
  * global timer at the end); NULL = off (the default). */
 SQE_API void sqe_debug_encoder_attention_timers(void *device_buffer);
+/* Diagnostics: role timers of sqe_encoder_gemm, int64 [grid][8] per launch (cycles: producer total / waiting for
+ * free stages; MMA issuer total / waiting for data / waiting for the epilogue; tiles; global timer); NULL = off. */
+SQE_API void sqe_debug_encoder_gemm_timers(void *device_buffer);
 
 /*
  * K5  query-cache lookup: top-1 + similarity threshold.
@@ -358,6 +362,16 @@ SQE_API int sqe_encoder_layernorm(const float *in, const float *gamma, const flo
 SQE_API int sqe_encoder_gemm(const void *X, int64_t ldx, const void *W, const float *bias, int64_t m, int n,
                      int k, int epilogue, void *out0, int64_t ld0, void *out1, int64_t ld1, int n_split,
                      int q_cols, float q_scale, const float *residual, int64_t ldr, void *stream);
+/* The same products for m <= 128 token rows (one query, a few queries): operands swapped (weight
+ * rows are the M operand, n_tok = m rounded up to 16 the N operand), K split over ~100 CTAs, partial
+ * tiles summed in split order by the last CTA of a feature tile (deterministic), same epilogues.
+ * n % 128 == 0, n <= 4096; workspace: sqe_encoder_gemm_small_workspace_bytes(), zero-initialised once
+ * (its tickets return to zero after every launch).  SQE_E_UNSUPPORTED for shapes it does not take. */
+SQE_API int64_t sqe_encoder_gemm_small_workspace_bytes(void);
+SQE_API int sqe_encoder_gemm_small(const void *X, int64_t ldx, const void *W, const float *bias, int64_t m, int n,
+                           int k, int epilogue, void *out0, int64_t ld0, void *out1, int64_t ld1, int n_split,
+                           int q_cols, float q_scale, const float *residual, int64_t ldr, void *workspace,
+                           int64_t workspace_bytes, void *stream);
 SQE_API int sqe_encoder_attention(const void *qk, const void *vt, int64_t t_pad, const int32_t *tiles,
                           int n_tiles, int max_len, void *ctx, void *stream);
 SQE_API int sqe_encoder_pool(const float *h, const int32_t *first_token, int n_seq, float *out, int64_t ldo,
@@ -367,7 +381,9 @@ SQE_API int sqe_encoder_pool(const float *h, const int32_t *first_token, int n_s
  * The whole forward pass in ONE call (what `GpuEmbeddingEncoder` issues per packed batch): embed_ln,
  * then per layer  QKV gemm -> attention -> output gemm (+ residual) -> LayerNorm -> FFN gemm (gelu) ->
  * FFN gemm (+ residual) -> LayerNorm,  then CLS pooling -- 2 + 7 n_layers kernel launches on `stream`,
- * nothing else (capturable in a CUDA graph).  The structs hold DEVICE pointers; the structs
+ * nothing else (capturable in a CUDA graph).  rows_used = token rows of the packed batch that are in use
+ * (<= t_pad; 0 = all): with rows_used <= 32 and a workspace in the buffers the linear layers take
+ * sqe_encoder_gemm_small.  The structs hold DEVICE pointers; the structs
  * themselves (and the `layers` array) live in HOST memory and are read during the call only.
  */
 typedef struct SqeEncoderLayer {
@@ -397,12 +413,14 @@ typedef struct SqeEncoderBuffers {      /* activations of one packed batch, t_pa
     void *vt;                   /* [1024, t_pad] fp16 */
     void *ctx;                  /* [t_pad, 1024] fp16 */
     void *ffn;                  /* [t_pad, intermediate] fp16 */
+    void *small_ws;             /* zero-initialised workspace of sqe_encoder_gemm_small, or NULL */
+    int64_t small_ws_bytes;
 } SqeEncoderBuffers;
 
 SQE_API int sqe_encoder_forward(const SqeEncoderWeights *weights_host, const SqeEncoderBuffers *buffers_host,
                         const int32_t *ids, const int32_t *pos, const int32_t *tiles, int n_tiles,
-                        int max_len, const int32_t *first_token, int n_seq, float *out, int64_t ldo,
-                        void *stream);
+                        int max_len, const int32_t *first_token, int n_seq, int64_t rows_used, float *out,
+                        int64_t ldo, void *stream);
 
 #ifdef __cplusplus
 }

@@ -60,4 +60,17 @@ for name, (n, k, epi) in shapes.items():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         print(f"{name:10s} form {form}: {ms * 1e3:8.1f} us  {2.0 * M * n * k / ms / 1e9:8.1f} TFLOP/s  {same}")
+        if os.environ.get("ENC_TIMERS"):
+            dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+            nat.load().sqe_debug_encoder_gemm_timers(dbg.data_ptr())
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            nat.load().sqe_debug_encoder_gemm_timers(None)
+            d = dbg.cpu().numpy().astype(float)
+            lead = d[d[:, 5] > 0]
+            tiles = lead[:, 5].mean()
+            print(f"           issuer: {lead[:, 2].mean() / tiles:8.0f} cycles per tile ({k // 64 * 512} at the issue floor), "
+                  f"waiting for data {lead[:, 3].mean() / tiles:7.0f}, for the epilogue {lead[:, 4].mean() / tiles:7.0f}; "
+                  f"producer waiting for free stages {d[:, 1].mean() / tiles:7.0f}")
 nat.tuning_set(nat.SQE_TUNE_ENC_GEMM_FORM, 0)

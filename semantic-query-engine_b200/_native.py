@@ -31,6 +31,7 @@ PROTOTYPES = [
     ("sqe_tuning_set", c_int, [c_int, c_int]),
     ("sqe_debug_k2_timers", None, [c_void_p]),
     ("sqe_debug_encoder_attention_timers", None, [c_void_p]),
+    ("sqe_debug_encoder_gemm_timers", None, [c_void_p]),
     ("sqe_normalize_cast", c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     ("sqe_topk_gemv_workspace_bytes", c_int64, [c_int, c_int]),
     ("sqe_topk_gemv", c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
@@ -76,7 +77,11 @@ PROTOTYPES = [
     ("sqe_encoder_attention", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     ("sqe_encoder_pool", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     ("sqe_encoder_forward", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
-                                    c_void_p, c_int64, c_void_p]),
+                                    c_int64, c_void_p, c_int64, c_void_p]),
+    ("sqe_encoder_gemm_small_workspace_bytes", c_int64, []),
+    ("sqe_encoder_gemm_small", c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
+                                       c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
+                                       c_int64, c_void_p]),
 ]
 
 
@@ -92,7 +97,8 @@ class SqeEncoderWeights(ctypes.Structure):
 
 
 class SqeEncoderBuffers(ctypes.Structure):
-    _fields_ = [("t_pad", c_int64)] + [(n, c_void_p) for n in ("h32", "h16", "sum32", "qk", "vt", "ctx", "ffn")]
+    _fields_ = [("t_pad", c_int64)] + [(n, c_void_p) for n in ("h32", "h16", "sum32", "qk", "vt", "ctx", "ffn", "small_ws")] + \
+               [("small_ws_bytes", c_int64)]
 
 
 
@@ -130,6 +136,7 @@ LAUNCHES_PER_CALL = {
     "sqe_encoder_gemm": 1,
     "sqe_encoder_attention": 1,
     "sqe_encoder_pool": 1,
+    "sqe_encoder_gemm_small": 1,
     "sqe_encoder_forward": 0,                 # 2 + 7 n_layers, counted by the caller
 }
 SQE_ENC_EPI_SPLIT, SQE_ENC_EPI_RES_F32, SQE_ENC_EPI_GELU = 0, 1, 2
@@ -175,6 +182,7 @@ SQE_TUNE_K2_CTA_GROUP = 0
 SQE_TUNE_K2_EPILOGUE_MODE = 1      # diagnostics only
 SQE_TUNE_K2_D_HINT = 2
 SQE_TUNE_K2_WINDOW = 3
+SQE_TUNE_ENC_SMALL = 5         # 0 = few-token passes take the swap-AB split-K GEMM (default), 1 = never
 SQE_TUNE_ENC_GEMM_FORM = 4     # 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs
 
 

@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsqe_b200.so")
 
 SOURCES = ["api.cu", "normalize_cast.cu", "topk_gemv.cu", "topk_prefilter.cu", "topk_batched.cu", "topk_batched_i8.cu", "exchange.cu",
-           "encoder_gemm.cu", "encoder_attn.cu", "encoder_rows.cu"]
+           "encoder_gemm.cu", "encoder_gemm_small.cu", "encoder_attn.cu", "encoder_rows.cu"]
 COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

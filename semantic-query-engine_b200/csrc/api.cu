@@ -16,6 +16,7 @@ void* g_k2_debug = nullptr;
 int g_k2_epilogue_mode = 0;
 int g_k2_d_hint = 0;
 int g_k2_window = 0;
+int g_enc_small = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -105,6 +106,11 @@ int sqe_tuning_set(int knob, int value) {
         g_k2_d_hint = value;
         return old;
     }
+    if (knob == SQE_TUNE_ENC_SMALL && value >= 0 && value <= 1) {
+        const int old = g_enc_small;
+        g_enc_small = value;
+        return old;
+    }
     if (knob == SQE_TUNE_ENC_GEMM_FORM && value >= 0 && value <= 4) {
         const int old = g_enc_gemm_form;
         g_enc_gemm_form = value;
@@ -117,6 +123,8 @@ int sqe_tuning_set(int knob, int value) {
 void sqe_debug_k2_timers(void* device_buffer) { g_k2_debug = device_buffer; }
 
 void sqe_debug_encoder_attention_timers(void* device_buffer) { g_enc_attn_debug = device_buffer; }
+
+void sqe_debug_encoder_gemm_timers(void* device_buffer) { g_enc_gemm_debug = device_buffer; }
 
 int sqe_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     DevInfo d;
@@ -515,6 +523,29 @@ int sqe_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bia
                                       residual, ldr, d.sm_count, static_cast<cudaStream_t>(stream)));
 }
 
+int64_t sqe_encoder_gemm_small_workspace_bytes(void) { return encoder_gemm_small_workspace_bytes(); }
+
+int sqe_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
+                           int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
+                           float q_scale, const float* residual, int64_t ldr, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
+    if (m == 0) return SQE_OK;
+    if (epilogue < SQE_ENC_EPI_SPLIT || epilogue > SQE_ENC_EPI_GELU) { set_error("encoder_gemm_small: bad epilogue %d", epilogue); return SQE_E_ARG; }
+    if (!X || !W || !bias || !out0 || !workspace || !aligned16(X) || !aligned16(W) || !aligned16(workspace) || ldx < k ||
+        ldx % 8 != 0 || (epilogue == SQE_ENC_EPI_RES_F32 && !residual) ||
+        (epilogue == SQE_ENC_EPI_SPLIT && (n_split < 0 || n_split > n || (n_split < n && (!out1 || ld1 < m))))) {
+        set_error("encoder_gemm_small: null / unaligned pointer or bad leading dimension");
+        return SQE_E_ARG;
+    }
+    DevInfo d;
+    int rc = device_info(&d);
+    if (rc != SQE_OK) return rc;
+    rc = launch_encoder_gemm_small(X, ldx, W, bias, m, n, k, epilogue, out0, ld0, out1, ld1, n_split, q_cols, q_scale,
+                                   residual, ldr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (rc == -1) { set_error("encoder_gemm_small: shape not taken (m=%lld n=%d k=%d; m <= 128, n %% 128 == 0, n <= 4096)", (long long)m, n, k); return SQE_E_UNSUPPORTED; }
+    return rc == 0 ? SQE_OK : SQE_E_CUDA;
+}
+
 int sqe_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const int32_t* tiles, int n_tiles,
                           int max_len, void* ctx, void* stream) {
     if (n_tiles < 0 || n_tiles > 0x7fffffff / 16 || t_pad < 0 || t_pad % 8 != 0 || t_pad >= (1LL << 31) - 1024) {
@@ -545,7 +576,7 @@ int sqe_encoder_pool(const float* h, const int32_t* first_token, int n_seq, floa
 
 int sqe_encoder_forward(const SqeEncoderWeights* w, const SqeEncoderBuffers* b, const int32_t* ids, const int32_t* pos,
                         const int32_t* tiles, int n_tiles, int max_len, const int32_t* first_token, int n_seq,
-                        float* out, int64_t ldo, void* stream) {
+                        int64_t rows_used, float* out, int64_t ldo, void* stream) {
     if (!w || !b || !w->layers || w->n_layers < 1 || w->intermediate < 256 || w->intermediate % 256 != 0) {
         set_error("encoder_forward: bad weights (layers / intermediate size)");
         return SQE_E_ARG;
@@ -553,23 +584,34 @@ int sqe_encoder_forward(const SqeEncoderWeights* w, const SqeEncoderBuffers* b, 
     const int64_t m = b->t_pad;
     if (m <= 0 || m % 128 != 0) { set_error("encoder_forward: t_pad must be a positive multiple of 128"); return SQE_E_ARG; }
     const int H = SQE_ENC_HIDDEN, I = w->intermediate;
+    if (rows_used < 0 || rows_used > m) { set_error("encoder_forward: rows_used out of range"); return SQE_E_ARG; }
+    // a handful of tokens (one or two queries): the swap-AB split-K form of the four products; its last-CTA
+    // reduction grows with the token count, beyond 32 rows the 128 x 64 tiles are as fast
+    const bool small = g_enc_small == 0 && rows_used > 0 && rows_used <= 32 && b->small_ws != nullptr &&
+                       b->small_ws_bytes >= encoder_gemm_small_workspace_bytes() && I <= 4096;
+    const int64_t mg = small ? (rows_used + 15) / 16 * 16 : m;        // whole 16-row groups (filler rows are zeros)
+    auto gemm = [&](const void* X, int64_t ldx, const void* W, const float* bias, int n, int k, int epi, void* out0,
+                    int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols, float q_scale, const float* res,
+                    int64_t ldr) {
+        if (small)
+            return sqe_encoder_gemm_small(X, ldx, W, bias, mg, n, k, epi, out0, ld0, out1, ld1, n_split, q_cols, q_scale,
+                                          res, ldr, b->small_ws, b->small_ws_bytes, stream);
+        return sqe_encoder_gemm(X, ldx, W, bias, mg, n, k, epi, out0, ld0, out1, ld1, n_split, q_cols, q_scale, res, ldr,
+                                stream);
+    };
     int rc = sqe_encoder_embed_ln(ids, pos, w->word_emb, w->vocab, w->pos_emb, w->max_pos, w->type_emb, w->emb_gamma,
                                   w->emb_beta, w->eps, m, b->h32, b->h16, stream);
     for (int l = 0; l < w->n_layers && rc == SQE_OK; ++l) {
         const SqeEncoderLayer& L = w->layers[l];
-        rc = sqe_encoder_gemm(b->h16, H, L.wqkv, L.bqkv, m, 3 * H, H, SQE_ENC_EPI_SPLIT, b->qk, 2 * H, b->vt, m, 2 * H, H,
-                              0.125f, nullptr, 0, stream);
+        rc = gemm(b->h16, H, L.wqkv, L.bqkv, 3 * H, H, SQE_ENC_EPI_SPLIT, b->qk, 2 * H, b->vt, m, 2 * H, H, 0.125f, nullptr, 0);
         if (rc == SQE_OK) rc = sqe_encoder_attention(b->qk, b->vt, m, tiles, n_tiles, max_len, b->ctx, stream);
         if (rc == SQE_OK)
-            rc = sqe_encoder_gemm(b->ctx, H, L.wo, L.bo, m, H, H, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f,
-                                  b->h32, H, stream);
+            rc = gemm(b->ctx, H, L.wo, L.bo, H, H, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f, b->h32, H);
         if (rc == SQE_OK) rc = sqe_encoder_layernorm(b->sum32, L.ln1_gamma, L.ln1_beta, w->eps, m, b->h32, b->h16, stream);
         if (rc == SQE_OK)
-            rc = sqe_encoder_gemm(b->h16, H, L.w1, L.b1, m, I, H, SQE_ENC_EPI_GELU, b->ffn, I, nullptr, 0, 0, 0, 1.0f, nullptr,
-                                  0, stream);
+            rc = gemm(b->h16, H, L.w1, L.b1, I, H, SQE_ENC_EPI_GELU, b->ffn, I, nullptr, 0, 0, 0, 1.0f, nullptr, 0);
         if (rc == SQE_OK)
-            rc = sqe_encoder_gemm(b->ffn, I, L.w2, L.b2, m, H, I, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f,
-                                  b->h32, H, stream);
+            rc = gemm(b->ffn, I, L.w2, L.b2, H, I, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f, b->h32, H);
         if (rc == SQE_OK) rc = sqe_encoder_layernorm(b->sum32, L.ln2_gamma, L.ln2_beta, w->eps, m, b->h32, b->h16, stream);
     }
     if (rc == SQE_OK) rc = sqe_encoder_pool(b->h32, first_token, n_seq, out, ldo, stream);

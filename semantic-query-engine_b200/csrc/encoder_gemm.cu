@@ -8,7 +8,7 @@
 // share a row block of X are adjacent so X is read from HBM once and W stays in L2.
 //
 // Two geometries:
-// (5 operand stages of 32 KB for pairs, 7 of 24 KB for single CTAs, + 36 KB of epilogue staging)
+// (6 operand stages of 32 KB for pairs, 8 of 24 KB for single CTAs, + 18 KB of epilogue staging)
 //   <BN = 256, CG = 2>  a CTA pair computes a 256 x 256 tile (cta_group::2, each CTA stages its 128
 //                       rows of X and half of the W rows): the throughput form (ingest batches);
 //   <BN = 64,  CG = 1>  128 x 64 tiles: the latency form (a handful of queries: M = 128, so the
@@ -41,11 +41,14 @@ struct GemmCfg {
     static constexpr int kBRows = BN / CG;               // W rows this CTA stages per chunk
     static constexpr int kBBytes = kBRows * kChunkK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // epilogue staging: per warp a 32 x 32 fp32 strip, rows padded to 36 floats (16-byte aligned,
-    // conflict-free for the row-per-lane 128-bit stores)
+    // epilogue staging: per warp HALF a 32 x 32 fp32 strip (16 rows at a time), rows padded to 36
+    // floats (16-byte aligned, conflict-free for the row-per-lane 128-bit stores).  The rest of the
+    // shared memory is operand stages -- although a sixth stage measurably changes nothing: the main
+    // loop waits for data a quarter of the time with five stages AND with six (role timers,
+    // profiles/r2b_encoder_gemm_timers.txt), i.e. the L2 -> SM rate binds, not the latency
     static constexpr int kStageRowFloats = 36;
-    static constexpr int kStagingBytes = 8 * 32 * kStageRowFloats * 4;       // 36 KB
-    static constexpr int kStages = (226 * 1024 - kStagingBytes - 1024) / kStageBytes;     // 5 x 32 KB or 7 x 24 KB
+    static constexpr int kStagingBytes = 8 * 16 * kStageRowFloats * 4;       // 18 KB
+    static constexpr int kStages = (226 * 1024 - kStagingBytes - 1024) / kStageBytes;     // 6 x 32 KB or 8 x 24 KB
     static constexpr int kTmemCols = 2 * BN;             // two accumulators
     static constexpr int kOffStaging = kStages * kStageBytes;
     static constexpr int kOffBar = kOffStaging + kStagingBytes;
@@ -70,6 +73,7 @@ struct GemmArgs {
     float q_scale;
     const float* residual;    // kEpiResF32: [m, ldr] fp32
     int64_t ldr;
+    long long* dbg;           // diagnostics: [CTA][8] role timers in cycles (null in production)
 };
 
 // gelu(x) = x Phi(x) = 0.5 x (1 + erf(x / sqrt 2)), the erf form BERT uses.  erf by Abramowitz &
@@ -162,11 +166,15 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const uint64_t pol_w = ptx::policy_evict_last();   // the weights are re-read by every row block
             int stage = 0;
             uint32_t phase = 0;
+            long long t_wait = 0;
+            const long long t_begin = a.dbg ? clock64() : 0;
             for (int t = unit; t < n_tiles; t += a.n_units) {
                 const int x_row = m_tile(t) * C::kTileM + static_cast<int>(rank) * kBM;
                 const int w_row = n_tile(t) * BN + static_cast<int>(rank) * C::kBRows;
                 for (int kc = 0; kc < n_chunks; ++kc) {
+                    const long long w0 = a.dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                    if (a.dbg) t_wait += clock64() - w0;
                     const uint32_t sa = base + stage * C::kStageBytes;
                     if constexpr (CG == 1) {
                         const uint32_t fb = bar_full + 8 * stage;
@@ -191,6 +199,10 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (a.dbg) {
+                a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;          // producer: total, waiting for free stages
+                a.dbg[blockIdx.x * 8 + 1] = t_wait;
+            }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
@@ -199,13 +211,19 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int i = 0;
+            long long t_wfull = 0, t_wtempty = 0;
+            const long long t_begin = a.dbg ? clock64() : 0;
             for (int t = unit; t < n_tiles; t += a.n_units, ++i) {
                 const int acc = i & 1;
+                const long long w0 = a.dbg ? clock64() : 0;
                 ptx::mbar_wait(bar_tempty + 8 * acc, ((i >> 1) & 1) ^ 1u);   // the epilogue drained it
+                if (a.dbg) t_wtempty += clock64() - w0;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kc = 0; kc < n_chunks; ++kc) {
+                    const long long w1 = a.dbg ? clock64() : 0;
                     ptx::mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
+                    if (a.dbg) t_wfull += clock64() - w1;
                     ptx::tc_fence_after();
                     const uint32_t sa = base + stage * C::kStageBytes;
                     const uint64_t da = make_sw128_desc(sa);
@@ -222,6 +240,15 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 if constexpr (CG == 1) ptx::umma_commit(bar_tfull + 8 * acc);
                 else ptx::umma_commit_cg2(bar_tfull + 8 * acc, static_cast<uint16_t>(0x3u << leader));
             }
+            if (a.dbg) {
+                a.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin;          // MMA issuer: total, waiting for data, for the epilogue
+                a.dbg[blockIdx.x * 8 + 3] = t_wfull;
+                a.dbg[blockIdx.x * 8 + 4] = t_wtempty;
+                a.dbg[blockIdx.x * 8 + 5] = i;                             // tiles
+                unsigned long long gt;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                a.dbg[blockIdx.x * 8 + 6] = static_cast<long long>(gt);
+            }
         }
     } else {
         // ---------------------------------------------------------------- epilogue
@@ -234,7 +261,7 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int half = (warp - 2) >> 2;                      // which half of the tile's columns
         constexpr int kStrips = BN / 64;                       // strips of 32 columns per warp
         constexpr int RS = C::kStageRowFloats;
-        float* stg = reinterpret_cast<float*>(sm + C::kOffStaging) + (warp - 2) * 32 * RS;
+        float* stg = reinterpret_cast<float*>(sm + C::kOffStaging) + (warp - 2) * 16 * RS;
         const int sub_row = lane >> 3;                         // row of a 4-row group in the coalesced phase
         const int c4 = (lane & 7) * 4;                         // first of this lane's 4 columns there
         int i = 0;
@@ -281,33 +308,39 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                 }
                 ptx::tmem_wait_ld();
-                float* srow = stg + lane * RS;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
                 const float qs = (EPI == kEpiSplit && col0 < a.q_cols) ? a.q_scale : 1.0f;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const int64_t row = row0 + 4 * g + sub_row;
-                    float4 y = *reinterpret_cast<const float4*>(stg + (4 * g + sub_row) * RS + c4);
-                    y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
-                    if constexpr (EPI == kEpiResF32) {
-                        y.x += r4[g].x; y.y += r4[g].y; y.z += r4[g].z; y.w += r4[g].w;
-                        if (row < a.m)
-                            *reinterpret_cast<float4*>(static_cast<float*>(a.out0) + row * a.ld0 + col0 + c4) = y;
-                    } else {
-                        if constexpr (EPI == kEpiGelu) {
-                            y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
-                        } else {
-                            y.x *= qs; y.y *= qs; y.z *= qs; y.w *= qs;
-                        }
-                        if (row < a.m)
-                            *reinterpret_cast<uint2*>(static_cast<__half*>(a.out0) + row * a.ld0 + col0 + c4) =
-                                make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+                for (int hp = 0; hp < 2; ++hp) {               // rows 0..15, then 16..31 of the strip
+                    if ((lane >> 4) == hp) {
+                        float* srow = stg + (lane & 15) * RS;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        const int g = 4 * hp + gg;
+                        const int64_t row = row0 + 4 * g + sub_row;
+                        float4 y = *reinterpret_cast<const float4*>(stg + (4 * gg + sub_row) * RS + c4);
+                        y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+                        if constexpr (EPI == kEpiResF32) {
+                            y.x += r4[g].x; y.y += r4[g].y; y.z += r4[g].z; y.w += r4[g].w;
+                            if (row < a.m)
+                                *reinterpret_cast<float4*>(static_cast<float*>(a.out0) + row * a.ld0 + col0 + c4) = y;
+                        } else {
+                            if constexpr (EPI == kEpiGelu) {
+                                y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
+                            } else {
+                                y.x *= qs; y.y *= qs; y.z *= qs; y.w *= qs;
+                            }
+                            if (row < a.m)
+                                *reinterpret_cast<uint2*>(static_cast<__half*>(a.out0) + row * a.ld0 + col0 + c4) =
+                                    make_uint2(pack_half2(y.x, y.y), pack_half2(y.z, y.w));
+                        }
+                    }
+                    __syncwarp();                              // the buffer is rewritten by the next half / strip
                 }
-                __syncwarp();                                  // the strip buffer is rewritten by the next strip
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -383,6 +416,7 @@ static int launch_gemm_t(const void* X, const void* W, GemmArgs a, int64_t ldx, 
 
 }  // namespace enc
 
+void* g_enc_gemm_debug = nullptr;     // diagnostics: device buffer [grid][8] i64 of role timers
 int g_enc_gemm_form = 0;        // 0 auto, 1 = <64, 1>, 2 = <256, 2> pairs, 3 = <256, 2> in clusters of four (X multicast)
 
 int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
@@ -403,6 +437,7 @@ int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* 
     a.q_scale = q_scale;
     a.residual = residual;
     a.ldr = ldr;
+    a.dbg = static_cast<long long*>(g_enc_gemm_debug);
     if (m == 0) return 0;
     // pairs once there are enough 256 x 256 tiles to occupy most of the chip
     int form = g_enc_gemm_form;

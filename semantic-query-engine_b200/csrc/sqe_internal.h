@@ -62,6 +62,11 @@ int launch_cache_finalize(const float* score, const int64_t* idx, int b, double 
 int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                         int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
                         float q_scale, const float* residual, int64_t ldr, int sm_count, cudaStream_t stream);
+int64_t encoder_gemm_small_workspace_bytes();
+int launch_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
+                              int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
+                              float q_scale, const float* residual, int64_t ldr, void* workspace, int64_t workspace_bytes,
+                              cudaStream_t stream);
 int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const void* tiles, int n_tiles,
                              int max_len, void* ctx, cudaStream_t stream);
 int launch_encoder_layernorm(const float* in, const float* gamma, const float* beta, float eps, int64_t rows,
@@ -79,7 +84,9 @@ extern int g_k2_cta_group;      // 0 auto, 1, 2
 extern int g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
 extern int g_k2_d_hint;         // retired experiment (accepted, ignored)
 extern int g_k2_window;         // retired experiment (accepted, ignored)
+extern void* g_enc_gemm_debug;  // encoder_gemm.cu: role timers per CTA, or null
 extern void* g_enc_attn_debug;  // encoder_attn.cu: phase time stamps per CTA, or null
+extern int g_enc_small;        // 0 = few-token forward passes take the swap-AB split-K GEMM, 1 = never
 extern int g_enc_gemm_form;    // 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs (encoder_gemm.cu)
 extern void* g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
 

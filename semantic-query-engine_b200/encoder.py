@@ -346,8 +346,14 @@ class _Buffers:
         self.meta_host = [torch.zeros(self.meta_cap, dtype=torch.int32).pin_memory() for _ in range(2)]
         self.meta_done = [None, None]
         self.turn = 0
+        # query-sized capacities carry the workspace of the few-token GEMM (partial tiles + tickets)
+        self.small_ws = None
+        if t_pad <= 128:
+            self.small_ws = torch.zeros(int(nat.load().sqe_encoder_gemm_small_workspace_bytes()), dtype=torch.uint8, device=dev)
         self.c = nat.SqeEncoderBuffers(t_pad, self.h32.data_ptr(), self.h16.data_ptr(), self.sum32.data_ptr(),
-                                       self.qk.data_ptr(), self.vt.data_ptr(), self.ctx.data_ptr(), self.ffn.data_ptr())
+                                       self.qk.data_ptr(), self.vt.data_ptr(), self.ctx.data_ptr(), self.ffn.data_ptr(),
+                                       0 if self.small_ws is None else self.small_ws.data_ptr(),
+                                       0 if self.small_ws is None else self.small_ws.numel())
         self.graph_out = torch.zeros(t_pad // 8, HIDDEN, dtype=torch.float32, device=dev)     # one row per sequence
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
         self.seen: Dict[tuple, int] = {}
@@ -453,44 +459,46 @@ class GpuEmbeddingEncoder:
             if out is None:
                 out = torch.empty((n, HIDDEN), dtype=torch.float32, device=dev)
             max_len = max(lens)
-            key = (n_tiles, (max_len + 63) // 64, n, o_first, o_tiles)
+            rows_used = int(first[-1]) + lens[-1]           # token rows in use (the last sequence's end)
+            key = (n_tiles, (max_len + 63) // 64, n, o_first, o_tiles, (rows_used + 15) // 16)
             graph = None
             if self.use_graphs and t_pad <= self.graph_max_tokens:
                 graph = b.graphs.get(key)
                 b.seen[key] = b.seen.get(key, 0) + 1
                 if graph is None and b.seen[key] == 2 and len(b.graphs) < 16:
-                    graph = self._capture(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, key)
+                    graph = self._capture(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, key, rows_used)
             if graph is not None:
                 graph.replay()
                 self.graph_replays += 1
                 out.copy_(b.graph_out[:n])
                 self.launches_last_forward = 2 + 7 * len(self.w.layers)
             else:
-                self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, out)
+                self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, out, rows_used)
         return out
 
     def _forward(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, first_d, n: int,
-                 out: torch.Tensor) -> None:
+                 out: torch.Tensor, rows_used: int = 0) -> None:
         """`sqe_encoder_forward` on the current stream: 2 + 7 layers kernel launches, one call."""
         dev = self.device
         with torch.cuda.device(dev):
             nat.call("sqe_encoder_forward", ctypes.addressof(self.w.c_struct()), ctypes.addressof(b.c),
                      ids_d.data_ptr(), pos_d.data_ptr(), tiles_d.data_ptr(), n_tiles, max_len, first_d.data_ptr(), n,
-                     out.data_ptr(), out.stride(0), torch.cuda.current_stream(dev).cuda_stream)
+                     rows_used, out.data_ptr(), out.stride(0), torch.cuda.current_stream(dev).cuda_stream)
         self.launches_last_forward = 2 + 7 * len(self.w.layers)
         nat.launch_count += self.launches_last_forward
 
-    def _capture(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, first_d, n: int, key):
+    def _capture(self, b: _Buffers, ids_d, pos_d, tiles_d, n_tiles: int, max_len: int, first_d, n: int, key,
+                 rows_used: int = 0):
         """Capture the forward pass of this batch shape (it reads the metadata from fixed device
         addresses, so a replay serves any batch of the same shape).  None if capture fails."""
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         try:
-            self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, b.graph_out)     # warm: attributes set
+            self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, b.graph_out, rows_used)     # warm: attributes set
             cur.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode="thread_local"):
-                self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, b.graph_out)
+                self._forward(b, ids_d, pos_d, tiles_d, n_tiles, max_len, first_d, n, b.graph_out, rows_used)
         except Exception as e:                              # noqa: BLE001 -- the eager path still works
             print(f"[sqe_b200] encoder graph capture failed ({e}); staying on direct launches")
             self.use_graphs = False
@@ -521,6 +529,7 @@ class GpuEmbeddingEncoder:
         if n == 0:
             return out
         lens = [len(s) for s in seqs]
+        out.record_stream(self.stream)                      # allocated on the caller's stream, written on ours
         with torch.cuda.stream(self.stream):
             for i, j in self._batches(lens):
                 self.forward_ids(seqs[i:j], out=out[i:j])

@@ -101,6 +101,71 @@ def test_gemm_qkv_split_epilogue(sqe, gemm_form, m):
     assert bool((qk[m:] == 7.0).all()) and bool((vt[:, m:] == 7.0).all())
 
 
+@pytest.mark.parametrize("m", [1, 16, 17, 100, 128])
+@pytest.mark.parametrize("n,k,epi", [(3072, 1024, 0), (1024, 1024, 1), (4096, 1024, 2), (1024, 4096, 1)])
+def test_gemm_small_swap_ab_split_k(sqe, m, n, k, epi):
+    """The few-token form (weights as the M operand, K split over CTAs, last-CTA reduction) against
+    fp32 torch, every epilogue; repeated launches are bit-identical (fixed summation order) and the
+    tickets return to zero."""
+    nat = sqe._native
+    g = _gen(m * 7 + n + k + epi)
+    x = _randn(g, 128, k, dtype=torch.float16)
+    w = _randn(g, n, k, s=0.03, dtype=torch.float16)
+    bias = _randn(g, n, s=0.5)
+    res = _randn(g, 128, n)
+    ws = torch.zeros(int(nat.load().sqe_encoder_gemm_small_workspace_bytes()), dtype=torch.uint8, device=dev())
+    y = x[:m].float() @ w.float().T + bias
+    outs = []
+    for _ in range(2):
+        if epi == 1:
+            out0, out1 = torch.full((128, n), 7.0, device=dev()), None
+        elif epi == 2:
+            out0, out1 = torch.full((128, n), 7.0, device=dev(), dtype=torch.float16), None
+        else:
+            out0 = torch.full((128, 2 * H), 7.0, device=dev(), dtype=torch.float16)
+            out1 = torch.full((H, 128), 7.0, device=dev(), dtype=torch.float16)
+        nat.call("sqe_encoder_gemm_small", x.data_ptr(), k, w.data_ptr(), bias.data_ptr(), m, n, k, epi, out0.data_ptr(),
+                 out0.stride(0), 0 if out1 is None else out1.data_ptr(), 128, 2 * H if epi == 0 else 0, H if epi == 0 else 0,
+                 0.125, res.data_ptr() if epi == 1 else 0, n, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append((out0, out1))
+    assert torch.equal(outs[0][0], outs[1][0]) and not ws[:4096].any()
+    out0, out1 = outs[0]
+    tol = lambda want: want.abs() * 6e-4 + 2e-4                                   # noqa: E731
+    if epi == 1:
+        assert float((out0[:m] - (y + res[:m])).abs().max()) < 2e-4
+    elif epi == 2:
+        want = 0.5 * y * (1.0 + torch.erf(y / math.sqrt(2.0)))
+        assert bool(((out0[:m].float() - want).abs() <= tol(want)).all())
+    else:
+        y[:, :H] *= 0.125
+        assert bool(((out0[:m].float() - y[:, :2 * H]).abs() <= tol(y[:, :2 * H])).all())
+        assert bool(((out1[:, :m].float() - y[:, 2 * H:].T).abs() <= tol(y[:, 2 * H:].T)).all())
+        assert bool((out1[:, m:] == 7.0).all())
+    assert bool((out0[m:] == 7.0).all())                                          # rows >= m are left alone
+
+
+def test_few_token_forward_matches_the_tile_form(sqe):
+    """A query takes the swap-AB split-K products; with the knob off it takes the 128 x 64 tiles: the
+    same embedding up to the summation order, and both agree with the oracle."""
+    nat = sqe._native
+    w, e = _pair(sqe, 25, layers=3)
+    e.use_graphs = False
+    g = torch.Generator().manual_seed(10)
+    for lens in ([9], [3, 20], [16, 8], [32]):
+        seqs = [torch.randint(0, 2000, (n,), generator=g).tolist() for n in lens]
+        small = e.embed_token_ids(seqs)
+        torch.cuda.synchronize()
+        old = nat.tuning_set(nat.SQE_TUNE_ENC_SMALL, 1)
+        try:
+            tiles = e.embed_token_ids(seqs)
+            torch.cuda.synchronize()
+        finally:
+            nat.tuning_set(nat.SQE_TUNE_ENC_SMALL, old)
+        assert float((small - tiles).abs().max()) < 5e-3, lens                       # fp16 round-off of intermediates flips
+        assert float((small.cpu() - bo.bert_embed(w, seqs)).abs().max()) < 3e-2, lens
+
+
 def test_gemm_argument_errors(sqe):
     nat = sqe._native
     x = torch.zeros((128, H), device=dev(), dtype=torch.float16)
@@ -283,10 +348,10 @@ def test_drop_in_coroutines_and_retrieval_end_to_end(sqe):
     want = bo.bert_embed(w, [bo.encode_text(t, vocab) for t in chunks if t.strip()]).numpy()
     assert np.abs(emb[[0, 1, 2, 4]] - want).max() < 2e-2
     q = asyncio.run(main.embed_query("gene expression, tumor cells"))
-    assert q.shape == (1, 1024) and np.abs(q[0] - emb[1]).max() < 1e-3
+    assert q.shape == (1, 1024) and np.abs(q[0] - emb[1]).max() < 5e-3          # alone: few-token products
     assert asyncio.run(main.embed_query(" ")).size == 0
     one = asyncio.run(main.ollama_embed_text("patient tumor binding?"))
-    assert isinstance(one, list) and len(one) == 1024 and abs(one[0] - float(emb[2, 0])) < 1e-3
+    assert isinstance(one, list) and len(one) == 1024 and abs(one[0] - float(emb[2, 0])) < 5e-3
     index = sqe.GpuCorpusIndex(dtype="fp32")
     index.add_embeddings(emb, [{"doc_id": f"d{i}", "text": t} for i, t in enumerate(chunks)])
     hits = index.search(q, k=2)

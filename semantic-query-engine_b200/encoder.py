@@ -373,7 +373,7 @@ class GpuEmbeddingEncoder:
         self.tok = tokenizer
         self.max_batch_tokens = max(int(max_batch_tokens), MAX_TOKENS)
         self.blank_policy = blank_policy
-        self._bufs: Dict[int, _Buffers] = {}
+        self._bufs: Dict[Tuple[int, int], _Buffers] = {}
         self._lock = threading.Lock()
         self.stream = torch.cuda.Stream(device=self.device)
         self.launches_last_forward = 0
@@ -386,11 +386,18 @@ class GpuEmbeddingEncoder:
 
     # ------------------------------------------------------------------ device forward
     def _buffers(self, t_pad: int) -> _Buffers:
-        b = self._bufs.get(t_pad)
+        """Activation buffers for this token capacity ON THE CURRENT STREAM: a forward pass only
+        orders itself against earlier work of its own stream, so two streams (say the ingest thread's
+        `embed_texts` and a MicroBatcher's compute stream) must never share a set."""
+        key = (t_pad, torch.cuda.current_stream(self.device).cuda_stream)
+        b = self._bufs.get(key)
         if b is None:
-            if len(self._bufs) >= 4:                        # keep the few capacities that recur
-                self._bufs.pop(next(iter(self._bufs)))
-            b = self._bufs[t_pad] = _Buffers(t_pad, self.w.intermediate, self.device)
+            if len(self._bufs) >= 6:                        # keep the few capacities that recur
+                old = next(iter(self._bufs))
+                if old[1] != key[1]:                        # another stream's set may still be in use there
+                    torch.cuda.synchronize(self.device)
+                self._bufs.pop(old)
+            b = self._bufs[key] = _Buffers(t_pad, self.w.intermediate, self.device)
         return b
 
     @staticmethod

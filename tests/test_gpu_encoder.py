@@ -392,3 +392,52 @@ def test_micro_batcher_serves_text_queries_through_the_encoder(sqe):
         assert mb.batches < mb.requests                                           # requests were coalesced
     finally:
         mb.close()
+
+
+def test_a_transformers_checkpoint_loads_and_reproduces_the_library(sqe, tmp_path):
+    """`EncoderWeights.load` on files written by the `transformers` library (a BertModel of the
+    mxbai-embed-large geometry, 2 layers, random weights; both the torch and the safetensors format) +
+    `WordPieceTokenizer.from_file` on a vocab.txt: the GPU embeddings equal what the library computes for
+    the same texts with its own padded batch + attention mask (CLS token of the last hidden state)."""
+    tr = pytest.importorskip("transformers")
+    torch.manual_seed(123)
+    cfg = tr.BertConfig(hidden_size=1024, num_hidden_layers=2, num_attention_heads=16, intermediate_size=4096,
+                        vocab_size=len(VOCAB), max_position_embeddings=512)
+    model = tr.BertModel(cfg).eval()                                              # with its (unused) pooler
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if "query.weight" in name or "key.weight" in name:
+                prm.normal_(0.0, 0.05)
+            elif prm.dim() == 2 and "embeddings" not in name:
+                prm.normal_(0.0, 0.03)
+            elif "embeddings" in name and prm.dim() == 2:
+                prm.normal_(0.0, 0.4)
+    vocab_file = tmp_path / "vocab.txt"
+    vocab_file.write_text("\n".join(VOCAB) + "\n", encoding="utf-8")
+    tok = sqe.WordPieceTokenizer.from_file(str(vocab_file))
+    texts = ["the cells bind the protein.", "gene expression, tumor cells", "patient " * 300]
+    seqs = [tok.encode(t) for t in texts]
+    L = max(map(len, seqs))
+    ids = torch.zeros(len(seqs), L, dtype=torch.long)
+    mask = torch.zeros(len(seqs), L, dtype=torch.long)
+    for i, sq in enumerate(seqs):
+        ids[i, : len(sq)] = torch.tensor(sq)
+        mask[i, : len(sq)] = 1
+    with torch.no_grad():
+        want = model(input_ids=ids, attention_mask=mask).last_hidden_state[:, 0].numpy()
+    pt = tmp_path / "pytorch_model.bin"
+    torch.save({"bert." + k: v for k, v in model.state_dict().items()}, str(pt))          # a task-head style prefix
+    paths = [str(pt)]
+    try:
+        from safetensors.torch import save_file
+        st = tmp_path / "model.safetensors"
+        save_file({k: v.contiguous() for k, v in model.state_dict().items()}, str(st))
+        paths.append(str(st))
+    except ImportError:
+        pass
+    for path in paths:
+        e = sqe.GpuEmbeddingEncoder(sqe.EncoderWeights.load(path, device=dev()), tok)
+        got = e.embed_texts(texts)
+        assert np.abs(got - want).max() < 2e-2, path
+        cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
+        assert cos.min() > 0.9999

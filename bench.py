@@ -1595,7 +1595,7 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
         e2e = {"value": tokens / dt, "unit": "tokens/s", "h2d_bytes_per_step": int(buf.meta_cap * 4),
                "d2h_bytes_per_step": n_seq * 1024 * 4, "ms_per_step": dt * 1e3, "chunks_per_s": n_seq / dt,
                "api": "GpuEmbeddingEncoder.embed_token_ids(host token lists) -> host fp32 [64, 1024]"}
-        # the same from TEXT: 64 chunks of 512 words through the WordPiece tokeniser (synthetic vocabulary
+        # the same from TEXT: 256 chunks of 512 words through the WordPiece tokeniser (synthetic vocabulary
         # of 30522 entries, Zipf word frequencies), i.e. embed_texts_in_batches(chunks) -> np.ndarray
         words = ["".join(rng.choice(list("abcdefghijklmnopqrstuvwxyz"), int(rng.integers(2, 10)))) for _ in range(40000)]
         specials = ["[PAD]", "[UNK]", "[CLS]", "[SEP]"] + list("abcdefghijklmnopqrstuvwxyz") + \
@@ -1605,8 +1605,9 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
             if len(vocab) < 30522:
                 vocab.setdefault(t_, len(vocab))
         et = sqe_b200.GpuEmbeddingEncoder(w, sqe_b200.WordPieceTokenizer(vocab), max_batch_tokens=n_seq * seq_len)
-        zipf = rng.zipf(1.3, size=n_seq * 512) % 40000
-        chunks = [" ".join(words[j] for j in zipf[i * 512:(i + 1) * 512]) + "." for i in range(n_seq)]
+        n_txt = 4 * n_seq                                        # four forward passes: tokenising overlaps the GPU
+        zipf = rng.zipf(1.3, size=n_txt * 512) % 40000
+        chunks = [" ".join(words[j] for j in zipf[i * 512:(i + 1) * 512]) + "." for i in range(n_txt)]
         for _ in range(2):
             et.embed_texts(chunks)
         t0 = time.perf_counter()
@@ -1614,9 +1615,10 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
             emb = et.embed_texts(chunks)
         dtt = (time.perf_counter() - t0) / esteps
         ntok = sum(len(et.tok.encode(c)) for c in chunks)
-        e2e["from_text"] = {"value": ntok / dtt, "unit": "tokens/s", "chunks_per_s": n_seq / dtt, "ms_per_step": dtt * 1e3,
-                            "tokens": ntok, "api": "GpuEmbeddingEncoder.embed_texts(64 chunks x 512 words) -> np.ndarray "
-                                                   "[64, 1024] (tokeniser + packing + H2D + 24 layers + D2H)"}
+        e2e["from_text"] = {"value": ntok / dtt, "unit": "tokens/s", "chunks_per_s": n_txt / dtt, "ms_per_step": dtt * 1e3,
+                            "tokens": ntok, "api": f"GpuEmbeddingEncoder.embed_texts({n_txt} chunks x 512 words) -> np.ndarray "
+                                                   f"[{n_txt}, 1024] (tokeniser + packing + H2D + 24 layers + D2H; "
+                                                   f"{n_txt // n_seq} forward passes of {n_seq} chunks)"}
         del et
     # ---- one query (16 tokens): the latency the /ask handler sees instead of an HTTP round trip
     q = [rng.integers(0, 30522, size=16).tolist()]
@@ -1663,7 +1665,14 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
                          "kernel": "encoder_gemm_kernel<256, 2, *> (the four linear layers of a block)",
                          "kernel_share_of_step": layers * gemm_ms / ms,
                          "kernel_ms": gemm_ms, "algorithmic_flops_per_launch": lin_flops / layers,
-                         "peak_source": peaks["source"], "traffic": None,
+                         "peak_source": peaks["source"],
+                         "traffic": (load_traffic("encoder_gemm_block_64x512") or {}).get("dram_bytes_per_launch")
+                         if (n_seq, seq_len) == (64, 512) else None,
+                         "traffic_source": "from profile (profiles/r2b_encoder_block_full.json: dram bytes of the four GEMM launches "
+                                           "of a block; algorithmic: 64 MB X + 24 MB W + 192 MB Q|K|V^T, 64 + 2 + 128 + 128, "
+                                           "64 + 8 + 256, 256 + 8 + 128 + 128 MB = 1.45 GB)",
+                         "l2_note": "binding resource: L2 -> SM delivery (ncu: 61.5 M sectors = 1.97 GB through the L2 in 161 us for "
+                                    "QKV = 6,960 B per SM clock chip-wide; B300_MICROARCH.md measures the cap at ~6,300)",
                          "whole_step_tflops": (lin_flops + att_flops) / (ms * 1e-3) / 1e12},
             "breakdown": breakdown, "query_latency_ms": query_ms, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

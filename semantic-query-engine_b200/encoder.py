@@ -543,9 +543,27 @@ class GpuEmbeddingEncoder:
         return out
 
     def embed_texts_device(self, texts: Sequence[str]) -> torch.Tensor:
+        """[n, 1024] fp32 on the device (asynchronous on `self.stream`).  Texts are tokenised batch by
+        batch: while the GPU runs the forward pass of one batch of up to `max_batch_tokens` tokens the
+        host tokenises and packs the next, so an ingest runs at the slower of the two, not their sum."""
         if self.tok is None:
             raise RuntimeError("this encoder was built without a tokenizer (pass token ids instead)")
-        return self.embed_token_ids([self.tok.encode(t) for t in texts])
+        n = len(texts)
+        out = torch.empty((n, HIDDEN), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        out.record_stream(self.stream)
+        with torch.cuda.stream(self.stream):
+            first, batch, tokens = 0, [], 0
+            for i, text in enumerate(texts):
+                ids = self.tok.encode(text)
+                if batch and tokens + len(ids) > self.max_batch_tokens:
+                    self.forward_ids(batch, out=out[first:i])
+                    first, batch, tokens = i, [], 0
+                batch.append(ids)
+                tokens += len(ids)
+            self.forward_ids(batch, out=out[first:n])
+        return out
 
     def embed_texts(self, texts: Sequence[str]) -> np.ndarray:
         """Host array [n, 1024] fp32; blank texts give zero rows (embedding_gen.py:147-148)."""

@@ -40,6 +40,29 @@ def test_latest_default_line_has_the_contract_keys():
         assert pf["identical_to_exact_scan"] is True and pf["value"] > line["secondary"]["value"]
 
 
+def test_encode_line_has_the_contract_keys():
+    """`bench.py --workload encode` (the embedding encoder) as printed on B200."""
+    found = list(_lines("r2b_final_bench_encode.json"))
+    assert found
+    for path, line in found:
+        assert BASE_KEYS <= set(line), (path, BASE_KEYS - set(line))
+        assert line["unit"] == "tokens/s" and line["value"] > 5e5 and line["dtype"] == "f16" and "random-init" in line["data"]
+        assert "model" not in line["config"] and line["config"]["workload"].startswith("64 chunks x 512 tokens")
+        assert line["gpu_launches"] == line["steps"] * 170                      # 2 + 7 x 24 per forward pass
+        roof = line["roofline"]
+        assert roof["bound"] == "tensor" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+        e2e = line["e2e"]
+        assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] == 64 * 1024 * 4
+        assert e2e["from_text"]["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+        assert set(line["breakdown"]["per_gemm"]) == {"qkv", "attn_out", "ffn1_gelu", "ffn2"}
+
+
+def test_default_line_carries_the_encoder_block():
+    for _, line in _lines("r2b_final_bench_default.json"):
+        enc = line["encoder"]
+        assert enc["tokens_per_s"] > 5e5 and enc["gpu_launches"] == enc["steps"] * 170 and enc["query_latency_ms_16_tokens"] > 0
+
+
 def test_reference_arm_line():
     found = list(_lines("r1_final2_bench_reference.json"))
     assert found

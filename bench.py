@@ -224,10 +224,52 @@ def cpu_reference_sample(b: int, rows: int, k: int, total_rows: int, seed: int =
     return dt, qps, 0.0
 
 
+def run_reference_arm_encode(args):
+    """`--impl reference --workload encode`: the CPU restatement of the embedding step (oracle/bert_oracle.py,
+    fp32 torch on every host core -- the reference itself delegates this step to an Ollama server that
+    cannot exist here) on a bounded sample: 2 chunks x 512 tokens through 2 of the 24 layers per step, scaled."""
+    import torch
+    from oracle import bert_oracle as bo
+    cores = cpu_use_all_cores()
+    torch.set_num_threads(cores)
+    steps = args.steps or 3
+    warmup = args.warmup if args.warmup is not None else 1
+    layers_run, layers, seq_len, n = 2, 24, 512, 2
+    w = bo.random_bert_weights(0, layers=layers_run, vocab=1000)
+    rng = np.random.default_rng(0)
+    sample = [rng.integers(0, 1000, size=seq_len).tolist() for _ in range(n)]
+    for _ in range(warmup):
+        bo.bert_embed(w, sample[:1])
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        bo.bert_embed(w, sample)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times)) * layers / layers_run
+    value = n * seq_len / dt
+    what = (f"oracle/bert_oracle.py (fp32 torch, {cores} threads) on {n} chunks x {seq_len} tokens x {layers_run} layers per step, "
+            f"time scaled by {layers}/{layers_run} to the 24-layer model")
+    print(json.dumps({
+        "impl": "reference", "metric": "tokens/sec BERT-large embedding encoder (mxbai-embed-large geometry), 64 chunks x 512 tokens",
+        "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic token ids, random-init weights of the mxbai-embed-large architecture",
+        "config": {"workload": "64 chunks x 512 tokens, 24-layer BERT-large encoder, CLS pooling "
+                               "(app/main.py:36-37 BATCH_SIZE x CHUNK_SIZE; main.py:134-169)"},
+        "sample_config": {"chunks": n, "tokens_per_chunk": seq_len, "layers_run": layers_run, "scaled_to_layers": layers,
+                          "arithmetic": "fp32 torch restatement of transformers.BertModel (the reference's own code is an HTTP "
+                                        "call to an Ollama server)"},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": what},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "encode":
+        return run_reference_arm_encode(args)
     b = {"b1024": 256, "b1": 1, "cache64": 64}.get(args.workload, 256)
     sample_rows = 1_000_000 if args.workload != "cache64" else 250_000
     total_rows = args.rows if args.workload != "cache64" else 1_000_000

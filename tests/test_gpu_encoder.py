@@ -441,3 +441,43 @@ def test_a_transformers_checkpoint_loads_and_reproduces_the_library(sqe, tmp_pat
         assert np.abs(got - want).max() < 2e-2, path
         cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
         assert cos.min() > 0.9999
+
+
+def test_ingest_thread_and_text_serving_share_one_encoder(sqe):
+    """The reference embeds chunks from an executor thread (main.py:449-455) while requests embed
+    queries (main.py:676).  Here the ingest thread runs `embed_texts` on the encoder's stream and a
+    MicroBatcher runs text requests on ITS compute stream with the same encoder object (activation
+    buffers are per stream): both must equal what they produce alone."""
+    import threading
+    w = bo.random_bert_weights(35, layers=2, vocab=len(VOCAB))
+    vocab = {t: i for i, t in enumerate(VOCAB)}
+    e = sqe.GpuEmbeddingEncoder(sqe.EncoderWeights.from_state_dict(w, device=dev()), sqe.WordPieceTokenizer(vocab))
+    rng = np.random.default_rng(6)
+    words = VOCAB[-13:-3]
+    chunks = list(dict.fromkeys(" ".join(rng.choice(words, int(rng.integers(3, 30)))) + " ." for _ in range(120)))
+    alone = e.embed_texts(chunks)
+    index = sqe.GpuCorpusIndex(dtype="fp32")
+    index.add_embeddings(alone, [{"doc_id": f"d{i}", "text": t} for i, t in enumerate(chunks)])
+    mb = sqe.MicroBatcher(index, max_batch=32, max_wait_s=1e-3, depth=2, encoder=e)
+    errors, ingested = [], []
+
+    def ingest():
+        try:
+            for _ in range(6):
+                ingested.append(e.embed_texts(chunks))
+        except Exception as ex:                                                   # noqa: BLE001
+            errors.append(ex)
+    t = threading.Thread(target=ingest)
+    t.start()
+    try:
+        for rep in range(6):
+            futs = [mb.submit_text(chunks[i], 1) for i in range(0, len(chunks), 3)]
+            for i, f in zip(range(0, len(chunks), 3), futs):
+                hit = f.result(timeout=60)[0]
+                assert hit[0]["doc_id"] == f"d{i}" and hit[1] > 0.9999, (rep, i, hit)
+    finally:
+        t.join()
+        mb.close()
+    assert not errors, errors
+    for got in ingested:
+        assert np.array_equal(got, alone)                                         # same batches, same stream: bit-identical

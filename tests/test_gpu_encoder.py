@@ -481,3 +481,25 @@ def test_ingest_thread_and_text_serving_share_one_encoder(sqe):
     assert not errors, errors
     for got in ingested:
         assert np.array_equal(got, alone)                                         # same batches, same stream: bit-identical
+
+
+def test_random_length_mixes_against_the_oracle(sqe):
+    """Fuzz of the packing / attention work list: 24 random batches (1..40 sequences of 1..512 tokens, some
+    all-short, some all-long, token budgets that split a batch) through a one-layer model vs the oracle."""
+    w, e = _pair(sqe, 41, layers=1)
+    rng = np.random.default_rng(12)
+    worst = 0.0
+    for trial in range(24):
+        n = int(rng.integers(1, 41))
+        hi = int(rng.choice([8, 64, 130, 512]))
+        lens = [int(x) for x in rng.integers(1, hi + 1, size=n)]
+        if trial % 5 == 0:
+            lens[int(rng.integers(0, n))] = 512
+        e.max_batch_tokens = int(rng.choice([512, 2048, 32768]))
+        seqs = [rng.integers(0, 2000, size=m).tolist() for m in lens]
+        got = e.embed_token_ids(seqs)
+        torch.cuda.synchronize()
+        err = float((got.cpu() - bo.bert_embed(w, seqs)).abs().max())
+        worst = max(worst, err)
+        assert err < 1e-2, (trial, lens, err)
+    assert worst > 0.0

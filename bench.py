@@ -1574,19 +1574,21 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
     def gemms():
         enc.gemm(buf.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, buf.qk, m=t_pad, out1=buf.vt, n_split=2 * H,
                  q_cols=H, q_scale=0.125)
-        enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
+        enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum_a, m=t_pad, residual=buf.sum_b,
+                 res_stats=buf.stats_b, res_gamma=L["g2"], res_beta=L["b2"])
         enc.gemm(buf.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, buf.ffn, m=t_pad)
-        enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
+        enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum_b, m=t_pad, residual=buf.sum_a,
+                 res_stats=buf.stats_a, res_gamma=L["g1"], res_beta=L["b1"])
 
     def one(which):
         return {
             "qkv": lambda: enc.gemm(buf.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, buf.qk, m=t_pad, out1=buf.vt,
                                     n_split=2 * H, q_cols=H, q_scale=0.125),
-            "attn_out": lambda: enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad,
-                                         residual=buf.h32),
+            "attn_out": lambda: enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum_a, m=t_pad,
+                                         residual=buf.sum_b, res_stats=buf.stats_b, res_gamma=L["g2"], res_beta=L["b2"]),
             "ffn1_gelu": lambda: enc.gemm(buf.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, buf.ffn, m=t_pad),
-            "ffn2": lambda: enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad,
-                                     residual=buf.h32),
+            "ffn2": lambda: enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum_b, m=t_pad,
+                                     residual=buf.sum_a, res_stats=buf.stats_a, res_gamma=L["g1"], res_beta=L["b1"]),
         }[which]
 
     gemm_ms = timed(gemms, 24)
@@ -1613,13 +1615,14 @@ def run_encode(args, torch, sqe_b200, nat, dev, peaks, compact=False):
         except Exception as ex:                              # noqa: BLE001
             yard = {"error": str(ex)[:200]}
     attn_ms = timed(lambda: enc.attention(buf.qk, buf.vt, tiles_d, tiles.shape[0], seq_len, buf.ctx), 24)
-    ln_ms = timed(lambda: enc.layernorm(buf.sum32, L["g1"], L["b1"], 1e-12, buf.h32, buf.h16, rows=t_pad), 24)
+    ln_ms = timed(lambda: enc.layernorm(buf.sum_a, L["g1"], L["b1"], 1e-12, None, buf.h16, rows=t_pad, stats=buf.stats_a), 24)
     gemm_tflops = lin_flops / layers / (gemm_ms * 1e-3) / 1e12
     breakdown = {"per_layer_ms": {"gemms": gemm_ms, "attention": attn_ms, "layernorm_x2": 2 * ln_ms},
                  "per_layer_sum_x_layers_ms": layers * (gemm_ms + attn_ms + 2 * ln_ms), "per_gemm": per_gemm,
                  "cublas_fp16_yardstick_no_epilogue": yard,
                  "attention_tflops": att_flops / layers / (attn_ms * 1e-3) / 1e12,
-                 "layernorm_gbs": t_pad * 1024 * (4 + 4 + 2) / (ln_ms * 1e-3) / 1e9}
+                 "layernorm_gbs": t_pad * (1024 * (4 + 2) + 8) / (ln_ms * 1e-3) / 1e9,
+                 "layernorm_bytes_per_row": 1024 * (4 + 2) + 8}
     # ---- end to end: host token lists -> packing -> H2D -> 24 layers -> D2H of the embeddings
     e2e = None
     if not args.no_e2e:

@@ -325,6 +325,7 @@ SQE_API int sqe_cache_top1_prefiltered(const void *C, int dtype, int64_t n, int 
  * of 8 rows, nothing else separates them); buffers
  * that feed a tensor-core operand are fp16, the residual stream and LayerNorm are fp32.
  *
+ *   (plain forms first; the statistics forms that sqe_encoder_forward uses are described below)
  *   sqe_encoder_embed_ln   rows of word_emb[ids] + pos_emb[pos] + type_emb[0] -> LayerNorm ->
  *                          out_f32 [rows, 1024] and its fp16 copy out_f16; ids < 0 = padding row
  *                          (written as zeros).
@@ -353,15 +354,27 @@ SQE_API int sqe_cache_top1_prefiltered(const void *C, int dtype, int64_t n, int 
 #define SQE_ENC_EPI_SPLIT 0
 #define SQE_ENC_EPI_RES_F32 1
 #define SQE_ENC_EPI_GELU 2
+/*
+ * The LayerNorm STATISTICS form (what sqe_encoder_forward uses): a LayerNorm's fp32 output is only ever read
+ * as the residual of the next residual GEMM, so it is never stored.  `stats` (float [rows][2] = {mean, rstd}):
+ *   sqe_encoder_layernorm  stats != NULL: also writes the row statistics; out_f32 may then be NULL;
+ *   sqe_encoder_embed_ln   stats != NULL: out_f32 receives the PRE-LayerNorm sum, stats its statistics;
+ *   sqe_encoder_gemm(_small), SQE_ENC_EPI_RES_F32, res_stats != NULL: the residual operand is
+ *       LayerNorm(residual) = ((residual - mean) * rstd) * res_gamma + res_beta, recomputed with the LayerNorm
+ *       kernel's own operations (bit-identical to the output it would have stored);
+ *   sqe_encoder_pool       stats != NULL: h holds pre-LayerNorm sums, out = LayerNorm(h[first_token]).
+ * 10 -> 6 KB of HBM traffic per row and LayerNorm; results bit-identical to the plain form.
+ */
 SQE_API int sqe_encoder_embed_ln(const int32_t *ids, const int32_t *pos, const float *word_emb, int vocab,
                          const float *pos_emb, int max_pos, const float *type_emb, const float *gamma,
                          const float *beta, float eps, int64_t rows, float *out_f32, void *out_f16,
-                         void *stream);
+                         float *stats, void *stream);
 SQE_API int sqe_encoder_layernorm(const float *in, const float *gamma, const float *beta, float eps,
-                          int64_t rows, float *out_f32, void *out_f16, void *stream);
+                          int64_t rows, float *out_f32, void *out_f16, float *stats, void *stream);
 SQE_API int sqe_encoder_gemm(const void *X, int64_t ldx, const void *W, const float *bias, int64_t m, int n,
                      int k, int epilogue, void *out0, int64_t ld0, void *out1, int64_t ld1, int n_split,
-                     int q_cols, float q_scale, const float *residual, int64_t ldr, void *stream);
+                     int q_cols, float q_scale, const float *residual, int64_t ldr, const float *res_stats,
+                     const float *res_gamma, const float *res_beta, void *stream);
 /* The same products for m <= 128 token rows (one query, a few queries): operands swapped (weight
  * rows are the M operand, n_tok = m rounded up to 16 the N operand), K split over ~100 CTAs, partial
  * tiles summed in split order by the last CTA of a feature tile (deterministic), same epilogues.
@@ -370,12 +383,13 @@ SQE_API int sqe_encoder_gemm(const void *X, int64_t ldx, const void *W, const fl
 SQE_API int64_t sqe_encoder_gemm_small_workspace_bytes(void);
 SQE_API int sqe_encoder_gemm_small(const void *X, int64_t ldx, const void *W, const float *bias, int64_t m, int n,
                            int k, int epilogue, void *out0, int64_t ld0, void *out1, int64_t ld1, int n_split,
-                           int q_cols, float q_scale, const float *residual, int64_t ldr, void *workspace,
+                           int q_cols, float q_scale, const float *residual, int64_t ldr, const float *res_stats,
+                           const float *res_gamma, const float *res_beta, void *workspace,
                            int64_t workspace_bytes, void *stream);
 SQE_API int sqe_encoder_attention(const void *qk, const void *vt, int64_t t_pad, const int32_t *tiles,
                           int n_tiles, int max_len, void *ctx, void *stream);
 SQE_API int sqe_encoder_pool(const float *h, const int32_t *first_token, int n_seq, float *out, int64_t ldo,
-                     void *stream);
+                     const float *stats, const float *gamma, const float *beta, void *stream);
 
 /*
  * The whole forward pass in ONE call (what `GpuEmbeddingEncoder` issues per packed batch): embed_ln,
@@ -406,9 +420,9 @@ typedef struct SqeEncoderWeights {
 
 typedef struct SqeEncoderBuffers {      /* activations of one packed batch, t_pad rows (t_pad % 128 == 0) */
     int64_t t_pad;
-    float *h32;                 /* [t_pad, 1024] residual stream */
-    void *h16;                  /* [t_pad, 1024] fp16 copy (tensor-core operand) */
-    float *sum32;               /* [t_pad, 1024] pre-LayerNorm sums */
+    float *sum_a, *sum_b;       /* [t_pad, 1024] pre-LayerNorm sums (the residual stream), ping-pong */
+    float *stats_a, *stats_b;   /* [t_pad, 2] {mean, rstd} of the rows of sum_a / sum_b */
+    void *h16;                  /* [t_pad, 1024] fp16 LayerNorm output (tensor-core operand) */
     void *qk;                   /* [t_pad, 2048] fp16 */
     void *vt;                   /* [1024, t_pad] fp16 */
     void *ctx;                  /* [t_pad, 1024] fp16 */

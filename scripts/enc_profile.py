@@ -29,10 +29,12 @@ def block():
     enc.gemm(buf.h16, L["wqkv"], L["bqkv"], nat.SQE_ENC_EPI_SPLIT, buf.qk, m=t_pad, out1=buf.vt, n_split=2 * H,
              q_cols=H, q_scale=0.125)
     enc.attention(buf.qk, buf.vt, tiles_d, tiles.shape[0], seq_len, buf.ctx)
-    enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
-    enc.layernorm(buf.sum32, L["g1"], L["b1"], 1e-12, buf.h32, buf.h16, rows=t_pad)
+    enc.gemm(buf.ctx, L["wo"], L["bo"], nat.SQE_ENC_EPI_RES_F32, buf.sum_a, m=t_pad, residual=buf.sum_b,
+                 res_stats=buf.stats_b, res_gamma=L["g2"], res_beta=L["b2"])
+    enc.layernorm(buf.sum_a, L["g1"], L["b1"], 1e-12, None, buf.h16, rows=t_pad, stats=buf.stats_a)
     enc.gemm(buf.h16, L["w1"], L["bi"], nat.SQE_ENC_EPI_GELU, buf.ffn, m=t_pad)
-    enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum32, m=t_pad, residual=buf.h32)
+    enc.gemm(buf.ffn, L["w2"], L["bo2"], nat.SQE_ENC_EPI_RES_F32, buf.sum_b, m=t_pad, residual=buf.sum_a,
+                 res_stats=buf.stats_a, res_gamma=L["g1"], res_beta=L["b1"])
 
 
 first_d = torch.from_numpy(first).to(dev)

@@ -70,18 +70,21 @@ PROTOTYPES = [
                                             c_int, c_int, POINTER(c_void_p), c_int64, c_uint32, c_int,
                                             c_void_p, c_int64, c_void_p]),
     ("sqe_encoder_embed_ln", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
-                                     c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p]),
-    ("sqe_encoder_layernorm", c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("sqe_encoder_layernorm", c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     ("sqe_encoder_gemm", c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
-                                 c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64, c_void_p]),
+                                 c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
     ("sqe_encoder_attention", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    ("sqe_encoder_pool", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    ("sqe_encoder_pool", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     ("sqe_encoder_forward", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_int64, c_void_p, c_int64, c_void_p]),
     ("sqe_encoder_gemm_small_workspace_bytes", c_int64, []),
     ("sqe_encoder_gemm_small", c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                        c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
-                                       c_int64, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 ]
 
 
@@ -97,8 +100,8 @@ class SqeEncoderWeights(ctypes.Structure):
 
 
 class SqeEncoderBuffers(ctypes.Structure):
-    _fields_ = [("t_pad", c_int64)] + [(n, c_void_p) for n in ("h32", "h16", "sum32", "qk", "vt", "ctx", "ffn", "small_ws")] + \
-               [("small_ws_bytes", c_int64)]
+    _fields_ = [("t_pad", c_int64)] + [(n, c_void_p) for n in ("sum_a", "sum_b", "stats_a", "stats_b", "h16", "qk", "vt",
+                                                                 "ctx", "ffn", "small_ws")] + [("small_ws_bytes", c_int64)]
 
 
 

@@ -456,7 +456,8 @@ static int rc_map(int rc) { return rc == 0 ? SQE_OK : (rc == -1 ? SQE_E_ARG : SQ
 
 int sqe_encoder_embed_ln(const int32_t* ids, const int32_t* pos, const float* word_emb, int vocab,
                          const float* pos_emb, int max_pos, const float* type_emb, const float* gamma,
-                         const float* beta, float eps, int64_t rows, float* out_f32, void* out_f16, void* stream) {
+                         const float* beta, float eps, int64_t rows, float* out_f32, void* out_f16, float* stats,
+                         void* stream) {
     if (rows < 0 || vocab < 1 || max_pos < 1) { set_error("encoder_embed_ln: bad sizes"); return SQE_E_ARG; }
     if (rows == 0) return SQE_OK;
     if (!ids || !pos || !word_emb || !pos_emb || !type_emb || !gamma || !beta || !out_f32 || !out_f16 ||
@@ -469,27 +470,28 @@ int sqe_encoder_embed_ln(const int32_t* ids, const int32_t* pos, const float* wo
     int rc = device_info(&d);
     if (rc != SQE_OK) return rc;
     return rc_map(launch_encoder_embed_ln(ids, pos, word_emb, pos_emb, type_emb, gamma, beta, eps, rows, vocab, max_pos,
-                                          out_f32, out_f16, static_cast<cudaStream_t>(stream)));
+                                          out_f32, out_f16, stats, static_cast<cudaStream_t>(stream)));
 }
 
 int sqe_encoder_layernorm(const float* in, const float* gamma, const float* beta, float eps, int64_t rows,
-                          float* out_f32, void* out_f16, void* stream) {
+                          float* out_f32, void* out_f16, float* stats, void* stream) {
     if (rows < 0) { set_error("encoder_layernorm: negative rows"); return SQE_E_ARG; }
     if (rows == 0) return SQE_OK;
-    if (!in || !gamma || !beta || !out_f32 || !out_f16 || !aligned16(in) || !aligned16(gamma) || !aligned16(beta) ||
-        !aligned16(out_f32) || !aligned16(out_f16)) {
+    if (!in || !gamma || !beta || (!out_f32 && !stats) || !out_f16 || !aligned16(in) || !aligned16(gamma) || !aligned16(beta) ||
+        !aligned16(out_f32) || !aligned16(out_f16) || (reinterpret_cast<uintptr_t>(stats) & 7u) != 0) {
         set_error("encoder_layernorm: null or unaligned pointer");
         return SQE_E_ARG;
     }
     DevInfo d;
     int rc = device_info(&d);
     if (rc != SQE_OK) return rc;
-    return rc_map(launch_encoder_layernorm(in, gamma, beta, eps, rows, out_f32, out_f16, static_cast<cudaStream_t>(stream)));
+    return rc_map(launch_encoder_layernorm(in, gamma, beta, eps, rows, out_f32, out_f16, stats, static_cast<cudaStream_t>(stream)));
 }
 
 int sqe_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                      int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
-                     float q_scale, const float* residual, int64_t ldr, void* stream) {
+                     float q_scale, const float* residual, int64_t ldr, const float* res_stats, const float* res_gamma,
+                     const float* res_beta, void* stream) {
     if (m < 0 || m >= (1LL << 31) - 256 || n < 256 || n % 256 != 0 || k < 64 || k % 64 != 0) {
         set_error("encoder_gemm: need 0 <= m < 2^31, n %% 256 == 0, k %% 64 == 0 (m=%lld n=%d k=%d)", (long long)m, n, k);
         return SQE_E_ARG;
@@ -516,20 +518,31 @@ int sqe_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bia
         set_error("encoder_gemm: residual null / unaligned / too narrow");
         return SQE_E_ARG;
     }
+    if (res_stats && (epilogue != SQE_ENC_EPI_RES_F32 || !res_gamma || !res_beta || !aligned16(res_gamma) || !aligned16(res_beta) ||
+                      (reinterpret_cast<uintptr_t>(res_stats) & 7u) != 0)) {
+        set_error("encoder_gemm: LayerNorm statistics need the residual epilogue and aligned gamma / beta");
+        return SQE_E_ARG;
+    }
     DevInfo d;
     int rc = device_info(&d);
     if (rc != SQE_OK) return rc;
     return rc_map(launch_encoder_gemm(X, ldx, W, bias, m, n, k, epilogue, out0, ld0, out1, ld1, n_split, q_cols, q_scale,
-                                      residual, ldr, d.sm_count, static_cast<cudaStream_t>(stream)));
+                                      residual, ldr, res_stats, res_gamma, res_beta, d.sm_count,
+                                      static_cast<cudaStream_t>(stream)));
 }
 
 int64_t sqe_encoder_gemm_small_workspace_bytes(void) { return encoder_gemm_small_workspace_bytes(); }
 
 int sqe_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                            int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
-                           float q_scale, const float* residual, int64_t ldr, void* workspace, int64_t workspace_bytes,
+                           float q_scale, const float* residual, int64_t ldr, const float* res_stats,
+                           const float* res_gamma, const float* res_beta, void* workspace, int64_t workspace_bytes,
                            void* stream) {
     if (m == 0) return SQE_OK;
+    if (res_stats && (epilogue != SQE_ENC_EPI_RES_F32 || !res_gamma || !res_beta)) {
+        set_error("encoder_gemm_small: LayerNorm statistics need the residual epilogue, gamma and beta");
+        return SQE_E_ARG;
+    }
     if (epilogue < SQE_ENC_EPI_SPLIT || epilogue > SQE_ENC_EPI_GELU) { set_error("encoder_gemm_small: bad epilogue %d", epilogue); return SQE_E_ARG; }
     if (!X || !W || !bias || !out0 || !workspace || !aligned16(X) || !aligned16(W) || !aligned16(workspace) || ldx < k ||
         ldx % 8 != 0 || (epilogue == SQE_ENC_EPI_RES_F32 && !residual) ||
@@ -541,7 +554,8 @@ int sqe_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const floa
     int rc = device_info(&d);
     if (rc != SQE_OK) return rc;
     rc = launch_encoder_gemm_small(X, ldx, W, bias, m, n, k, epilogue, out0, ld0, out1, ld1, n_split, q_cols, q_scale,
-                                   residual, ldr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                                   residual, ldr, res_stats, res_gamma, res_beta, workspace, workspace_bytes,
+                                   static_cast<cudaStream_t>(stream));
     if (rc == -1) { set_error("encoder_gemm_small: shape not taken (m=%lld n=%d k=%d; m <= 128, n %% 128 == 0, n <= 4096)", (long long)m, n, k); return SQE_E_UNSUPPORTED; }
     return rc == 0 ? SQE_OK : SQE_E_CUDA;
 }
@@ -564,14 +578,18 @@ int sqe_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const i
     return rc_map(launch_encoder_attention(qk, vt, t_pad, tiles, n_tiles, max_len, ctx, static_cast<cudaStream_t>(stream)));
 }
 
-int sqe_encoder_pool(const float* h, const int32_t* first_token, int n_seq, float* out, int64_t ldo, void* stream) {
+int sqe_encoder_pool(const float* h, const int32_t* first_token, int n_seq, float* out, int64_t ldo, const float* stats,
+                     const float* gamma, const float* beta, void* stream) {
     if (n_seq < 0 || ldo < SQE_ENC_HIDDEN || ldo % 4 != 0) { set_error("encoder_pool: bad sizes"); return SQE_E_ARG; }
     if (n_seq == 0) return SQE_OK;
-    if (!h || !first_token || !out || !aligned16(h) || !aligned16(out)) { set_error("encoder_pool: null or unaligned pointer"); return SQE_E_ARG; }
+    if (!h || !first_token || !out || !aligned16(h) || !aligned16(out) || (stats && (!gamma || !beta || !aligned16(gamma) || !aligned16(beta)))) {
+        set_error("encoder_pool: null or unaligned pointer");
+        return SQE_E_ARG;
+    }
     DevInfo d;
     int rc = device_info(&d);
     if (rc != SQE_OK) return rc;
-    return rc_map(launch_encoder_pool(h, first_token, n_seq, out, ldo, static_cast<cudaStream_t>(stream)));
+    return rc_map(launch_encoder_pool(h, first_token, n_seq, out, ldo, stats, gamma, beta, static_cast<cudaStream_t>(stream)));
 }
 
 int sqe_encoder_forward(const SqeEncoderWeights* w, const SqeEncoderBuffers* b, const int32_t* ids, const int32_t* pos,
@@ -590,31 +608,45 @@ int sqe_encoder_forward(const SqeEncoderWeights* w, const SqeEncoderBuffers* b, 
     const bool small = g_enc_small == 0 && rows_used > 0 && rows_used <= 32 && b->small_ws != nullptr &&
                        b->small_ws_bytes >= encoder_gemm_small_workspace_bytes() && I <= 4096;
     const int64_t mg = small ? (rows_used + 15) / 16 * 16 : m;        // whole 16-row groups (filler rows are zeros)
+    // LayerNorm statistics form: a LayerNorm stores its fp16 output (the next operand) and {mean, rstd} per row;
+    // its fp32 output, needed only as the next residual, is recomputed in that GEMM's epilogue from the
+    // pre-LayerNorm sum (bit-identical).  sum_b = the sum the current residual comes from, sum_a the other buffer.
     auto gemm = [&](const void* X, int64_t ldx, const void* W, const float* bias, int n, int k, int epi, void* out0,
                     int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols, float q_scale, const float* res,
-                    int64_t ldr) {
+                    const float* rstats, const float* rgamma, const float* rbeta) {
         if (small)
             return sqe_encoder_gemm_small(X, ldx, W, bias, mg, n, k, epi, out0, ld0, out1, ld1, n_split, q_cols, q_scale,
-                                          res, ldr, b->small_ws, b->small_ws_bytes, stream);
-        return sqe_encoder_gemm(X, ldx, W, bias, mg, n, k, epi, out0, ld0, out1, ld1, n_split, q_cols, q_scale, res, ldr,
-                                stream);
+                                          res, H, rstats, rgamma, rbeta, b->small_ws, b->small_ws_bytes, stream);
+        return sqe_encoder_gemm(X, ldx, W, bias, mg, n, k, epi, out0, ld0, out1, ld1, n_split, q_cols, q_scale, res, H,
+                                rstats, rgamma, rbeta, stream);
     };
+    if (!b->sum_a || !b->sum_b || !b->stats_a || !b->stats_b) { set_error("encoder_forward: null buffer"); return SQE_E_ARG; }
     int rc = sqe_encoder_embed_ln(ids, pos, w->word_emb, w->vocab, w->pos_emb, w->max_pos, w->type_emb, w->emb_gamma,
-                                  w->emb_beta, w->eps, m, b->h32, b->h16, stream);
+                                  w->emb_beta, w->eps, m, b->sum_b, b->h16, b->stats_b, stream);
+    const float* pg = w->emb_gamma;                            // the LayerNorm whose output is the current residual
+    const float* pb = w->emb_beta;
     for (int l = 0; l < w->n_layers && rc == SQE_OK; ++l) {
         const SqeEncoderLayer& L = w->layers[l];
-        rc = gemm(b->h16, H, L.wqkv, L.bqkv, 3 * H, H, SQE_ENC_EPI_SPLIT, b->qk, 2 * H, b->vt, m, 2 * H, H, 0.125f, nullptr, 0);
+        rc = gemm(b->h16, H, L.wqkv, L.bqkv, 3 * H, H, SQE_ENC_EPI_SPLIT, b->qk, 2 * H, b->vt, m, 2 * H, H, 0.125f, nullptr,
+                  nullptr, nullptr, nullptr);
         if (rc == SQE_OK) rc = sqe_encoder_attention(b->qk, b->vt, m, tiles, n_tiles, max_len, b->ctx, stream);
         if (rc == SQE_OK)
-            rc = gemm(b->ctx, H, L.wo, L.bo, H, H, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f, b->h32, H);
-        if (rc == SQE_OK) rc = sqe_encoder_layernorm(b->sum32, L.ln1_gamma, L.ln1_beta, w->eps, m, b->h32, b->h16, stream);
+            rc = gemm(b->ctx, H, L.wo, L.bo, H, H, SQE_ENC_EPI_RES_F32, b->sum_a, H, nullptr, 0, 0, 0, 1.0f, b->sum_b,
+                      b->stats_b, pg, pb);
         if (rc == SQE_OK)
-            rc = gemm(b->h16, H, L.w1, L.b1, I, H, SQE_ENC_EPI_GELU, b->ffn, I, nullptr, 0, 0, 0, 1.0f, nullptr, 0);
+            rc = sqe_encoder_layernorm(b->sum_a, L.ln1_gamma, L.ln1_beta, w->eps, m, nullptr, b->h16, b->stats_a, stream);
         if (rc == SQE_OK)
-            rc = gemm(b->ffn, I, L.w2, L.b2, H, I, SQE_ENC_EPI_RES_F32, b->sum32, H, nullptr, 0, 0, 0, 1.0f, b->h32, H);
-        if (rc == SQE_OK) rc = sqe_encoder_layernorm(b->sum32, L.ln2_gamma, L.ln2_beta, w->eps, m, b->h32, b->h16, stream);
+            rc = gemm(b->h16, H, L.w1, L.b1, I, H, SQE_ENC_EPI_GELU, b->ffn, I, nullptr, 0, 0, 0, 1.0f, nullptr, nullptr,
+                      nullptr, nullptr);
+        if (rc == SQE_OK)
+            rc = gemm(b->ffn, I, L.w2, L.b2, H, I, SQE_ENC_EPI_RES_F32, b->sum_b, H, nullptr, 0, 0, 0, 1.0f, b->sum_a,
+                      b->stats_a, L.ln1_gamma, L.ln1_beta);
+        if (rc == SQE_OK)
+            rc = sqe_encoder_layernorm(b->sum_b, L.ln2_gamma, L.ln2_beta, w->eps, m, nullptr, b->h16, b->stats_b, stream);
+        pg = L.ln2_gamma;
+        pb = L.ln2_beta;
     }
-    if (rc == SQE_OK) rc = sqe_encoder_pool(b->h32, first_token, n_seq, out, ldo, stream);
+    if (rc == SQE_OK) rc = sqe_encoder_pool(b->sum_b, first_token, n_seq, out, ldo, b->stats_b, pg, pb, stream);
     return rc;
 }
 

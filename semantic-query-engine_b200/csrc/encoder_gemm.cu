@@ -73,6 +73,12 @@ struct GemmArgs {
     float q_scale;
     const float* residual;    // kEpiResF32: [m, ldr] fp32
     int64_t ldr;
+    // the residual is LayerNorm(residual) when res_stats != null: per row {mean, rstd} (written by the
+    // LayerNorm kernel, which then does not have to store its fp32 output at all) + that LayerNorm's
+    // gamma / beta; recomputed with the LayerNorm kernel's own operations, so the value is bit-identical
+    const float2* res_stats;
+    const float* res_gamma;
+    const float* res_beta;
     long long* dbg;           // diagnostics: [CTA][8] role timers in cycles (null in production)
 };
 
@@ -269,6 +275,16 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const int acc = i & 1;
             const int64_t row0 = static_cast<int64_t>(m_tile(t)) * C::kTileM + rank * kBM + quarter * 32;
             const int col_t = n_tile(t) * BN + half * (BN / 2);
+            [[maybe_unused]] float2 rst[8];                   // {mean, rstd} of this lane's 8 rows (every strip of the tile)
+            if constexpr (EPI == kEpiResF32) {
+                if (a.res_stats != nullptr) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int64_t row = row0 + 4 * g + sub_row;
+                        rst[g] = (row < a.m) ? __ldg(a.res_stats + row) : make_float2(0.f, 0.f);
+                    }
+                }
+            }
             ptx::mbar_wait(bar_tfull + 8 * acc, (i >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
@@ -305,6 +321,17 @@ encoder_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         const int64_t row = row0 + 4 * g + sub_row;
                         r4[g] = (row < a.m) ? __ldg(reinterpret_cast<const float4*>(a.residual + row * a.ldr + col0 + c4))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (a.res_stats != nullptr) {              // residual = LayerNorm(residual), as the LN kernel computes it
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.res_gamma + col0 + c4));
+                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.res_beta + col0 + c4));
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            r4[g].x = fmaf((r4[g].x - rst[g].x) * rst[g].y, g4.x, e4.x);
+                            r4[g].y = fmaf((r4[g].y - rst[g].x) * rst[g].y, g4.y, e4.y);
+                            r4[g].z = fmaf((r4[g].z - rst[g].x) * rst[g].y, g4.z, e4.z);
+                            r4[g].w = fmaf((r4[g].w - rst[g].x) * rst[g].y, g4.w, e4.w);
+                        }
                     }
                 }
                 ptx::tmem_wait_ld();
@@ -421,7 +448,8 @@ int g_enc_gemm_form = 0;        // 0 auto, 1 = <64, 1>, 2 = <256, 2> pairs, 3 = 
 
 int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                         int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
-                        float q_scale, const float* residual, int64_t ldr, int sm_count, cudaStream_t stream) {
+                        float q_scale, const float* residual, int64_t ldr, const float* res_stats,
+                        const float* res_gamma, const float* res_beta, int sm_count, cudaStream_t stream) {
     using namespace enc;
     GemmArgs a = {};
     a.m = m;
@@ -437,6 +465,9 @@ int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* 
     a.q_scale = q_scale;
     a.residual = residual;
     a.ldr = ldr;
+    a.res_stats = reinterpret_cast<const float2*>(res_stats);
+    a.res_gamma = res_gamma;
+    a.res_beta = res_beta;
     a.dbg = static_cast<long long*>(g_enc_gemm_debug);
     if (m == 0) return 0;
     // pairs once there are enough 256 x 256 tiles to occupy most of the chip

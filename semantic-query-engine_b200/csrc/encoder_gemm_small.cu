@@ -41,6 +41,9 @@ struct SmallArgs {
     float q_scale;
     const float* residual;
     int64_t ldr;
+    const float2* res_stats;  // != null: the residual is LayerNorm(residual) with these row statistics, gamma, beta
+    const float* res_gamma;
+    const float* res_beta;
     float* partials;          // [n / 128][splits][n_tok][128]
     unsigned* tickets;        // [n / 128], zero between launches
     int epi;
@@ -168,7 +171,16 @@ encoder_gemm_small_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
         }
         y[0] += bias.x; y[1] += bias.y; y[2] += bias.z; y[3] += bias.w;
         if (a.epi == kSEpiResF32) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + static_cast<int64_t>(t) * a.ldr + col));
+            float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + static_cast<int64_t>(t) * a.ldr + col));
+            if (a.res_stats != nullptr) {                      // as the LayerNorm kernel computes it (bit-identical)
+                const float2 st = __ldg(a.res_stats + t);
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.res_gamma + col));
+                const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.res_beta + col));
+                r.x = fmaf((r.x - st.x) * st.y, g4.x, e4.x);
+                r.y = fmaf((r.y - st.x) * st.y, g4.y, e4.y);
+                r.z = fmaf((r.z - st.x) * st.y, g4.z, e4.z);
+                r.w = fmaf((r.w - st.x) * st.y, g4.w, e4.w);
+            }
             *reinterpret_cast<float4*>(static_cast<float*>(a.out0) + static_cast<int64_t>(t) * a.ld0 + col) =
                 make_float4(y[0] + r.x, y[1] + r.y, y[2] + r.z, y[3] + r.w);
         } else if (a.epi == kSEpiSplit && col >= a.n_split) {
@@ -202,7 +214,8 @@ int64_t encoder_gemm_small_workspace_bytes() {
 // rows <= 128 token rows.  Returns -1 for arguments this form does not take (the caller falls back).
 int launch_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                               int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
-                              float q_scale, const float* residual, int64_t ldr, void* workspace, int64_t workspace_bytes,
+                              float q_scale, const float* residual, int64_t ldr, const float* res_stats,
+                              const float* res_gamma, const float* res_beta, void* workspace, int64_t workspace_bytes,
                               cudaStream_t stream) {
     using namespace enc;
     if (m < 1 || m > 128 || n % 128 != 0 || n > 4096 || k % kChunkK != 0 || workspace == nullptr ||
@@ -229,6 +242,9 @@ int launch_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const f
     a.q_scale = q_scale;
     a.residual = residual;
     a.ldr = ldr;
+    a.res_stats = reinterpret_cast<const float2*>(res_stats);
+    a.res_gamma = res_gamma;
+    a.res_beta = res_beta;
     a.epi = epilogue;
     a.tickets = static_cast<unsigned*>(workspace);
     a.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 4096);

@@ -61,21 +61,23 @@ int launch_cache_finalize(const float* score, const int64_t* idx, int b, double 
 // ENC  embedding encoder (encoder_gemm.cu, encoder_attn.cu, encoder_rows.cu)
 int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                         int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
-                        float q_scale, const float* residual, int64_t ldr, int sm_count, cudaStream_t stream);
+                        float q_scale, const float* residual, int64_t ldr, const float* res_stats,
+                        const float* res_gamma, const float* res_beta, int sm_count, cudaStream_t stream);
 int64_t encoder_gemm_small_workspace_bytes();
 int launch_encoder_gemm_small(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                               int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
-                              float q_scale, const float* residual, int64_t ldr, void* workspace, int64_t workspace_bytes,
+                              float q_scale, const float* residual, int64_t ldr, const float* res_stats,
+                              const float* res_gamma, const float* res_beta, void* workspace, int64_t workspace_bytes,
                               cudaStream_t stream);
 int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const void* tiles, int n_tiles,
                              int max_len, void* ctx, cudaStream_t stream);
 int launch_encoder_layernorm(const float* in, const float* gamma, const float* beta, float eps, int64_t rows,
-                             float* out32, void* out16, cudaStream_t stream);
+                             float* out32, void* out16, float* stats, cudaStream_t stream);
 int launch_encoder_embed_ln(const int32_t* ids, const int32_t* pos, const float* word, const float* position,
                             const float* type0, const float* gamma, const float* beta, float eps, int64_t rows,
-                            int vocab, int max_pos, float* out32, void* out16, cudaStream_t stream);
+                            int vocab, int max_pos, float* out32, void* out16, float* stats, cudaStream_t stream);
 int launch_encoder_pool(const float* h, const int32_t* first_token, int n_seq, float* out, int64_t ldo,
-                        cudaStream_t stream);
+                        const float* stats, const float* gamma, const float* beta, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 

@@ -294,8 +294,10 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
 
 def gemm(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int, out0: torch.Tensor, *,
          m: Optional[int] = None, out1: Optional[torch.Tensor] = None, n_split: int = 0, q_cols: int = 0,
-         q_scale: float = 1.0, residual: Optional[torch.Tensor] = None) -> None:
-    """`sqe_encoder_gemm` on the current stream: out0 (+ out1) = epilogue(x[:m] @ w.T + bias)."""
+         q_scale: float = 1.0, residual: Optional[torch.Tensor] = None, res_stats: Optional[torch.Tensor] = None,
+         res_gamma: Optional[torch.Tensor] = None, res_beta: Optional[torch.Tensor] = None) -> None:
+    """`sqe_encoder_gemm` on the current stream: out0 (+ out1) = epilogue(x[:m] @ w.T + bias).  With
+    `res_stats` ([rows, 2] = mean, rstd) the residual operand is LayerNorm(residual) recomputed on the fly."""
     dev = x.device
     if not x.is_cuda:
         raise RuntimeError("sqe_b200 has no CPU path: tensors must live on a CUDA device")
@@ -304,16 +306,17 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int, ou
     with torch.cuda.device(dev):
         nat.call("sqe_encoder_gemm", x.data_ptr(), x.stride(0), w.data_ptr(), bias.data_ptr(), m, n, k, epilogue,
                  out0.data_ptr(), out0.stride(0), _ptr(out1), 0 if out1 is None else out1.stride(0), n_split, q_cols,
-                 q_scale, _ptr(residual), 0 if residual is None else residual.stride(0),
-                 torch.cuda.current_stream(dev).cuda_stream)
+                 q_scale, _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(res_stats), _ptr(res_gamma),
+                 _ptr(res_beta), torch.cuda.current_stream(dev).cuda_stream)
 
 
-def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps: float, out32: torch.Tensor,
-              out16: torch.Tensor, rows: Optional[int] = None) -> None:
+def layernorm(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps: float, out32: Optional[torch.Tensor],
+              out16: torch.Tensor, rows: Optional[int] = None, stats: Optional[torch.Tensor] = None) -> None:
+    """`sqe_encoder_layernorm`; with `stats` ([rows, 2]) the row statistics are written and out32 may be None."""
     dev = x.device
     with torch.cuda.device(dev):
         nat.call("sqe_encoder_layernorm", x.data_ptr(), g.data_ptr(), b.data_ptr(), eps,
-                 x.shape[0] if rows is None else rows, out32.data_ptr(), out16.data_ptr(),
+                 x.shape[0] if rows is None else rows, _ptr(out32), out16.data_ptr(), _ptr(stats),
                  torch.cuda.current_stream(dev).cuda_stream)
 
 
@@ -331,9 +334,11 @@ class _Buffers:
     def __init__(self, t_pad: int, inter: int, dev: torch.device):
         z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=dev)          # noqa: E731
         self.t_pad = t_pad
-        self.h32 = z(t_pad, HIDDEN, dt=torch.float32)      # residual stream
-        self.h16 = z(t_pad, HIDDEN, dt=torch.float16)      # its tensor-core operand copy
-        self.sum32 = z(t_pad, HIDDEN, dt=torch.float32)    # pre-LayerNorm sums
+        self.sum_a = z(t_pad, HIDDEN, dt=torch.float32)    # pre-LayerNorm sums = the fp32 residual stream (ping-pong):
+        self.sum_b = z(t_pad, HIDDEN, dt=torch.float32)    # a LayerNorm's fp32 output is recomputed where it is needed
+        self.stats_a = z(t_pad, 2, dt=torch.float32)       # {mean, rstd} of the rows of sum_a / sum_b
+        self.stats_b = z(t_pad, 2, dt=torch.float32)
+        self.h16 = z(t_pad, HIDDEN, dt=torch.float16)      # LayerNorm output as the next tensor-core operand
         self.qk = z(t_pad, 2 * HIDDEN, dt=torch.float16)   # Q / 8 | K
         self.vt = z(HIDDEN, t_pad, dt=torch.float16)       # V^T
         self.ctx = z(t_pad, HIDDEN, dt=torch.float16)
@@ -350,7 +355,8 @@ class _Buffers:
         self.small_ws = None
         if t_pad <= 128:
             self.small_ws = torch.zeros(int(nat.load().sqe_encoder_gemm_small_workspace_bytes()), dtype=torch.uint8, device=dev)
-        self.c = nat.SqeEncoderBuffers(t_pad, self.h32.data_ptr(), self.h16.data_ptr(), self.sum32.data_ptr(),
+        self.c = nat.SqeEncoderBuffers(t_pad, self.sum_a.data_ptr(), self.sum_b.data_ptr(), self.stats_a.data_ptr(),
+                                       self.stats_b.data_ptr(), self.h16.data_ptr(),
                                        self.qk.data_ptr(), self.vt.data_ptr(), self.ctx.data_ptr(), self.ffn.data_ptr(),
                                        0 if self.small_ws is None else self.small_ws.data_ptr(),
                                        0 if self.small_ws is None else self.small_ws.numel())

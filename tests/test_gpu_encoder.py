@@ -126,7 +126,8 @@ def test_gemm_small_swap_ab_split_k(sqe, m, n, k, epi):
             out1 = torch.full((H, 128), 7.0, device=dev(), dtype=torch.float16)
         nat.call("sqe_encoder_gemm_small", x.data_ptr(), k, w.data_ptr(), bias.data_ptr(), m, n, k, epi, out0.data_ptr(),
                  out0.stride(0), 0 if out1 is None else out1.data_ptr(), 128, 2 * H if epi == 0 else 0, H if epi == 0 else 0,
-                 0.125, res.data_ptr() if epi == 1 else 0, n, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                 0.125, res.data_ptr() if epi == 1 else 0, n, 0, 0, 0, ws.data_ptr(), ws.numel(),
+                 torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         outs.append((out0, out1))
     assert torch.equal(outs[0][0], outs[1][0]) and not ws[:4096].any()
@@ -192,6 +193,53 @@ def test_layernorm_matches_torch(sqe):
     assert bool((o32[5] - beta).abs().max() < 1e-6)
 
 
+def test_layernorm_statistics_form_is_bit_identical(sqe, gemm_form):
+    """The form the forward pass uses: LayerNorm stores only its fp16 output + {mean, rstd}; the residual
+    GEMM (both tile forms and the few-token form) recomputes the fp32 output from the pre-LayerNorm sum.
+    Same bits as LayerNorm-then-plain-residual."""
+    nat = sqe._native
+    g = _gen(77 + gemm_form)
+    m, n, k = 300, H, H
+    pre = _randn(g, m, H, s=2.0) + 0.5                                            # the pre-LayerNorm sum
+    gamma, beta = 1.0 + _randn(g, H, s=0.2), _randn(g, H, s=0.2)
+    o32 = torch.empty_like(pre)
+    o16 = torch.empty((m, H), device=dev(), dtype=torch.float16)
+    sqe.encoder.layernorm(pre, gamma, beta, 1e-12, o32, o16)                      # plain form
+    stats = torch.zeros((m, 2), device=dev())
+    o16s = torch.empty_like(o16)
+    sqe.encoder.layernorm(pre, gamma, beta, 1e-12, None, o16s, stats=stats)       # statistics form
+    assert torch.equal(o16, o16s)
+    mean = pre.mean(dim=1)
+    assert float((stats[:, 0] - mean).abs().max()) < 1e-5
+    x = _randn(g, m, k, dtype=torch.float16)
+    w = _randn(g, n, k, s=0.03, dtype=torch.float16)
+    bias = _randn(g, n, s=0.5)
+    a = torch.empty((m, n), device=dev())
+    b = torch.empty((m, n), device=dev())
+    sqe.encoder.gemm(x, w, bias, nat.SQE_ENC_EPI_RES_F32, a, residual=o32)
+    sqe.encoder.gemm(x, w, bias, nat.SQE_ENC_EPI_RES_F32, b, residual=pre, res_stats=stats, res_gamma=gamma, res_beta=beta)
+    assert torch.equal(a, b)
+    # few-token form (16 rows)
+    ws = torch.zeros(int(nat.load().sqe_encoder_gemm_small_workspace_bytes()), dtype=torch.uint8, device=dev())
+    outs = []
+    for res, st in ((o32, None), (pre, stats)):
+        o = torch.zeros((16, n), device=dev())
+        nat.call("sqe_encoder_gemm_small", x.data_ptr(), k, w.data_ptr(), bias.data_ptr(), 16, n, k, 1, o.data_ptr(), n, 0, 0,
+                 0, 0, 1.0, res.data_ptr(), H, 0 if st is None else st.data_ptr(), 0 if st is None else gamma.data_ptr(),
+                 0 if st is None else beta.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    # pooling from the sum + statistics
+    first = torch.tensor([0, 7, 299], dtype=torch.int32, device=dev())
+    p0 = torch.empty((3, H), device=dev())
+    p1 = torch.empty((3, H), device=dev())
+    nat.call("sqe_encoder_pool", o32.data_ptr(), first.data_ptr(), 3, p0.data_ptr(), H, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+    nat.call("sqe_encoder_pool", pre.data_ptr(), first.data_ptr(), 3, p1.data_ptr(), H, stats.data_ptr(), gamma.data_ptr(),
+             beta.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(p0, p1) and torch.equal(p0, o32[first.long()])
+
+
 def test_embed_ln_matches_torch(sqe):
     nat = sqe._native
     g = _gen(4)
@@ -205,12 +253,27 @@ def test_embed_ln_matches_torch(sqe):
     o16 = torch.full((rows, H), 9.0, device=dev(), dtype=torch.float16)
     nat.call("sqe_encoder_embed_ln", ids.data_ptr(), pos.data_ptr(), word.data_ptr(), vocab, pos_e.data_ptr(),
              max_pos, type_e[0].contiguous().data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-12, rows,
-             o32.data_ptr(), o16.data_ptr(), torch.cuda.current_stream().cuda_stream)
+             o32.data_ptr(), o16.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
     safe = ids.clamp(min=0).long()
     want = torch.nn.functional.layer_norm((word[safe] + type_e[0]) + pos_e[pos.long()], (H,), gamma, beta, eps=1e-12)
     want[[7, 100]] = 0.0
     assert float((o32 - want).abs().max()) < 2e-5
     assert torch.equal(o16, o32.half())
+    # statistics form: out_f32 = the PRE-LayerNorm sum, stats = {mean, rstd}; the fp16 output is the same
+    s32 = torch.full((rows, H), 9.0, device=dev())
+    s16 = torch.full((rows, H), 9.0, device=dev(), dtype=torch.float16)
+    stats = torch.full((rows, 2), 9.0, device=dev())
+    nat.call("sqe_encoder_embed_ln", ids.data_ptr(), pos.data_ptr(), word.data_ptr(), vocab, pos_e.data_ptr(),
+             max_pos, type_e[0].contiguous().data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-12, rows,
+             s32.data_ptr(), s16.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    pre = (word[safe] + type_e[0]) + pos_e[pos.long()]
+    pre[[7, 100]] = 0.0
+    assert torch.equal(s32, pre) and torch.equal(s16, o16)
+    keep = torch.ones(rows, dtype=torch.bool, device=dev())
+    keep[[7, 100]] = False
+    assert float((stats[keep, 0] - pre[keep].mean(dim=1)).abs().max()) < 1e-5
+    recomputed = torch.addcmul(beta, (s32 - stats[:, :1]) * stats[:, 1:], gamma)
+    assert float((recomputed[keep] - o32[keep]).abs().max()) < 1e-6
 
 
 # ------------------------------------------------------------------------------- attention

@@ -60,6 +60,30 @@ def test_oracle_matches_transformers_live_at_hidden_1024():
         assert float((got - want[i, : len(s)]).abs().max()) < 5e-5
 
 
+def test_oracle_matches_transformers_live_at_full_depth():
+    """All 24 layers of the mxbai-embed-large geometry (seeded weights of the oracle loaded into the
+    library's BertModel), CLS embeddings of a padded, masked batch: the quantity the GPU tests compare."""
+    tr = pytest.importorskip("transformers")
+    w = bo.random_bert_weights(9, layers=24, vocab=300)
+    cfg = tr.BertConfig(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                        vocab_size=300, max_position_embeddings=512)
+    m = tr.BertModel(cfg, add_pooling_layer=False).eval()
+    missing, unexpected = m.load_state_dict(w, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing)
+    g = torch.Generator().manual_seed(4)
+    seqs = [torch.randint(0, 300, (n,), generator=g).tolist() for n in (5, 40, 17)]
+    L = max(map(len, seqs))
+    ids = torch.zeros(len(seqs), L, dtype=torch.long)
+    mask = torch.zeros(len(seqs), L, dtype=torch.long)
+    for i, s in enumerate(seqs):
+        ids[i, : len(s)] = torch.tensor(s)
+        mask[i, : len(s)] = 1
+    with torch.no_grad():
+        want = m(input_ids=ids, attention_mask=mask).last_hidden_state[:, 0]
+    got = bo.bert_embed(w, seqs)
+    assert float((got - want).abs().max()) < 2e-4                     # fp32 round-off through 24 blocks
+
+
 def test_tokenizers_agree_with_the_library_golden():
     d = json.load(open(os.path.join(GOLDEN, "bert_wordpiece.json"), encoding="utf-8"))
     vocab = {t: i for i, t in enumerate(d["vocab"])}

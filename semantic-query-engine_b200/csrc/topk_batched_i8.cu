@@ -52,9 +52,18 @@ struct CfgI8 {
     static constexpr int kQTile = kRowsPerCta * CG;
     static constexpr int kBRows = kTileN / CG;
     static constexpr int kBBytes = kBRows * kChunkI8;
-    static constexpr int kStageBytes = kABytes + kBBytes;          // 48 KB / 32 KB, as for 16-bit operands
+    // ASTAT (pairs with several q-tiles in flight, i.e. b > 256): the unit's int8 QUERY tile stays in
+    // shared memory for the whole kernel (128 rows x 1024 B = 128 KB per CTA -- half of what a 16-bit
+    // tile needs, which is why K2 cannot do this) and only the shard rows stream through the ring.
+    // Without it every d-tile re-fetches the query tile from L2: 32 KB per K chunk and CTA = 128 B per
+    // SM clock at the int8 rate, three times what the L2 delivers (~43 B per SM clock chip-wide): the
+    // main loop alone took 6.8 ms for a floor of 3.6.  With it the ring carries 16 KB per chunk.
+    static constexpr bool kAStat = (CG == 2) && !DEEP;
+    static constexpr int kAResident = kAStat ? kNumChunksI8 * kABytes : 0;      // 128 KB
+    static constexpr int kStageBytes = (kAStat ? 0 : kABytes) + kBBytes;   // 48 KB / 32 KB as for 16-bit operands; 16 KB
     static constexpr int kStages = (CG == 1) ? 4 : (DEEP ? 6 : 4);
-    static constexpr int kOffMeta = kStages * kStageBytes;
+    static constexpr int kOffStages = kAResident;
+    static constexpr int kOffMeta = kOffStages + kStages * kStageBytes;
     static constexpr int kOffXbuf = kOffMeta + kMetaBufs * kMetaBytes;     // per epilogue warp: 32 words of transpose
     static constexpr int kXbufWords = 32 + kTileN;                         // buffer + the tile's 256 row scales, packed
     static constexpr int kOffThr = kOffXbuf + 4 * kXbufWords * 4;
@@ -299,6 +308,9 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const uint32_t bar_tfull = bar_empty + 8 * kStages;        // [2]
     const uint32_t bar_tempty = bar_tfull + 16;                // [2]
     const uint32_t bar_meta = bar_tempty + 16;                 // [kMetaBufs]
+    const uint32_t bar_a = bar_meta + 8 * kMetaBufs;           // ASTAT: the resident query tile has landed
+    constexpr bool ASTAT = C::kAStat;
+    const uint32_t stage0 = base + C::kOffStages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + C::kOffTmemPtr);
     uint32_t* epi_done = tmem_ptr_smem + 1;
 
@@ -314,6 +326,7 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             ptx::mbar_init(bar_tempty + 8 * acc, 4 * CG);
         }
         for (int m = 0; m < kMetaBufs; ++m) ptx::mbar_init(bar_meta + 8 * m, 1);
+        ptx::mbar_init(bar_a, 1);
         *epi_done = 0u;
         ptx::fence_barrier_init();
     }
@@ -339,6 +352,14 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             // its slowest unit does, so waiting costs nothing.
             uint32_t* my_prog = a.ws_prog + group * n_qt;
             const bool gate = (rank == 0) && (n_qt > 1) && (a.window > 0);
+            if constexpr (ASTAT) {
+                if (my_tiles > 0) {                              // the query tile, once: eight 16 KB chunks per CTA
+                    if (rank == 0) ptx::mbar_expect_tx(bar_a, 2 * C::kAResident);
+                    const uint32_t ab = ptx::mapa(bar_a, 0);
+                    for (int kc = 0; kc < kNumChunksI8; ++kc)
+                        ptx::tma_load_3d_cg2(base + kc * kABytes, &tmap_q, kc * kChunkI8, 0, q_row, ab, pol_q);
+                }
+            }
             for (int i = 0; i < my_tiles; ++i) {
                 const int t = group + i * n_groups;
                 const int d_row = t * kTileN + static_cast<int>(rank) * C::kBRows;
@@ -366,12 +387,16 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                         bulk_copy_g2s(base + C::kOffMeta + mb * kMetaBytes, a.meta + static_cast<size_t>(t) * kTileN,
                                       rows * 16u, bar_meta + 8 * mb);
                     }
-                    const uint32_t sa = base + stage * C::kStageBytes;
+                    const uint32_t sa = stage0 + stage * C::kStageBytes;
                     if constexpr (CG == 1) {
                         const uint32_t fb = bar_full + 8 * stage;
                         ptx::mbar_expect_tx(fb, C::kStageBytes);
                         ptx::tma_load_3d_hint(sa, &tmap_q, kc * kChunkI8, 0, q_row, fb, pol_q);
                         ptx::tma_load_3d(sa + kABytes, &tmap_d, kc * kChunkI8, 0, d_row, fb);
+                    } else if constexpr (ASTAT) {
+                        if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
+                        const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
+                        ptx::tma_load_3d_cg2_nohint(sa, &tmap_d, kc * kChunkI8, 0, d_row, fb);      // shard rows only
                     } else {
                         if (rank == 0) ptx::mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);
                         const uint32_t fb = ptx::mapa(bar_full + 8 * stage, 0);
@@ -388,6 +413,12 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         if (lane == 0 && rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (ASTAT) {
+                if (my_tiles > 0) {
+                    ptx::mbar_wait(bar_a, 0);                   // the resident query tile (both CTAs' halves)
+                    ptx::tc_fence_after();
+                }
+            }
             for (int i = 0; i < my_tiles; ++i) {
                 const int acc = i & 1;
                 const uint32_t acc_phase = (i >> 1) & 1;
@@ -397,9 +428,9 @@ topk_batched_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 for (int kc = 0; kc < kNumChunksI8; ++kc) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = base + stage * C::kStageBytes;
-                    const uint64_t da = make_sw128_desc(sa);
-                    const uint64_t db = make_sw128_desc(sa + kABytes);
+                    const uint32_t sa = stage0 + stage * C::kStageBytes;
+                    const uint64_t da = make_sw128_desc(ASTAT ? base + kc * kABytes : sa);
+                    const uint64_t db = make_sw128_desc(ASTAT ? sa : sa + kABytes);
 #pragma unroll
                     for (int k4 = 0; k4 < kChunkI8 / kUmmaKI8; ++k4)     // 32 int8 = 32 bytes: +2 in 16-B units
                         umma_i8(tmem_d, da + 2 * k4, db + 2 * k4, a.idesc, (kc | k4) != 0 ? 1u : 0u, CG == 2);

@@ -19,11 +19,11 @@ from .corpus import EMBED_DIM, GpuCorpusIndex
 from .sharded import ShardedCorpusIndex, shard_bounds
 from .serving import MicroBatcher, UserIndexRegistry, build_context_text, group_hits_by_doc
 from .encoder import EncoderWeights, GpuEmbeddingEncoder, WordPieceTokenizer, install_encoder
-from . import encoder, ops, plugin
+from . import encoder, gguf_model, ops, plugin
 
 __all__ = [
     "GpuCorpusIndex", "GpuQueryCache", "cosine_similarity", "ShardedCorpusIndex", "shard_bounds", "ops", "plugin",
     "MicroBatcher", "UserIndexRegistry", "build_context_text", "group_hits_by_doc",
     "NativeLibraryMissing", "SqeError", "EMBED_DIM", "CACHE_SIM_THRESHOLD", "REDIS_MAX_ITEMS",
-    "REDIS_CACHE_LIST", "GpuEmbeddingEncoder", "EncoderWeights", "WordPieceTokenizer", "install_encoder", "encoder",
+    "REDIS_CACHE_LIST", "GpuEmbeddingEncoder", "EncoderWeights", "WordPieceTokenizer", "install_encoder", "encoder", "gguf_model",
 ]

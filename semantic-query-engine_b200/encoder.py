@@ -99,6 +99,16 @@ class WordPieceTokenizer:
             vocab = {line.rstrip("\n"): i for i, line in enumerate(f)}
         return cls(vocab, **kw)
 
+    @classmethod
+    def from_gguf(cls, path_or_file, **kw) -> "WordPieceTokenizer":
+        """The vocabulary inside a BERT GGUF file -- the blob an Ollama server holds for
+        `mxbai-embed-large` (gguf_model.py restores BERT's own spelling of the pieces)."""
+        from . import gguf_model as gm
+        if isinstance(path_or_file, gm.GgufFile):
+            return cls(gm.wordpiece_vocab(path_or_file), **kw)
+        with gm.GgufFile(path_or_file) as g:
+            return cls(gm.wordpiece_vocab(g), **kw)
+
     def _split(self, text: str) -> List[str]:
         """Words and single punctuation / CJK characters, in order.  One `str.translate` (drop
         control characters, blank out whitespace, put spaces around punctuation and CJK) and one
@@ -227,6 +237,30 @@ class EncoderWeights:
         else:
             sd = torch.load(path, map_location="cpu", weights_only=True)
         return cls.from_state_dict(sd, device=device)
+
+    @classmethod
+    def from_gguf(cls, path_or_file, device=None) -> "EncoderWeights":
+        """A BERT GGUF file (what `ollama pull mxbai-embed-large` stores; F32 / F16 / BF16 / Q8_0 / Q4_0 /
+        Q4_1 tensors).  The file's hyper-parameters must be the ones the kernels are built for: 16 heads of
+        64, hidden 1024, CLS pooling, bidirectional attention."""
+        from . import gguf_model as gm
+        g = path_or_file if isinstance(path_or_file, gm.GgufFile) else gm.GgufFile(path_or_file)
+        try:
+            sd, cfg = gm.bert_state_dict(g)
+        finally:
+            if g is not path_or_file:
+                g.close()
+        if cfg["heads"] != HEADS or cfg["hidden"] != HIDDEN:
+            raise ValueError(f"{cfg['heads']} heads x hidden {cfg['hidden']}: the kernels are built for "
+                             f"{HEADS} x {HIDDEN} (mxbai-embed-large)")
+        if cfg["pooling"] not in (gm.POOLING_CLS, gm.POOLING_NONE):
+            raise ValueError(f"pooling type {cfg['pooling']}: the encoder returns the [CLS] state (pooling type "
+                             f"{gm.POOLING_CLS}, what mxbai-embed-large uses)")
+        if cfg["causal"]:
+            raise ValueError("causal attention: not a BERT encoder")
+        if cfg["max_positions"] > MAX_TOKENS:
+            raise ValueError(f"{cfg['max_positions']} positions: the kernels are built for {MAX_TOKENS}")
+        return cls.from_state_dict(sd, device=device, eps=cfg["eps"])
 
     @classmethod
     def random_init(cls, seed: int = 0, layers: int = 24, device=None, vocab: int = 30522,
@@ -389,6 +423,24 @@ class GpuEmbeddingEncoder:
         self.graph_max_tokens = graph_max_tokens
         self.graph_replays = 0
         nat.load()                                          # fail loudly when the CUDA library is missing
+
+    @classmethod
+    def from_gguf(cls, path: str, device=None, **kw) -> "GpuEmbeddingEncoder":
+        """Weights AND vocabulary from one BERT GGUF file."""
+        from . import gguf_model as gm
+        with gm.GgufFile(path) as g:
+            tok = WordPieceTokenizer.from_gguf(g)
+            w = EncoderWeights.from_gguf(g, device=device)
+        return cls(w, tok, **kw)
+
+    @classmethod
+    def from_ollama(cls, name: str = "mxbai-embed-large", models_dir: Optional[str] = None, device=None,
+                    **kw) -> "GpuEmbeddingEncoder":
+        """The model the reference asks its Ollama server for (`EMBED_MODEL_NAME`, app/main.py:29),
+        loaded from that server's model store (`~/.ollama/models` or $OLLAMA_MODELS) instead of
+        being called over HTTP."""
+        from . import gguf_model as gm
+        return cls.from_gguf(gm.find_ollama_model(name, models_dir), device=device, **kw)
 
     # ------------------------------------------------------------------ device forward
     def _buffers(self, t_pad: int) -> _Buffers:

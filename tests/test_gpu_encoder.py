@@ -566,3 +566,44 @@ def test_random_length_mixes_against_the_oracle(sqe):
         worst = max(worst, err)
         assert err < 1e-2, (trial, lens, err)
     assert worst > 0.0
+
+
+def test_the_ollama_model_file_loads_and_runs(sqe, tmp_path):
+    """The deployment's own checkpoint: a BERT GGUF file (written here by the `gguf` library the way
+    llama.cpp's converter writes mxbai-embed-large: F16 matrices, F32 vectors / position table, rewritten
+    vocabulary) inside an Ollama model store.  `GpuEmbeddingEncoder.from_ollama` finds the blob through
+    the manifest, reads weights AND vocabulary from it; the embeddings are bit-identical to an encoder
+    built from the tensors the file holds, and agree with the oracle on the ORIGINAL fp32 weights within
+    the fp16 storage error.  A Q8_0 file of the same model loads too."""
+    pytest.importorskip("gguf")
+    import json
+    from gguf_fixture import write_bert_gguf
+    w = bo.random_bert_weights(77, layers=2, vocab=len(VOCAB))
+    root = tmp_path / "models"
+    (root / "blobs").mkdir(parents=True)
+    digest = "sha256:" + "5e" * 32
+    blob = root / "blobs" / digest.replace(":", "-")
+    held = write_bert_gguf(str(blob), w, VOCAB, ftype="f16")
+    man = root / "manifests" / "registry.ollama.ai" / "library" / "mxbai-embed-large"
+    man.mkdir(parents=True)
+    (man / "latest").write_text(json.dumps({"schemaVersion": 2, "layers": [
+        {"mediaType": "application/vnd.ollama.image.model", "digest": digest}]}))
+    e = sqe.GpuEmbeddingEncoder.from_ollama("mxbai-embed-large", models_dir=str(root), device=dev())
+    assert len(e.w.layers) == 2 and e.w.vocab_size == len(VOCAB) and e.tok.cls_id == VOCAB.index("[CLS]")
+    texts = ["the cells bind the protein.", "gene expression, tumor cells?", "patient " * 200, "x"]
+    got = e.embed_texts(texts)
+    vocab = {t: i for i, t in enumerate(VOCAB)}
+    same = sqe.GpuEmbeddingEncoder(
+        sqe.EncoderWeights.from_state_dict({k: torch.from_numpy(v) for k, v in held.items()}, device=dev()),
+        sqe.WordPieceTokenizer(vocab))
+    assert np.array_equal(got, same.embed_texts(texts))
+    seqs = [bo.encode_text(t, vocab) for t in texts]
+    want = bo.bert_embed(w, seqs).numpy()
+    assert np.abs(got - want).max() < 2e-2
+    cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
+    assert cos.min() > 0.9999
+    q8 = str(tmp_path / "q8.gguf")
+    write_bert_gguf(q8, w, VOCAB, ftype="q8_0")
+    got8 = sqe.GpuEmbeddingEncoder.from_gguf(q8, device=dev()).embed_texts(texts)
+    cos8 = (got8 * want).sum(1) / (np.linalg.norm(got8, axis=1) * np.linalg.norm(want, axis=1))
+    assert cos8.min() > 0.999

@@ -11,12 +11,12 @@
 namespace sqe {
 
 static thread_local char g_err[512] = "";
-int g_k2_cta_group = 0;
-void* g_k2_debug = nullptr;
-int g_k2_epilogue_mode = 0;
-int g_k2_d_hint = 0;
-int g_k2_window = 0;
-int g_enc_small = 0;
+std::atomic<int> g_k2_cta_group{0};
+std::atomic<void*> g_k2_debug{nullptr};
+std::atomic<int> g_k2_epilogue_mode{0};
+std::atomic<int> g_k2_d_hint{0};
+std::atomic<int> g_k2_window{0};
+std::atomic<int> g_enc_small{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -87,34 +87,22 @@ const char* sqe_last_error(void) { return g_err; }
 
 int sqe_tuning_set(int knob, int value) {
     if (knob == SQE_TUNE_K2_CTA_GROUP && value >= 0 && value <= 2) {
-        const int old = g_k2_cta_group;
-        g_k2_cta_group = value;
-        return old;
+        return g_k2_cta_group.exchange(value);
     }
     if (knob == SQE_TUNE_K2_EPILOGUE_MODE && value >= 0 && value <= 3) {
-        const int old = g_k2_epilogue_mode;
-        g_k2_epilogue_mode = value;
-        return old;
+        return g_k2_epilogue_mode.exchange(value);
     }
     if (knob == SQE_TUNE_K2_WINDOW && value >= -1 && value <= 1024) {
-        const int old = g_k2_window;
-        g_k2_window = value;
-        return old;
+        return g_k2_window.exchange(value);
     }
     if (knob == SQE_TUNE_K2_D_HINT && value >= 0 && value <= 4) {
-        const int old = g_k2_d_hint;
-        g_k2_d_hint = value;
-        return old;
+        return g_k2_d_hint.exchange(value);
     }
     if (knob == SQE_TUNE_ENC_SMALL && value >= 0 && value <= 1) {
-        const int old = g_enc_small;
-        g_enc_small = value;
-        return old;
+        return g_enc_small.exchange(value);
     }
     if (knob == SQE_TUNE_ENC_GEMM_FORM && value >= 0 && value <= 4) {
-        const int old = g_enc_gemm_form;
-        g_enc_gemm_form = value;
-        return old;
+        return g_enc_gemm_form.exchange(value);
     }
     set_error("tuning_set: unknown knob %d / value %d", knob, value);
     return SQE_E_ARG;
@@ -605,7 +593,7 @@ int sqe_encoder_forward(const SqeEncoderWeights* w, const SqeEncoderBuffers* b, 
     if (rows_used < 0 || rows_used > m) { set_error("encoder_forward: rows_used out of range"); return SQE_E_ARG; }
     // a handful of tokens (one or two queries): the swap-AB split-K form of the four products; its last-CTA
     // reduction grows with the token count, beyond 32 rows the 128 x 64 tiles are as fast
-    const bool small = g_enc_small == 0 && rows_used > 0 && rows_used <= 32 && b->small_ws != nullptr &&
+    const bool small = g_enc_small.load() == 0 && rows_used > 0 && rows_used <= 32 && b->small_ws != nullptr &&
                        b->small_ws_bytes >= encoder_gemm_small_workspace_bytes() && I <= 4096;
     const int64_t mg = small ? (rows_used + 15) / 16 * 16 : m;        // whole 16-row groups (filler rows are zeros)
     // LayerNorm statistics form: a LayerNorm stores its fp16 output (the next operand) and {mean, rstd} per row;

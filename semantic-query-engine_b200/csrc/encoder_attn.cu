@@ -337,7 +337,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __gr
 
 }  // namespace enc
 
-void* g_enc_attn_debug = nullptr;      // diagnostics: device buffer [entries * 16][8] i64 of cycles per phase
+std::atomic<void*> g_enc_attn_debug{nullptr};     // diagnostics: device buffer [entries * 16][8] i64 of cycles per phase
 
 int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, const void* tiles, int n_tiles,
                              int max_len, void* ctx, cudaStream_t stream) {
@@ -347,7 +347,7 @@ int launch_encoder_attention(const void* qk, const void* vt, int64_t t_pad, cons
     a.tiles = static_cast<const int4*>(tiles);
     a.ctx = static_cast<__half*>(ctx);
     a.s_max = (max_len + 63) & ~63;
-    a.dbg = static_cast<long long*>(g_enc_attn_debug);
+    a.dbg = static_cast<long long*>(g_enc_attn_debug.load());
     a.tmem_cols = 64;
     while (a.tmem_cols < static_cast<uint32_t>(a.s_max)) a.tmem_cols *= 2;
     CUtensorMap tq, tv;

@@ -443,8 +443,8 @@ static int launch_gemm_t(const void* X, const void* W, GemmArgs a, int64_t ldx, 
 
 }  // namespace enc
 
-void* g_enc_gemm_debug = nullptr;     // diagnostics: device buffer [grid][8] i64 of role timers
-int g_enc_gemm_form = 0;        // 0 auto, 1 = <64, 1>, 2 = <256, 2> pairs, 3 = <256, 2> in clusters of four (X multicast)
+std::atomic<void*> g_enc_gemm_debug{nullptr};    // diagnostics: device buffer [grid][8] i64 of role timers
+std::atomic<int> g_enc_gemm_form{0};     // 0 auto, 1 = <64, 1>, 2 = <256, 2> pairs, 3 = <256, 2> in clusters of four (X multicast)
 
 int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* bias, int64_t m, int n, int k,
                         int epilogue, void* out0, int64_t ld0, void* out1, int64_t ld1, int n_split, int q_cols,
@@ -468,10 +468,10 @@ int launch_encoder_gemm(const void* X, int64_t ldx, const void* W, const float* 
     a.res_stats = reinterpret_cast<const float2*>(res_stats);
     a.res_gamma = res_gamma;
     a.res_beta = res_beta;
-    a.dbg = static_cast<long long*>(g_enc_gemm_debug);
+    a.dbg = static_cast<long long*>(g_enc_gemm_debug.load());
     if (m == 0) return 0;
     // pairs once there are enough 256 x 256 tiles to occupy most of the chip
-    int form = g_enc_gemm_form;
+    int form = g_enc_gemm_form.load();
     if (form == 0) form = (((m + 255) / 256) * (n / 256) >= sm_count / 4) ? 2 : 1;
     if (form == 4 && (n / 256) % 4 != 0) form = 3;            // clusters of eight take n-tiles four at a time
     if (form == 3 && (n / 256) % 2 != 0) form = 2;            // clusters of four take n-tiles two at a time

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace sqe {
 
 // K1
@@ -81,15 +83,16 @@ int launch_encoder_pool(const float* h, const int32_t* first_token, int n_seq, f
 
 void set_error(const char* fmt, ...);
 
-// tuning knobs (api.cu)
-extern int g_k2_cta_group;      // 0 auto, 1, 2
-extern int g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
-extern int g_k2_d_hint;         // retired experiment (accepted, ignored)
-extern int g_k2_window;         // retired experiment (accepted, ignored)
-extern void* g_enc_gemm_debug;  // encoder_gemm.cu: role timers per CTA, or null
-extern void* g_enc_attn_debug;  // encoder_attn.cu: phase time stamps per CTA, or null
-extern int g_enc_small;        // 0 = few-token forward passes take the swap-AB split-K GEMM, 1 = never
-extern int g_enc_gemm_form;    // 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs (encoder_gemm.cu)
-extern void* g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
+// tuning knobs and diagnostics buffers (api.cu).  Process-wide, set from any thread while other threads
+// launch: atomics, and a launcher reads a knob ONCE per call.
+extern std::atomic<int> g_k2_cta_group;      // 0 auto, 1, 2
+extern std::atomic<int> g_k2_epilogue_mode;  // 0 normal; diagnostics only: 1 = TMEM loads only, 2 = no epilogue (results invalid)
+extern std::atomic<int> g_k2_d_hint;         // retired experiment (accepted, ignored)
+extern std::atomic<int> g_k2_window;         // K2p sibling progress window: 0 = default (8 tiles), -1 = unbounded, n = n tiles
+extern std::atomic<void*> g_enc_gemm_debug;  // encoder_gemm.cu: role timers per CTA, or null
+extern std::atomic<void*> g_enc_attn_debug;  // encoder_attn.cu: phase time stamps per CTA, or null
+extern std::atomic<int> g_enc_small;         // 0 = few-token forward passes take the swap-AB split-K GEMM, 1 = never
+extern std::atomic<int> g_enc_gemm_form;     // 0 auto, 1 = 128 x 64 tiles, 2 = 256 x 256 tiles on CTA pairs (encoder_gemm.cu)
+extern std::atomic<void*> g_k2_debug;        // device buffer [grid][8] u64 of role timers, or null
 
 }  // namespace sqe

@@ -1050,8 +1050,8 @@ template <int R, int CG, bool TOP1, bool DEEP, bool NARROW = false, bool DBG_OK 
 static int launch_batched_r(const CUtensorMap& tq, const CUtensorMap& td, K2Args a, float* out_score,
                             int64_t* out_idx, int64_t idx_offset, cudaStream_t stream) {
     using C = k2::Cfg<CG, R, TOP1, DEEP, NARROW>;
-    a.dbg = reinterpret_cast<unsigned long long*>(g_k2_debug);
-    a.epi_mode = g_k2_epilogue_mode;
+    a.dbg = reinterpret_cast<unsigned long long*>(g_k2_debug.load());
+    a.epi_mode = g_k2_epilogue_mode.load();
     if (a.n_dtiles > 0) {
         int rc;
         if constexpr (DBG_OK) {
@@ -1180,7 +1180,7 @@ int launch_topk_batched(const void* D, int dtype, int64_t n, const void* Q, int 
         return -3;
     }
     // CTA pairs whenever more than one 128-query tile is in flight (sqe_tuning_set overrides)
-    int cg = g_k2_cta_group;
+    int cg = g_k2_cta_group.load();
     if (cg == 0) cg = (b > k2::kRowsPerCta) ? 2 : 1;
     if (cg == 2)
         return launch_batched_cg<2>(D, dtype, n, Q, b, k, out_score, out_idx, idx_offset, ws, sm_count, stream);

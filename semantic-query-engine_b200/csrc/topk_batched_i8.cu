@@ -932,9 +932,10 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
     a.ws_logs = reinterpret_cast<uint64_t*>(w + kI8HdrBytes);
     a.meta = static_cast<const float4*>(meta);
     a.qmeta = qmeta;
-    a.epi_mode = g_k2_epilogue_mode;
+    a.epi_mode = g_k2_epilogue_mode.load();                    // read once: the exact pass below uses the same value
     a.ws_prog = reinterpret_cast<uint32_t*>(w + 4096 + 2048);     // second half of the arrivals page (zeroed per launch)
-    a.window = g_k2_window > 0 ? g_k2_window : (g_k2_window < 0 ? 0 : 8);
+    const int window_knob = g_k2_window.load();
+    a.window = window_knob > 0 ? window_knob : (window_knob < 0 ? 0 : 8);
     a.ws_spill = reinterpret_cast<uint64_t*>(spill);
     a.ws_clogs = reinterpret_cast<uint64_t*>(clogs);
     a.log_cap = k2i::kLogCapMax;
@@ -995,7 +996,7 @@ static int launch_i8_t(const void* D, int dtype, int64_t n, const void* D8, cons
             static_cast<const T*>(D), static_cast<uint32_t>(n), Qst, bc, static_cast<int>(b_pad), k, a.ws_clogs, a.ws_ccounts,
             a.ws_over, a.ws_spill_cnt, a.ws_spill, a.ws_tau, n_dtiles > 0 ? n_groups : 0, a.gpad, a.log_cap, a.meta,
             qmeta, out_score + static_cast<int64_t>(q0) * k, out_idx + static_cast<int64_t>(q0) * k, idx_offset,
-            out_rescored ? out_rescored + q0 : nullptr, g_k2_epilogue_mode == 3 ? 1 : 0);
+            out_rescored ? out_rescored + q0 : nullptr, a.epi_mode == 3 ? 1 : 0);
         e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("search_batched_prefiltered: rescore launch: %s", cudaGetErrorString(e)); return -2; }
     }

@@ -52,11 +52,10 @@ def write_bert_gguf(path: str, sd: Dict[str, "np.ndarray"], vocab: Sequence[str]
     w.add_token_types([3 if (t.startswith("[") and t.endswith("]")) else 1 for t in vocab])
     w.add_token_type_count(2)
     ids = {t: i for i, t in enumerate(vocab)}
-    w.add_unk_token_id(ids["[UNK]"])
-    w.add_sep_token_id(ids["[SEP]"])
-    w.add_pad_token_id(ids["[PAD]"])
-    w.add_mask_token_id(ids["[MASK]"])
-    w.add_bos_token_id(ids["[CLS]"])
+    for tok, add in (("[UNK]", w.add_unk_token_id), ("[SEP]", w.add_sep_token_id), ("[PAD]", w.add_pad_token_id),
+                     ("[MASK]", w.add_mask_token_id), ("[CLS]", w.add_bos_token_id)):
+        if tok in ids:
+            add(ids[tok])
     tmap = gguf.get_tensor_name_map(gguf.MODEL_ARCH.BERT, layers)
     qt = {"q8_0": gguf.GGMLQuantizationType.Q8_0, "q4_0": gguf.GGMLQuantizationType.Q4_0,
           "q4_1": gguf.GGMLQuantizationType.Q4_1}

@@ -192,3 +192,96 @@ def test_reference_lifespan_ingest_of_32717_chunks_then_websocket_requests(ref_m
     print(f"reference lifespan ingest: {n_chunks} chunks of {n_docs} files through run_in_executor(add_embeddings); "
           f"{len(requests)} websocket requests through main.ask_websocket_endpoint, {len(prompts)} prompts, "
           f"cache {cache.freqs()}")
+
+
+def test_reference_ingest_and_requests_from_text_with_the_gpu_encoder(ref_main, tmp_path):
+    """Nothing stubbed between the text and the prompt: `install_encoder(main)` + `plugin.install(main)`,
+    then the reference's own `build_embeddings_from_scratch` (main.py:413-456: list the PMC directory,
+    `basic_cleaning`, `chunk_text`, `embed_texts_in_batches`, `run_in_executor(add_embeddings)`) and
+    `ask_websocket_endpoint` (main.py:650-735: `embed_query`, `lfu_cache_get`, `os_search`, context,
+    `lfu_cache_put`) run with the embedding step AND the retrieval step on the GPU.  Expected hits: the
+    CPU oracles end to end (bert_oracle embeddings of the same chunks -> numpy_oracle top-k)."""
+    sqe, m = ref_main
+    import oracle
+    from oracle import bert_oracle as bo
+    vocab_list = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + \
+        [w for w in ("gene tumor protein cell patient dose trial cohort enzyme receptor pathway mutation tissue "
+                     "serum marker assay sample therapy response control binding expression growth signal").split()] + \
+        ["##s", "##ing", "##ed", ".", ","]
+    vocab = {t: i for i, t in enumerate(vocab_list)}
+    words = vocab_list[5:-5]
+    rng = np.random.default_rng(7)
+    pmc = tmp_path / "PMC"
+    pmc.mkdir()
+    n_files = 48
+    for d in range(n_files):
+        n_words = int(rng.integers(6, 60)) if d % 12 else m.CHUNK_SIZE + int(rng.integers(5, 40))   # a few two-chunk files
+        text = " ".join(str(rng.choice(words)) + ("s" if rng.random() < 0.2 else "") for _ in range(n_words))
+        (pmc / f"PMC{7000 + d}.txt").write_text(text + " .\n")
+    (pmc / "notes.txt").write_text("ignored")
+    w = bo.random_bert_weights(91, layers=2, vocab=len(vocab_list))
+    dev = torch.device("cuda", 0)
+    enc = sqe.GpuEmbeddingEncoder(sqe.EncoderWeights.from_state_dict(w, device=dev), sqe.WordPieceTokenizer(vocab))
+    sqe.install_encoder(m, enc)
+    cache = sqe.plugin.install(m, dtype="fp32", strict=True)
+    m.EMB_DIR = str(pmc)
+    prompts = []
+    _stub_generation(m, prompts)
+
+    async def lifespan():
+        async with m.lifespan(m.app):
+            pass
+    asyncio.run(lifespan())
+    index = m.rag_model.os_indexer
+    docs = []
+    for fname in os.listdir(str(pmc)):
+        if fname.startswith("PMC") and fname.endswith(".txt"):
+            for chunk in m.chunk_text(m.basic_cleaning((pmc / fname).read_text()), m.CHUNK_SIZE):
+                docs.append({"doc_id": fname, "text": chunk})
+    assert index.num_rows == len(docs) > n_files and index._docs == docs
+
+    # the oracle's view of the same corpus and queries
+    emb = bo.bert_embed(w, [bo.encode_text(d["text"], vocab) for d in docs]).numpy()
+    d_n = oracle.normalize_rows(emb)
+    free = "tumor gene expression in patient serum"
+    f_n = oracle.normalize_rows(bo.bert_embed(w, [bo.encode_text(free, vocab)]).numpy())
+    # random-weight encoders put all texts in a narrow cone (mean cosine ~0.8 here, some pairs above the
+    # cache threshold 0.96): pick query chunks that are no cache hits for one another or for the free text
+    picks = []
+    for i in range(len(docs)):
+        if all(float(d_n[i] @ d_n[j]) < 0.92 for j in picks) and float(d_n[i] @ f_n[0]) < 0.92:
+            picks.append(i)
+        if len(picks) == 3:
+            break
+    assert len(picks) == 3
+    queries = [docs[i]["text"] for i in picks] + [free, "   "]
+    requests = [{"query": q, "top_k": 4} for q in queries] + [{"query": queries[0], "top_k": 4}]
+    results = _drive(m, requests, prompts)
+    n_prompts = 0
+    for req, res in zip(requests[: len(queries)], results):
+        q = req["query"]
+        if not q.strip():
+            assert res["sent"] == ["[ERROR] Empty query."] and res["prompt"] is None
+            continue
+        n_prompts += 1
+        q_n = oracle.normalize_rows(bo.bert_embed(w, [bo.encode_text(q, vocab)]).numpy())
+        s, idx = oracle.topk_cosine(d_n, q_n, 5)
+        s, idx = s[0], idx[0]
+        # ranks whose oracle score is separated from the next by more than the fp16-operand error of the
+        # GPU encoder (a few 1e-3 on a cosine) must come out identically; the handler's prompt holds them
+        sure = 0
+        while sure < 4 and s[sure] - s[sure + 1] > 2e-2:
+            sure += 1
+        hits = index.search(asyncio.run(m.embed_query(q)), k=4)
+        assert [h[0] for h in hits[:sure]] == [docs[int(r)] for r in idx[:sure]], (q[:40], s, sure)
+        assert all(abs(h[1] - float(sc)) < 1e-2 for h, sc in zip(hits, s)), (hits, s)
+        assert res["prompt"] == (f"User Query:\n{q}\n\nContext:\n{sqe.build_context_text(hits)}\n"
+                                 "--- End of context ---\n\nProvide your concise answer now.")
+        assert res["sent"] == ["Answer ", f"#{n_prompts}"]
+    for i, res in zip(picks, results):                                  # a chunk's own text finds that chunk first
+        assert f"--- Document ID: {docs[i]['doc_id']} ---\n" in res["prompt"].split("Context:\n")[1][:60]
+    # the repeated first query is answered from the cache (cos = 1 >= 0.96): no new prompt, freq 2
+    assert results[-1] == {"sent": ["Answer #1"], "prompt": None} and len(prompts) == n_prompts
+    assert cache.freqs()[-1] == 2 and sorted(cache.freqs()) == [1] * (n_prompts - 1) + [2]
+    print(f"reference text ingest with the GPU encoder: {len(docs)} chunks of {n_files} files, "
+          f"{len(requests)} websocket requests, {len(prompts)} prompts, cache {cache.freqs()}")

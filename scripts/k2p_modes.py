@@ -6,6 +6,8 @@ import torch
 import sqe_b200
 from sqe_b200 import ops
 nat = sqe_b200._native
+if os.environ.get("SQE_LIB"):                             # an experimental build of the library (before the first call)
+    nat.LIB_PATH = os.path.abspath(os.environ["SQE_LIB"])
 rows, b, K = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 dev = torch.device("cuda", 0)
 D = torch.empty((rows, 1024), dtype=torch.bfloat16, device=dev)
@@ -15,7 +17,7 @@ for lo in range(0, rows, 250_000):
     ops.normalize_cast(torch.randn((min(250_000, rows - lo), 1024), generator=gen, device=dev), "bf16", out=D[lo:lo + 250_000])
 d8, meta = ops.quantize_rows(D)
 q = torch.randn((b, 1024), generator=torch.Generator().manual_seed(99)).to(dev)
-for mode in (0, 1, 2):
+for mode in [int(m) for m in os.environ.get("K2P_MODES", "0,1,2").split(",")]:
     nat.tuning_set(nat.SQE_TUNE_K2_EPILOGUE_MODE, mode)
     for _ in range(3):
         ops.search_batched_prefiltered(D, d8, meta, q, K)
@@ -26,5 +28,5 @@ for mode in (0, 1, 2):
         ops.search_batched_prefiltered(D, d8, meta, q, K)
     e1.record()
     torch.cuda.synchronize()
-    print(f"rows={rows} b={b} k={K} epilogue_mode={mode}: {e0.elapsed_time(e1) / 5:.3f} ms per call", flush=True)
+    print(f"lib={os.path.basename(nat.LIB_PATH)} rows={rows} b={b} k={K} epilogue_mode={mode}: {e0.elapsed_time(e1) / 5:.3f} ms per call", flush=True)
 nat.tuning_set(nat.SQE_TUNE_K2_EPILOGUE_MODE, 0)

@@ -42,7 +42,16 @@ constexpr int kNumChunksI8 = kDim / kChunkI8;      // 8
 constexpr int kUmmaKI8 = 32;                       // elements per tcgen05.mma kind::i8
 constexpr int kLogCapMax = 1024;                   // entries per (query, group) candidate log
 constexpr int kSpillCap = 8192;                    // entries per query of the shared spill area (full logs)
-constexpr int kMetaBufs = 4;                       // row-constant tiles in flight (see the producer)
+#ifndef SQE_I8_META_BUFS
+#define SQE_I8_META_BUFS 4
+#endif
+#ifndef SQE_I8_ASTAT_STAGES
+#define SQE_I8_ASTAT_STAGES 4
+#endif
+#ifndef SQE_I8_MIN_THR_SLOTS
+#define SQE_I8_MIN_THR_SLOTS 4
+#endif
+constexpr int kMetaBufs = SQE_I8_META_BUFS;        // row-constant tiles in flight (see the producer)
 constexpr int kMetaBytes = kTileN * 16;            // {sd, eps, nd, 0} per shard row of a d-tile
 constexpr float kSlack = 4e-6f;                    // as in topk_prefilter.cu (pf::kSlack, pf::kInflate)
 constexpr float kInflate = 1.001f;
@@ -61,7 +70,7 @@ struct CfgI8 {
     static constexpr bool kAStat = (CG == 2) && !DEEP;
     static constexpr int kAResident = kAStat ? kNumChunksI8 * kABytes : 0;      // 128 KB
     static constexpr int kStageBytes = (kAStat ? 0 : kABytes) + kBBytes;   // 48 KB / 32 KB as for 16-bit operands; 16 KB
-    static constexpr int kStages = (CG == 1) ? 4 : (DEEP ? 6 : 4);
+    static constexpr int kStages = (CG == 1) ? 4 : (DEEP ? 6 : (R == 1 ? SQE_I8_ASTAT_STAGES : 4));
     static constexpr int kOffStages = kAResident;
     static constexpr int kOffMeta = kOffStages + kStages * kStageBytes;
     static constexpr int kOffXbuf = kOffMeta + kMetaBufs * kMetaBytes;     // per epilogue warp: 32 words of transpose
@@ -74,7 +83,7 @@ struct CfgI8 {
     static constexpr int kOffBar = kOffThr + kThrSlots * kThrSlotBytes;
     static constexpr int kOffTmemPtr = kOffBar + 32 * 8;
     static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;
-    static_assert(kThrSlots >= 4 && kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(kThrSlots >= (R == 1 ? SQE_I8_MIN_THR_SLOTS : 4) && kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 }  // namespace k2i
 

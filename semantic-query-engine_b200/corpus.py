@@ -107,15 +107,27 @@ class GpuCorpusIndex:
         new = torch.empty((cap, ops.ROW_ELEMS[self.dtype]), dtype=ops.TORCH_DTYPES[self.dtype], device=self.device)
         if self._shard is not None and self._rows:
             new[: self._rows].copy_(self._shard[: self._rows])
-        self._shard = new
+        c8 = cm = None
         if self.prefilter:
             c8 = torch.empty((cap, EMBED_DIM), dtype=torch.int8, device=self.device)
             cm = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
             if self._coarse8 is not None and self._rows:
                 c8[: self._rows].copy_(self._coarse8[: self._rows])
                 cm[: self._rows].copy_(self._coarse_meta[: self._rows])
+        # Searches read `_shard` / `_coarse*` without the ingest lock and may run on other streams (a
+        # MicroBatcher's compute stream): the new buffers become visible only once the copies into them
+        # have finished, and the old ones are released only after every kernel that may still read them
+        # has (a search that picked up the old pointers just before the swap).
+        old = (self._shard, self._coarse8, self._coarse_meta)
+        if old[0] is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+        self._shard = new
+        if self.prefilter:
             self._coarse8, self._coarse_meta = c8, cm
         self._capacity = cap
+        if old[0] is not None:
+            torch.cuda.synchronize(self.device)
+        del old
 
     def enable_prefilter(self) -> None:
         """Turn the prefiltered scan on for an index that was built without it: allocate the int8

@@ -285,3 +285,84 @@ def test_reference_ingest_and_requests_from_text_with_the_gpu_encoder(ref_main, 
     assert cache.freqs()[-1] == 2 and sorted(cache.freqs()) == [1] * (n_prompts - 1) + [2]
     print(f"reference text ingest with the GPU encoder: {len(docs)} chunks of {n_files} files, "
           f"{len(requests)} websocket requests, {len(prompts)} prompts, cache {cache.freqs()}")
+
+
+def test_reference_upload_service_from_text_with_the_gpu_encoder(tmp_path):
+    """The upload micro-service, literally: the reference's own `upload_text` handler
+    (embedding_gen.py:315-410: authorisation, file checks, save, `chunk_text`, `embed_texts_in_batches`,
+    `bulk_index_embeddings`) with `install_encoder` + `plugin.install_embedding_gen` -- files in, per-user GPU
+    indices out; only Postgres is stubbed.  Expected payload from the handler's own rules, expected vectors
+    from the CPU oracles."""
+    import io
+    import types
+    root = _reference_root()
+    if root is None:
+        pytest.skip("no copy of the reference's app/ here (scripts/stage_reference.sh stages one for a GPU run)")
+    import oracle
+    import sqe_b200 as sqe
+    from oracle import bert_oracle as bo
+    from oracle import ref_loader
+    sqe._native.load()
+    ref_loader.REFERENCE_ROOT = root
+    eg = ref_loader.load_reference_embedding_gen(base_index_name="docs")
+    vocab_list = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + \
+        "gene tumor protein cell patient dose trial cohort enzyme receptor pathway mutation".split() + ["##s", ".", ","]
+    vocab = {t: i for i, t in enumerate(vocab_list)}
+    w = bo.random_bert_weights(19, layers=2, vocab=len(vocab_list))
+    dev = torch.device("cuda", 0)
+    enc = sqe.GpuEmbeddingEncoder(sqe.EncoderWeights.from_state_dict(w, device=dev), sqe.WordPieceTokenizer(vocab))
+    reg = sqe.plugin.install_embedding_gen(eg, dtype="fp32", strict=True)
+    sqe.install_encoder(eg, enc)
+    assert enc.blank_policy == "embedding_gen"
+
+    async def authorised(user_id):                                   # embedding_gen.py:282-309, Postgres stubbed
+        return user_id != "mallory"
+    eg.check_user_authorized_in_postgres = authorised
+    eg.BASE_UPLOAD_DIR = str(tmp_path / "uploads")
+    clock = [1700000000.7]
+    eg.time = types.SimpleNamespace(time=lambda: clock[0])             # doc_id = f"{stem}_{int(time.time())}"
+
+    class Upload:
+        def __init__(self, filename, text):
+            self.filename, self.file = filename, io.BytesIO(text.encode("utf-8"))
+
+    rng = np.random.default_rng(3)
+    words = vocab_list[5:-3]
+
+    def text_of(n_words):
+        return " ".join(str(rng.choice(words)) + ("s" if rng.random() < 0.25 else "") for _ in range(n_words)) + " ."
+    paper, notes, bobs = text_of(eg.CHUNK_SIZE + 40), text_of(25), text_of(60)
+    msg = asyncio.run(eg.upload_text(user_id="alice", files=[Upload("paper.txt", paper), Upload("notes.txt", notes)]))
+    assert msg == "Uploaded 2 files & embedded documents for user='alice'."
+    assert asyncio.run(eg.upload_text(user_id="bob", files=[Upload("b.txt", bobs)])).startswith("Uploaded 1 files")
+    assert sorted(os.listdir(tmp_path / "uploads" / "alice")) == ["notes_1700000000.txt", "paper_1700000000.txt"]
+
+    want_docs = [("paper_1700000000", c) for c in eg.chunk_text(paper, eg.CHUNK_SIZE)] + \
+                [("notes_1700000000", c) for c in eg.chunk_text(notes, eg.CHUNK_SIZE)]
+    assert len(want_docs) == 3
+    idx = reg.get("alice")
+    assert idx is not None and idx.index_name == "docs-alice" and idx.num_rows == 3 and reg.get("bob").num_rows == 1
+    assert [idx._source(r) for r in range(3)] == [{"doc_id": d, "text": c} for d, c in want_docs]
+    assert [idx.doc_id_of(r) for r in range(3)] == ["paper_1700000000_0", "paper_1700000000_1", "notes_1700000000_0"]
+    # stored rows = normalised encoder outputs: against the fp32 oracles (fp16-operand error of the GPU encoder)
+    want = oracle.normalize_rows(bo.bert_embed(w, [bo.encode_text(c, vocab) for _, c in want_docs]).numpy())
+    got = idx.shard.float().cpu().numpy()
+    assert np.abs(got - want).max() < 2e-3 and (got * want).sum(1).min() > 0.9999
+    # a chunk's own text finds that chunk in its owner's index, and nothing in another user's
+    q = asyncio.run(eg.embed_texts_in_batches([want_docs[1][1]]))
+    hit = reg.search("alice", q, k=1)[0]
+    assert hit[0] == {"doc_id": "paper_1700000000", "text": want_docs[1][1]} and hit[1] > 0.9999
+    assert reg.search("bob", q, k=3)[0][0]["doc_id"] == "b_1700000000" and reg.search("carol", q, k=3) == []
+    # a later re-upload is a NEW document (the timestamp is part of the doc_id): rows are appended
+    clock[0] += 60.0
+    asyncio.run(eg.upload_text(user_id="alice", files=[Upload("notes.txt", notes)]))
+    assert idx.num_rows == 4 and idx.doc_id_of(3) == "notes_1700000060_0"
+    # the handler's refusals are unchanged (embedding_gen.py:332-336, :351-355, :386-390)
+    for uid, files, status in (("mallory", [Upload("a.txt", "gene")], 403), ("alice", [Upload("a.pdf", "gene")], 403),
+                               ("alice", [Upload("a.txt", "   ")], 400), ("alice", [], 400)):
+        with pytest.raises(eg.HTTPException) as ei:
+            asyncio.run(eg.upload_text(user_id=uid, files=files))
+        assert ei.value.status_code == status
+    assert idx.num_rows == 4
+    print(f"reference upload service with the GPU encoder: 3 uploads of 2 users, indices "
+          f"{ {u: reg.get(u).num_rows for u in ('alice', 'bob')} }, 4 refusals")
